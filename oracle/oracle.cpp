@@ -1,0 +1,761 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY.
+//
+// CPU restatement of the mixed-precision GMRES hot path of iamsonderr/icl-mixed-precision-gmres.
+// Nothing in the product (icl-mixed-precision-gmres_b200/, include/) may link, import or call this
+// file; only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs do,
+// and only as the checker / the reported CPU baseline.
+//
+// Every routine cites the reference file:line (relative to /root/reference) whose behaviour it
+// restates.  The arithmetic that the reference delegates to un-vendored vendor libraries (Intel MKL
+// cblas / sparse BLAS, "Intel MKL" README.txt:11, link line Makefile:13; cuBLAS/cuSPARSE from CUDA 10)
+// is restated from the published BLAS reference semantics (netlib BLAS level 1/2: sdot, snrm2, saxpy,
+// sscal, srotg, srot, sgemv, strsv; CSR y = alpha*A*x + beta*y).  Reduction order is unspecified by
+// BLAS; this oracle uses a FIXED blocked order (independent of thread count) so goldens reproduce.
+//
+// Pinning: the reference has no tests or golden vectors.  The oracle is pinned
+// against oracle/_ref — the reference's own gmres.cpp / Orthogonalization.hpp / IterUtil.hpp /
+// kernels_mkl.cpp / gmres_perf_test.cpp compiled unmodified against a host Kokkos shim and the oneMKL
+// that ships inside libtorch_cpu.so (see oracle/Makefile, tests/test_oracle_vs_ref.py).
+//
+// Build: make -C oracle   (g++ -O2 -fopenmp -ffp-contract=off; FMA is used explicitly where BLAS
+// implementations use it, so results do not depend on compiler contraction).
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <random>
+#include <vector>
+
+#if defined(_OPENMP)
+#include <omp.h>
+#endif
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// BLAS-1 restatements.  Reduction block: fixed 1024-element blocks accumulated in T with fma, block
+// partials combined sequentially in double (cheap, deterministic, at least as accurate as any BLAS).
+// ------------------------------------------------------------------------------------------------
+constexpr size_t RBLK = 1024;
+
+template <class T>
+inline T fma_t(T a, T b, T c) { return std::fma(a, b, c); }
+
+// kernels.hpp:33-37 / kernels_mkl.cpp:73-95 (cblas_?dot)
+template <class T>
+T dot(size_t n, const T* x, const T* y) {
+    const size_t nb = (n + RBLK - 1) / RBLK;
+    std::vector<double> part(nb);
+#pragma omp parallel for schedule(static)
+    for (long b = 0; b < (long)nb; ++b) {
+        const size_t lo = b * RBLK, hi = std::min(n, lo + RBLK);
+        T acc = 0;
+        for (size_t i = lo; i < hi; ++i) acc = fma_t(x[i], y[i], acc);
+        part[b] = (double)acc;
+    }
+    double s = 0;
+    for (size_t b = 0; b < nb; ++b) s += part[b];
+    return (T)s;
+}
+
+// kernels.hpp:40-44 / kernels_mkl.cpp:97-115 (cblas_?nrm2).  BLAS nrm2 is overflow-safe (scaled); the
+// values on this path are O(1)..O(1e5), so the unscaled blocked form is within rounding of it.
+template <class T>
+T nrm2(size_t n, const T* x) {
+    const size_t nb = (n + RBLK - 1) / RBLK;
+    std::vector<double> part(nb);
+#pragma omp parallel for schedule(static)
+    for (long b = 0; b < (long)nb; ++b) {
+        const size_t lo = b * RBLK, hi = std::min(n, lo + RBLK);
+        T acc = 0;
+        for (size_t i = lo; i < hi; ++i) acc = fma_t(x[i], x[i], acc);
+        part[b] = (double)acc;
+    }
+    double s = 0;
+    for (size_t b = 0; b < nb; ++b) s += part[b];
+    return (T)std::sqrt(s);
+}
+
+// kernels.hpp:47-51 / kernels_mkl.cpp:118-146 (cblas_?axpy): y += alpha*x
+template <class T>
+void axpy(size_t n, T alpha, const T* x, T* y) {
+#pragma omp parallel for schedule(static)
+    for (long i = 0; i < (long)n; ++i) y[i] = fma_t(alpha, x[i], y[i]);
+}
+
+// kernels.hpp:59-60 / kernels_cuda.cpp:264-288: y -= alpha*x   (y = fma(-alpha, x, y))
+template <class T>
+void naxpy(size_t n, T alpha, const T* x, T* y) {
+#pragma omp parallel for schedule(static)
+    for (long i = 0; i < (long)n; ++i) y[i] = fma_t(-alpha, x[i], y[i]);
+}
+
+// kernels.hpp:64-66 / kernels_cuda.cpp:309-331: y = alpha*x  (copy then scal)
+template <class T>
+void scal_out(size_t n, T alpha, const T* x, T* y) {
+#pragma omp parallel for schedule(static)
+    for (long i = 0; i < (long)n; ++i) y[i] = alpha * x[i];
+}
+
+// kernels.hpp:11-20: element-wise assign with implicit conversion (the fp64<->fp32 casts)
+template <class A, class B>
+void copy_cast(size_t n, const A* x, B* y) {
+#pragma omp parallel for schedule(static)
+    for (long i = 0; i < (long)n; ++i) y[i] = (B)x[i];
+}
+
+// kernels.hpp:104-106 / kernels_mkl.cpp:207-219: BLAS rotg, then the reference overwrites b with 0.
+// netlib srotg: roe = (|a|>|b|)?a:b; scale=|a|+|b|; r = sign(roe)*scale*sqrt((a/scale)^2+(b/scale)^2)
+template <class T>
+void rotg(T& a, T& b, T& c, T& s) {
+    const T roe = (std::fabs(a) > std::fabs(b)) ? a : b;
+    const T scale = std::fabs(a) + std::fabs(b);
+    T r;
+    if (scale == T(0)) {
+        c = 1; s = 0; r = 0;
+    } else {
+        const T as = a / scale, bs = b / scale;
+        r = scale * std::sqrt(as * as + bs * bs);
+        r = std::copysign(T(1), roe) * r;
+        c = a / r;
+        s = b / r;
+    }
+    a = r;
+    b = 0;  // kernels_mkl.cpp:210,218 / kernels_cuda.cpp:404,418
+}
+
+// kernels.hpp:109-111 / kernels_mkl.cpp:221-233 (cblas_?rot, n=1)
+template <class T>
+void rot1(T& a, T& b, T c, T s) {
+    const T t = c * a + s * b;
+    b = c * b - s * a;
+    a = t;
+}
+
+// kernels.hpp:113-114 / kernels_mkl.cpp:235-257 / kernels_cuda.cpp:448-494: k = c.n() rotations applied
+// in order to (a[j], a[j+1]); touches a[0..k].
+template <class T>
+void rot_vec(size_t k, T* a, const T* c, const T* s) {
+    for (size_t j = 0; j < k; ++j) rot1(a[j], a[j + 1], c[j], s[j]);
+}
+
+// kernels.hpp:118-125 / kernels_mkl.cpp:264-288 (cblas_?gemv, column-major, lda = stride).
+// trans: y[j] = alpha * sum_i M[i,j] x[i] + beta*y[j]    (M is nrows x ncols base dims)
+template <class T>
+void gemv_t(size_t nrows, size_t ncols, T alpha, const T* M, size_t ld, const T* x, T beta, T* y) {
+    for (size_t j = 0; j < ncols; ++j) {
+        const T d = dot<T>(nrows, M + j * ld, x);
+        y[j] = (beta == T(0)) ? alpha * d : fma_t(alpha, d, beta * y[j]);
+    }
+}
+// no-trans: y = alpha*M*x + beta*y, per row sequential in j (netlib column sweep order)
+template <class T>
+void gemv_n(size_t nrows, size_t ncols, T alpha, const T* M, size_t ld, const T* x, T beta, T* y) {
+#pragma omp parallel for schedule(static)
+    for (long i = 0; i < (long)nrows; ++i) {
+        T acc = (beta == T(0)) ? T(0) : beta * y[i];
+        for (size_t j = 0; j < ncols; ++j) acc = fma_t(alpha * x[j], M[i + j * ld], acc);
+        y[i] = acc;
+    }
+}
+
+// kernels.hpp:128-129 / kernels_mkl.cpp:291-321 (cblas_?trsv Upper, NoTrans, NonUnit; netlib column form)
+template <class T>
+void trsv_upper(size_t n, const T* A, size_t ld, T* x) {
+    for (size_t jj = n; jj-- > 0;) {
+        if (x[jj] != T(0)) {
+            x[jj] = x[jj] / A[jj + jj * ld];
+            const T t = x[jj];
+            for (size_t i = jj; i-- > 0;) x[i] = fma_t(-t, A[i + jj * ld], x[i]);
+        }
+    }
+}
+
+// kernels.hpp:159-160 / kernels_mkl.cpp:326-352 (mkl_sparse_?_mv, general, 0-based CSR)
+template <class T>
+void spmv(int nrows, const int* row_map, const int* inds, const T* vals, T alpha, const T* x, T beta, T* y) {
+#pragma omp parallel for schedule(static)
+    for (int r = 0; r < nrows; ++r) {
+        T acc = 0;
+        for (int p = row_map[r]; p < row_map[r + 1]; ++p) acc = fma_t(vals[p], x[inds[p]], acc);
+        y[r] = (beta == T(0)) ? alpha * acc : fma_t(alpha, acc, beta * y[r]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Orthogonalization.hpp restated.  orth: 0 = CGS (:76-89), 1 = MGS (:91-107), 2 = CGSR<2> (:109-136)
+// ------------------------------------------------------------------------------------------------
+template <class T>
+struct GS {
+    size_t n, m;
+    int orth;
+    std::vector<T> v;        // n x (m+1) column-major (types.hpp:115-118 LayoutLeft)  Orthogonalization.hpp:27-30
+    std::vector<T> weights;  // CGSR scratch  Orthogonalization.hpp:113,118
+    GS(size_t n_, size_t m_, int orth_) : n(n_), m(m_), orth(orth_), v(n_ * (m_ + 1), T(0)), weights(m_, T(0)) {}
+    T* col(size_t j) { return v.data() + j * n; }
+
+    // Orthogonalization.hpp:36-45
+    T first_vector(const T* w) {
+        const T beta = nrm2<T>(n, w);
+        if (beta != T(0)) scal_out<T>(n, 1 / beta, w, col(0));
+        else std::fill(col(0), col(0) + n, T(0));
+        return beta;
+    }
+    // Orthogonalization.hpp:82-88 / :98-106 / :120-135
+    void orthogonalize(size_t k, T* w, T* h, size_t ldh) {
+        T* hcol = h + k * ldh;
+        const size_t k1 = k + 1;
+        if (orth == 1) {
+            for (size_t j = 0; j < k1; ++j) {
+                hcol[j] = dot<T>(n, w, col(j));
+                naxpy<T>(n, hcol[j], col(j), w);
+            }
+            return;
+        }
+        gemv_t<T>(n, k1, T(1), v.data(), n, w, T(0), hcol);
+        gemv_n<T>(n, k1, T(-1), v.data(), n, hcol, T(1), w);
+        if (orth == 2) {
+            gemv_t<T>(n, k1, T(1), v.data(), n, w, T(0), weights.data());
+            gemv_n<T>(n, k1, T(-1), v.data(), n, weights.data(), T(1), w);
+            for (size_t j = 0; j < k1; ++j) hcol[j] = fma_t(T(1), weights[j], hcol[j]);  // axpy(1,weights,h_col) :133
+        }
+    }
+    // Orthogonalization.hpp:51-60
+    void add_vector(size_t k, T* w, T* h, size_t ldh) {
+        orthogonalize(k, w, h, ldh);
+        const T hf = nrm2<T>(n, w);
+        h[(k + 1) + k * ldh] = hf;
+        scal_out<T>(n, 1 / hf, w, col(k + 1));
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// IterUtil.hpp restated.  kind: 0 Convergence (:17-81), 1 RelPrecRes (:139-169),
+// 2 RepeatIteration (:84-137), 3 LostOrthogonality (:172-227)
+// ------------------------------------------------------------------------------------------------
+enum Action { NEXT = 0, CONVERGED = 1, RESTART = 2, ABORTED = 3 };
+
+template <class T>
+struct Conv {
+    int kind;
+    double tol, rtol;
+    size_t rlen, max_restarts;
+    size_t total_iters = 0, total_restarts = 0;
+    double restart_tol;
+    size_t second_len = 0;
+    bool first_iteration = true;
+    double loss_sq = 0;
+    std::vector<T> S, u;
+    GS<T>* gs = nullptr;
+
+    Conv(int kind_, double tol_, double rtol_, size_t rlen_, size_t maxr_)
+        : kind(kind_), tol(tol_), rtol(rtol_), rlen(rlen_), max_restarts(maxr_), restart_tol(rtol_) {
+        if (kind == 3) { S.assign((rlen + 1) * (rlen + 1), T(0)); u.assign(rlen + 1, T(0)); }
+    }
+    void setup(GS<T>& g) {  // IterUtil.hpp:35-37, :189-193
+        gs = &g;
+        if (kind == 3) std::fill(S.begin(), S.end(), T(0));
+        total_iters = 0;
+    }
+    Action base_initial(double res, double normalization) {  // IterUtil.hpp:42-51
+        total_restarts++;
+        if (total_restarts > max_restarts) return ABORTED;
+        if (res / normalization > tol) return NEXT;
+        return CONVERGED;
+    }
+    Action check_initial(double res, double normalization, double pres, double pb) {
+        if (kind == 1) restart_tol = pres / pb * rtol;                        // :150-153
+        if (kind == 2 && first_iteration) restart_tol = pres / pb * rtol;     // :99-104
+        if (kind == 3) loss_sq = 0;                                           // :195-198
+        return base_initial(res, normalization);
+    }
+    Action base_check(size_t k) {  // IterUtil.hpp:57-65
+        total_iters++;
+        if (rlen <= k) return RESTART;
+        return NEXT;
+    }
+    Action check(size_t k, double res, double bnorm) {
+        const Action a = base_check(k);
+        if (kind == 0) return a;
+        if (kind == 1) {  // :155-165
+            if (a != NEXT) return a;
+            return (res / bnorm <= restart_tol) ? RESTART : NEXT;
+        }
+        if (kind == 2) {  // :106-133
+            if (first_iteration) {
+                if (a != NEXT) { first_iteration = false; second_len = k; return a; }
+                if (res / bnorm <= restart_tol) { first_iteration = false; second_len = k; return RESTART; }
+                return NEXT;
+            }
+            if (a != NEXT) return a;
+            return (second_len <= k) ? RESTART : NEXT;
+        }
+        // kind 3, :200-223.  u = V[:,0:k+1]^T V[:,k+1]; s_col = u - S[0:k+1,0:k+1] u; loss += s_col.s_col
+        if (a != NEXT) return a;
+        const size_t k1 = k + 1, ldS = rlen + 1, n = gs->n;
+        gemv_t<T>(n, k1, T(1), gs->v.data(), n, gs->col(k + 1), T(0), u.data());
+        T* scol = S.data() + (k + 1) * ldS;
+        for (size_t j = 0; j < k1; ++j) scol[j] = u[j];
+        gemv_n<T>(k1, k1, T(-1), S.data(), ldS, u.data(), T(1), scol);
+        loss_sq += (double)dot<T>(k1, scol, scol);
+        return (loss_sq >= rtol * rtol) ? RESTART : NEXT;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Drivers.  History record layout (doubles): per inner iteration arnoldi_residual/Minvb_norm; per
+// restart {r_norm, normalization, beta, x_norm}.
+// ------------------------------------------------------------------------------------------------
+struct Stats {
+    int64_t status;          // 1 converged, 3 aborted
+    int64_t total_iters;
+    int64_t total_restarts;  // Convergence::total_restarts (counts check_initial calls)
+    int64_t outer_i;         // i at exit (gmres.cpp:186)
+    double rel_prec_res;     // printed "rel prec res norm" (gmres.cpp:186)
+    double b_norm, Minvb_norm, A_norm;
+    int64_t n_hist_inner, n_hist_outer;
+};
+
+struct Hist {
+    double* inner; int64_t cap_inner;
+    double* outer; int64_t cap_outer;
+    int64_t ni = 0, no = 0;
+    void push_inner(double v) { if (inner && ni < cap_inner) inner[ni] = v; ni++; }
+    void push_outer(double a, double b, double c, double d) {
+        if (outer && no + 1 <= cap_outer) { outer[4 * no] = a; outer[4 * no + 1] = b; outer[4 * no + 2] = c; outer[4 * no + 3] = d; }
+        no++;
+    }
+};
+
+// Givens bookkeeping shared by both drivers.  gmres.cpp:106-110 (baseline: rot on h(range1,k), cos(range))
+// and gmres.cpp:219-222 (mixed: rot on h(range,k)) apply the same k rotations to h[0..k].
+template <class T>
+double givens_step(size_t k, T* h, size_t ldh, T* cs, T* sn, T* s) {
+    T* hcol = h + k * ldh;
+    rot_vec<T>(k, hcol, cs, sn);
+    rotg<T>(hcol[k], hcol[k + 1], cs[k], sn[k]);
+    rot1<T>(s[k], s[k + 1], cs[k], sn[k]);
+    return std::fabs((double)s[k + 1]);
+}
+
+// gmres.cpp:135-245 gmres_singleUpdate.  jac32: optional Jacobi diagonal (types.hpp:381-448; apply = gdmv
+// kernels.hpp:131-151: y = 0*y + 1*diag*x -> with beta==0 still computes beta*y; y finite here).
+void gmres_mixed(Conv<float>& conv, int orth, int n, const int* row_map, const int* inds, const double* vals64,
+                 const float* vals32, const float* jac32, const double* b, double* x, Stats& st, Hist& hist) {
+    const size_t m = conv.rlen;
+    const size_t nnz = row_map[n];
+    GS<float> gs(n, m, orth);
+    std::vector<float> cs(m + 1, 0.f), sn(m + 1, 0.f), s(m + 1, 0.f), w(n, 0.f), h((m + 1) * m, 0.f);
+    std::vector<double> r_accum(n, 0.0);
+    const size_t ldh = m + 1;
+    auto applyM = [&](float* v) { if (jac32) for (int i = 0; i < n; ++i) v[i] = 0.f * v[i] + 1.f * jac32[i] * v[i]; };
+
+    conv.setup(gs);
+    const double b_norm = nrm2<double>(n, b);                       // gmres.cpp:162
+    copy_cast<double, float>(n, b, w.data());                       // :163
+    applyM(w.data());                                               // :164
+    const double Minvb_norm = nrm2<float>(n, w.data());             // :165
+    const double A_norm = nrm2<float>(nnz, vals32);                 // :168 (Frobenius over the value array)
+    st.b_norm = b_norm; st.Minvb_norm = Minvb_norm; st.A_norm = A_norm;
+
+    for (size_t i = 0; true; ++i) {
+        std::copy(b, b + n, r_accum.begin());                                           // :173
+        spmv<double>(n, row_map, inds, vals64, -1.0, x, 1.0, r_accum.data());            // :174
+        copy_cast<double, float>(n, r_accum.data(), w.data());                          // :175
+        const double r_norm = nrm2<float>(n, w.data());                                 // :176
+        applyM(w.data());                                                               // :177
+        const float beta = nrm2<float>(n, w.data());                                    // :179
+        const double x_norm = nrm2<double>(n, x);                                       // :181
+        hist.push_outer(r_norm, b_norm + A_norm * x_norm, beta, x_norm);
+        const Action a0 = conv.check_initial(r_norm, b_norm + A_norm * x_norm, beta, Minvb_norm);  // :184
+        if (a0 == CONVERGED) { st.status = 1; st.rel_prec_res = double(beta / Minvb_norm); st.outer_i = i; return; }
+        if (a0 == ABORTED) { st.status = 3; st.outer_i = i; return; }
+
+        gs.first_vector(w.data());                                                      // :196
+        std::fill(s.begin(), s.end(), 0.f); s[0] = beta;                                // :198-206
+
+        size_t k;
+        bool go = true;
+        for (k = 0; go; ++k) {
+            spmv<float>(n, row_map, inds, vals32, 1.f, gs.col(k), 0.f, w.data());       // :212-213
+            applyM(w.data());                                                           // :214
+            gs.add_vector(k, w.data(), h.data(), ldh);                                  // :217
+            const double ares = givens_step<float>(k, h.data(), ldh, cs.data(), sn.data(), s.data());  // :219-226
+            hist.push_inner(ares / Minvb_norm);
+            const Action a = conv.check(k + 1, ares, Minvb_norm);                       // :227
+            if (a == RESTART) go = false;
+            else if (a == ABORTED) { st.status = 3; st.outer_i = i; return; }
+            // iteration_converged is never returned by any Convergence::check (IterUtil.hpp) - dead branch :228-232
+        }
+        // solution_update gmres.cpp:276-290 + Orthogonalization.hpp:67-73
+        trsv_upper<float>(k, h.data(), ldh, s.data());
+        gemv_n<float>(n, k, 1.f, gs.v.data(), n, s.data(), 0.f, w.data());
+        copy_cast<float, double>(n, w.data(), r_accum.data());
+        axpy<double>(n, 1.0, r_accum.data(), x);
+    }
+}
+
+// gmres.cpp:24-133 gmres_baseline<Orth,Device,Type,PrecType>.  prec_is_float models typesafe_apply
+// (gmres.cpp:12-22): when PrecType != Type the vector is cast to PrecType, preconditioned, cast back.
+template <class T>
+void gmres_uniform(Conv<T>& conv, int orth, bool prec_is_float, int n, const int* row_map, const int* inds,
+                   const T* vals, const T* jac, const T* b, T* x, Stats& st, Hist& hist) {
+    const size_t m = conv.rlen;
+    const size_t nnz = row_map[n];
+    GS<T> gs(n, m, orth);
+    std::vector<T> cs(m + 1, T(0)), sn(m + 1, T(0)), s(m + 1, T(0)), w(n, T(0)), h((m + 1) * m, T(0));
+    const size_t ldh = m + 1;
+    const bool roundtrip = prec_is_float && sizeof(T) == 8;
+    auto applyM = [&](T* v) {
+        if (roundtrip) for (int i = 0; i < n; ++i) {
+            float t = (float)v[i];
+            if (jac) t = 0.f * t + 1.f * (float)jac[i] * t;
+            v[i] = (T)t;
+        } else if (jac) for (int i = 0; i < n; ++i) v[i] = T(0) * v[i] + T(1) * jac[i] * v[i];
+    };
+
+    conv.setup(gs);
+    const T b_norm = nrm2<T>(n, b);                                  // gmres.cpp:54
+    std::copy(b, b + n, w.begin());                                  // :56
+    applyM(w.data());                                                // :57
+    const T Minvb_norm = nrm2<T>(n, w.data());                       // :58
+    const T A_norm = nrm2<T>(nnz, vals);                             // :60
+    st.b_norm = b_norm; st.Minvb_norm = Minvb_norm; st.A_norm = A_norm;
+
+    for (size_t i = 0; true; ++i) {
+        std::copy(b, b + n, w.begin());                                          // :65
+        spmv<T>(n, row_map, inds, vals, T(-1), x, T(1), w.data());               // :66
+        const T r_norm = nrm2<T>(n, w.data());                                   // :67
+        applyM(w.data());                                                        // :68
+        const T beta = nrm2<T>(n, w.data());                                     // :70
+        const T x_norm = nrm2<T>(n, x);                                          // :72
+        const double normalization = b_norm + A_norm * x_norm;                   // :74 (Type arithmetic, widened)
+        hist.push_outer(r_norm, normalization, beta, x_norm);
+        const Action a0 = conv.check_initial(r_norm, normalization, beta, Minvb_norm);
+        if (a0 == CONVERGED) { st.status = 1; st.rel_prec_res = double(T(beta / Minvb_norm)); st.outer_i = i; return; }
+        if (a0 == ABORTED) { st.status = 3; st.outer_i = i; return; }
+
+        gs.first_vector(w.data());                                               // :84
+        std::fill(s.begin(), s.end(), T(0)); s[0] = beta;                        // :86-93
+
+        size_t k;
+        bool go = true;
+        for (k = 0; go; ++k) {
+            spmv<T>(n, row_map, inds, vals, T(1), gs.col(k), T(0), w.data());    // :100
+            applyM(w.data());                                                    // :101
+            gs.add_vector(k, w.data(), h.data(), ldh);                           // :104
+            const double ares = givens_step<T>(k, h.data(), ldh, cs.data(), sn.data(), s.data());  // :106-114
+            hist.push_inner(ares / (double)Minvb_norm);
+            const Action a = conv.check(k + 1, ares, Minvb_norm);                // :115
+            if (a == RESTART) go = false;
+            else if (a == ABORTED) { st.status = 3; st.outer_i = i; return; }
+        }
+        // solution_update gmres.cpp:291-303 + Orthogonalization.hpp:62-65 (gemv beta = 1 straight into x)
+        trsv_upper<T>(k, h.data(), ldh, s.data());
+        gemv_n<T>(n, k, T(1), gs.v.data(), n, s.data(), T(1), x);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Synthetic inputs (the reference ships no generators).  All CSR in LoadMatrix-canonical
+// form (LoadMatrix.hpp:62-145): 0-based int32, ascending columns, diagonal always present, values
+// fp32-representable.  These constants are FROZEN: the product's device generators
+// must reproduce them bit-exactly.
+// ------------------------------------------------------------------------------------------------
+constexpr double CD27_DIAG = 26.0;   // HPCG-style 27-point diffusion: diag 26, off-diag -1 (weakly dominant interior rows)   // 26 (HPCG-style 27-point diffusion) + 1 (shift => strict dominance)
+constexpr double CD27_CX = 0.5, CD27_CY = 0.25, CD27_CZ = 0.125;  // convection on the +-x, +-y, +-z faces
+
+inline uint64_t splitmix64(uint64_t z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+inline uint64_t pl_hash(uint64_t seed, uint64_t row, uint64_t slot) {
+    return splitmix64(splitmix64(seed ^ (row * 0xD1342543DE82EF95ull)) + slot);
+}
+// power-law row length: number of OFF-diagonal entries of row i.  g = leading zeros of a uniform 64-bit
+// word capped at gmax (P(g>=t)=2^-t => P(len>=L) ~ lmin/L), interpolated inside the octave with 16
+// further bits.  Integer-only so CPU and GPU agree bit-exactly.
+inline int64_t pl_rowlen(uint64_t seed, int64_t i, int64_t n, int lmin, int gmax) {
+    const uint64_t hsh = pl_hash(seed, (uint64_t)i, 0);
+    int g = 0;
+    while (g < gmax && !((hsh >> (63 - g)) & 1ull)) ++g;
+    const int64_t base = (int64_t)lmin << g;
+    const int64_t frac = (int64_t)(hsh & 0xFFFFull);
+    int64_t len = base + ((base * frac) >> 16);
+    if (len > n - 1) len = n - 1;
+    return len;
+}
+// s-th off-diagonal column of row i (ascending in s, distinct, never == i): stratified draw in [0,n-1)
+inline int64_t pl_col(uint64_t seed, int64_t i, int64_t n, int64_t len, int64_t s) {
+    const int64_t lo = (int64_t)(((__int128)s * (n - 1)) / len);
+    const int64_t hi = (int64_t)(((__int128)(s + 1) * (n - 1)) / len);
+    const int64_t width = hi - lo;  // >= 1 because len <= n-1
+    const int64_t c = lo + (int64_t)(pl_hash(seed, (uint64_t)i, (uint64_t)(2 * s + 1)) % (uint64_t)width);
+    return c + (c >= i ? 1 : 0);
+}
+inline double pl_val(uint64_t seed, int64_t i, int64_t s) {
+    const uint64_t hsh = pl_hash(seed, (uint64_t)i, (uint64_t)(2 * s + 2));
+    int k = (int)(hsh % 127u) - 63;  // [-63, 63]
+    if (k == 0) k = 1;
+    return (double)k / 64.0;
+}
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+int orc_num_threads() {
+#if defined(_OPENMP)
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+// gmres_perf_test.cpp:39-51 rand_vect: libstdc++ mt19937(seed) + uniform_real_distribution<float>, sequential
+void orc_rand_vect(int64_t n, uint32_t seed, double* out) {
+    std::mt19937 engine(seed);
+    std::uniform_real_distribution<float> dist;
+    for (int64_t i = 0; i < n; ++i) out[i] = dist(engine);
+}
+
+// ---- generators ---------------------------------------------------------------------------------
+int64_t orc_lap2d_nnz(int64_t N) { return 5 * N * N - 4 * N; }
+void orc_gen_lap2d(int64_t N, int* row_map, int* inds, double* vals) {
+    int64_t p = 0;
+    for (int64_t y = 0; y < N; ++y)
+        for (int64_t x = 0; x < N; ++x) {
+            const int64_t i = x + N * y;
+            row_map[i] = (int)p;
+            if (y > 0) { inds[p] = (int)(i - N); vals[p++] = -1.0; }
+            if (x > 0) { inds[p] = (int)(i - 1); vals[p++] = -1.0; }
+            inds[p] = (int)i; vals[p++] = 4.0;
+            if (x < N - 1) { inds[p] = (int)(i + 1); vals[p++] = -1.0; }
+            if (y < N - 1) { inds[p] = (int)(i + N); vals[p++] = -1.0; }
+        }
+    row_map[N * N] = (int)p;
+}
+
+int64_t orc_cd27_nnz(int64_t N) { const int64_t t = 3 * N - 2; return t * t * t; }
+void orc_gen_cd27(int64_t N, int* row_map, int* inds, double* vals) {
+    int64_t p = 0;
+    for (int64_t z = 0; z < N; ++z)
+        for (int64_t y = 0; y < N; ++y)
+            for (int64_t x = 0; x < N; ++x) {
+                const int64_t i = x + N * (y + N * z);
+                row_map[i] = (int)p;
+                for (int dz = -1; dz <= 1; ++dz)
+                    for (int dy = -1; dy <= 1; ++dy)
+                        for (int dx = -1; dx <= 1; ++dx) {
+                            const int64_t xx = x + dx, yy = y + dy, zz = z + dz;
+                            if (xx < 0 || xx >= N || yy < 0 || yy >= N || zz < 0 || zz >= N) continue;
+                            double v = -1.0;
+                            const int na = (dx != 0) + (dy != 0) + (dz != 0);
+                            if (na == 0) v = CD27_DIAG;
+                            else if (na == 1) v += dx * CD27_CX + dy * CD27_CY + dz * CD27_CZ;
+                            inds[p] = (int)(xx + N * (yy + N * zz));
+                            vals[p++] = v;
+                        }
+            }
+    row_map[N * N * N] = (int)p;
+}
+
+// power-law: pass 1 (row_map) and pass 2 (fill).  lmin: minimum off-diagonals; gmax: octaves.
+int64_t orc_powerlaw_rowmap(int64_t n, uint64_t seed, int lmin, int gmax, int* row_map) {
+    int64_t p = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        row_map[i] = (int)p;
+        p += pl_rowlen(seed, i, n, lmin, gmax) + 1;
+    }
+    row_map[n] = (int)p;
+    return p;
+}
+void orc_gen_powerlaw(int64_t n, uint64_t seed, int lmin, int gmax, const int* row_map, int* inds, double* vals) {
+#pragma omp parallel for schedule(dynamic, 1024)
+    for (int64_t i = 0; i < n; ++i) {
+        const int64_t len = pl_rowlen(seed, i, n, lmin, gmax);
+        int64_t p = row_map[i];
+        double absum = 0;
+        int64_t dpos = -1;
+        bool placed = false;
+        for (int64_t s = 0; s < len; ++s) {
+            const int64_t c = pl_col(seed, i, n, len, s);
+            if (!placed && c > i) { dpos = p; inds[p++] = (int)i; placed = true; }
+            const double v = pl_val(seed, i, s);
+            absum += std::fabs(v);
+            inds[p] = (int)c;
+            vals[p++] = v;
+        }
+        if (!placed) { dpos = p; inds[p++] = (int)i; }
+        vals[dpos] = 1.0 + absum;  // exact: multiples of 1/64 below 2^17
+    }
+}
+
+// ---- per-op entry points (KATs) -----------------------------------------------------------------
+void orc_spmv_f32(int n, const int* rm, const int* in, const float* v, float a, const float* x, float b, float* y) { spmv<float>(n, rm, in, v, a, x, b, y); }
+void orc_spmv_f64(int n, const int* rm, const int* in, const double* v, double a, const double* x, double b, double* y) { spmv<double>(n, rm, in, v, a, x, b, y); }
+float orc_dot_f32(int64_t n, const float* x, const float* y) { return dot<float>(n, x, y); }
+double orc_dot_f64(int64_t n, const double* x, const double* y) { return dot<double>(n, x, y); }
+float orc_nrm2_f32(int64_t n, const float* x) { return nrm2<float>(n, x); }
+double orc_nrm2_f64(int64_t n, const double* x) { return nrm2<double>(n, x); }
+void orc_axpy_f32(int64_t n, float a, const float* x, float* y) { axpy<float>(n, a, x, y); }
+void orc_axpy_f64(int64_t n, double a, const double* x, double* y) { axpy<double>(n, a, x, y); }
+void orc_naxpy_f32(int64_t n, float a, const float* x, float* y) { naxpy<float>(n, a, x, y); }
+void orc_naxpy_f64(int64_t n, double a, const double* x, double* y) { naxpy<double>(n, a, x, y); }
+void orc_scal_f32(int64_t n, float a, const float* x, float* y) { scal_out<float>(n, a, x, y); }
+void orc_scal_f64(int64_t n, double a, const double* x, double* y) { scal_out<double>(n, a, x, y); }
+void orc_cast_f64_f32(int64_t n, const double* x, float* y) { copy_cast<double, float>(n, x, y); }
+void orc_cast_f32_f64(int64_t n, const float* x, double* y) { copy_cast<float, double>(n, x, y); }
+void orc_gemv_f32(int trans, int64_t nr, int64_t nc, float a, const float* M, int64_t ld, const float* x, float b, float* y) {
+    if (trans) gemv_t<float>(nr, nc, a, M, ld, x, b, y); else gemv_n<float>(nr, nc, a, M, ld, x, b, y);
+}
+void orc_gemv_f64(int trans, int64_t nr, int64_t nc, double a, const double* M, int64_t ld, const double* x, double b, double* y) {
+    if (trans) gemv_t<double>(nr, nc, a, M, ld, x, b, y); else gemv_n<double>(nr, nc, a, M, ld, x, b, y);
+}
+void orc_trsv_upper_f32(int64_t n, const float* A, int64_t ld, float* x) { trsv_upper<float>(n, A, ld, x); }
+void orc_trsv_upper_f64(int64_t n, const double* A, int64_t ld, double* x) { trsv_upper<double>(n, A, ld, x); }
+void orc_rotg_f32(float* a, float* b, float* c, float* s) { rotg<float>(*a, *b, *c, *s); }
+void orc_rotg_f64(double* a, double* b, double* c, double* s) { rotg<double>(*a, *b, *c, *s); }
+void orc_rot_vec_f32(int64_t k, float* a, const float* c, const float* s) { rot_vec<float>(k, a, c, s); }
+void orc_rot_vec_f64(int64_t k, double* a, const double* c, const double* s) { rot_vec<double>(k, a, c, s); }
+double orc_givens_step_f32(int64_t k, float* h, int64_t ldh, float* cs, float* sn, float* s) { return givens_step<float>(k, h, ldh, cs, sn, s); }
+double orc_givens_step_f64(int64_t k, double* h, int64_t ldh, double* cs, double* sn, double* s) { return givens_step<double>(k, h, ldh, cs, sn, s); }
+
+// GS::add_vector on a caller-supplied basis (V is n x (k+2) column-major, ld = n): orthogonalise w against
+// V[:,0:k+1], write h[0..k+1] (column k of H, contiguous) and V[:,k+1] = w/h[k+1].  Orthogonalization.hpp:51-60
+void orc_add_vector_f32(int orth, int64_t n, int64_t k, float* V, float* w, float* hcol) {
+    GS<float> gs(n, k + 1, orth);
+    std::copy(V, V + n * (k + 1), gs.v.begin());
+    std::vector<float> h((k + 2) * (k + 1), 0.f);
+    gs.add_vector(k, w, h.data(), k + 2);
+    for (int64_t j = 0; j <= k + 1; ++j) hcol[j] = h[j + k * (k + 2)];
+    std::copy(gs.col(k + 1), gs.col(k + 1) + n, V + n * (k + 1));
+}
+void orc_add_vector_f64(int orth, int64_t n, int64_t k, double* V, double* w, double* hcol) {
+    GS<double> gs(n, k + 1, orth);
+    std::copy(V, V + n * (k + 1), gs.v.begin());
+    std::vector<double> h((k + 2) * (k + 1), 0.0);
+    gs.add_vector(k, w, h.data(), k + 2);
+    for (int64_t j = 0; j <= k + 1; ++j) hcol[j] = h[j + k * (k + 2)];
+    std::copy(gs.col(k + 1), gs.col(k + 1) + n, V + n * (k + 1));
+}
+
+// Jacobi diagonal, types.hpp:395-430: 1/diag with an eps_float*||A||_inf floor (sign-preserving)
+void orc_jacobi_diag_f64(int n, const int* rm, const int* in, const double* v, double* diag) {
+    double alpha = 0;
+    for (int i = 0; i < n; ++i) {
+        double s = 0;
+        for (int p = rm[i]; p < rm[i + 1]; ++p) s += std::fabs(v[p]);
+        if (alpha < s) alpha = s;
+    }
+    alpha *= (double)std::numeric_limits<float>::epsilon();
+    for (int i = 0; i < n; ++i) {
+        int j = rm[i];
+        while (in[j] < i) ++j;
+        if (v[j] >= 0) diag[i] = 1 / ((v[j] < alpha) ? alpha : v[j]);
+        else diag[i] = 1 / ((v[j] > -alpha) ? -alpha : v[j]);
+    }
+}
+void orc_jacobi_diag_f32(int n, const int* rm, const int* in, const float* v, float* diag) {
+    float alpha = 0;
+    for (int i = 0; i < n; ++i) {
+        float s = 0;
+        for (int p = rm[i]; p < rm[i + 1]; ++p) s += std::fabs(v[p]);
+        if (alpha < s) alpha = s;
+    }
+    alpha *= std::numeric_limits<float>::epsilon();
+    for (int i = 0; i < n; ++i) {
+        int j = rm[i];
+        while (in[j] < i) ++j;
+        if (v[j] >= 0) diag[i] = 1 / ((v[j] < alpha) ? alpha : v[j]);
+        else diag[i] = 1 / ((v[j] > -alpha) ? -alpha : v[j]);
+    }
+}
+
+// ---- solver -------------------------------------------------------------------------------------
+// mode: 0 mixed (gmres_singleUpdate), 1 baseline (double,double), 2 single-prec (double,float), 3 single (float,float)
+// orth: 0 cgs, 1 mgs, 2 cgsr(2).  conv_kind: see Conv.  prec: 0 identity, 1 jacobi.
+// vals64 is the fp64 matrix.  Modes 1-3 follow DoBaselineProblem (gmres_perf_test.cpp:53-118): the solver
+// matrix is the fp32-rounded one (quirk, :66 + implicit conversion) and b is cast to Type (:97-98).
+// stats_out: Stats; hist_inner[cap_inner], hist_outer[4*cap_outer] may be null.
+int orc_gmres(int mode, int orth, int conv_kind, int prec, int64_t rlen, double tol, double rtol, int64_t max_restarts,
+              int n, const int* row_map, const int* inds, const double* vals64, const double* b, double* x,
+              Stats* st, double* hist_inner, int64_t cap_inner, double* hist_outer, int64_t cap_outer) {
+    std::memset(st, 0, sizeof(Stats));
+    Hist hist{hist_inner, cap_inner, hist_outer, cap_outer};
+    const size_t nnz = row_map[n];
+    std::vector<float> vals32(nnz);
+    copy_cast<double, float>(nnz, vals64, vals32.data());  // types_cuda.hpp:82-101 precision-cast ctor
+    if (mode == 0) {
+        Conv<float> conv(conv_kind, tol, rtol, rlen, max_restarts);
+        std::vector<float> jac;
+        if (prec == 1) { jac.resize(n); orc_jacobi_diag_f32(n, row_map, inds, vals32.data(), jac.data()); }  // Jacobi<float>(A) gmres_perf_test.cpp:149
+        gmres_mixed(conv, orth, n, row_map, inds, vals64, vals32.data(), prec == 1 ? jac.data() : nullptr, b, x, *st, hist);
+        st->total_iters = conv.total_iters; st->total_restarts = conv.total_restarts;
+    } else if (mode == 1 || mode == 2) {
+        std::vector<double> vals_rt(nnz);
+        copy_cast<float, double>(nnz, vals32.data(), vals_rt.data());  // fp64 -> fp32 -> fp64
+        Conv<double> conv(conv_kind, tol, rtol, rlen, max_restarts);
+        std::vector<double> jac;
+        if (prec == 1) {
+            jac.resize(n);
+            if (mode == 1) orc_jacobi_diag_f64(n, row_map, inds, vals64, jac.data());       // Jacobi<double>(A)
+            else { std::vector<float> j32(n); orc_jacobi_diag_f32(n, row_map, inds, vals32.data(), j32.data()); copy_cast<float, double>(n, j32.data(), jac.data()); }
+        }
+        gmres_uniform<double>(conv, orth, mode == 2, n, row_map, inds, vals_rt.data(), prec == 1 ? jac.data() : nullptr, b, x, *st, hist);
+        st->total_iters = conv.total_iters; st->total_restarts = conv.total_restarts;
+    } else {
+        Conv<float> conv(conv_kind, tol, rtol, rlen, max_restarts);
+        std::vector<float> jac, b32(n), x32(n);
+        if (prec == 1) { jac.resize(n); orc_jacobi_diag_f32(n, row_map, inds, vals32.data(), jac.data()); }
+        copy_cast<double, float>(n, b, b32.data());
+        copy_cast<double, float>(n, x, x32.data());
+        gmres_uniform<float>(conv, orth, false, n, row_map, inds, vals32.data(), prec == 1 ? jac.data() : nullptr, b32.data(), x32.data(), *st, hist);
+        copy_cast<float, double>(n, x32.data(), x);
+        st->total_iters = conv.total_iters; st->total_restarts = conv.total_restarts;
+    }
+    st->n_hist_inner = hist.ni; st->n_hist_outer = hist.no;
+    return 0;
+}
+
+// A bounded sample of the hot loop for the CPU baseline: `iters` GMRES-IR inner iterations (SpMV fp32 +
+// add_vector with `orth`) starting from column k0 of a basis filled with orthonormal-ish data are not
+// needed; instead the caller just runs orc_gmres with max_restarts small.  (kept out on purpose)
+
+// ---- 1-D row partition + halo index sets (new functionality, the oracle defines it) --
+// rank r owns rows [floor(r*n/P), floor((r+1)*n/P)).  Local CSR slab: columns in [lo,hi) -> c-lo;
+// remote columns -> n_local + rank in the ascending sorted-unique list of remote globals (halo_cols).
+void orc_partition_bounds(int64_t n, int P, int64_t* bounds) {
+    for (int r = 0; r <= P; ++r) bounds[r] = (int64_t)(((__int128)r * n) / P);
+}
+// returns number of halo columns; if halo_cols != null fills it (size >= return value) and local_inds
+// (size nnz_local).  Call once with nulls to size.
+int64_t orc_partition_local(int64_t n, int P, int r, const int* row_map, const int* inds, int64_t* halo_cols, int* local_inds) {
+    const int64_t lo = (int64_t)(((__int128)r * n) / P), hi = (int64_t)(((__int128)(r + 1) * n) / P);
+    std::vector<int64_t> remote;
+    for (int64_t p = row_map[lo]; p < row_map[hi]; ++p) {
+        const int64_t c = inds[p];
+        if (c < lo || c >= hi) remote.push_back(c);
+    }
+    std::sort(remote.begin(), remote.end());
+    remote.erase(std::unique(remote.begin(), remote.end()), remote.end());
+    if (halo_cols) std::copy(remote.begin(), remote.end(), halo_cols);
+    if (local_inds) {
+        const int64_t nl = hi - lo;
+        for (int64_t p = row_map[lo]; p < row_map[hi]; ++p) {
+            const int64_t c = inds[p];
+            int64_t lc;
+            if (c >= lo && c < hi) lc = c - lo;
+            else lc = nl + (std::lower_bound(remote.begin(), remote.end(), c) - remote.begin());
+            local_inds[p - row_map[lo]] = (int)lc;
+        }
+    }
+    return (int64_t)remote.size();
+}
+
+}  // extern "C"
