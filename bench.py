@@ -1,0 +1,287 @@
+#!/usr/bin/env python
+"""bench.py — GMRES-IR time-to-solution / inner iterations per second on the B200 backend.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload cd27:256]
+
+One "step" = one complete GMRES-IR solve (x0 = 0 -> the reference's stopping rule) of the BASELINE.json workload:
+synthetic 3-D 27-point convection-diffusion, 256^3 = 16.7 M rows, 449 M nonzeros, GMRES-IR(100), CGS2, identity
+preconditioner, tol 1e-6 (configs[2], the configuration the metric is quoted on; it fits one GPU).
+Prints ONE JSON line (rank 0).  `value` = inner iterations of all timed solves / device time (CUDA events, inputs
+resident in HBM); `e2e` = the same through the host-buffer C-ABI call (H2D + plan + solve + D2H per step);
+`roofline` = algorithmic bytes / CUDA-event time of the dominant kernel class, measured inside the timed region.
+For N > 1 the driver launches this file under torchrun; ranks own 1-D row blocks.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "gmres_ir_inner_iterations_per_sec"
+UNIT = "it/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cd27:256")
+    ap.add_argument("--rlen", type=int, default=100)
+    ap.add_argument("--tol", type=float, default=1e-6)
+    ap.add_argument("--orth", default="cgsr")
+    ap.add_argument("--max-restarts", type=int, default=1000)
+    ap.add_argument("--cpu-sample", default="cd27:96", help="bounded sample of the workload for the CPU baseline")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    return ap.parse_args()
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [l.strip().split(",") for l in open(self.f.name) if l.strip()]
+        os.unlink(self.f.name)
+        sm, mx, pw, reasons = [], [], [], set()
+        for r in rows:
+            try:
+                r = [c.strip() for c in r]
+                sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
+                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_reference_run(sample, rlen, tol, orth, max_restarts, full_rows):
+    """The reference's CPU implementation of the path on this box's host cores, on a bounded sample of the workload.
+    Uses oracle/_ref (the reference's own sources built against the MKL inside libtorch) when present, else the oracle
+    port.  Returns dict(value=<it/s scaled to the full workload>, ...)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import oracle as orc
+    try:
+        import oracle_ref
+        have_ref = oracle_ref.available()
+    except Exception:
+        have_ref = False
+    rm, ind, val = orc.gen(sample)
+    n = len(rm) - 1
+    xt = orc.rand_vect(n, 42)
+    b = np.zeros(n)
+    orc.spmv(rm, ind, val, 1.0, xt, 0.0, b)
+    t0 = time.perf_counter()
+    if have_ref:
+        r = oracle_ref.gmres(rm, ind, val, b, mode="mixed", orth=orth, rlen=rlen, tol=tol, max_restarts=max_restarts)
+        kind, cores = "reference", oracle_ref.num_threads()
+    else:
+        r = orc.gmres(rm, ind, val, b, mode="mixed", orth=orth, rlen=rlen, tol=tol, max_restarts=max_restarts)
+        kind, cores = "port", orc.num_threads()
+    dt = r.get("gmres_seconds", time.perf_counter() - t0)
+    its = int(r["total_iters"])
+    scale = n / float(full_rows)
+    return {"value": its / dt * scale, "unit": UNIT, "cores": int(cores), "kind": kind, "seconds": dt, "iters": its,
+            "sample": f"{sample} ({n} rows = {scale:.4f} of the workload's rows), one full GMRES-IR({rlen}) solve: {its} inner iterations in "
+                      f"{dt:.2f} s; it/s scaled by the row ratio to {full_rows} rows (every kernel on the path is bandwidth-bound, cost ~ rows)"}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    kind, N = args.workload.split(":")[0], int(args.workload.split(":")[1])
+    full_rows = N ** 3 if kind == "cd27" else (N * N if kind == "lap2d" else N)
+    vals, total_it, total_t = [], 0, 0.0
+    last = None
+    for i in range(args.warmup + args.steps):
+        last = cpu_reference_run(args.cpu_sample, args.rlen, args.tol, args.orth, args.max_restarts, full_rows)
+        if i >= args.warmup:
+            total_it += last["iters"]; total_t += last["seconds"]
+    scale = last["value"] / (last["iters"] / last["seconds"])
+    value = total_it / total_t * scale
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * total_t / max(args.steps, 1) / scale, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32 inner / f64 outer (CPU)", "data": "synthetic",
+            "config": {"workload": args.workload, "restart_length": args.rlen, "tol": args.tol, "orth": args.orth, "prec": "identity"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": last["cores"], "kind": last["kind"], "sample": last["sample"]},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import gmres_b200 as g
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the B200 backend has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import bench_dist
+        bench_dist.main(args, rank, world, local_rank)
+        return
+
+    dev = f"cuda:{local_rank}"
+    ctx = g.Context(local_rank)
+    peak, peak_src = measured_peaks()
+
+    # ---- problem (device-resident; construction is outside the timed region like gmres_perf_test.cpp:408-421) ----
+    rm, ind, val = ctx.gen(args.workload)
+    n, nnz = rm.numel() - 1, ind.numel()
+    A = g.CSR(ctx, rm, ind)
+    xt = torch.from_numpy(ctx.rand_vect(n, 42)).to(dev)
+    b = torch.zeros(n, dtype=torch.float64, device=dev)
+    ctx.spmv(A, val, 1.0, xt, 0.0, b)
+    val32 = torch.empty(nnz, dtype=torch.float32, device=dev)
+    ctx.copy(val, val32)  # SparseMatrix<float>(A): the reference's "prec" window, gmres_perf_test.cpp:135-136
+    x = torch.zeros(n, dtype=torch.float64, device=dev)
+    kw = dict(mode="mixed", orth=args.orth, conv="base", prec="identity", rlen=args.rlen, tol=args.tol, max_restarts=args.max_restarts)
+
+    def solve():
+        x.zero_()
+        return ctx.gmres(A, val, b, x, vals32=val32, hist_cap=1, **kw)
+
+    for _ in range(args.warmup):
+        r = solve()
+    torch.cuda.synchronize()
+
+    # ---- timed region: K solves, device time from CUDA events; per-kernel-class timers on ----
+    ctx.prof_enable(True)
+    ctx.prof_reset()
+    sampler = ClockSampler(local_rank)
+    launches0 = ctx.launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    iters = restarts = 0
+    status = 1
+    for _ in range(args.steps):
+        r = solve()
+        iters += r["total_iters"]; restarts += r["total_restarts"]; status = r["status"]
+    e1.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    total_ms = e0.elapsed_time(e1)
+    launches = ctx.launches() - launches0
+    prof = ctx.prof_get()
+    ctx.prof_enable(False)
+
+    # post-solve check the reference prints (gmres_perf_test.cpp:169-178)
+    res = b.clone(); ctx.spmv(A, val, -1.0, x, 1.0, res)
+    res_norm = ctx.nrm2(res)
+    err = x - xt
+    err_norm = ctx.nrm2(err)
+    b_norm = ctx.nrm2(b)
+
+    value = iters / (total_ms * 1e-3)
+    kernels = {}
+    for name, p in prof.items():
+        if p["launches"] == 0:
+            continue
+        gbs = p["bytes"] / (p["ms"] * 1e-3) / 1e9 if p["ms"] > 0 else 0.0
+        kernels[name] = {"ms_total": round(p["ms"], 3), "share": round(p["ms"] / total_ms, 4), "launches": p["launches"],
+                         "avg_ms": round(p["ms"] / p["launches"], 4), "algorithmic_GB_per_launch": round(p["bytes"] / p["launches"] / 1e9, 5),
+                         "achieved_GBps": round(gbs, 1), "frac_of_peak": round(gbs / peak, 4)}
+    dom = max((k for k in kernels if k in ("vpass", "spmv_f32", "gemvn", "spmv_f64")), key=lambda k: kernels[k]["ms_total"])
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_GBps"], "peak": peak, "unit": "GB/s",
+                "frac": kernels[dom]["frac_of_peak"], "traffic": None, "peak_source": peak_src,
+                "note": "achieved = algorithmic bytes (SURVEY.md §8d / DESIGN.md §4) of all launches of this kernel class in the timed region / "
+                        "their CUDA-event time on the launching stream"}
+    prof_path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(prof_path):
+        try:
+            roofline["traffic"] = json.load(open(prof_path)).get(dom)
+        except Exception:
+            pass
+
+    # ---- end to end through the host-buffer C-ABI entry point (pinned host memory) ----
+    e2e = None
+    if not args.no_e2e:
+        h_rm = torch.empty(rm.shape, dtype=rm.dtype, pin_memory=True); h_rm.copy_(rm)
+        h_ind = torch.empty(ind.shape, dtype=ind.dtype, pin_memory=True); h_ind.copy_(ind)
+        h_val = torch.empty(val.shape, dtype=val.dtype, pin_memory=True); h_val.copy_(val)
+        h_b = torch.empty(b.shape, dtype=b.dtype, pin_memory=True); h_b.copy_(b)
+        h_x = torch.zeros(n, dtype=torch.float64).pin_memory()
+        torch.cuda.synchronize()
+        h_x.zero_(); ctx.gmres_host(h_rm, h_ind, h_val, h_b, h_x, hist_cap=1, **kw)  # warm
+        t0 = time.perf_counter()
+        it2 = 0
+        for _ in range(args.e2e_steps):
+            h_x.zero_()
+            r2 = ctx.gmres_host(h_rm, h_ind, h_val, h_b, h_x, hist_cap=1, **kw)
+            it2 += r2["total_iters"]
+        dt = time.perf_counter() - t0
+        h2d = h_rm.numel() * 4 + h_ind.numel() * 4 + h_val.numel() * 8 + 2 * n * 8
+        e2e = {"value": it2 / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(n * 8),
+               "ms_per_step": 1e3 * dt / args.e2e_steps, "steps": args.e2e_steps, "h2d_ms": r2["h2d_ms"], "solve_ms": r2["solve_ms"],
+               "d2h_ms": r2["d2h_ms"], "call": "mpg_gmres_solve_host (pinned host CSR + b in, x out)"}
+        del h_rm, h_ind, h_val, h_b
+
+    # ---- CPU baseline on this box's host cores (bounded sample) ----
+    cpu = None
+    if not args.no_cpu_baseline:
+        c = cpu_reference_run(args.cpu_sample, args.rlen, args.tol, args.orth, args.max_restarts, n)
+        cpu = {k: c[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32 inner / f64 outer", "data": "synthetic",
+            "config": {"workload": args.workload, "n_rows": n, "nnz": nnz, "restart_length": args.rlen, "tol": args.tol, "orth": args.orth,
+                       "prec": "identity", "iters_per_solve": iters // max(args.steps, 1), "restarts_per_solve": restarts // max(args.steps, 1),
+                       "time_to_solution_s": total_ms * 1e-3 / args.steps, "status": int(status),
+                       "resNorm": res_norm, "errNorm": err_norm, "rel_res": res_norm / b_norm,
+                       "l2": "working set (matrix 7.2 GB + basis 6.8 GB) >> 126 MB L2; no flush needed"},
+            "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

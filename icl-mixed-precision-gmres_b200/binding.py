@@ -1,0 +1,330 @@
+"""ctypes binding of include/mpgmres_b200.h.  Device operands are torch CUDA tensors (PyTorch is used for device
+memory, streams and torch.distributed only); host operands are numpy arrays or pinned torch CPU tensors."""
+import ctypes as C
+import os
+import re
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+_LIB = None
+
+MODES = {"mixed": 0, "baseline": 1, "single-prec": 2, "single": 3}
+ORTHS = {"cgs": 0, "mgs": 1, "cgsr": 2}
+CONVS = {"base": 0, "relprecres": 1, "repeat": 2, "orthloss": 3}
+PRECS = {"identity": 0, "jacobi": 1}
+
+
+class MpgError(RuntimeError):
+    pass
+
+
+class GmresParams(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("orth", C.c_int32), ("conv", C.c_int32), ("prec", C.c_int32),
+                ("restart_length", C.c_int64), ("tol", C.c_double), ("restart_tol", C.c_double),
+                ("max_restarts", C.c_int64)]
+
+
+class GmresStats(C.Structure):
+    _fields_ = [("status", C.c_int64), ("total_iters", C.c_int64), ("total_restarts", C.c_int64),
+                ("outer_i", C.c_int64), ("rel_prec_res", C.c_double), ("b_norm", C.c_double),
+                ("Minvb_norm", C.c_double), ("A_norm", C.c_double), ("n_hist_inner", C.c_int64),
+                ("n_hist_outer", C.c_int64), ("solve_ms", C.c_double), ("h2d_ms", C.c_double), ("d2h_ms", C.c_double),
+                ("launches", C.c_int64)]
+
+
+def library_path():
+    return os.path.join(_HERE, "lib", "libmpgmres_b200.so")
+
+
+def header_symbols():
+    """every function name declared in include/mpgmres_b200.h"""
+    txt = open(os.path.join(_ROOT, "include", "mpgmres_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(mpg_[a-z0-9_]+)\s*\(", txt)))
+
+
+def exported_symbols():
+    import subprocess
+    out = subprocess.run(["nm", "-D", "--defined-only", library_path()], capture_output=True, text=True, check=True).stdout
+    return sorted(set(l.split()[-1] for l in out.splitlines() if " T " in l and l.split()[-1].startswith("mpg_")))
+
+
+def load_library():
+    """Load the CUDA backend.  Fails loudly if it has not been built: there is no fallback path."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not os.path.exists(path):
+        raise MpgError(f"{path} is missing: build it with `python icl-mixed-precision-gmres_b200/build.py` "
+                       "(the CUDA extension is the only implementation; there is no CPU fallback)")
+    try:  # torch brings libcudart.so.12 into the process; harmless if it is already resolvable
+        import torch  # noqa: F401
+    except Exception:
+        pass
+    L = C.CDLL(path)
+    L.mpg_version.restype = C.c_char_p
+    L.mpg_last_error.restype = C.c_char_p
+    L.mpg_last_error.argtypes = [C.c_void_p]
+    L.mpg_ctx_stream.restype = C.c_void_p
+    L.mpg_launch_count.restype = C.c_int64
+    L.mpg_lap2d_nnz.restype = C.c_int64
+    L.mpg_cd27_nnz.restype = C.c_int64
+    L.mpg_lap2d_nnz.argtypes = [C.c_int64]
+    L.mpg_cd27_nnz.argtypes = [C.c_int64]
+    _LIB = L
+    return L
+
+
+def _ptr(t):
+    """device/host pointer of a torch tensor, numpy array, int or None"""
+    if t is None:
+        return C.c_void_p(0)
+    if isinstance(t, int):
+        return C.c_void_p(t)
+    if hasattr(t, "data_ptr"):
+        return C.c_void_p(t.data_ptr())
+    return C.c_void_p(t.ctypes.data)
+
+
+def _sfx(t):
+    import torch
+    return {torch.float32: "f32", torch.float64: "f64"}[t.dtype]
+
+
+def _sc(t, v):
+    import torch
+    return C.c_float(v) if t.dtype == torch.float32 else C.c_double(v)
+
+
+class CSR:
+    """mpg_csr handle: CSR structure + SpMV plan (values are passed per call, fp32 and fp64 share the structure)."""
+
+    def __init__(self, ctx, row_map, inds, ncols=None):
+        self.ctx, self.row_map, self.inds = ctx, row_map, inds
+        self.nrows = row_map.numel() - 1
+        self.ncols = self.nrows if ncols is None else ncols
+        self.nnz = inds.numel()
+        self.h = C.c_void_p()
+        ctx._chk(ctx.L.mpg_csr_create(ctx.h, C.c_int(self.nrows), C.c_int(self.ncols), C.c_int64(self.nnz), _ptr(row_map),
+                                      _ptr(inds), C.byref(self.h)))
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.ctx.L.mpg_csr_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+class Context:
+    def __init__(self, device=0):
+        import torch
+        self.L = load_library()
+        if not torch.cuda.is_available():
+            raise MpgError("no CUDA device: the B200 backend has no CPU fallback")
+        self.device = device
+        self.h = C.c_void_p()
+        rc = self.L.mpg_ctx_create(C.c_int(device), C.byref(self.h))
+        if rc != 0:
+            raise MpgError(f"mpg_ctx_create failed with code {rc}")
+        # run on torch's current stream so torch allocations / copies and our kernels are stream-ordered
+        self.use_torch_stream()
+
+    def use_torch_stream(self):
+        import torch
+        s = torch.cuda.current_stream(self.device).cuda_stream
+        self._chk(self.L.mpg_ctx_set_stream(self.h, C.c_void_p(s)))
+
+    def close(self):
+        if self.h:
+            self.L.mpg_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise MpgError(f"mpgmres_b200 error {rc}: {self.L.mpg_last_error(self.h).decode()}")
+
+    def sync(self):
+        self._chk(self.L.mpg_sync(self.h))
+
+    def launches(self):
+        return self.L.mpg_launch_count(self.h)
+
+    def set_tuning(self, key, value):
+        self._chk(self.L.mpg_set_tuning(self.h, key.encode(), C.c_int(value)))
+
+    PROF_CLASSES = ["spmv_f32", "spmv_f64", "vpass", "gemvn", "elementwise", "reduce", "small", "gemvt"]
+
+    def prof_enable(self, on=True):
+        self._chk(self.L.mpg_prof_enable(self.h, C.c_int(int(on))))
+
+    def prof_reset(self):
+        self._chk(self.L.mpg_prof_reset(self.h))
+
+    def prof_get(self):
+        """{class: {"ms", "bytes", "launches"}} accumulated since the last reset (device time from CUDA events)"""
+        out = {}
+        for i, name in enumerate(self.PROF_CLASSES):
+            ms, by, ln = C.c_double(), C.c_double(), C.c_int64()
+            self._chk(self.L.mpg_prof_get(self.h, C.c_int(i), C.byref(ms), C.byref(by), C.byref(ln)))
+            out[name] = {"ms": ms.value, "bytes": by.value, "launches": ln.value}
+        return out
+
+    # ---- generators ----
+    def gen(self, spec):
+        """'lap2d:N' | 'cd27:N' | 'powerlaw:n[:seed[:lmin[:gmax]]]' -> (row_map, inds, vals64) torch CUDA tensors"""
+        import torch
+        kind, *a = spec.split(":")
+        a = [int(v) for v in a]
+        dev = f"cuda:{self.device}"
+        if kind in ("lap2d", "cd27"):
+            N = a[0]
+            n = N * N if kind == "lap2d" else N ** 3
+            nnz = self.L.mpg_lap2d_nnz(N) if kind == "lap2d" else self.L.mpg_cd27_nnz(N)
+            rm = torch.empty(n + 1, dtype=torch.int32, device=dev)
+            ind = torch.empty(nnz, dtype=torch.int32, device=dev)
+            val = torch.empty(nnz, dtype=torch.float64, device=dev)
+            fn = self.L.mpg_gen_lap2d if kind == "lap2d" else self.L.mpg_gen_cd27
+            self._chk(fn(self.h, C.c_int64(N), _ptr(rm), _ptr(ind), _ptr(val)))
+            return rm, ind, val
+        if kind == "powerlaw":
+            n = a[0]
+            seed = a[1] if len(a) > 1 else 7
+            lmin = a[2] if len(a) > 2 else 2
+            gmax = a[3] if len(a) > 3 else 15
+            rm = torch.empty(n + 1, dtype=torch.int32, device=dev)
+            nnz = C.c_int64()
+            self._chk(self.L.mpg_gen_powerlaw_rowmap(self.h, C.c_int64(n), C.c_uint64(seed), C.c_int(lmin), C.c_int(gmax), _ptr(rm), C.byref(nnz)))
+            ind = torch.empty(nnz.value, dtype=torch.int32, device=dev)
+            val = torch.empty(nnz.value, dtype=torch.float64, device=dev)
+            self._chk(self.L.mpg_gen_powerlaw_fill(self.h, C.c_int64(n), C.c_uint64(seed), C.c_int(lmin), C.c_int(gmax), _ptr(rm), _ptr(ind), _ptr(val)))
+            return rm, ind, val
+        raise ValueError(spec)
+
+    def rand_vect(self, n, seed=42):
+        import numpy as np
+        out = np.empty(n, dtype=np.float64)
+        self._chk(self.L.mpg_rand_vect_host(C.c_int64(n), C.c_uint32(seed), _ptr(out)))
+        return out
+
+    # ---- BLAS-1 ----
+    def dot(self, x, y):
+        r = (C.c_float if _sfx(x) == "f32" else C.c_double)()
+        self._chk(getattr(self.L, "mpg_dot_" + _sfx(x))(self.h, C.c_int64(x.numel()), _ptr(x), _ptr(y), C.byref(r)))
+        return r.value
+
+    def nrm2(self, x):
+        r = (C.c_float if _sfx(x) == "f32" else C.c_double)()
+        self._chk(getattr(self.L, "mpg_nrm2_" + _sfx(x))(self.h, C.c_int64(x.numel()), _ptr(x), C.byref(r)))
+        return r.value
+
+    def dot_dev(self, x, y, out):
+        self._chk(getattr(self.L, "mpg_dot_dev_" + _sfx(x))(self.h, C.c_int64(x.numel()), _ptr(x), _ptr(y), _ptr(out)))
+
+    def nrm2_dev(self, x, out):
+        self._chk(getattr(self.L, "mpg_nrm2_dev_" + _sfx(x))(self.h, C.c_int64(x.numel()), _ptr(x), _ptr(out)))
+
+    def axpy(self, alpha, x, y):
+        self._chk(getattr(self.L, "mpg_axpy_" + _sfx(x))(self.h, C.c_int64(x.numel()), _sc(x, alpha), _ptr(x), _ptr(y)))
+
+    def axpy_dev(self, alpha_dev, x, y):
+        self._chk(getattr(self.L, "mpg_axpy_dev_" + _sfx(x))(self.h, C.c_int64(x.numel()), _ptr(alpha_dev), _ptr(x), _ptr(y)))
+
+    def naxpy_dev(self, alpha_dev, x, y):
+        self._chk(getattr(self.L, "mpg_naxpy_dev_" + _sfx(x))(self.h, C.c_int64(x.numel()), _ptr(alpha_dev), _ptr(x), _ptr(y)))
+
+    def scal(self, alpha, x, y):
+        self._chk(getattr(self.L, "mpg_scal_" + _sfx(x))(self.h, C.c_int64(x.numel()), _sc(x, alpha), _ptr(x), _ptr(y)))
+
+    def scal_dev(self, alpha_dev, x, y):
+        self._chk(getattr(self.L, "mpg_scal_dev_" + _sfx(x))(self.h, C.c_int64(x.numel()), _ptr(alpha_dev), _ptr(x), _ptr(y)))
+
+    def copy(self, x, y):
+        self._chk(getattr(self.L, f"mpg_copy_{_sfx(x)}_{_sfx(y)}")(self.h, C.c_int64(x.numel()), _ptr(x), _ptr(y)))
+
+    def fill(self, alpha, x):
+        self._chk(getattr(self.L, "mpg_fill_" + _sfx(x))(self.h, C.c_int64(x.numel()), _sc(x, alpha), _ptr(x)))
+
+    def gdmv(self, alpha, diag, x, beta, y):
+        self._chk(getattr(self.L, "mpg_gdmv_" + _sfx(x))(self.h, C.c_int64(x.numel()), _sc(x, alpha), _ptr(diag), _ptr(x), _sc(x, beta), _ptr(y)))
+
+    # ---- Givens / LS ----
+    def rotg(self, a, b, c, s):
+        self._chk(getattr(self.L, "mpg_rotg_" + _sfx(a))(self.h, _ptr(a), _ptr(b), _ptr(c), _ptr(s)))
+
+    def rot(self, a, b, c, s):
+        self._chk(getattr(self.L, "mpg_rot_" + _sfx(a))(self.h, _ptr(a), _ptr(b), _ptr(c), _ptr(s)))
+
+    def rot_vec(self, k, a, c, s):
+        self._chk(getattr(self.L, "mpg_rot_vec_" + _sfx(a))(self.h, C.c_int64(k), _ptr(a), _ptr(c), _ptr(s)))
+
+    def trsv(self, A, n, ld, x, upper=True, trans=False):
+        self._chk(getattr(self.L, "mpg_trsv_" + _sfx(A))(self.h, C.c_int(int(upper)), C.c_int(int(trans)), C.c_int64(n), _ptr(A), C.c_int64(ld), _ptr(x)))
+
+    def givens_step(self, k, h, ldh, cs, sn, s, resid):
+        self._chk(getattr(self.L, "mpg_givens_step_" + _sfx(h))(self.h, C.c_int64(k), _ptr(h), C.c_int64(ldh), _ptr(cs), _ptr(sn), _ptr(s), _ptr(resid)))
+
+    # ---- BLAS-2 / sparse ----
+    def gemv(self, trans, nrows_base, ncols_base, alpha, M, ld, x, beta, y):
+        self._chk(getattr(self.L, "mpg_gemv_" + _sfx(M))(self.h, C.c_int(int(trans)), C.c_int64(nrows_base), C.c_int64(ncols_base), _sc(M, alpha),
+                                                         _ptr(M), C.c_int64(ld), _ptr(x), _sc(M, beta), _ptr(y)))
+
+    def spmv(self, A, vals, alpha, x, beta, y):
+        self._chk(getattr(self.L, "mpg_spmv_" + _sfx(vals))(self.h, A.h, _ptr(vals), _sc(vals, alpha), _ptr(x), _sc(vals, beta), _ptr(y)))
+
+    def residual_cast(self, A, vals64, b, x, r64, w32):
+        self._chk(self.L.mpg_residual_f64_cast_f32(self.h, A.h, _ptr(vals64), _ptr(b), _ptr(x), _ptr(r64), _ptr(w32)))
+
+    def add_vector(self, orth, n, k, V, ldv, w, hcol):
+        self._chk(getattr(self.L, "mpg_add_vector_" + _sfx(V))(self.h, C.c_int(ORTHS[orth]), C.c_int64(n), C.c_int64(k), _ptr(V), C.c_int64(ldv), _ptr(w), _ptr(hcol)))
+
+    def jacobi_diag(self, A, vals, diag):
+        self._chk(getattr(self.L, "mpg_jacobi_diag_" + _sfx(vals))(self.h, A.h, _ptr(vals), _ptr(diag)))
+
+    # ---- solver ----
+    @staticmethod
+    def params(mode="mixed", orth="cgsr", conv="base", prec="identity", rlen=50, tol=1e-6, rtol=0.0, max_restarts=1000000):
+        return GmresParams(MODES[mode], ORTHS[orth], CONVS[conv], PRECS[prec], rlen, tol, rtol, max_restarts)
+
+    def gmres(self, A, vals64, b, x, vals32=None, hist_cap=None, **kw):
+        """device-resident solve; x (torch float64 CUDA tensor) holds x0 on entry and the solution on exit"""
+        import numpy as np
+        p = self.params(**kw)
+        st = GmresStats()
+        cap_outer = min(int(p.max_restarts) + 2, 100000)
+        cap_inner = hist_cap if hist_cap is not None else min(cap_outer * int(p.restart_length), 4000000)
+        hi = np.zeros(max(cap_inner, 1), np.float64)
+        ho = np.zeros(4 * cap_outer, np.float64)
+        self._chk(self.L.mpg_gmres_solve(self.h, C.byref(p), A.h, _ptr(vals64), _ptr(vals32), _ptr(b), _ptr(x), C.byref(st),
+                                         _ptr(hi), C.c_int64(cap_inner), _ptr(ho), C.c_int64(cap_outer)))
+        return self._result(st, hi, ho, cap_inner, cap_outer)
+
+    def gmres_host(self, row_map, inds, vals64, b, x, hist_cap=None, **kw):
+        """end-to-end solve from HOST buffers (numpy arrays or pinned torch CPU tensors); x is updated in place"""
+        import numpy as np
+        p = self.params(**kw)
+        st = GmresStats()
+        cap_outer = min(int(p.max_restarts) + 2, 100000)
+        cap_inner = hist_cap if hist_cap is not None else min(cap_outer * int(p.restart_length), 4000000)
+        hi = np.zeros(max(cap_inner, 1), np.float64)
+        ho = np.zeros(4 * cap_outer, np.float64)
+        nrows = (row_map.numel() if hasattr(row_map, "numel") else len(row_map)) - 1
+        nnz = inds.numel() if hasattr(inds, "numel") else len(inds)
+        self._chk(self.L.mpg_gmres_solve_host(self.h, C.byref(p), C.c_int(nrows), C.c_int64(nnz), _ptr(row_map), _ptr(inds), _ptr(vals64),
+                                              _ptr(b), _ptr(x), C.byref(st), _ptr(hi), C.c_int64(cap_inner), _ptr(ho), C.c_int64(cap_outer)))
+        return self._result(st, hi, ho, cap_inner, cap_outer)
+
+    @staticmethod
+    def _result(st, hi, ho, cap_inner, cap_outer):
+        res = {f: getattr(st, f) for f, _ in GmresStats._fields_}
+        res["hist_inner"] = hi[:min(st.n_hist_inner, cap_inner)].copy()
+        res["hist_outer"] = ho[:4 * min(st.n_hist_outer, cap_outer)].reshape(-1, 4).copy()
+        return res

@@ -1,0 +1,587 @@
+// blas1.cu — context, device memory, BLAS-1, casts, Givens / least-squares kernels.
+// Reference surface: kernels.hpp:11-114,128-151; reference CUDA backend: kernels_cuda.cpp:111-494,538-572.
+#include <random>
+
+#include "common.cuh"
+
+using namespace mpg;
+
+// =====================================================================================================
+// context
+// =====================================================================================================
+extern "C" const char* mpg_version(void) { return "mpgmres_b200 0.1 (sm_100a)"; }
+
+extern "C" int mpg_ctx_create(int device, mpg_ctx** out) {
+    if (!out) return MPG_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0 || device >= ndev) {
+        // no CPU fallback: the product path fails loudly without a CUDA device
+        fprintf(stderr, "mpgmres_b200: no usable CUDA device (%s)\n", e == cudaSuccess ? "device index out of range" : cudaGetErrorString(e));
+        return MPG_ERR_CUDA;
+    }
+    mpg_ctx* ctx = new mpg_ctx();
+    ctx->device = device;
+    MPG_CUDA(ctx, cudaSetDevice(device));
+    cudaDeviceProp prop;
+    MPG_CUDA(ctx, cudaGetDeviceProperties(&prop, device));
+    ctx->num_sms = prop.multiProcessorCount;
+    MPG_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+    ctx->stream = ctx->own_stream;
+    MPG_CUDA(ctx, cudaMalloc(&ctx->partials, sizeof(double) * (size_t)kMaxPartBlocks * (kMaxCols + 8)));
+    MPG_CUDA(ctx, cudaMalloc(&ctx->ticket, sizeof(unsigned int) * 4));
+    MPG_CUDA(ctx, cudaMemset(ctx->ticket, 0, sizeof(unsigned int) * 4));
+    MPG_CUDA(ctx, cudaMalloc(&ctx->dscal, sizeof(double) * 1024));
+    MPG_CUDA(ctx, cudaMemset(ctx->dscal, 0, sizeof(double) * 1024));
+    MPG_CUDA(ctx, cudaMallocHost(&ctx->hscal, sizeof(double) * 64));
+    *out = ctx;
+    return MPG_OK;
+}
+
+extern "C" int mpg_ctx_destroy(mpg_ctx* ctx) {
+    if (!ctx) return MPG_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->ws && ctx->ws_free) ctx->ws_free(ctx->ws);
+    for (auto& r : ctx->prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    for (auto e : ctx->prof_pool) cudaEventDestroy(e);
+    cudaFree(ctx->partials);
+    cudaFree(ctx->ticket);
+    cudaFree(ctx->dscal);
+    cudaFreeHost(ctx->hscal);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+    return MPG_OK;
+}
+
+extern "C" int mpg_ctx_set_stream(mpg_ctx* ctx, void* s) {
+    if (!ctx) return MPG_ERR_ARG;
+    ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
+    return MPG_OK;
+}
+extern "C" void* mpg_ctx_stream(mpg_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+extern "C" int mpg_sync(mpg_ctx* ctx) {
+    MPG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MPG_OK;
+}
+extern "C" const char* mpg_last_error(mpg_ctx* ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
+extern "C" int mpg_num_sms(mpg_ctx* ctx) { return ctx ? ctx->num_sms : 0; }
+extern "C" int64_t mpg_launch_count(mpg_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int mpg_set_tuning(mpg_ctx* ctx, const char* key, int value) {
+    if (!ctx || !key) return MPG_ERR_ARG;
+    const std::string k(key);
+    if (k == "spmv_ctas_per_sm") ctx->tune.spmv_ctas_per_sm = value;
+    else if (k == "vpass_stages") ctx->tune.vpass_stages = value;
+    else if (k == "vpass_bulk") ctx->tune.vpass_bulk = value;
+    else if (k == "vpass_serpentine") ctx->tune.vpass_serpentine = value;
+    else if (k == "gemvn_ctas_per_sm") ctx->tune.gemvn_ctas_per_sm = value;
+    else if (k == "red_ctas_per_sm") ctx->tune.red_ctas_per_sm = value;
+    else if (k == "use_graph") ctx->tune.use_graph = value;
+    else return fail(ctx, MPG_ERR_ARG, "unknown tuning key " + k);
+    return MPG_OK;
+}
+
+extern "C" int mpg_prof_enable(mpg_ctx* ctx, int on) {
+    if (!ctx) return MPG_ERR_ARG;
+    ctx->prof_on = on != 0;
+    return MPG_OK;
+}
+static int prof_fold(mpg_ctx* ctx) {
+    MPG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (auto& r : ctx->prof_pending) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, r.a, r.b);
+        ctx->prof_ms[r.cls] += ms;
+        ctx->prof_bytes[r.cls] += r.bytes;
+        ctx->prof_launches[r.cls] += 1;
+        ctx->prof_pool.push_back(r.a);
+        ctx->prof_pool.push_back(r.b);
+    }
+    ctx->prof_pending.clear();
+    return MPG_OK;
+}
+extern "C" int mpg_prof_reset(mpg_ctx* ctx) {
+    if (!ctx) return MPG_ERR_ARG;
+    MPG_TRY(prof_fold(ctx));
+    for (int c = 0; c < MPG_PROF_NCLASS; ++c) { ctx->prof_ms[c] = 0; ctx->prof_bytes[c] = 0; ctx->prof_launches[c] = 0; }
+    return MPG_OK;
+}
+extern "C" int mpg_prof_get(mpg_ctx* ctx, int cls, double* ms, double* bytes, int64_t* launches) {
+    if (!ctx || cls < 0 || cls >= MPG_PROF_NCLASS) return MPG_ERR_ARG;
+    MPG_TRY(prof_fold(ctx));
+    if (ms) *ms = ctx->prof_ms[cls];
+    if (bytes) *bytes = ctx->prof_bytes[cls];
+    if (launches) *launches = ctx->prof_launches[cls];
+    return MPG_OK;
+}
+
+// =====================================================================================================
+// device memory
+// =====================================================================================================
+extern "C" int mpg_malloc(mpg_ctx* ctx, size_t bytes, void** dptr) {
+    MPG_REQUIRE(ctx, dptr != nullptr, "mpg_malloc: null out pointer");
+    *dptr = nullptr;
+    if (bytes == 0) return MPG_OK;
+    MPG_CUDA(ctx, cudaMalloc(dptr, bytes));
+    MPG_CUDA(ctx, cudaMemsetAsync(*dptr, 0, bytes, ctx->stream));
+    return MPG_OK;
+}
+extern "C" int mpg_free(mpg_ctx* ctx, void* dptr) {
+    if (!dptr) return MPG_OK;
+    MPG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    MPG_CUDA(ctx, cudaFree(dptr));
+    return MPG_OK;
+}
+extern "C" int mpg_memcpy_h2d(mpg_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    MPG_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return MPG_OK;
+}
+extern "C" int mpg_memcpy_d2h(mpg_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    MPG_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    MPG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MPG_OK;
+}
+extern "C" int mpg_memcpy_d2d(mpg_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    MPG_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    return MPG_OK;
+}
+extern "C" int mpg_memset_zero(mpg_ctx* ctx, void* dst, size_t bytes) {
+    MPG_CUDA(ctx, cudaMemsetAsync(dst, 0, bytes, ctx->stream));
+    return MPG_OK;
+}
+
+extern "C" int mpg_rand_vect_host(int64_t n, uint32_t seed, double* out) {
+    if (!out || n < 0) return MPG_ERR_ARG;
+    // gmres_perf_test.cpp:39-51: floats are drawn so x is identical whether it is later used as fp32 or fp64
+    std::mt19937 engine(seed);
+    std::uniform_real_distribution<float> dist;
+    for (int64_t i = 0; i < n; ++i) out[i] = dist(engine);
+    return MPG_OK;
+}
+
+// =====================================================================================================
+// reductions: dot, nrm2
+// =====================================================================================================
+namespace {
+
+constexpr int RED_THREADS = 256;
+
+template <class T, bool IS_NRM2>
+__global__ void __launch_bounds__(RED_THREADS) reduce_kernel(int64_t n, const T* __restrict__ x, const T* __restrict__ y,
+                                                              double* partials, unsigned int* ticket, T* out) {
+    constexpr int VEC = 16 / sizeof(T);
+    using V = typename std::conditional<sizeof(T) == 4, float4, double2>::type;
+    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t gstride = (int64_t)gridDim.x * blockDim.x;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
+    T acc[VEC];
+#pragma unroll
+    for (int c = 0; c < VEC; ++c) acc[c] = T(0);
+    int64_t done = 0;
+    if (aligned) {
+        const int64_t nv = n / VEC;
+        const V* xv = reinterpret_cast<const V*>(x);
+        const V* yv = reinterpret_cast<const V*>(y);
+        for (int64_t i = gtid; i < nv; i += gstride) {
+            const V a = ldg_stream(xv + i);
+            const V b = IS_NRM2 ? a : ldg_stream(yv + i);
+            const T* pa = reinterpret_cast<const T*>(&a);
+            const T* pb = reinterpret_cast<const T*>(&b);
+#pragma unroll
+            for (int c = 0; c < VEC; ++c) acc[c] = fma(pa[c], pb[c], acc[c]);
+        }
+        done = nv * VEC;
+    }
+    for (int64_t i = done + gtid; i < n; i += gstride) {
+        const T a = x[i];
+        const T b = IS_NRM2 ? a : y[i];
+        acc[0] = fma(a, b, acc[0]);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int c = 0; c < VEC; ++c) s += (double)acc[c];
+    s = warp_sum(s);
+    __shared__ double wsum[RED_THREADS / 32];
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < RED_THREADS / 32; ++w) t += wsum[w];
+        partials[blockIdx.x] = t;
+    }
+    if (grid_last_block(ticket)) {
+        if (threadIdx.x < 32) {
+            const double t = reduce_partials_column(partials, 1, gridDim.x, 0);
+            if (threadIdx.x == 0) *out = IS_NRM2 ? (T)sqrt(t) : (T)t;
+        }
+    }
+}
+
+template <class T, bool IS_NRM2>
+int launch_reduce(mpg_ctx* ctx, int64_t n, const T* x, const T* y, T* out_dev) {
+    const int64_t per_block = RED_THREADS * (16 / sizeof(T)) * 4;
+    int grid = (int)std::min<int64_t>(std::max<int64_t>(1, cdiv(n, per_block)), (int64_t)ctx->num_sms * ctx->tune.red_ctas_per_sm);
+    grid = std::min(grid, kMaxPartBlocks);
+    ProfScope prof(ctx, MPG_PROF_REDUCE, (double)n * sizeof(T) * (IS_NRM2 ? 1 : 2));
+    reduce_kernel<T, IS_NRM2><<<grid, RED_THREADS, 0, ctx->stream>>>(n, x, y, ctx->partials, ctx->ticket, out_dev);
+    MPG_CHECK_LAUNCH(ctx);
+    return MPG_OK;
+}
+
+template <class T>
+int to_host(mpg_ctx* ctx, const T* dev, T* host) {
+    MPG_CUDA(ctx, cudaMemcpyAsync(ctx->hscal, dev, sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+    MPG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    memcpy(host, ctx->hscal, sizeof(T));
+    return MPG_OK;
+}
+
+}  // namespace
+
+namespace mpg {
+// internal entry points used by solver.cu
+int dot_dev(mpg_ctx* ctx, int64_t n, const float* x, const float* y, float* out) { return launch_reduce<float, false>(ctx, n, x, y, out); }
+int dot_dev(mpg_ctx* ctx, int64_t n, const double* x, const double* y, double* out) { return launch_reduce<double, false>(ctx, n, x, y, out); }
+int nrm2_dev(mpg_ctx* ctx, int64_t n, const float* x, float* out) { return launch_reduce<float, true>(ctx, n, x, x, out); }
+int nrm2_dev(mpg_ctx* ctx, int64_t n, const double* x, double* out) { return launch_reduce<double, true>(ctx, n, x, x, out); }
+}  // namespace mpg
+
+#define MPG_DEF_RED(SFX, T)                                                                                          \
+    extern "C" int mpg_dot_dev_##SFX(mpg_ctx* ctx, int64_t n, const T* x, const T* y, T* r) {                        \
+        MPG_REQUIRE(ctx, n >= 0 && r, "dot: bad args");                                                              \
+        return launch_reduce<T, false>(ctx, n, x, y, r);                                                             \
+    }                                                                                                                \
+    extern "C" int mpg_nrm2_dev_##SFX(mpg_ctx* ctx, int64_t n, const T* x, T* r) {                                   \
+        MPG_REQUIRE(ctx, n >= 0 && r, "nrm2: bad args");                                                             \
+        return launch_reduce<T, true>(ctx, n, x, x, r);                                                              \
+    }                                                                                                                \
+    extern "C" int mpg_dot_##SFX(mpg_ctx* ctx, int64_t n, const T* x, const T* y, T* r) {                            \
+        MPG_REQUIRE(ctx, n >= 0 && r, "dot: bad args");                                                              \
+        MPG_TRY((launch_reduce<T, false>(ctx, n, x, y, reinterpret_cast<T*>(ctx->dscal))));                          \
+        return to_host<T>(ctx, reinterpret_cast<T*>(ctx->dscal), r);                                                 \
+    }                                                                                                                \
+    extern "C" int mpg_nrm2_##SFX(mpg_ctx* ctx, int64_t n, const T* x, T* r) {                                       \
+        MPG_REQUIRE(ctx, n >= 0 && r, "nrm2: bad args");                                                             \
+        MPG_TRY((launch_reduce<T, true>(ctx, n, x, x, reinterpret_cast<T*>(ctx->dscal))));                           \
+        return to_host<T>(ctx, reinterpret_cast<T*>(ctx->dscal), r);                                                 \
+    }
+MPG_DEF_RED(f32, float)
+MPG_DEF_RED(f64, double)
+
+// =====================================================================================================
+// element-wise kernels.  One template: OP selects the arithmetic; 16-byte vector path when every
+// pointer is 16-byte aligned, scalar otherwise.  The scalar `alpha` comes from the host or, for the
+// Scalar<T,Device> overloads, from device memory (read once per thread through the read-only path).
+// =====================================================================================================
+namespace {
+
+enum EwOp { EW_AXPY, EW_NAXPY, EW_SCAL, EW_COPY, EW_FILL, EW_GDMV };
+
+template <class TX, class TY, int OP>
+__device__ __forceinline__ TY ew_apply(TX x, TY y, TY alpha, TY beta, TY d) {
+    if (OP == EW_AXPY) return fma(alpha, (TY)x, y);          // y += alpha*x   (cublas?axpy)
+    if (OP == EW_NAXPY) return fma(-alpha, (TY)x, y);        // y -= alpha*x   (kernels_cuda.cpp:264-288)
+    if (OP == EW_SCAL) return alpha * (TY)x;                 // y = alpha*x    (copy + cublas?scal)
+    if (OP == EW_COPY) return (TY)x;                         // RN conversion  (kernels.hpp:11-20)
+    if (OP == EW_FILL) return alpha;
+    // gdmv, kernels.hpp:143-145: beta*y + (alpha*diag)*x, every operation rounded (no contraction) so the
+    // result does not depend on the compiler's fma choices
+    if (sizeof(TY) == 4) return (TY)__fadd_rn(__fmul_rn((float)beta, (float)y), __fmul_rn(__fmul_rn((float)alpha, (float)d), (float)x));
+    return (TY)__dadd_rn(__dmul_rn((double)beta, (double)y), __dmul_rn(__dmul_rn((double)alpha, (double)d), (double)x));
+}
+
+template <class T>
+__device__ __forceinline__ void load4(const T* p, T v[4]) {
+    if (sizeof(T) == 4) {
+        const float4 t = *reinterpret_cast<const float4*>(p);
+        v[0] = (T)t.x; v[1] = (T)t.y; v[2] = (T)t.z; v[3] = (T)t.w;
+    } else {
+        const double2 a = *reinterpret_cast<const double2*>(p);
+        const double2 b = *reinterpret_cast<const double2*>(p + 2);
+        v[0] = (T)a.x; v[1] = (T)a.y; v[2] = (T)b.x; v[3] = (T)b.y;
+    }
+}
+template <class T>
+__device__ __forceinline__ void store4(T* p, const T v[4]) {
+    if (sizeof(T) == 4) {
+        *reinterpret_cast<float4*>(p) = make_float4((float)v[0], (float)v[1], (float)v[2], (float)v[3]);
+    } else {
+        *reinterpret_cast<double2*>(p) = make_double2((double)v[0], (double)v[1]);
+        *reinterpret_cast<double2*>(p + 2) = make_double2((double)v[2], (double)v[3]);
+    }
+}
+
+template <class TX, class TY, int OP>
+__global__ void __launch_bounds__(256) ew_kernel(int64_t n, TY alpha, const TY* __restrict__ alpha_dev, TY beta,
+                                                  const TX* x, const TY* diag, TY* y, int aligned) {
+    if (alpha_dev) alpha = __ldg(alpha_dev);
+    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t gstride = (int64_t)gridDim.x * blockDim.x;
+    constexpr bool READS_X = (OP != EW_FILL);
+    constexpr bool READS_Y = (OP == EW_AXPY || OP == EW_NAXPY || OP == EW_GDMV);
+    constexpr bool READS_D = (OP == EW_GDMV);
+    for (int64_t i0 = gtid * 4; i0 < n; i0 += gstride * 4) {
+        TX xv[4];
+        TY yv[4], dv[4];
+        const int cnt = (int)min((int64_t)4, n - i0);
+        if (aligned && cnt == 4) {
+            if (READS_X) load4<TX>(x + i0, xv);
+            if (READS_Y) load4<TY>(y + i0, yv);
+            if (READS_D) load4<TY>(diag + i0, dv);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) yv[c] = ew_apply<TX, TY, OP>(xv[c], yv[c], alpha, beta, dv[c]);
+            store4<TY>(y + i0, yv);
+        } else {
+            for (int c = 0; c < cnt; ++c) {
+                const TX xs = READS_X ? x[i0 + c] : TX(0);
+                const TY ys = READS_Y ? y[i0 + c] : TY(0);
+                const TY ds = READS_D ? diag[i0 + c] : TY(0);
+                y[i0 + c] = ew_apply<TX, TY, OP>(xs, ys, alpha, beta, ds);
+            }
+        }
+    }
+}
+
+template <class TX, class TY, int OP>
+int launch_ew(mpg_ctx* ctx, int64_t n, TY alpha, const TY* alpha_dev, TY beta, const TX* x, const TY* diag, TY* y) {
+    if (n <= 0) return MPG_OK;
+    const int grid = (int)std::min<int64_t>(cdiv(n, 256 * 4), (int64_t)ctx->num_sms * 16);
+    const int aligned = (((uintptr_t)x | (uintptr_t)diag | (uintptr_t)y) & 15) == 0;
+    const double ew_bytes = (double)n * ((OP != EW_FILL ? sizeof(TX) : 0) + sizeof(TY) * (1 + (OP == EW_AXPY || OP == EW_NAXPY || OP == EW_GDMV) + (OP == EW_GDMV)));
+    ProfScope prof(ctx, MPG_PROF_ELEMENTWISE, ew_bytes);
+    ew_kernel<TX, TY, OP><<<grid, 256, 0, ctx->stream>>>(n, alpha, alpha_dev, beta, x, diag, y, aligned);
+    MPG_CHECK_LAUNCH(ctx);
+    return MPG_OK;
+}
+
+}  // namespace
+
+namespace mpg {
+int scal_host(mpg_ctx* ctx, int64_t n, float a, const float* x, float* y) { return launch_ew<float, float, EW_SCAL>(ctx, n, a, nullptr, 0.f, x, nullptr, y); }
+int scal_host(mpg_ctx* ctx, int64_t n, double a, const double* x, double* y) { return launch_ew<double, double, EW_SCAL>(ctx, n, a, nullptr, 0.0, x, nullptr, y); }
+int scal_devp(mpg_ctx* ctx, int64_t n, const float* a, const float* x, float* y) { return launch_ew<float, float, EW_SCAL>(ctx, n, 0.f, a, 0.f, x, nullptr, y); }
+int scal_devp(mpg_ctx* ctx, int64_t n, const double* a, const double* x, double* y) { return launch_ew<double, double, EW_SCAL>(ctx, n, 0.0, a, 0.0, x, nullptr, y); }
+int naxpy_devp(mpg_ctx* ctx, int64_t n, const float* a, const float* x, float* y) { return launch_ew<float, float, EW_NAXPY>(ctx, n, 0.f, a, 0.f, x, nullptr, y); }
+int naxpy_devp(mpg_ctx* ctx, int64_t n, const double* a, const double* x, double* y) { return launch_ew<double, double, EW_NAXPY>(ctx, n, 0.0, a, 0.0, x, nullptr, y); }
+int axpy_host(mpg_ctx* ctx, int64_t n, float a, const float* x, float* y) { return launch_ew<float, float, EW_AXPY>(ctx, n, a, nullptr, 0.f, x, nullptr, y); }
+int axpy_host(mpg_ctx* ctx, int64_t n, double a, const double* x, double* y) { return launch_ew<double, double, EW_AXPY>(ctx, n, a, nullptr, 0.0, x, nullptr, y); }
+int cast_copy(mpg_ctx* ctx, int64_t n, const double* x, float* y) { return launch_ew<double, float, EW_COPY>(ctx, n, 0.f, nullptr, 0.f, x, nullptr, y); }
+int cast_copy(mpg_ctx* ctx, int64_t n, const float* x, double* y) { return launch_ew<float, double, EW_COPY>(ctx, n, 0.0, nullptr, 0.0, x, nullptr, y); }
+int cast_copy(mpg_ctx* ctx, int64_t n, const float* x, float* y) { return launch_ew<float, float, EW_COPY>(ctx, n, 0.f, nullptr, 0.f, x, nullptr, y); }
+int cast_copy(mpg_ctx* ctx, int64_t n, const double* x, double* y) { return launch_ew<double, double, EW_COPY>(ctx, n, 0.0, nullptr, 0.0, x, nullptr, y); }
+int fill_host(mpg_ctx* ctx, int64_t n, float a, float* x) { return launch_ew<float, float, EW_FILL>(ctx, n, a, nullptr, 0.f, nullptr, nullptr, x); }
+int fill_host(mpg_ctx* ctx, int64_t n, double a, double* x) { return launch_ew<double, double, EW_FILL>(ctx, n, a, nullptr, 0.0, nullptr, nullptr, x); }
+int gdmv_host(mpg_ctx* ctx, int64_t n, float a, const float* d, const float* x, float b, float* y) { return launch_ew<float, float, EW_GDMV>(ctx, n, a, nullptr, b, x, d, y); }
+int gdmv_host(mpg_ctx* ctx, int64_t n, double a, const double* d, const double* x, double b, double* y) { return launch_ew<double, double, EW_GDMV>(ctx, n, a, nullptr, b, x, d, y); }
+}  // namespace mpg
+
+#define MPG_DEF_EW(SFX, T)                                                                                              \
+    extern "C" int mpg_axpy_##SFX(mpg_ctx* c, int64_t n, T a, const T* x, T* y) { return mpg::axpy_host(c, n, a, x, y); } \
+    extern "C" int mpg_axpy_dev_##SFX(mpg_ctx* c, int64_t n, const T* a, const T* x, T* y) {                            \
+        return launch_ew<T, T, EW_AXPY>(c, n, T(0), a, T(0), x, nullptr, y);                                            \
+    }                                                                                                                   \
+    extern "C" int mpg_naxpy_dev_##SFX(mpg_ctx* c, int64_t n, const T* a, const T* x, T* y) { return mpg::naxpy_devp(c, n, a, x, y); } \
+    extern "C" int mpg_scal_##SFX(mpg_ctx* c, int64_t n, T a, const T* x, T* y) { return mpg::scal_host(c, n, a, x, y); } \
+    extern "C" int mpg_scal_dev_##SFX(mpg_ctx* c, int64_t n, const T* a, const T* x, T* y) { return mpg::scal_devp(c, n, a, x, y); } \
+    extern "C" int mpg_fill_##SFX(mpg_ctx* c, int64_t n, T a, T* x) { return mpg::fill_host(c, n, a, x); }              \
+    extern "C" int mpg_gdmv_##SFX(mpg_ctx* c, int64_t n, T a, const T* d, const T* x, T b, T* y) { return mpg::gdmv_host(c, n, a, d, x, b, y); }
+MPG_DEF_EW(f32, float)
+MPG_DEF_EW(f64, double)
+
+extern "C" int mpg_copy_f32_f32(mpg_ctx* c, int64_t n, const float* x, float* y) { return mpg::cast_copy(c, n, x, y); }
+extern "C" int mpg_copy_f64_f64(mpg_ctx* c, int64_t n, const double* x, double* y) { return mpg::cast_copy(c, n, x, y); }
+extern "C" int mpg_copy_f64_f32(mpg_ctx* c, int64_t n, const double* x, float* y) { return mpg::cast_copy(c, n, x, y); }
+extern "C" int mpg_copy_f32_f64(mpg_ctx* c, int64_t n, const float* x, double* y) { return mpg::cast_copy(c, n, x, y); }
+
+// =====================================================================================================
+// Givens rotations, triangular solve (tiny, latency-bound; one warp or one thread each)
+// =====================================================================================================
+namespace {
+
+// netlib ?rotg followed by b := 0 (kernels_cuda.cpp:394-420).  No FMA contraction: written with
+// explicit intrinsics so the rounding sequence equals the oracle's (a/scale, squares, sum, sqrt, product).
+template <class T> __device__ __forceinline__ T mul_rn(T a, T b);
+template <> __device__ __forceinline__ float mul_rn<float>(float a, float b) { return __fmul_rn(a, b); }
+template <> __device__ __forceinline__ double mul_rn<double>(double a, double b) { return __dmul_rn(a, b); }
+template <class T> __device__ __forceinline__ T add_rn(T a, T b);
+template <> __device__ __forceinline__ float add_rn<float>(float a, float b) { return __fadd_rn(a, b); }
+template <> __device__ __forceinline__ double add_rn<double>(double a, double b) { return __dadd_rn(a, b); }
+template <class T> __device__ __forceinline__ T div_rn(T a, T b);
+template <> __device__ __forceinline__ float div_rn<float>(float a, float b) { return __fdiv_rn(a, b); }
+template <> __device__ __forceinline__ double div_rn<double>(double a, double b) { return __ddiv_rn(a, b); }
+template <class T> __device__ __forceinline__ T sqrt_rn(T a);
+template <> __device__ __forceinline__ float sqrt_rn<float>(float a) { return __fsqrt_rn(a); }
+template <> __device__ __forceinline__ double sqrt_rn<double>(double a) { return __dsqrt_rn(a); }
+
+template <class T>
+__device__ __forceinline__ void dev_rotg(T& a, T& b, T& c, T& s) {
+    const T roe = (fabs(a) > fabs(b)) ? a : b;
+    const T scale = add_rn(fabs(a), fabs(b));
+    T r;
+    if (scale == T(0)) {
+        c = T(1); s = T(0); r = T(0);
+    } else {
+        const T as = div_rn(a, scale), bs = div_rn(b, scale);
+        r = mul_rn(scale, sqrt_rn(add_rn(mul_rn(as, as), mul_rn(bs, bs))));
+        r = mul_rn(copysign(T(1), roe), r);
+        c = div_rn(a, r);
+        s = div_rn(b, r);
+    }
+    a = r;
+    b = T(0);
+}
+// ?rot with n = 1: (a,b) <- (c a + s b, c b - s a), products and sums rounded separately like the oracle
+template <class T>
+__device__ __forceinline__ void dev_rot(T& a, T& b, T c, T s) {
+    const T t = add_rn(mul_rn(c, a), mul_rn(s, b));
+    b = add_rn(mul_rn(c, b), -mul_rn(s, a));
+    a = t;
+}
+
+template <class T>
+__global__ void rotg_kernel(T* a, T* b, T* c, T* s) {
+    T va = *a, vb = *b, vc, vs;
+    dev_rotg(va, vb, vc, vs);
+    *a = va; *b = vb; *c = vc; *s = vs;
+}
+template <class T>
+__global__ void rot_kernel(T* a, T* b, const T* c, const T* s) {
+    T va = *a, vb = *b;
+    dev_rot(va, vb, *c, *s);
+    *a = va; *b = vb;
+}
+template <class T>
+__global__ void rot_vec_kernel(int64_t k, T* a, const T* c, const T* s) {
+    if (k <= 0) return;
+    T cur = a[0];
+    for (int64_t j = 0; j < k; ++j) {
+        T nxt = a[j + 1];
+        dev_rot(cur, nxt, c[j], s[j]);
+        a[j] = cur;
+        cur = nxt;
+    }
+    a[k] = cur;
+}
+// gmres.cpp:219-226 in one launch.  One warp: lanes prefetch c/s/h into shared memory, lane 0 runs the
+// dependent rotation chain from shared memory.
+template <class T>
+__global__ void __launch_bounds__(32) givens_step_kernel(int64_t k, T* h, int64_t ldh, T* cs, T* sn, T* s, double* resid) {
+    extern __shared__ unsigned char smem_raw[];
+    T* sh = reinterpret_cast<T*>(smem_raw);        // k+2
+    T* sc = sh + (k + 2);                          // k
+    T* ss = sc + k;                                // k
+    T* hcol = h + k * ldh;
+    for (int64_t j = threadIdx.x; j < k + 2; j += 32) sh[j] = hcol[j];
+    for (int64_t j = threadIdx.x; j < k; j += 32) { sc[j] = cs[j]; ss[j] = sn[j]; }
+    __syncwarp();
+    if (threadIdx.x == 0) {
+        T cur = sh[0];
+        for (int64_t j = 0; j < k; ++j) {
+            T nxt = sh[j + 1];
+            dev_rot(cur, nxt, sc[j], ss[j]);
+            sh[j] = cur;
+            cur = nxt;
+        }
+        T hk1 = sh[k + 1], c, sv;
+        dev_rotg(cur, hk1, c, sv);
+        sh[k] = cur;
+        sh[k + 1] = hk1;
+        cs[k] = c;
+        sn[k] = sv;
+        T s0 = s[k], s1 = s[k + 1];
+        dev_rot(s0, s1, c, sv);
+        s[k] = s0;
+        s[k + 1] = s1;
+        if (resid) *resid = fabs((double)s1);
+    }
+    __syncwarp();
+    for (int64_t j = threadIdx.x; j < k + 2; j += 32) hcol[j] = sh[j];
+}
+
+// netlib ?trsv, Upper/NoTrans/NonUnit in column form (the oracle's order); Lower and Trans forms are the
+// row-oriented textbook loops.  n <= restart length, one thread: the solve is a dependent chain anyway.
+template <class T>
+__global__ void trsv_kernel(int upper, int trans, int64_t n, const T* A, int64_t ld, T* x) {
+    if (upper && !trans) {
+        for (int64_t j = n; j-- > 0;) {
+            if (x[j] != T(0)) {
+                x[j] = div_rn(x[j], A[j + j * ld]);
+                const T t = x[j];
+                for (int64_t i = j; i-- > 0;) x[i] = fma(-t, A[i + j * ld], x[i]);
+            }
+        }
+    } else if (!upper && !trans) {
+        for (int64_t j = 0; j < n; ++j) {
+            if (x[j] != T(0)) {
+                x[j] = div_rn(x[j], A[j + j * ld]);
+                const T t = x[j];
+                for (int64_t i = j + 1; i < n; ++i) x[i] = fma(-t, A[i + j * ld], x[i]);
+            }
+        }
+    } else if (upper && trans) {  // solve U^T x = b: forward substitution on columns of U
+        for (int64_t j = 0; j < n; ++j) {
+            T t = x[j];
+            for (int64_t i = 0; i < j; ++i) t = fma(-A[i + j * ld], x[i], t);
+            x[j] = div_rn(t, A[j + j * ld]);
+        }
+    } else {  // L^T x = b
+        for (int64_t j = n; j-- > 0;) {
+            T t = x[j];
+            for (int64_t i = n - 1; i > j; --i) t = fma(-A[i + j * ld], x[i], t);
+            x[j] = div_rn(t, A[j + j * ld]);
+        }
+    }
+}
+
+}  // namespace
+
+namespace mpg {
+template <class T>
+int givens_step(mpg_ctx* ctx, int64_t k, T* h, int64_t ldh, T* cs, T* sn, T* s, double* resid) {
+    const size_t smem = sizeof(T) * (size_t)(3 * k + 2);
+    ProfScope prof(ctx, MPG_PROF_SMALL, 0.0);
+    givens_step_kernel<T><<<1, 32, smem, ctx->stream>>>(k, h, ldh, cs, sn, s, resid);
+    MPG_CHECK_LAUNCH(ctx);
+    return MPG_OK;
+}
+template int givens_step<float>(mpg_ctx*, int64_t, float*, int64_t, float*, float*, float*, double*);
+template int givens_step<double>(mpg_ctx*, int64_t, double*, int64_t, double*, double*, double*, double*);
+template <class T>
+int trsv(mpg_ctx* ctx, int upper, int trans, int64_t n, const T* A, int64_t ld, T* x) {
+    if (n <= 0) return MPG_OK;
+    trsv_kernel<T><<<1, 1, 0, ctx->stream>>>(upper, trans, n, A, ld, x);
+    MPG_CHECK_LAUNCH(ctx);
+    return MPG_OK;
+}
+template int trsv<float>(mpg_ctx*, int, int, int64_t, const float*, int64_t, float*);
+template int trsv<double>(mpg_ctx*, int, int, int64_t, const double*, int64_t, double*);
+}  // namespace mpg
+
+#define MPG_DEF_LS(SFX, T)                                                                                     \
+    extern "C" int mpg_rotg_##SFX(mpg_ctx* ctx, T* a, T* b, T* c, T* s) {                                      \
+        rotg_kernel<T><<<1, 1, 0, ctx->stream>>>(a, b, c, s);                                                  \
+        MPG_CHECK_LAUNCH(ctx);                                                                                 \
+        return MPG_OK;                                                                                         \
+    }                                                                                                          \
+    extern "C" int mpg_rot_##SFX(mpg_ctx* ctx, T* a, T* b, const T* c, const T* s) {                           \
+        rot_kernel<T><<<1, 1, 0, ctx->stream>>>(a, b, c, s);                                                   \
+        MPG_CHECK_LAUNCH(ctx);                                                                                 \
+        return MPG_OK;                                                                                         \
+    }                                                                                                          \
+    extern "C" int mpg_rot_vec_##SFX(mpg_ctx* ctx, int64_t k, T* a, const T* c, const T* s) {                  \
+        rot_vec_kernel<T><<<1, 1, 0, ctx->stream>>>(k, a, c, s);                                               \
+        MPG_CHECK_LAUNCH(ctx);                                                                                 \
+        return MPG_OK;                                                                                         \
+    }                                                                                                          \
+    extern "C" int mpg_trsv_##SFX(mpg_ctx* ctx, int upper, int trans, int64_t n, const T* A, int64_t ld, T* x) { \
+        MPG_REQUIRE(ctx, n >= 0 && ld >= n, "trsv: bad dims");                                                 \
+        return mpg::trsv<T>(ctx, upper, trans, n, A, ld, x);                                                   \
+    }                                                                                                          \
+    extern "C" int mpg_givens_step_##SFX(mpg_ctx* ctx, int64_t k, T* h, int64_t ldh, T* cs, T* sn, T* s, double* r) { \
+        MPG_REQUIRE(ctx, k >= 0 && k + 2 <= kMaxCols + 2, "givens_step: bad k");                               \
+        return mpg::givens_step<T>(ctx, k, h, ldh, cs, sn, s, r);                                              \
+    }
+MPG_DEF_LS(f32, float)
+MPG_DEF_LS(f64, double)

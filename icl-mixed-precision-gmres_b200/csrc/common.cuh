@@ -1,0 +1,214 @@
+// common.cuh — context, error handling and device helpers shared by every translation unit of
+// libmpgmres_b200.so (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/mpgmres_b200.h"
+
+#define MPG_PROF_NCLASS 8
+namespace mpg {
+
+constexpr int kMaxCols = 256;          // widest basis block any fused kernel accepts (restart length + 1)
+constexpr int kMaxPartBlocks = 2048;   // upper bound on the grid of a reducing kernel
+
+struct Tuning {
+    int spmv_ctas_per_sm = 8;
+    int vpass_stages = 0;     // 0 = auto
+    int vpass_bulk = 1;       // use cp.async.bulk (TMA 1-D) staging when alignment allows
+    int vpass_serpentine = 1; // alternate traversal direction between consecutive V passes (L2 reuse)
+    int gemvn_ctas_per_sm = 4;
+    int red_ctas_per_sm = 4;
+    int use_graph = 0;
+};
+
+}  // namespace mpg
+
+struct mpg_ctx {
+    int device = 0;
+    int num_sms = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    std::string last_error;
+    int64_t launches = 0;
+    mpg::Tuning tune;
+
+    // reduction scratch: partials[kMaxPartBlocks][kMaxCols + 8] doubles + a ticket counter
+    double* partials = nullptr;
+    unsigned int* ticket = nullptr;
+    // small device scalars (results of host-return dot/nrm2, residual, 1/norm ...)
+    double* dscal = nullptr;   // 1024 doubles: [0,64) scalars, [64,64+264) coefficient scratch of mpg_add_vector_*
+    double* hscal = nullptr;   // pinned host mirror, 64 doubles
+    int vpass_parity = 0;      // serpentine direction toggle
+
+    // per-kernel-class device timers (CUDA events on the launching stream), off by default
+    bool prof_on = false;
+    struct ProfRec { int cls; cudaEvent_t a, b; double bytes; };
+    std::vector<ProfRec> prof_pending;
+    std::vector<cudaEvent_t> prof_pool;
+    double prof_ms[MPG_PROF_NCLASS] = {0};
+    double prof_bytes[MPG_PROF_NCLASS] = {0};
+    int64_t prof_launches[MPG_PROF_NCLASS] = {0};
+
+    // cached solver workspace (see solver.cu)
+    void* ws = nullptr;
+    void (*ws_free)(void*) = nullptr;
+};
+
+struct mpg_csr {
+    int nrows = 0, ncols = 0;
+    int64_t nnz = 0;
+    const int* row_map = nullptr;  // not owned
+    const int* inds = nullptr;     // not owned
+    // SpMV plan (owned): nnz-split tiles
+    int tile_nnz = 0;
+    int ntiles = 0;
+    int* tile_row = nullptr;       // [ntiles+1] row containing the first nonzero of each tile
+    void* carry = nullptr;         // [2*ntiles] doubles: carry_in / carry_out partial row sums
+    int device = 0;
+};
+
+namespace mpg {
+
+inline int fail(mpg_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->last_error = msg;
+    return code;
+}
+
+#define MPG_CUDA(ctx, expr)                                                                             \
+    do {                                                                                                \
+        cudaError_t _e = (expr);                                                                        \
+        if (_e != cudaSuccess)                                                                          \
+            return mpg::fail(ctx, MPG_ERR_CUDA,                                                         \
+                             std::string(#expr) + ": " + cudaGetErrorString(_e) + " @" + __FILE__ + ":" + \
+                                 std::to_string(__LINE__));                                             \
+    } while (0)
+
+#define MPG_CHECK_LAUNCH(ctx)                                                                       \
+    do {                                                                                            \
+        (ctx)->launches++;                                                                          \
+        cudaError_t _e = cudaGetLastError();                                                        \
+        if (_e != cudaSuccess)                                                                      \
+            return mpg::fail(ctx, MPG_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(_e) + \
+                                                    " @" + __FILE__ + ":" + std::to_string(__LINE__)); \
+    } while (0)
+
+#define MPG_REQUIRE(ctx, cond, msg)                                   \
+    do {                                                              \
+        if (!(cond)) return mpg::fail(ctx, MPG_ERR_ARG, (msg));       \
+    } while (0)
+
+#define MPG_TRY(expr)              \
+    do {                           \
+        int _rc = (expr);          \
+        if (_rc != MPG_OK) return _rc; \
+    } while (0)
+
+inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// RAII timer for one kernel (or a kernel + its fix-up) of class `cls`, carrying its ALGORITHMIC bytes
+// (compulsory traffic).  No-op unless mpg_prof_enable(ctx, 1).
+struct ProfScope {
+    mpg_ctx* ctx;
+    cudaEvent_t a = nullptr, b = nullptr;
+    int cls;
+    double bytes;
+    static cudaEvent_t get(mpg_ctx* c) {
+        if (!c->prof_pool.empty()) { cudaEvent_t e = c->prof_pool.back(); c->prof_pool.pop_back(); return e; }
+        cudaEvent_t e; cudaEventCreate(&e); return e;
+    }
+    ProfScope(mpg_ctx* c, int cls_, double bytes_) : ctx(c), cls(cls_), bytes(bytes_) {
+        if (!ctx->prof_on) return;
+        a = get(ctx); b = get(ctx);
+        cudaEventRecord(a, ctx->stream);
+    }
+    ~ProfScope() {
+        if (!a) return;
+        cudaEventRecord(b, ctx->stream);
+        ctx->prof_pending.push_back({cls, a, b, bytes});
+    }
+};
+
+// ---- device helpers ------------------------------------------------------------------------------------
+template <class T> struct Vec4;
+template <> struct Vec4<float> { using type = float4; };
+template <> struct Vec4<double> { using type = double4; };
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// streaming (read-once) loads: bypass L1 allocation so L1 stays available for gathered vectors
+__device__ __forceinline__ int4 ldg_stream(const int4* p) {
+    int4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ double2 ldg_stream(const double2* p) {
+    double2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float ldg_stream(const float* p) {
+    float r;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ double ldg_stream(const double* p) {
+    double r;
+    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ int ldg_stream(const int* p) {
+    int r;
+    asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
+
+// Deterministic grid-wide reduction of `ncols` running sums.
+//   1. every block calls block_reduce_store() to put its per-column partial (double) in
+//      partials[blockIdx.x * ld + j];
+//   2. grid_last_block() returns true in exactly one block — the last to arrive — after all partials are
+//      visible; that block sums them in a FIXED order (column per warp, blocks strided over lanes, xor
+//      tree) so the result does not depend on block scheduling.
+__device__ __forceinline__ bool grid_last_block(unsigned int* ticket) {
+    __shared__ bool is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(ticket, 1u);
+        is_last = (t == gridDim.x - 1);
+        if (is_last) *ticket = 0u;  // re-arm for the next launch (stream-ordered)
+    }
+    __syncthreads();
+    if (is_last) __threadfence();
+    return is_last;
+}
+
+// sum over blocks of partials[b*ld + j] for the calling warp's column j (all lanes get the result)
+__device__ __forceinline__ double reduce_partials_column(const double* partials, int ld, int nblocks, int j) {
+    const int lane = threadIdx.x & 31;
+    double acc = 0.0;
+    for (int b = lane; b < nblocks; b += 32) acc += __ldcg(partials + (size_t)b * ld + j);
+    return warp_sum(acc);
+}
+
+}  // namespace mpg

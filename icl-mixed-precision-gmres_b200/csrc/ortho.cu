@@ -1,0 +1,545 @@
+// ortho.cu — tall-skinny gemv pair and the fused Arnoldi orthogonalisation (GS::add_vector).
+// Reference surface: gemv kernels.hpp:118-125 (cublas?gemv, kernels_cuda.cpp:499-535); the callers are
+// CGS_Kernel / MGS_Kernel / CGSR_Kernel<...,2> and GS::add_vector, Orthogonalization.hpp:51-60,76-136.
+//
+// The basis V is n x (k+1), column-major, column stride ldv: k+1 independent contiguous streams.  All of
+// this is HBM-bound (0.5 flop/B), so the design goal is: touch every basis element once per pass, keep
+// the number of passes minimal, never round-trip through the host.
+//
+// CGS2 as the reference formulates it is 4 gemv passes (h = V'w; w -= Vh; c = V'w; w -= Vc).  Because
+// w' = w - V h is row-local, the second and third can share one read of V:
+//     pass A  vpass(h_in = none):  h = V' w
+//     pass B  vpass(h_in = h)   :  w' = w - V h,  c = V' w'        (V tile staged once in shared memory)
+//     pass C  gemvn(+norm)      :  w'' = w' - V c, ||w''||^2
+// = 3 passes with the same arithmetic per element (sequential-j fma for the updates).  The V tile
+// [TR rows x k1 columns] is brought into shared memory by k1 one-dimensional TMA bulk copies
+// (cp.async.bulk.shared::cluster.global + mbarrier complete_tx), multi-stage, so the loads are in flight
+// while the previous tile is being consumed; each element is read from HBM once and from shared memory
+// twice.  Partial dot products stay in registers across all tiles of a CTA (warp w owns columns
+// w, w+NW, ...), are written once per CTA as doubles, and the last CTA to finish sums them in a fixed
+// order (deterministic, no float atomics) and runs the tiny epilogue (h += c, ...).
+#include "common.cuh"
+
+using namespace mpg;
+
+namespace mpg {
+int scal_devp(mpg_ctx* ctx, int64_t n, const float* a, const float* x, float* y);
+int scal_devp(mpg_ctx* ctx, int64_t n, const double* a, const double* x, double* y);
+int naxpy_devp(mpg_ctx* ctx, int64_t n, const float* a, const float* x, float* y);
+int naxpy_devp(mpg_ctx* ctx, int64_t n, const double* a, const double* x, double* y);
+int dot_dev(mpg_ctx* ctx, int64_t n, const float* x, const float* y, float* out);
+int dot_dev(mpg_ctx* ctx, int64_t n, const double* x, const double* y, double* out);
+int axpy_host(mpg_ctx* ctx, int64_t n, float a, const float* x, float* y);
+int axpy_host(mpg_ctx* ctx, int64_t n, double a, const double* x, double* y);
+}  // namespace mpg
+
+namespace {
+
+// ---- mbarrier / TMA bulk helpers (sm_90+ PTX; on sm_100a these lower to SYNCS.* / UBLKCP) --------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+
+enum { FIN_COEF = 0, FIN_COEF_ACCUM = 1 };
+
+// ---------------------------------------------------------------------------------------------------------
+// vpass: optional row-local update w' = w - V h_in, then partial c = V' w'.
+//   TR   rows per tile = threads per CTA;  MAXJ  columns owned per warp (k1 <= MAXJ * TR/32)
+//   BULK TMA bulk staging (requires 16-byte aligned V, w, ldv*sizeof(T) % 16 == 0 and padded buffers)
+// Finalisation by the last CTA:  coef_out[j] = sum_j;  if fin == FIN_COEF_ACCUM also hcol[j] += sum_j,
+// else hcol[j] = sum_j  (hcol may alias coef_out when fin == FIN_COEF).
+// ---------------------------------------------------------------------------------------------------------
+template <class T, int TR, int MAXJ, bool BULK>
+__global__ void __launch_bounds__(TR, 1)
+vpass_kernel(int64_t n, int k1, const T* __restrict__ V, int64_t ldv, T* w, const T* h_in, int stages, int reverse,
+             double* partials, int ldp, unsigned int* ticket, int fin, T* coef_out, T* hcol) {
+    constexpr int NW = TR / 32;
+    constexpr int RPL = TR / 32;  // rows per lane in the dot phase
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const size_t stage_elems = (size_t)(k1 + 1) * TR;  // k1 columns of V + the w tile
+    T* tiles = reinterpret_cast<T*>(smem_raw);
+    T* h_s = tiles + stage_elems * stages;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(h_s + ((k1 + 3) & ~3) + 4);
+    bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(bars) + 7) & ~uintptr_t(7));
+
+    const int64_t ntiles = (n + TR - 1) / TR;
+    const int64_t my_count = (ntiles > blockIdx.x) ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+    if (h_in) for (int j = tid; j < k1; j += TR) h_s[j] = h_in[j];
+    if (BULK && tid == 0) {
+        for (int s = 0; s < stages; ++s) mbar_init(bars + s, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    auto tile_row0 = [&](int64_t it) -> int64_t {
+        int64_t tix = blockIdx.x + it * gridDim.x;
+        if (reverse) tix = ntiles - 1 - tix;
+        return tix * TR;
+    };
+    // producer: warp 0.  lane 0 arms the barrier with the byte count, then every lane issues its columns.
+    auto issue = [&](int64_t it) {
+        const int s = (int)(it % stages);
+        const int64_t row0 = tile_row0(it);
+        const int rows = (int)min((int64_t)TR, n - row0);
+        const uint32_t bytes = (uint32_t)(((size_t)rows * sizeof(T) + 15) & ~size_t(15));
+        T* st = tiles + stage_elems * s;
+        if (lane == 0) mbar_arrive_expect_tx(bars + s, bytes * (uint32_t)(k1 + 1));
+        __syncwarp();
+        for (int j = lane; j < k1; j += 32) bulk_g2s(st + (size_t)j * TR, V + (size_t)j * ldv + row0, bytes, bars + s);
+        if (lane == 0) bulk_g2s(st + (size_t)k1 * TR, w + row0, bytes, bars + s);
+    };
+
+    if (BULK && wid == 0) {
+        for (int64_t it = 0; it < min((int64_t)stages, my_count); ++it) issue(it);
+    }
+
+    T acc[MAXJ];
+#pragma unroll
+    for (int jj = 0; jj < MAXJ; ++jj) acc[jj] = T(0);
+
+    for (int64_t it = 0; it < my_count; ++it) {
+        const int s = BULK ? (int)(it % stages) : 0;
+        const int64_t row0 = tile_row0(it);
+        const int rows = (int)min((int64_t)TR, n - row0);
+        T* st = tiles + stage_elems * s;
+        T* ws = st + (size_t)k1 * TR;
+        if (BULK) {
+            mbar_wait(bars + s, (uint32_t)((it / stages) & 1));
+        } else {
+            // plain staging (unaligned / unpadded operands): coalesced column reads, one element per thread
+            if (tid < rows) {
+                for (int j = 0; j < k1; ++j) st[(size_t)j * TR + tid] = ldg_stream(V + (size_t)j * ldv + row0 + tid);
+                ws[tid] = w[row0 + tid];
+            }
+            __syncthreads();
+        }
+        // ---- phase 1: w' = w - V h  (row-local, sequential j like gemv-N) ----
+        if (h_in) {
+            T a = (tid < rows) ? ws[tid] : T(0);
+            if (tid < rows) {
+#pragma unroll 4
+                for (int j = 0; j < k1; ++j) a = fma(-h_s[j], st[(size_t)j * TR + tid], a);
+                w[row0 + tid] = a;
+            }
+            ws[tid] = a;
+            __syncthreads();
+        } else if (rows < TR) {
+            if (tid >= rows) ws[tid] = T(0);
+            __syncthreads();
+        }
+        // ---- phase 2: c_j += sum_rows V[row, j] * w'[row];  warp wid owns columns wid, wid+NW, ... ----
+        T wl[RPL];
+#pragma unroll
+        for (int i = 0; i < RPL; ++i) wl[i] = ws[lane + 32 * i];
+        if (rows == TR) {
+#pragma unroll
+            for (int jj = 0; jj < MAXJ; ++jj) {
+                const int j = wid + NW * jj;
+                if (j < k1) {
+                    const T* col = st + (size_t)j * TR + lane;
+                    T a = T(0);
+#pragma unroll
+                    for (int i = 0; i < RPL; ++i) a = fma(col[32 * i], wl[i], a);
+                    acc[jj] += a;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int jj = 0; jj < MAXJ; ++jj) {
+                const int j = wid + NW * jj;
+                if (j < k1) {
+                    const T* col = st + (size_t)j * TR + lane;
+                    T a = T(0);
+#pragma unroll
+                    for (int i = 0; i < RPL; ++i) a = (lane + 32 * i < rows) ? fma(col[32 * i], wl[i], a) : a;
+                    acc[jj] += a;
+                }
+            }
+        }
+        if (BULK) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // order our st.shared before the next bulk write
+        __syncthreads();  // everyone is done reading stage s
+        if (BULK && wid == 0 && it + stages < my_count) issue(it + stages);
+    }
+
+    // ---- per-CTA partials (one owner warp per column) ----
+#pragma unroll
+    for (int jj = 0; jj < MAXJ; ++jj) {
+        const int j = wid + NW * jj;
+        if (j < k1) {
+            const double s = warp_sum((double)acc[jj]);
+            if (lane == 0) partials[(size_t)blockIdx.x * ldp + j] = s;
+        }
+    }
+    if (grid_last_block(ticket)) {
+        for (int j = wid; j < k1; j += NW) {
+            const double s = reduce_partials_column(partials, ldp, gridDim.x, j);
+            if (lane == 0) {
+                const T c = (T)s;
+                if (fin == FIN_COEF_ACCUM) { coef_out[j] = c; hcol[j] = hcol[j] + c; }   // axpy(1, weights, h_col) Orthogonalization.hpp:133
+                else { coef_out[j] = c; if (hcol != coef_out) hcol[j] = c; }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// gemvn: y = beta*y + sum_j (alpha*x[j]) M[:,j]   (sequential j, fma) with optional fused outputs:
+//   NORM     accumulate ||y_new||^2; last CTA writes nrm = sqrt(sum) to norm_out[0] and 1/nrm to inv_out[0]
+//   XUPD     mixed solution update: x64 += (double) y_new (Orthogonalization.hpp:67-73); y_new is also stored
+// VEC rows per thread via 16-byte loads (VEC = 1: any alignment).
+// ---------------------------------------------------------------------------------------------------------
+template <class T, int VEC, bool NORM, bool XUPD>
+__global__ void __launch_bounds__(256) gemvn_kernel(int64_t n, int k1, const T* __restrict__ M, int64_t ld, T alpha, const T* x, T beta,
+                                                     T* y, double* x64, double* partials, unsigned int* ticket, T* norm_out, T* inv_out) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    T* ax = reinterpret_cast<T*>(smem_raw);
+    for (int j = threadIdx.x; j < k1; j += blockDim.x) ax[j] = alpha * x[j];
+    __syncthreads();
+    using V4 = typename std::conditional<sizeof(T) == 4, float4, double2>::type;
+    constexpr int UN = 8;
+    const int64_t nv = n / VEC;
+    double nsum = 0.0;
+    for (int64_t iv = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; iv < nv; iv += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = iv * VEC;
+        T acc[VEC];
+        if (beta == T(0)) {
+#pragma unroll
+            for (int c = 0; c < VEC; ++c) acc[c] = T(0);
+        } else if (VEC > 1) {
+            const V4 t = *reinterpret_cast<const V4*>(y + i);
+            const T* pt = reinterpret_cast<const T*>(&t);
+#pragma unroll
+            for (int c = 0; c < VEC; ++c) acc[c] = beta * pt[c];
+        } else {
+            acc[0] = beta * y[i];
+        }
+        int j = 0;
+        for (; j + UN <= k1; j += UN) {
+            if (VEC > 1) {
+                V4 buf[UN];
+#pragma unroll
+                for (int u = 0; u < UN; ++u) buf[u] = ldg_stream(reinterpret_cast<const V4*>(M + (size_t)(j + u) * ld + i));
+#pragma unroll
+                for (int u = 0; u < UN; ++u) {
+                    const T* pb = reinterpret_cast<const T*>(&buf[u]);
+                    const T a = ax[j + u];
+#pragma unroll
+                    for (int c = 0; c < VEC; ++c) acc[c] = fma(a, pb[c], acc[c]);
+                }
+            } else {
+                T buf[UN];
+#pragma unroll
+                for (int u = 0; u < UN; ++u) buf[u] = ldg_stream(M + (size_t)(j + u) * ld + i);
+#pragma unroll
+                for (int u = 0; u < UN; ++u) acc[0] = fma(ax[j + u], buf[u], acc[0]);
+            }
+        }
+        for (; j < k1; ++j) {
+            if (VEC > 1) {
+                const V4 b = ldg_stream(reinterpret_cast<const V4*>(M + (size_t)j * ld + i));
+                const T* pb = reinterpret_cast<const T*>(&b);
+                const T a = ax[j];
+#pragma unroll
+                for (int c = 0; c < VEC; ++c) acc[c] = fma(a, pb[c], acc[c]);
+            } else {
+                acc[0] = fma(ax[j], ldg_stream(M + (size_t)j * ld + i), acc[0]);
+            }
+        }
+        if (VEC > 1) {
+            V4 o;
+            T* po = reinterpret_cast<T*>(&o);
+#pragma unroll
+            for (int c = 0; c < VEC; ++c) po[c] = acc[c];
+            *reinterpret_cast<V4*>(y + i) = o;
+        } else {
+            y[i] = acc[0];
+        }
+        if (XUPD) {
+#pragma unroll
+            for (int c = 0; c < VEC; ++c) x64[i + c] = fma(1.0, (double)acc[c], x64[i + c]);   // copy(cast) + axpy(1.0, x_temp, x)
+        }
+        if (NORM) {
+            T q = T(0);
+#pragma unroll
+            for (int c = 0; c < VEC; ++c) q = fma(acc[c], acc[c], q);
+            nsum += (double)q;
+        }
+    }
+    // scalar tail rows (n % VEC)
+    if (VEC > 1 && blockIdx.x == 0 && threadIdx.x < (int)(n - nv * VEC)) {
+        const int64_t i = nv * VEC + threadIdx.x;
+        T a = (beta == T(0)) ? T(0) : beta * y[i];
+        for (int j = 0; j < k1; ++j) a = fma(ax[j], M[(size_t)j * ld + i], a);
+        y[i] = a;
+        if (XUPD) x64[i] = fma(1.0, (double)a, x64[i]);
+        if (NORM) nsum += (double)(a * a);
+    }
+    if (NORM) {
+        nsum = warp_sum(nsum);
+        __shared__ double wsum[8];
+        if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = nsum;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+            for (int w = 0; w < 8; ++w) t += wsum[w];
+            partials[blockIdx.x] = t;
+        }
+        if (grid_last_block(ticket)) {
+            if (threadIdx.x < 32) {
+                const double t = reduce_partials_column(partials, 1, gridDim.x, 0);
+                if (threadIdx.x == 0) {
+                    const T nrm = (T)sqrt(t);
+                    norm_out[0] = nrm;            // h(k+1,k) = nrm2(w)            Orthogonalization.hpp:55
+                    inv_out[0] = T(1) / nrm;      // 1/h_final formed in Type      Orthogonalization.hpp:59
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// generic gemv-T for the operator surface: y[j] = alpha * sum_i M[i,j] x[i] + beta*y[j], any ld / alignment.
+// NC columns per sweep with register accumulators; coalesced scalar loads; x re-read per sweep (L2).
+// ---------------------------------------------------------------------------------------------------------
+template <class T, int NC>
+__global__ void __launch_bounds__(256) gemvt_kernel(int64_t n, int ncols, const T* __restrict__ M, int64_t ld, T alpha, const T* __restrict__ x,
+                                                     T beta, T* y, double* partials, int ldp, unsigned int* ticket) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __shared__ double red[8][NC];
+    for (int j0 = 0; j0 < ncols; j0 += NC) {
+        T acc[NC];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) acc[c] = T(0);
+        const int nc = min(NC, ncols - j0);
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+            const T xi = __ldg(x + i);
+            T v[NC];
+#pragma unroll
+            for (int c = 0; c < NC; ++c) v[c] = (c < nc) ? ldg_stream(M + (size_t)(j0 + c) * ld + i) : T(0);
+#pragma unroll
+            for (int c = 0; c < NC; ++c) acc[c] = fma(v[c], xi, acc[c]);
+        }
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            const double s = warp_sum((double)acc[c]);
+            if (lane == 0) red[wid][c] = s;
+        }
+        __syncthreads();
+        if (threadIdx.x < nc) {
+            double t = 0.0;
+            for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+            partials[(size_t)blockIdx.x * ldp + j0 + threadIdx.x] = t;
+        }
+        __syncthreads();
+    }
+    if (grid_last_block(ticket)) {
+        for (int j = wid; j < ncols; j += 8) {
+            const double s = reduce_partials_column(partials, ldp, gridDim.x, j);
+            if (lane == 0) y[j] = (beta == T(0)) ? alpha * (T)s : fma(alpha, (T)s, beta * y[j]);
+        }
+    }
+}
+
+template <class T>
+bool aligned16(const T* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+constexpr size_t kMaxDynSmem = 227 * 1024;
+
+template <class T, int TR, int MAXJ, bool BULK>
+int launch_vpass_inst(mpg_ctx* ctx, int64_t n, int k1, const T* V, int64_t ldv, T* w, const T* h_in, int fin, T* coef_out, T* hcol) {
+    const size_t stage_bytes = (size_t)(k1 + 1) * TR * sizeof(T);
+    const size_t extra = sizeof(T) * (size_t)(((k1 + 3) & ~3) + 4) + 8 * 16 + 16;
+    int stages = BULK ? (int)std::min<size_t>(8, (kMaxDynSmem - extra) / stage_bytes) : 1;
+    if (BULK && ctx->tune.vpass_stages > 0) stages = std::min(stages, ctx->tune.vpass_stages);
+    if (stages < 1) return fail(ctx, MPG_ERR_ARG, "vpass: tile does not fit in shared memory");
+    // small k1: do not hog the SM with one CTA; aim for <= ~110 KB per CTA so two can be resident
+    if (BULK && stages > 2 && stage_bytes * stages > 110 * 1024) stages = std::max<int>(2, (int)((110 * 1024) / stage_bytes));
+    const size_t smem = stage_bytes * stages + extra;
+    const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, kMaxDynSmem / (smem + 1024)));
+    const int64_t ntiles = cdiv(n, TR);
+    const int grid = (int)std::min<int64_t>(std::min<int64_t>(ntiles, (int64_t)ctx->num_sms * ctas_per_sm), kMaxPartBlocks);
+    auto kern = vpass_kernel<T, TR, MAXJ, BULK>;
+    MPG_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
+    // algorithmic bytes (fused CGS2 = 3 k1 n s + 4 n s): pass A reads V only (w was just written by the
+    // SpMV and is counted there), pass B reads V, reads w, writes w'
+    ProfScope prof(ctx, MPG_PROF_VPASS, (double)k1 * n * sizeof(T) + (h_in ? 2.0 * n * sizeof(T) : 0.0));
+    const int reverse = ctx->tune.vpass_serpentine ? (ctx->vpass_parity & 1) : 0;
+    ctx->vpass_parity ^= 1;
+    kern<<<grid, TR, smem, ctx->stream>>>(n, k1, V, ldv, w, h_in, stages, reverse, ctx->partials, kMaxCols + 8, ctx->ticket, fin, coef_out, hcol);
+    MPG_CHECK_LAUNCH(ctx);
+    return MPG_OK;
+}
+
+template <class T>
+struct VpassCfg;
+template <> struct VpassCfg<float> { static constexpr int TR = 256; };
+template <> struct VpassCfg<double> { static constexpr int TR = 128; };
+
+template <class T, bool BULK>
+int launch_vpass_maxj(mpg_ctx* ctx, int64_t n, int k1, const T* V, int64_t ldv, T* w, const T* h_in, int fin, T* coef_out, T* hcol) {
+    constexpr int TR = VpassCfg<T>::TR;
+    constexpr int NW = TR / 32;
+    const int need = (k1 + NW - 1) / NW;
+    if (need <= 4) return launch_vpass_inst<T, TR, 4, BULK>(ctx, n, k1, V, ldv, w, h_in, fin, coef_out, hcol);
+    if (need <= 13) return launch_vpass_inst<T, TR, 13, BULK>(ctx, n, k1, V, ldv, w, h_in, fin, coef_out, hcol);
+    if (need <= 26) return launch_vpass_inst<T, TR, 26, BULK>(ctx, n, k1, V, ldv, w, h_in, fin, coef_out, hcol);
+    return fail(ctx, MPG_ERR_ARG, "vpass: too many columns");
+}
+
+}  // namespace
+
+namespace mpg {
+
+// max k1 the fused vpass supports for T (shared memory: one stage must fit twice; registers: MAXJ <= 26)
+template <class T>
+int vpass_max_cols() {
+    constexpr int TR = VpassCfg<T>::TR;
+    const int by_regs = 26 * (TR / 32);
+    const int by_smem = (int)((kMaxDynSmem - 4096) / 2 / (TR * sizeof(T))) - 1;
+    return std::min(by_regs, by_smem);
+}
+template int vpass_max_cols<float>();
+template int vpass_max_cols<double>();
+
+// `padded`: caller guarantees V columns and w can be read up to the next 16-byte boundary past row n
+template <class T>
+int vpass(mpg_ctx* ctx, int64_t n, int k1, const T* V, int64_t ldv, T* w, const T* h_in, int accumulate, T* coef_out, T* hcol, bool padded) {
+    const bool bulk_ok = ctx->tune.vpass_bulk && aligned16(V) && aligned16(w) && ((ldv * sizeof(T)) % 16 == 0) &&
+                         (padded || (n * sizeof(T)) % 16 == 0);
+    const int fin = accumulate ? FIN_COEF_ACCUM : FIN_COEF;
+    if (bulk_ok) return launch_vpass_maxj<T, true>(ctx, n, k1, V, ldv, w, h_in, fin, coef_out, hcol);
+    return launch_vpass_maxj<T, false>(ctx, n, k1, V, ldv, w, h_in, fin, coef_out, hcol);
+}
+template int vpass<float>(mpg_ctx*, int64_t, int, const float*, int64_t, float*, const float*, int, float*, float*, bool);
+template int vpass<double>(mpg_ctx*, int64_t, int, const double*, int64_t, double*, const double*, int, double*, double*, bool);
+
+template <class T>
+int gemvn(mpg_ctx* ctx, int64_t n, int k1, const T* M, int64_t ld, T alpha, const T* x, T beta, T* y, bool want_norm, T* norm_out, T* inv_out,
+          double* x64) {
+    if (n <= 0) return MPG_OK;
+    constexpr int VEC = 16 / sizeof(T);
+    const bool vec_ok = aligned16(M) && aligned16(y) && ((ld * sizeof(T)) % 16 == 0) && (!x64 || aligned16(x64));
+    const size_t smem = sizeof(T) * (size_t)std::max(k1, 1);
+    const int64_t work = vec_ok ? cdiv(n, VEC) : n;
+    int grid = (int)std::min<int64_t>(cdiv(work, 256), (int64_t)ctx->num_sms * ctx->tune.gemvn_ctas_per_sm);
+    grid = std::max(1, std::min(grid, kMaxPartBlocks));
+    // gemv-N: k1 n s + 2 n s (read y, write y) [+ 16 n for the fp64 x read-modify-write of the mixed update]
+    ProfScope prof(ctx, MPG_PROF_GEMVN, (double)k1 * n * sizeof(T) + (beta != T(0) ? 2.0 : 1.0) * n * sizeof(T) + (x64 ? 16.0 * n : 0.0));
+#define MPG_GEMVN(VV, NN, XX)                                                                                                   \
+    gemvn_kernel<T, VV, NN, XX><<<grid, 256, smem, ctx->stream>>>(n, k1, M, ld, alpha, x, beta, y, x64, ctx->partials, ctx->ticket, \
+                                                                  norm_out, inv_out)
+    if (vec_ok) {
+        if (want_norm) MPG_GEMVN(VEC, true, false);
+        else if (x64) MPG_GEMVN(VEC, false, true);
+        else MPG_GEMVN(VEC, false, false);
+    } else {
+        if (want_norm) MPG_GEMVN(1, true, false);
+        else if (x64) MPG_GEMVN(1, false, true);
+        else MPG_GEMVN(1, false, false);
+    }
+#undef MPG_GEMVN
+    MPG_CHECK_LAUNCH(ctx);
+    return MPG_OK;
+}
+template int gemvn<float>(mpg_ctx*, int64_t, int, const float*, int64_t, float, const float*, float, float*, bool, float*, float*, double*);
+template int gemvn<double>(mpg_ctx*, int64_t, int, const double*, int64_t, double, const double*, double, double*, bool, double*, double*, double*);
+
+template <class T>
+int gemvt(mpg_ctx* ctx, int64_t n, int ncols, const T* M, int64_t ld, T alpha, const T* x, T beta, T* y) {
+    if (ncols <= 0) return MPG_OK;
+    if (ncols > kMaxCols) return fail(ctx, MPG_ERR_ARG, "gemv-T: more than 256 columns");
+    int grid = (int)std::min<int64_t>(std::max<int64_t>(1, cdiv(n, 256 * 4)), (int64_t)ctx->num_sms * 4);
+    grid = std::min(grid, kMaxPartBlocks);
+    ProfScope prof(ctx, MPG_PROF_GEMVT, (double)ncols * n * sizeof(T) + (double)n * sizeof(T));
+    gemvt_kernel<T, 8><<<grid, 256, 0, ctx->stream>>>(n, ncols, M, ld, alpha, x, beta, y, ctx->partials, kMaxCols + 8, ctx->ticket);
+    MPG_CHECK_LAUNCH(ctx);
+    return MPG_OK;
+}
+template int gemvt<float>(mpg_ctx*, int64_t, int, const float*, int64_t, float, const float*, float, float*);
+template int gemvt<double>(mpg_ctx*, int64_t, int, const double*, int64_t, double, const double*, double, double*);
+
+// GS::add_vector (Orthogonalization.hpp:51-60).  scratch: >= k1 + 2 elements of T in device memory
+// (CGSR's `weights`, Orthogonalization.hpp:113, plus the 1/norm scalar).
+template <class T>
+int add_vector(mpg_ctx* ctx, int orth, int64_t n, int64_t k, T* V, int64_t ldv, T* w, T* hcol, T* scratch, bool padded) {
+    const int k1 = (int)k + 1;
+    T* weights = scratch;
+    T* inv = scratch + k1;
+    T* vnext = V + (size_t)(k + 1) * ldv;
+    if (orth == MPG_ORTH_MGS) {
+        // Orthogonalization.hpp:98-106: k+1 x { dot -> h(j,k) on device ; w -= h(j,k) v_j }
+        for (int j = 0; j < k1; ++j) {
+            MPG_TRY(dot_dev(ctx, n, w, V + (size_t)j * ldv, hcol + j));
+            MPG_TRY(naxpy_devp(ctx, n, hcol + j, V + (size_t)j * ldv, w));
+        }
+        // nrm2(w, h(k+1,k)) as a gemv-N with zero columns would be wasteful: reuse the NORM epilogue with k1 = 0
+        MPG_TRY(gemvn<T>(ctx, n, 0, V, ldv, T(0), hcol, T(1), w, true, hcol + k1, inv, nullptr));
+    } else {
+        const bool fused = k1 <= vpass_max_cols<T>();
+        if (fused) {
+            MPG_TRY(vpass<T>(ctx, n, k1, V, ldv, w, nullptr, 0, hcol, hcol, padded));                       // h = V'w          :82,:126
+            if (orth == MPG_ORTH_CGSR) {
+                MPG_TRY(vpass<T>(ctx, n, k1, V, ldv, w, hcol, 1, weights, hcol, padded));                   // w-=Vh; c=V'w; h+=c :127-133
+                MPG_TRY(gemvn<T>(ctx, n, k1, V, ldv, T(-1), weights, T(1), w, true, hcol + k1, inv, nullptr));  // w-=Vc; ||w||   :131,:55
+            } else {
+                MPG_TRY(gemvn<T>(ctx, n, k1, V, ldv, T(-1), hcol, T(1), w, true, hcol + k1, inv, nullptr));     // w-=Vh; ||w||   :87,:55
+            }
+        } else {
+            MPG_TRY(gemvt<T>(ctx, n, k1, V, ldv, T(1), w, T(0), hcol));
+            if (orth == MPG_ORTH_CGSR) {
+                MPG_TRY(gemvn<T>(ctx, n, k1, V, ldv, T(-1), hcol, T(1), w, false, nullptr, nullptr, nullptr));
+                MPG_TRY(gemvt<T>(ctx, n, k1, V, ldv, T(1), w, T(0), weights));
+                MPG_TRY(gemvn<T>(ctx, n, k1, V, ldv, T(-1), weights, T(1), w, true, hcol + k1, inv, nullptr));
+                MPG_TRY(axpy_host(ctx, k1, T(1), weights, hcol));                                               // h += c  :133
+            } else {
+                MPG_TRY(gemvn<T>(ctx, n, k1, V, ldv, T(-1), hcol, T(1), w, true, hcol + k1, inv, nullptr));
+            }
+        }
+    }
+    // V[:,k+1] = w * (1/h(k+1,k))   Orthogonalization.hpp:58-59 (one pass instead of copy + scal)
+    return scal_devp(ctx, n, inv, w, vnext);
+}
+template int add_vector<float>(mpg_ctx*, int, int64_t, int64_t, float*, int64_t, float*, float*, float*, bool);
+template int add_vector<double>(mpg_ctx*, int, int64_t, int64_t, double*, int64_t, double*, double*, double*, bool);
+
+}  // namespace mpg
+
+// ---- C ABI -------------------------------------------------------------------------------------------------
+#define MPG_DEF_GEMV(SFX, T)                                                                                                      \
+    extern "C" int mpg_gemv_##SFX(mpg_ctx* ctx, int trans, int64_t nr, int64_t nc, T alpha, const T* M, int64_t ld, const T* x,   \
+                                  T beta, T* y) {                                                                                 \
+        MPG_REQUIRE(ctx, nr >= 0 && nc >= 0 && ld >= nr, "gemv: bad dims");                                                       \
+        MPG_REQUIRE(ctx, nc <= kMaxCols, "gemv: at most 256 columns (restart length + 1)");                                       \
+        if (trans) return mpg::gemvt<T>(ctx, nr, (int)nc, M, ld, alpha, x, beta, y);                                              \
+        return mpg::gemvn<T>(ctx, nr, (int)nc, M, ld, alpha, x, beta, y, false, nullptr, nullptr, nullptr);                       \
+    }                                                                                                                             \
+    extern "C" int mpg_add_vector_##SFX(mpg_ctx* ctx, int orth, int64_t n, int64_t k, T* V, int64_t ldv, T* w, T* hcol) {         \
+        MPG_REQUIRE(ctx, n >= 0 && k >= 0 && k + 2 <= kMaxCols && ldv >= n, "add_vector: bad dims");                              \
+        MPG_REQUIRE(ctx, orth >= 0 && orth <= 2, "add_vector: bad orth");                                                         \
+        T* scratch = reinterpret_cast<T*>(ctx->dscal + 64); /* k1 + 2 <= 264 elements */                                          \
+        return mpg::add_vector<T>(ctx, orth, n, k, V, ldv, w, hcol, scratch, false);                                              \
+    }
+MPG_DEF_GEMV(f32, float)
+MPG_DEF_GEMV(f64, double)

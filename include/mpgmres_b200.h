@@ -1,0 +1,204 @@
+/*
+ * mpgmres_b200.h — C ABI of the B200-native (sm_100a) backend for the mixed-precision GMRES hot path of
+ * iamsonderr/icl-mixed-precision-gmres.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch/Kokkos types.  Every entry point
+ * names the reference interface it replaces (file:line relative to the reference tree).  The reference
+ * resolves its operator surface (kernels.hpp) at link time to one translation unit per backend
+ * (kernels_cuda.cpp / kernels_mkl.cpp); a new backend = template specialisations that forward to these
+ * functions (see INTEGRATION.md and include/b200/kernels_b200.hpp).
+ *
+ * Conventions
+ *   - All vector / matrix pointers are DEVICE pointers unless the name says _host.
+ *   - Dense matrices are column-major with leading dimension `ld` (types.hpp:115-118, LayoutLeft).
+ *   - CSR is 0-based int32 row_map[nrows+1] / inds[nnz] (types_cuda.hpp:66-70); fp32 and fp64 value arrays
+ *     share one structure (types_cuda.hpp:82-91), which is why mpg_csr carries no values.
+ *   - Work is stream-ordered on the context's stream and asynchronous unless the function returns a value
+ *     to the host (the reference relies on the same semantics).
+ *   - Return value: 0 on success, non-zero error code otherwise; mpg_last_error() gives the message.  The
+ *     reference surface returns void and ignores library status codes; the C++ shim aborts on non-zero.
+ *   - There is NO CPU fallback: without a CUDA device every compute entry point fails with MPG_ERR_CUDA.
+ */
+#ifndef MPGMRES_B200_H
+#define MPGMRES_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPG_OK 0
+#define MPG_ERR_CUDA 1
+#define MPG_ERR_ARG 2
+#define MPG_ERR_NCCL 3
+#define MPG_ERR_STATE 4
+
+typedef struct mpg_ctx mpg_ctx; /* replaces CudaLibSingleton, types_cuda.hpp:9-36: stream, reduction scratch, comm */
+typedef struct mpg_csr mpg_csr; /* CSR structure + SpMV plan; replaces cusparseMatDescr_t, types_cuda.hpp:50-60 */
+
+/* ---- context ----------------------------------------------------------------------------------------- */
+const char* mpg_version(void);
+int mpg_ctx_create(int device, mpg_ctx** out);
+int mpg_ctx_destroy(mpg_ctx* ctx);
+int mpg_ctx_set_stream(mpg_ctx* ctx, void* cuda_stream); /* NULL = the context's own stream */
+void* mpg_ctx_stream(mpg_ctx* ctx);
+int mpg_sync(mpg_ctx* ctx); /* Device::execution_space().fence(), gmres.cpp:113,225 */
+const char* mpg_last_error(mpg_ctx* ctx);
+int mpg_num_sms(mpg_ctx* ctx);
+int64_t mpg_launch_count(mpg_ctx* ctx);              /* kernels launched through this context so far */
+int mpg_set_tuning(mpg_ctx* ctx, const char* key, int value); /* kernel variant knobs, see DESIGN.md */
+
+/* ---- per-kernel-class device timers (CUDA events on the launching stream; the reference has none) -- */
+enum { MPG_PROF_SPMV_F32 = 0, MPG_PROF_SPMV_F64 = 1, MPG_PROF_VPASS = 2, MPG_PROF_GEMVN = 3, MPG_PROF_ELEMENTWISE = 4,
+       MPG_PROF_REDUCE = 5, MPG_PROF_SMALL = 6, MPG_PROF_GEMVT = 7 };
+int mpg_prof_enable(mpg_ctx* ctx, int on);
+int mpg_prof_reset(mpg_ctx* ctx);
+/* synchronises the stream, folds pending measurements; returns accumulated device ms, algorithmic bytes, launches */
+int mpg_prof_get(mpg_ctx* ctx, int cls, double* ms, double* bytes, int64_t* launches);
+
+/* ---- device memory (Kokkos::View allocation / deep_copy, types.hpp:18,60,118) -------------------------- */
+int mpg_malloc(mpg_ctx* ctx, size_t bytes, void** dptr); /* zero-filled like a Kokkos::View */
+int mpg_free(mpg_ctx* ctx, void* dptr);
+int mpg_memcpy_h2d(mpg_ctx* ctx, void* dst, const void* src_host, size_t bytes);
+int mpg_memcpy_d2h(mpg_ctx* ctx, void* dst_host, const void* src, size_t bytes); /* synchronises */
+int mpg_memcpy_d2d(mpg_ctx* ctx, void* dst, const void* src, size_t bytes);
+int mpg_memset_zero(mpg_ctx* ctx, void* dst, size_t bytes);
+
+/* ---- BLAS-1 --------------------------------------------------------------------------------------------
+ * dot   kernels.hpp:33-37   (kernels_cuda.cpp:111-165)     nrm2  kernels.hpp:40-44  (kernels_cuda.cpp:167-209)
+ * axpy  kernels.hpp:47-51   (kernels_cuda.cpp:212-262)     naxpy kernels.hpp:59-60  (kernels_cuda.cpp:264-288)
+ * scal  kernels.hpp:62-85   (kernels_cuda.cpp:291-392)     copy  kernels.hpp:11-30  fill kernels.hpp:88-101
+ * gdmv  kernels.hpp:131-151
+ * `_dev` variants take/return the scalar in device memory (the Scalar<T,Device> overloads); the others
+ * take host scalars / return to the host (and therefore synchronise), like the reference's two forms. */
+int mpg_dot_f32(mpg_ctx*, int64_t n, const float* x, const float* y, float* result_host);
+int mpg_dot_f64(mpg_ctx*, int64_t n, const double* x, const double* y, double* result_host);
+int mpg_dot_dev_f32(mpg_ctx*, int64_t n, const float* x, const float* y, float* result_dev);
+int mpg_dot_dev_f64(mpg_ctx*, int64_t n, const double* x, const double* y, double* result_dev);
+int mpg_nrm2_f32(mpg_ctx*, int64_t n, const float* x, float* result_host);
+int mpg_nrm2_f64(mpg_ctx*, int64_t n, const double* x, double* result_host);
+int mpg_nrm2_dev_f32(mpg_ctx*, int64_t n, const float* x, float* result_dev);
+int mpg_nrm2_dev_f64(mpg_ctx*, int64_t n, const double* x, double* result_dev);
+int mpg_axpy_f32(mpg_ctx*, int64_t n, float alpha, const float* x, float* y);
+int mpg_axpy_f64(mpg_ctx*, int64_t n, double alpha, const double* x, double* y);
+int mpg_axpy_dev_f32(mpg_ctx*, int64_t n, const float* alpha_dev, const float* x, float* y);
+int mpg_axpy_dev_f64(mpg_ctx*, int64_t n, const double* alpha_dev, const double* x, double* y);
+int mpg_naxpy_dev_f32(mpg_ctx*, int64_t n, const float* alpha_dev, const float* x, float* y);
+int mpg_naxpy_dev_f64(mpg_ctx*, int64_t n, const double* alpha_dev, const double* x, double* y);
+int mpg_scal_f32(mpg_ctx*, int64_t n, float alpha, const float* x, float* y); /* y = alpha*x; x may equal y */
+int mpg_scal_f64(mpg_ctx*, int64_t n, double alpha, const double* x, double* y);
+int mpg_scal_dev_f32(mpg_ctx*, int64_t n, const float* alpha_dev, const float* x, float* y);
+int mpg_scal_dev_f64(mpg_ctx*, int64_t n, const double* alpha_dev, const double* x, double* y);
+int mpg_copy_f32_f32(mpg_ctx*, int64_t n, const float* x, float* y);
+int mpg_copy_f64_f64(mpg_ctx*, int64_t n, const double* x, double* y);
+int mpg_copy_f64_f32(mpg_ctx*, int64_t n, const double* x, float* y); /* RN cast, gmres.cpp:163,175 */
+int mpg_copy_f32_f64(mpg_ctx*, int64_t n, const float* x, double* y); /* Orthogonalization.hpp:71 */
+int mpg_fill_f32(mpg_ctx*, int64_t n, float alpha, float* x);
+int mpg_fill_f64(mpg_ctx*, int64_t n, double alpha, double* x);
+int mpg_gdmv_f32(mpg_ctx*, int64_t n, float alpha, const float* diag, const float* x, float beta, float* y);
+int mpg_gdmv_f64(mpg_ctx*, int64_t n, double alpha, const double* diag, const double* x, double beta, double* y);
+
+/* ---- Givens / least squares (all scalars in device memory) -----------------------------------------------
+ * rotg kernels.hpp:104-106 (kernels_cuda.cpp:394-420: BLAS rotg, then b := 0)
+ * rot  kernels.hpp:109-114 (kernels_cuda.cpp:422-494)      trsv kernels.hpp:128-129 (kernels_cuda.cpp:538-572) */
+int mpg_rotg_f32(mpg_ctx*, float* a, float* b, float* c, float* s);
+int mpg_rotg_f64(mpg_ctx*, double* a, double* b, double* c, double* s);
+int mpg_rot_f32(mpg_ctx*, float* a, float* b, const float* c, const float* s);
+int mpg_rot_f64(mpg_ctx*, double* a, double* b, const double* c, const double* s);
+int mpg_rot_vec_f32(mpg_ctx*, int64_t k, float* a, const float* c, const float* s); /* touches a[0..k] */
+int mpg_rot_vec_f64(mpg_ctx*, int64_t k, double* a, const double* c, const double* s);
+int mpg_trsv_f32(mpg_ctx*, int upper, int trans, int64_t n, const float* A, int64_t ld, float* x);
+int mpg_trsv_f64(mpg_ctx*, int upper, int trans, int64_t n, const double* A, int64_t ld, double* x);
+/* Fused: apply the k stored rotations to column k of H, generate rotation k, rotate s, store |s[k+1]| (as a
+ * double) to resid_dev.  Replaces gmres.cpp:219-226 (4-5 launches + 1 blocking read) with one launch. */
+int mpg_givens_step_f32(mpg_ctx*, int64_t k, float* h, int64_t ldh, float* cs, float* sn, float* s, double* resid_dev);
+int mpg_givens_step_f64(mpg_ctx*, int64_t k, double* h, int64_t ldh, double* cs, double* sn, double* s, double* resid_dev);
+
+/* ---- BLAS-2: gemv  kernels.hpp:118-125 (kernels_cuda.cpp:499-535) ----------------------------------------
+ * y = alpha*op(M)*x + beta*y; M is nrows_base x ncols_base (the reference passes base dims + lda). */
+int mpg_gemv_f32(mpg_ctx*, int trans, int64_t nrows_base, int64_t ncols_base, float alpha, const float* M, int64_t ld,
+                 const float* x, float beta, float* y);
+int mpg_gemv_f64(mpg_ctx*, int trans, int64_t nrows_base, int64_t ncols_base, double alpha, const double* M, int64_t ld,
+                 const double* x, double beta, double* y);
+
+/* ---- Sparse: spmv  kernels.hpp:159-160 (kernels_cuda.cpp:576-614) ----------------------------------------- */
+int mpg_csr_create(mpg_ctx*, int nrows, int ncols, int64_t nnz, const int* row_map, const int* inds, mpg_csr** out);
+int mpg_csr_destroy(mpg_csr* A);
+int mpg_spmv_f32(mpg_ctx*, const mpg_csr* A, const float* vals, float alpha, const float* x, float beta, float* y);
+int mpg_spmv_f64(mpg_ctx*, const mpg_csr* A, const double* vals, double alpha, const double* x, double beta, double* y);
+/* Fused outer residual, replaces gmres.cpp:173-175 (copy + fp64 SpMV + cast kernel):
+ * r = b - A*x in fp64; w32 = (float) r; r64 may be NULL (then r is never stored). */
+int mpg_residual_f64_cast_f32(mpg_ctx*, const mpg_csr* A, const double* vals, const double* b, const double* x,
+                              double* r64, float* w32);
+
+/* ---- Fused Arnoldi step: GS::add_vector, Orthogonalization.hpp:51-60 + the kernels at :76-136 ------------
+ * orth: 0 CGS, 1 MGS, 2 CGSR<2> (CGS2).  V is n x (k+2) column-major with leading dimension ldv.
+ * In:  w (A*v_k), V[:,0:k+1].  Out: hcol[0..k] coefficients, hcol[k+1] = ||w_orth||, V[:,k+1] = w_orth/hcol[k+1];
+ * w is overwritten with w_orth.  No host synchronisation (the reference reads h(k+1,k) back, :56). */
+int mpg_add_vector_f32(mpg_ctx*, int orth, int64_t n, int64_t k, float* V, int64_t ldv, float* w, float* hcol);
+int mpg_add_vector_f64(mpg_ctx*, int orth, int64_t n, int64_t k, double* V, int64_t ldv, double* w, double* hcol);
+
+/* ---- Solver: gmres.hpp:15-32 (gmres.cpp:24-245) behind one entry point ------------------------------------ */
+enum { MPG_MODE_MIXED = 0, MPG_MODE_BASELINE = 1, MPG_MODE_SINGLE_PREC = 2, MPG_MODE_SINGLE = 3 }; /* gmres_perf_test.cpp:31-36 */
+enum { MPG_ORTH_CGS = 0, MPG_ORTH_MGS = 1, MPG_ORTH_CGSR = 2 };                                    /* :17-22 */
+enum { MPG_CONV_BASE = 0, MPG_CONV_RELPRECRES = 1, MPG_CONV_REPEAT = 2, MPG_CONV_ORTHLOSS = 3 };   /* :185-196 */
+enum { MPG_PREC_IDENTITY = 0, MPG_PREC_JACOBI = 1 };                                               /* :24-29 */
+
+typedef struct mpg_gmres_params {
+    int32_t mode, orth, conv, prec;
+    int64_t restart_length; /* --rlen  */
+    double tol;             /* --tol   */
+    double restart_tol;     /* --rtol  */
+    int64_t max_restarts;   /* --max-restarts */
+} mpg_gmres_params;
+
+typedef struct mpg_gmres_stats {
+    int64_t status; /* 1 converged, 3 aborted (iteration_action, IterUtil.hpp:10-15) */
+    int64_t total_iters;
+    int64_t total_restarts;
+    int64_t outer_i;
+    double rel_prec_res; /* the printed "rel prec res norm", gmres.cpp:186 */
+    double b_norm, Minvb_norm, A_norm;
+    int64_t n_hist_inner, n_hist_outer;
+    double solve_ms;   /* device time of the solve (CUDA events), excluding transfers */
+    double h2d_ms, d2h_ms; /* only set by the _host entry point */
+    int64_t launches;  /* kernels launched by this solve */
+} mpg_gmres_stats;
+
+/* Device-resident operands.  vals32 may be NULL (cast from vals64 internally, types_cuda.hpp:82-101).
+ * hist_inner_host[cap_inner]: |s(k+1)|/Minvb_norm per inner iteration; hist_outer_host[4*cap_outer]:
+ * {r_norm, b_norm + A_norm*x_norm, beta, x_norm} per check_initial.  Either may be NULL. */
+int mpg_gmres_solve(mpg_ctx*, const mpg_gmres_params* p, const mpg_csr* A, const double* vals64, const float* vals32,
+                    const double* b, double* x, mpg_gmres_stats* stats, double* hist_inner_host, int64_t cap_inner,
+                    double* hist_outer_host, int64_t cap_outer);
+/* End-to-end: HOST CSR + b in, x out (H2D, plan, solve, D2H inside).  x_host holds x0 on entry. */
+int mpg_gmres_solve_host(mpg_ctx*, const mpg_gmres_params* p, int nrows, int64_t nnz, const int* row_map_host,
+                         const int* inds_host, const double* vals64_host, const double* b_host, double* x_host,
+                         mpg_gmres_stats* stats, double* hist_inner_host, int64_t cap_inner, double* hist_outer_host,
+                         int64_t cap_outer);
+/* Jacobi<T>::get_diag_vals, types.hpp:395-430 */
+int mpg_jacobi_diag_f32(mpg_ctx*, const mpg_csr* A, const float* vals, float* diag);
+int mpg_jacobi_diag_f64(mpg_ctx*, const mpg_csr* A, const double* vals, double* diag);
+
+/* ---- Synthetic inputs (the reference has none).  Definitions frozen in oracle/oracle.cpp. -- */
+int64_t mpg_lap2d_nnz(int64_t N);
+int64_t mpg_cd27_nnz(int64_t N);
+int mpg_gen_lap2d(mpg_ctx*, int64_t N, int* row_map, int* inds, double* vals);
+int mpg_gen_cd27(mpg_ctx*, int64_t N, int* row_map, int* inds, double* vals);
+int mpg_gen_powerlaw_rowmap(mpg_ctx*, int64_t n, uint64_t seed, int lmin, int gmax, int* row_map, int64_t* nnz_host);
+int mpg_gen_powerlaw_fill(mpg_ctx*, int64_t n, uint64_t seed, int lmin, int gmax, const int* row_map, int* inds, double* vals);
+/* gmres_perf_test.cpp:39-51 rand_vect (host; libstdc++ mt19937 + uniform_real_distribution<float>) */
+int mpg_rand_vect_host(int64_t n, uint32_t seed, double* out_host);
+
+/* ---- 1-D row partition (new functionality, host-side, bit-exact vs the oracle) ------------- */
+int mpg_partition_bounds(int64_t n, int P, int64_t* bounds_host /* P+1 */);
+/* halo_cols_host/local_inds_host may be NULL to query sizes.  Returns the halo count through *n_halo. */
+int mpg_partition_local(int64_t n, int P, int r, const int* row_map_host, const int* inds_host, int64_t* n_halo,
+                        int64_t* halo_cols_host, int* local_inds_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPGMRES_B200_H */

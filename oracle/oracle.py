@@ -91,7 +91,7 @@ def gen_cd27(N):
     return rm, ind, val
 
 
-def gen_powerlaw(n, seed=7, lmin=3, gmax=15):
+def gen_powerlaw(n, seed=7, lmin=2, gmax=15):
     rm = np.empty(n + 1, np.int32)
     nnz = lib().orc_powerlaw_rowmap(_i64(n), C.c_uint64(seed), C.c_int(lmin), C.c_int(gmax), _p(rm))
     ind, val = np.empty(nnz, np.int32), np.empty(nnz, np.float64)

@@ -1,0 +1,278 @@
+"""GPU parity, operator by operator: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+Bit-exact where the arithmetic is element-local (casts, axpy, scal, gemv-N, rotations, trsv, generators, index sets);
+a stated summation-order bound where a reduction's order is unspecified by BLAS (dot, nrm2, gemv-T, SpMV)."""
+import numpy as np
+import pytest
+
+from util import EPS, dev, fortran_dev, host, summation_bound
+
+pytestmark = pytest.mark.gpu
+
+SIZES = [0, 1, 3, 31, 257, 1000, 4099, 100003]
+
+
+def _rng(seed):
+    return np.random.default_rng(seed)
+
+
+@pytest.mark.parametrize("spec", ["lap2d:1", "lap2d:2", "lap2d:37", "cd27:1", "cd27:2", "cd27:11", "powerlaw:2", "powerlaw:3000", "powerlaw:20000:11:2:10"])
+def test_generators_bit_exact(ctx, orc, spec):
+    rm, ind, val = ctx.gen(spec)
+    ctx.sync()
+    rm_o, ind_o, val_o = orc.gen(spec)
+    np.testing.assert_array_equal(host(rm), rm_o)
+    np.testing.assert_array_equal(host(ind), ind_o)
+    np.testing.assert_array_equal(host(val), val_o)
+
+
+def test_rand_vect_bit_exact(ctx, orc):
+    np.testing.assert_array_equal(ctx.rand_vect(5000, 42), orc.rand_vect(5000, 42))
+    np.testing.assert_array_equal(ctx.rand_vect(100, 7), orc.rand_vect(100, 7))
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("n", SIZES)
+def test_elementwise_ops_bit_exact(ctx, orc, dt, n):
+    import torch
+    r = _rng(n + 1)
+    x = r.standard_normal(n).astype(dt)
+    y = r.standard_normal(n).astype(dt)
+    d = r.standard_normal(n).astype(dt)
+    a = dt(-0.731)
+    xd, adev = dev(x), dev(np.array([a], dt))
+    # axpy (host and device alpha), naxpy, scal (host / device alpha), fill, gdmv
+    yd = dev(y); ctx.axpy(float(a), xd, yd); np.testing.assert_array_equal(host(yd), orc.axpy(a, x, y.copy()))
+    yd = dev(y); ctx.axpy_dev(adev, xd, yd); np.testing.assert_array_equal(host(yd), orc.axpy(a, x, y.copy()))
+    yd = dev(y); ctx.naxpy_dev(adev, xd, yd); np.testing.assert_array_equal(host(yd), orc.naxpy(a, x, y.copy()))
+    yd = dev(y); ctx.scal(float(a), xd, yd); np.testing.assert_array_equal(host(yd), orc.scal(a, x))
+    yd = dev(y); ctx.scal_dev(adev, xd, yd); np.testing.assert_array_equal(host(yd), orc.scal(a, x))
+    xs = dev(x); ctx.scal(float(a), xs, xs); np.testing.assert_array_equal(host(xs), orc.scal(a, x))  # in place
+    yd = dev(y); ctx.fill(1.25, yd); np.testing.assert_array_equal(host(yd), np.full(n, 1.25, dt))
+    yd = dev(y); ctx.gdmv(2.0, dev(d), xd, 0.5, yd)
+    np.testing.assert_array_equal(host(yd), (dt(0.5) * y + dt(2.0) * d * x).astype(dt))  # kernels.hpp:143-145 association
+    # casts: round to nearest
+    other = np.float64 if dt == np.float32 else np.float32
+    od = torch.empty(n, dtype=torch.float64 if other == np.float64 else torch.float32, device="cuda:0")
+    ctx.copy(xd, od); np.testing.assert_array_equal(host(od), x.astype(other))
+    sd = torch.empty_like(xd); ctx.copy(xd, sd); np.testing.assert_array_equal(host(sd), x)
+
+
+def test_elementwise_ops_unaligned_views(ctx, orc):
+    # sub-range views (types.hpp:73-76) are not 16-byte aligned: the scalar path must give the same bits
+    r = _rng(9)
+    x = r.standard_normal(1003).astype(np.float32)
+    y = r.standard_normal(1003).astype(np.float32)
+    xd, yd = dev(x), dev(y)
+    ctx.axpy(0.3, xd[1:1000], yd[3:1002])
+    ref = y.copy(); ref[3:1002] = orc.axpy(np.float32(0.3), x[1:1000].copy(), y[3:1002].copy())
+    np.testing.assert_array_equal(host(yd), ref)
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("n", SIZES + [1 << 20])
+def test_dot_nrm2(ctx, orc, dt, n):
+    r = _rng(n + 2)
+    x = r.standard_normal(n).astype(dt)
+    y = r.standard_normal(n).astype(dt)
+    xd, yd = dev(x), dev(y)
+    x64, y64 = x.astype(np.float64), y.astype(np.float64)
+    exact = float(x64 @ y64)
+    bound = summation_bound(float(np.abs(x64 * y64).sum()), n, dt)
+    got = ctx.dot(xd, yd)
+    assert abs(got - exact) <= bound
+    assert abs(got - orc.dot(x, y)) <= 2 * bound
+    nexact = float(np.linalg.norm(x64))
+    got = ctx.nrm2(xd)
+    assert abs(got - nexact) <= 4 * EPS[np.dtype(dt)] * nexact * max(1.0, np.sqrt(n) / 8)
+    assert abs(got - orc.nrm2(x)) <= 8 * EPS[np.dtype(dt)] * nexact * max(1.0, np.sqrt(n) / 8)
+    # device-result forms (Scalar<T,Device> overloads) agree with the host-return forms exactly
+    import torch
+    out = torch.zeros(2, dtype=xd.dtype, device="cuda:0")
+    ctx.dot_dev(xd, yd, out[0:1]); ctx.nrm2_dev(xd, out[1:2])
+    o = host(out)
+    assert o[0] == dt(ctx.dot(xd, yd)) and o[1] == dt(ctx.nrm2(xd))
+    # deterministic: same bits on repeat
+    assert ctx.dot(xd, yd) == ctx.dot(xd, yd)
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_rotations_and_trsv_bit_exact(ctx, orc, dt):
+    import torch
+    tdt = torch.float32 if dt == np.float32 else torch.float64
+    for a, b in [(3.0, 4.0), (-3.0, 4.0), (4.0, -3.0), (-4.0, -3.0), (0.0, 2.0), (2.0, 0.0), (0.0, 0.0), (1e-20, 1e-21), (0.3, 0.7)]:
+        t = torch.tensor([a, b, 9.0, 9.0], dtype=tdt, device="cuda:0")
+        ctx.rotg(t[0:1], t[1:2], t[2:3], t[3:4])
+        np.testing.assert_array_equal(host(t), np.array(orc.rotg(a, b, dt), dtype=dt))
+    r = _rng(4)
+    m = 25
+    H = np.asfortranarray(np.triu(r.standard_normal((m + 1, m)), -1).astype(dt))
+    Hd = fortran_dev(H)
+    cs, sn, s = np.zeros(m + 1, dt), np.zeros(m + 1, dt), np.zeros(m + 1, dt)
+    s[0] = 2.5
+    csd, snd, sd = dev(cs), dev(sn), dev(s)
+    resid = torch.zeros(m, dtype=torch.float64, device="cuda:0")
+    Ho = H.copy()
+    res_o = []
+    for k in range(m):
+        ctx.givens_step(k, Hd, m + 1, csd, snd, sd, resid[k:k + 1])
+        res_o.append(orc.givens_step(k, Ho, cs, sn, s))
+    np.testing.assert_array_equal(host(Hd).reshape(m, m + 1).T, Ho)
+    np.testing.assert_array_equal(host(csd), cs)
+    np.testing.assert_array_equal(host(snd), sn)
+    np.testing.assert_array_equal(host(sd), s)
+    np.testing.assert_array_equal(host(resid), np.array(res_o))
+    # the three separate surface calls (rot Vect, rotg, rot Scalar; gmres.cpp:219-222) give the same bits as the fused step
+    H2, c2, s2, rhs = fortran_dev(H), dev(np.zeros(m + 1, dt)), dev(np.zeros(m + 1, dt)), dev(np.eye(1, m + 1, 0, dtype=dt).ravel() * dt(2.5))
+    for k in range(m):
+        col = H2[k * (m + 1):(k + 1) * (m + 1)]
+        ctx.rot_vec(k, col, c2, s2)
+        ctx.rotg(col[k:k + 1], col[k + 1:k + 2], c2[k:k + 1], s2[k:k + 1])
+        ctx.rot(rhs[k:k + 1], rhs[k + 1:k + 2], c2[k:k + 1], s2[k:k + 1])
+    np.testing.assert_array_equal(host(H2), host(Hd))
+    np.testing.assert_array_equal(host(rhs), host(sd))
+    # trsv in place on s (gmres.cpp:285-288)
+    y = s[:m].copy(); orc.trsv_upper(Ho, m, y)
+    ctx.trsv(Hd, m, m + 1, sd)
+    np.testing.assert_array_equal(host(sd)[:m], y)
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("n,k,pad", [(1, 1, 0), (5, 3, 0), (1000, 1, 0), (4099, 7, 0), (4099, 7, 5), (100003, 33, 0), (50000, 101, 0), (65536, 26, 0)])
+def test_gemv(ctx, orc, dt, n, k, pad):
+    r = _rng(n + k)
+    ld = n + pad
+    M = np.zeros((ld, k), dt, order="F")
+    M[:n] = r.standard_normal((n, k)).astype(dt)
+    x = r.standard_normal(n).astype(dt)
+    c = r.standard_normal(k).astype(dt)
+    Md, xd, cd = fortran_dev(M), dev(x), dev(c)
+    # gemv-T: h = 0.5*M'x + 2*c
+    hd = dev(c)
+    ctx.gemv(True, n, k, 0.5, Md, ld, xd, 2.0, hd)
+    M64 = M[:n].astype(np.float64)
+    exact = 0.5 * (M64.T @ x.astype(np.float64)) + 2.0 * c
+    bound = 0.5 * summation_bound(float((np.abs(M64) * np.abs(x.astype(np.float64))[:, None]).sum(axis=0).max()), n, dt) + 4 * EPS[np.dtype(dt)] * np.abs(exact).max()
+    assert np.max(np.abs(host(hd) - exact)) <= bound
+    ho = c.copy(); orc.gemv(True, M[:n] if pad == 0 else np.asfortranarray(M[:n]), k, 0.5, x, 2.0, ho)
+    assert np.max(np.abs(host(hd) - ho)) <= 2 * bound
+    # gemv-N: y = -1*M c + 1*y : sequential-j fma per row => bit-exact with the oracle
+    y = r.standard_normal(n).astype(dt)
+    yd = dev(y)
+    ctx.gemv(False, n, k, -1.0, Md, ld, cd, 1.0, yd)
+    yo = y.copy(); orc.gemv(False, np.asfortranarray(M[:n]), k, -1.0, c, 1.0, yo)
+    np.testing.assert_array_equal(host(yd), yo)
+    yd = dev(np.full(n, np.nan, dt))
+    ctx.gemv(False, n, k, 1.0, Md, ld, cd, 0.0, yd)   # beta = 0 ignores y
+    yo = np.zeros(n, dt); orc.gemv(False, np.asfortranarray(M[:n]), k, 1.0, c, 0.0, yo)
+    np.testing.assert_array_equal(host(yd), yo)
+
+
+@pytest.mark.parametrize("spec", ["lap2d:1", "lap2d:3", "lap2d:64", "lap2d:300", "cd27:2", "cd27:20", "cd27:40", "powerlaw:2", "powerlaw:5000", "powerlaw:200000"])
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_spmv(ctx, g, orc, spec, dt):
+    rm, ind, val = orc.gen(spec)
+    n = len(rm) - 1
+    r = _rng(n)
+    x = r.standard_normal(n).astype(dt)
+    y = r.standard_normal(n).astype(dt)
+    v = val.astype(dt)
+    rmd, indd, vd, xd = dev(rm), dev(ind), dev(v), dev(x)
+    A = g.CSR(ctx, rmd, indd)
+    import scipy.sparse as sp
+    As = sp.csr_matrix((val, ind, rm), shape=(n, n))
+    absrow = abs(As) @ np.abs(x.astype(np.float64))
+    maxlen = int(np.diff(rm).max())
+    for alpha, beta in [(1.0, 0.0), (-1.0, 1.0), (0.5, -2.0)]:
+        yd = dev(y if beta != 0 else np.full(n, np.nan, dt))
+        ctx.spmv(A, vd, alpha, xd, beta, yd)
+        exact = alpha * (As @ x.astype(np.float64)) + (beta * y.astype(np.float64) if beta != 0 else 0)
+        bound = summation_bound(abs(alpha) * absrow + abs(beta) * np.abs(y), maxlen, dt)
+        got = host(yd)
+        assert np.all(np.abs(got - exact) <= bound), f"max excess {np.max(np.abs(got - exact) - bound)}"
+        yo = orc.spmv(rm, ind, v, alpha, x, beta, y.copy())
+        assert np.all(np.abs(got - yo) <= 2 * bound)
+    # deterministic
+    y1, y2 = dev(y), dev(y)
+    ctx.spmv(A, vd, 1.0, xd, 0.0, y1); ctx.spmv(A, vd, 1.0, xd, 0.0, y2)
+    np.testing.assert_array_equal(host(y1), host(y2))
+
+
+@pytest.mark.parametrize("spec", ["lap2d:50", "cd27:15", "powerlaw:30000"])
+def test_fused_residual_cast(ctx, g, orc, spec):
+    """r = b - A x (fp64) and w = (float) r in one kernel == the reference's copy + spmv + copy (gmres.cpp:173-175)"""
+    import torch
+    rm, ind, val = orc.gen(spec)
+    n = len(rm) - 1
+    r = _rng(n)
+    x, b = r.standard_normal(n), r.standard_normal(n)
+    A = g.CSR(ctx, dev(rm), dev(ind))
+    vd, xd, bd = dev(val), dev(x), dev(b)
+    r64 = torch.empty(n, dtype=torch.float64, device="cuda:0")
+    w32 = torch.empty(n, dtype=torch.float32, device="cuda:0")
+    ctx.residual_cast(A, vd, bd, xd, r64, w32)
+    ref = bd.clone(); ctx.spmv(A, vd, -1.0, xd, 1.0, ref)
+    np.testing.assert_array_equal(host(r64), host(ref))                     # same kernel path, same bits
+    np.testing.assert_array_equal(host(w32), host(r64).astype(np.float32))  # RN cast
+    w_only = torch.empty(n, dtype=torch.float32, device="cuda:0")
+    ctx.residual_cast(A, vd, bd, xd, None, w_only)                          # r never stored
+    np.testing.assert_array_equal(host(w_only), host(w32))
+    ro = b.copy(); orc.spmv(rm, ind, val, -1.0, x, 1.0, ro)
+    import scipy.sparse as sp
+    absrow = abs(sp.csr_matrix((val, ind, rm), shape=(n, n))) @ np.abs(x) + np.abs(b)
+    assert np.all(np.abs(host(r64) - ro) <= 2 * summation_bound(absrow, int(np.diff(rm).max()), np.float64))
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("orth", ["cgsr", "cgs", "mgs"])
+@pytest.mark.parametrize("n,k", [(4, 0), (1000, 0), (1000, 3), (4099, 12), (65536, 31), (100003, 50), (30000, 100)])
+def test_add_vector(ctx, orc, dt, orth, n, k):
+    """GS::add_vector (Orthogonalization.hpp:51-60) fused on the device vs the oracle's gemv-by-gemv restatement"""
+    import torch
+    if orth == "mgs" and k > 31:
+        pytest.skip("MGS is k+1 x (dot, naxpy); covered at small k")
+    r = _rng(n * 7 + k)
+    Q, _ = np.linalg.qr(r.standard_normal((n, k + 1)))
+    V = np.zeros((n, k + 2), dt, order="F")
+    V[:, :k + 1] = Q.astype(dt)
+    w0 = (Q @ r.standard_normal(k + 1) * 3 + r.standard_normal(n)).astype(dt)
+    Vo, wo = V.copy(order="F"), w0.copy()
+    ho = orc.add_vector(orth, Vo, k, wo)
+    Vd, wd = fortran_dev(V), dev(w0)
+    hd = torch.zeros(k + 2, dtype=wd.dtype, device="cuda:0")
+    ctx.add_vector(orth, n, k, Vd, n, wd, hd)
+    hg, wg = host(hd), host(wd)
+    vg = host(Vd).reshape(k + 2, n)[k + 1]
+    u = EPS[np.dtype(dt)]
+    scale = float(np.linalg.norm(w0.astype(np.float64)))
+    c = 40.0 * np.sqrt(k + 1)
+    assert np.max(np.abs(hg - ho)) <= c * u * scale, f"h: {np.max(np.abs(hg - ho))} vs {c * u * scale}"
+    assert np.linalg.norm(wg.astype(np.float64) - wo) <= c * u * scale
+    assert np.linalg.norm(vg.astype(np.float64) - Vo[:, k + 1]) <= c * u * scale / max(float(ho[k + 1]), 1e-30) + 8 * u
+    # normalisation is w * (1/h) with the reciprocal formed in Type (Orthogonalization.hpp:58-59): exact given w, h
+    np.testing.assert_array_equal(vg, (wg * (dt(1) / hg[k + 1])).astype(dt))
+    # independent property checks in fp64: Arnoldi relation and orthogonality of the new column
+    V64 = np.concatenate([V[:, :k + 1].astype(np.float64), vg.astype(np.float64)[:, None]], axis=1)
+    assert np.linalg.norm(V64 @ hg.astype(np.float64) - w0.astype(np.float64)) <= c * u * scale
+    lim = (60 if orth != "cgs" else 60 * max(1.0, scale / max(float(hg[k + 1]), 1e-30))) * u * np.sqrt(n)
+    assert np.max(np.abs(V64[:, :k + 1].T @ V64[:, k + 1])) <= lim
+    # deterministic
+    Vd2, wd2, hd2 = fortran_dev(V), dev(w0), torch.zeros_like(hd)
+    ctx.add_vector(orth, n, k, Vd2, n, wd2, hd2)
+    np.testing.assert_array_equal(host(hd2), hg)
+    np.testing.assert_array_equal(host(wd2), wg)
+
+
+def test_jacobi_diag_bit_exact(ctx, g, orc):
+    import ctypes as C
+    import torch
+    for spec in ["lap2d:20", "powerlaw:4000"]:
+        rm, ind, val = orc.gen(spec)
+        n = len(rm) - 1
+        A = g.CSR(ctx, dev(rm), dev(ind))
+        for dt, fn in [(np.float32, orc.lib().orc_jacobi_diag_f32), (np.float64, orc.lib().orc_jacobi_diag_f64)]:
+            v = val.astype(dt)
+            do = np.empty(n, dt)
+            fn(C.c_int(n), rm.ctypes.data_as(C.c_void_p), ind.ctypes.data_as(C.c_void_p), v.ctypes.data_as(C.c_void_p), do.ctypes.data_as(C.c_void_p))
+            dd = torch.empty(n, dtype=torch.float32 if dt == np.float32 else torch.float64, device="cuda:0")
+            ctx.jacobi_diag(A, dev(v), dd)
+            np.testing.assert_array_equal(host(dd), do)
