@@ -57,7 +57,12 @@ extern "C" int mpg_ctx_destroy(mpg_ctx* ctx) {
 
 extern "C" int mpg_ctx_set_stream(mpg_ctx* ctx, void* s) {
     if (!ctx) return MPG_ERR_ARG;
-    ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
+    ctx->stream = (cudaStream_t)s;  // NULL is a valid handle: the CUDA legacy default stream
+    return MPG_OK;
+}
+extern "C" int mpg_ctx_use_own_stream(mpg_ctx* ctx) {
+    if (!ctx) return MPG_ERR_ARG;
+    ctx->stream = ctx->own_stream;
     return MPG_OK;
 }
 extern "C" void* mpg_ctx_stream(mpg_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
@@ -74,7 +79,11 @@ extern "C" int mpg_set_tuning(mpg_ctx* ctx, const char* key, int value) {
     const std::string k(key);
     if (k == "spmv_ctas_per_sm") ctx->tune.spmv_ctas_per_sm = value;
     else if (k == "vpass_stages") ctx->tune.vpass_stages = value;
-    else if (k == "vpass_bulk") ctx->tune.vpass_bulk = value;
+    else if (k == "fuse_min_cols") ctx->tune.fuse_min_cols = value;
+    else if (k == "gemvt_rb") ctx->tune.gemvt_rb = value;
+    else if (k == "gemvt_rows_per_block") ctx->tune.gemvt_rows_per_block = value;
+    else if (k == "passA_rb") ctx->tune.passA_rb = value;
+    else if (k == "cgs2_fused") ctx->tune.cgs2_fused = value;
     else if (k == "vpass_serpentine") ctx->tune.vpass_serpentine = value;
     else if (k == "gemvn_ctas_per_sm") ctx->tune.gemvn_ctas_per_sm = value;
     else if (k == "red_ctas_per_sm") ctx->tune.red_ctas_per_sm = value;

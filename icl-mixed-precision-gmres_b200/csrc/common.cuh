@@ -21,8 +21,12 @@ constexpr int kMaxPartBlocks = 2048;   // upper bound on the grid of a reducing 
 struct Tuning {
     int spmv_ctas_per_sm = 8;
     int vpass_stages = 0;     // 0 = auto
-    int vpass_bulk = 1;       // use cp.async.bulk (TMA 1-D) staging when alignment allows
     int vpass_serpentine = 1; // alternate traversal direction between consecutive V passes (L2 reuse)
+    int gemvt_rb = 1;         // register row-block kernel for gemv-T
+    int gemvt_rows_per_block = 8192;
+    int passA_rb = 0;         // use gemvt_rb for the first CGS pass (h = V'w) instead of the staged vpass kernel
+    int fuse_min_cols = 16;   // basis width from which the staged fused kernel beats the register kernels (tools/tune.py)
+    int cgs2_fused = 1;       // fused update + gemv-T second pass (3 passes) vs separate gemv-N, gemv-T (4 passes)
     int gemvn_ctas_per_sm = 4;
     int red_ctas_per_sm = 4;
     int use_graph = 0;
@@ -84,6 +88,7 @@ inline int fail(mpg_ctx* ctx, int code, const std::string& msg) {
 #define MPG_CUDA(ctx, expr)                                                                             \
     do {                                                                                                \
         cudaError_t _e = (expr);                                                                        \
+        if (_e != cudaSuccess) (void)cudaGetLastError(); /* do not leave a stale error for later calls */ \
         if (_e != cudaSuccess)                                                                          \
             return mpg::fail(ctx, MPG_ERR_CUDA,                                                         \
                              std::string(#expr) + ": " + cudaGetErrorString(_e) + " @" + __FILE__ + ":" + \

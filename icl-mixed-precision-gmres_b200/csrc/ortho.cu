@@ -15,9 +15,12 @@
 // [TR rows x k1 columns] is brought into shared memory by k1 one-dimensional TMA bulk copies
 // (cp.async.bulk.shared::cluster.global + mbarrier complete_tx), multi-stage, so the loads are in flight
 // while the previous tile is being consumed; each element is read from HBM once and from shared memory
-// twice.  Partial dot products stay in registers across all tiles of a CTA (warp w owns columns
+// twice.  (Since round 1b: one 2-D TMA tensor load per tile issued by a dedicated producer warp.)
+// Partial dot products stay in registers across all tiles of a CTA (warp w owns columns
 // w, w+NW, ...), are written once per CTA as doubles, and the last CTA to finish sums them in a fixed
 // order (deterministic, no float atomics) and runs the tiny epilogue (h += c, ...).
+#include <cuda.h>
+
 #include "common.cuh"
 
 using namespace mpg;
@@ -44,11 +47,6 @@ __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     do {
@@ -62,98 +60,112 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 
 enum { FIN_COEF = 0, FIN_COEF_ACCUM = 1 };
 
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(dst)),
+                 "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
 // ---------------------------------------------------------------------------------------------------------
-// vpass: optional row-local update w' = w - V h_in, then partial c = V' w'.
-//   TR   rows per tile = threads per CTA;  MAXJ  columns owned per warp (k1 <= MAXJ * TR/32)
-//   BULK TMA bulk staging (requires 16-byte aligned V, w, ldv*sizeof(T) % 16 == 0 and padded buffers)
-// Finalisation by the last CTA:  coef_out[j] = sum_j;  if fin == FIN_COEF_ACCUM also hcol[j] += sum_j,
-// else hcol[j] = sum_j  (hcol may alias coef_out when fin == FIN_COEF).
+// vpass: optional row-local update w' = w - V h_in, then partial c = V' w'   (one read of V from HBM).
+//
+// Warp-specialised: CT = 2*TR compute threads + one producer warp.  The producer brings a whole
+// [TR rows x k1 columns] tile of V into shared memory with ONE 2-D TMA tensor load (cp.async.bulk.tensor.2d,
+// box = TR x k1; rows past n are zero-filled by the hardware, so there is no tail handling) plus a 1-D tensor
+// load for the w tile, signalling full[s]; it re-fills a stage as soon as the consumers release it through
+// empty[s].  Loads therefore stay in flight while the consumers work on the other stage(s).
+//   phase 1 (only with h_in): the two halves of the compute threads each take half of the columns for all TR
+//            rows (warp-uniform split -> conflict-free shared memory reads), partial sums are combined;
+//   phase 2: warp q owns columns q, q+NW, ...; lanes own rows lane+32i; accumulators live in registers
+//            across all tiles of the CTA.
+// The last CTA to finish sums the per-CTA partials in a fixed order and runs the epilogue
+//   coef_out[j] = c_j ;  hcol[j] = c_j  (FIN_COEF)  or  hcol[j] += c_j  (FIN_COEF_ACCUM, Orthogonalization.hpp:133).
 // ---------------------------------------------------------------------------------------------------------
-template <class T, int TR, int MAXJ, bool BULK>
-__global__ void __launch_bounds__(TR, 1)
-vpass_kernel(int64_t n, int k1, const T* __restrict__ V, int64_t ldv, T* w, const T* h_in, int stages, int reverse,
-             double* partials, int ldp, unsigned int* ticket, int fin, T* coef_out, T* hcol) {
-    constexpr int NW = TR / 32;
-    constexpr int RPL = TR / 32;  // rows per lane in the dot phase
+template <class T, int TR, int MAXJ>
+__global__ void __launch_bounds__(2 * TR + 32, 1)
+vpass_kernel(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapW, int64_t n, int k1, T* w, const T* h_in,
+             int stages, int reverse, double* partials, int ldp, unsigned int* ticket, int fin, T* coef_out, T* hcol) {
+    constexpr int CT = 2 * TR;         // compute threads
+    constexpr int NW = CT / 32;        // compute warps
+    constexpr int RPL = TR / 32;       // rows per lane in the dot phase
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const size_t stage_elems = (size_t)(k1 + 1) * TR;  // k1 columns of V + the w tile
+    const size_t stage_elems = (size_t)(k1 + 2) * TR;  // k1 columns of V, the w tile, the phase-1 partial
     T* tiles = reinterpret_cast<T*>(smem_raw);
     T* h_s = tiles + stage_elems * stages;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(h_s + ((k1 + 3) & ~3) + 4);
-    bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(bars) + 7) & ~uintptr_t(7));
+    uint64_t* full = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(h_s + ((k1 + 3) & ~3) + 4) + 7) & ~uintptr_t(7));
+    uint64_t* empty = full + stages;
 
     const int64_t ntiles = (n + TR - 1) / TR;
     const int64_t my_count = (ntiles > blockIdx.x) ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-
-    if (h_in) for (int j = tid; j < k1; j += TR) h_s[j] = h_in[j];
-    if (BULK && tid == 0) {
-        for (int s = 0; s < stages; ++s) mbar_init(bars + s, 1);
-        fence_mbar_init();
-    }
-    __syncthreads();
-
     auto tile_row0 = [&](int64_t it) -> int64_t {
         int64_t tix = blockIdx.x + it * gridDim.x;
         if (reverse) tix = ntiles - 1 - tix;
         return tix * TR;
     };
-    // producer: warp 0.  lane 0 arms the barrier with the byte count, then every lane issues its columns.
-    auto issue = [&](int64_t it) {
-        const int s = (int)(it % stages);
-        const int64_t row0 = tile_row0(it);
-        const int rows = (int)min((int64_t)TR, n - row0);
-        const uint32_t bytes = (uint32_t)(((size_t)rows * sizeof(T) + 15) & ~size_t(15));
-        T* st = tiles + stage_elems * s;
-        if (lane == 0) mbar_arrive_expect_tx(bars + s, bytes * (uint32_t)(k1 + 1));
-        __syncwarp();
-        for (int j = lane; j < k1; j += 32) bulk_g2s(st + (size_t)j * TR, V + (size_t)j * ldv + row0, bytes, bars + s);
-        if (lane == 0) bulk_g2s(st + (size_t)k1 * TR, w + row0, bytes, bars + s);
-    };
 
-    if (BULK && wid == 0) {
-        for (int64_t it = 0; it < min((int64_t)stages, my_count); ++it) issue(it);
+    if (h_in) for (int j = tid; j < k1; j += CT + 32) h_s[j] = h_in[j];
+    if (tid == 0) {
+        for (int s = 0; s < stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        fence_mbar_init();
     }
+    __syncthreads();
 
     T acc[MAXJ];
 #pragma unroll
     for (int jj = 0; jj < MAXJ; ++jj) acc[jj] = T(0);
 
-    for (int64_t it = 0; it < my_count; ++it) {
-        const int s = BULK ? (int)(it % stages) : 0;
-        const int64_t row0 = tile_row0(it);
-        const int rows = (int)min((int64_t)TR, n - row0);
-        T* st = tiles + stage_elems * s;
-        T* ws = st + (size_t)k1 * TR;
-        if (BULK) {
-            mbar_wait(bars + s, (uint32_t)((it / stages) & 1));
-        } else {
-            // plain staging (unaligned / unpadded operands): coalesced column reads, one element per thread
-            if (tid < rows) {
-                for (int j = 0; j < k1; ++j) st[(size_t)j * TR + tid] = ldg_stream(V + (size_t)j * ldv + row0 + tid);
-                ws[tid] = w[row0 + tid];
+    if (wid == NW) {
+        // ===== producer warp =====
+        if (lane == 0) {
+            const uint32_t bytes = (uint32_t)((size_t)(k1 + 1) * TR * sizeof(T));
+            for (int64_t it = 0; it < my_count; ++it) {
+                const int s = (int)(it % stages);
+                if (it >= stages) mbar_wait(empty + s, (uint32_t)(((it / stages) - 1) & 1));
+                T* st = tiles + stage_elems * s;
+                const int row0 = (int)tile_row0(it);
+                mbar_arrive_expect_tx(full + s, bytes);
+                tma_load_2d(st, &mapV, row0, 0, full + s);
+                tma_load_2d(st + (size_t)k1 * TR, &mapW, row0, 0, full + s);
             }
-            __syncthreads();
         }
-        // ---- phase 1: w' = w - V h  (row-local, sequential j like gemv-N) ----
-        if (h_in) {
-            T a = (tid < rows) ? ws[tid] : T(0);
-            if (tid < rows) {
-#pragma unroll 4
-                for (int j = 0; j < k1; ++j) a = fma(-h_s[j], st[(size_t)j * TR + tid], a);
-                w[row0 + tid] = a;
+    } else {
+        // ===== consumers =====
+        const int half = tid / TR;          // warp-uniform: which half of the columns in phase 1
+        const int row = tid - half * TR;
+        const int jsplit = (k1 + 1) / 2;
+        for (int64_t it = 0; it < my_count; ++it) {
+            const int s = (int)(it % stages);
+            const int64_t row0 = tile_row0(it);
+            const int rows = (int)min((int64_t)TR, n - row0);
+            T* st = tiles + stage_elems * s;
+            T* ws = st + (size_t)k1 * TR;
+            T* ps = ws + TR;
+            mbar_wait(full + s, (uint32_t)((it / stages) & 1));
+            if (h_in) {
+                // ---- phase 1: w' = w - V h ----
+                const int jb = half ? jsplit : 0, je = half ? k1 : jsplit;
+                T a = half ? T(0) : ws[row];
+                const T* col = st + row;
+#pragma unroll 8
+                for (int j = jb; j < je; ++j) a = fma(-h_s[j], col[(size_t)j * TR], a);
+                if (half) ps[row] = a;
+                named_bar_sync(1, CT);
+                if (!half) {
+                    a += ps[row];
+                    ws[row] = a;
+                    if (row < rows) w[row0 + row] = a;
+                }
+                named_bar_sync(1, CT);
             }
-            ws[tid] = a;
-            __syncthreads();
-        } else if (rows < TR) {
-            if (tid >= rows) ws[tid] = T(0);
-            __syncthreads();
-        }
-        // ---- phase 2: c_j += sum_rows V[row, j] * w'[row];  warp wid owns columns wid, wid+NW, ... ----
-        T wl[RPL];
+            // ---- phase 2: c_j += sum_rows V[row, j] * w'[row] (rows past n are zero in both operands) ----
+            T wl[RPL];
 #pragma unroll
-        for (int i = 0; i < RPL; ++i) wl[i] = ws[lane + 32 * i];
-        if (rows == TR) {
+            for (int i = 0; i < RPL; ++i) wl[i] = ws[lane + 32 * i];
 #pragma unroll
             for (int jj = 0; jj < MAXJ; ++jj) {
                 const int j = wid + NW * jj;
@@ -165,40 +177,28 @@ vpass_kernel(int64_t n, int k1, const T* __restrict__ V, int64_t ldv, T* w, cons
                     acc[jj] += a;
                 }
             }
-        } else {
-#pragma unroll
-            for (int jj = 0; jj < MAXJ; ++jj) {
-                const int j = wid + NW * jj;
-                if (j < k1) {
-                    const T* col = st + (size_t)j * TR + lane;
-                    T a = T(0);
-#pragma unroll
-                    for (int i = 0; i < RPL; ++i) a = (lane + 32 * i < rows) ? fma(col[32 * i], wl[i], a) : a;
-                    acc[jj] += a;
-                }
-            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // order our shared-memory accesses before the next TMA write
+            named_bar_sync(1, CT);
+            if (tid == 0) mbar_arrive(empty + s);
         }
-        if (BULK) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // order our st.shared before the next bulk write
-        __syncthreads();  // everyone is done reading stage s
-        if (BULK && wid == 0 && it + stages < my_count) issue(it + stages);
-    }
-
-    // ---- per-CTA partials (one owner warp per column) ----
+        // ---- per-CTA partials (one owner warp per column) ----
 #pragma unroll
-    for (int jj = 0; jj < MAXJ; ++jj) {
-        const int j = wid + NW * jj;
-        if (j < k1) {
-            const double s = warp_sum((double)acc[jj]);
-            if (lane == 0) partials[(size_t)blockIdx.x * ldp + j] = s;
+        for (int jj = 0; jj < MAXJ; ++jj) {
+            const int j = wid + NW * jj;
+            if (j < k1) {
+                const double sred = warp_sum((double)acc[jj]);
+                if (lane == 0) partials[(size_t)blockIdx.x * ldp + j] = sred;
+            }
         }
     }
     if (grid_last_block(ticket)) {
-        for (int j = wid; j < k1; j += NW) {
-            const double s = reduce_partials_column(partials, ldp, gridDim.x, j);
+        for (int j = wid; j < k1; j += NW + 1) {
+            const double sred = reduce_partials_column(partials, ldp, gridDim.x, j);
             if (lane == 0) {
-                const T c = (T)s;
-                if (fin == FIN_COEF_ACCUM) { coef_out[j] = c; hcol[j] = hcol[j] + c; }   // axpy(1, weights, h_col) Orthogonalization.hpp:133
-                else { coef_out[j] = c; if (hcol != coef_out) hcol[j] = c; }
+                const T c = (T)sred;
+                coef_out[j] = c;
+                if (fin == FIN_COEF_ACCUM) hcol[j] = hcol[j] + c;   // axpy(1, weights, h_col) Orthogonalization.hpp:133
+                else if (hcol != coef_out) hcol[j] = c;
             }
         }
     }
@@ -362,34 +362,119 @@ __global__ void __launch_bounds__(256) gemvt_kernel(int64_t n, int ncols, const 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// gemvt_rb: h[j] = sum_i M[i,j] x[i] for tall-skinny column-major M, register accumulators, no staging.
+// A CTA owns whole row blocks of RB rows; for each block it sweeps the columns NC at a time: NC independent
+// 16-byte streaming loads in flight per thread, x (RB*s bytes) is re-read per sweep from L1, never from HBM.
+// One partial per (row block, column) -> the last CTA adds them in block order (deterministic).
+// Requires 16-byte aligned M, x and ld*sizeof(T) % 16 == 0; rows beyond n in the last vector are masked.
+// ---------------------------------------------------------------------------------------------------------
+template <class T, int NC>
+__global__ void __launch_bounds__(256, 2) gemvt_rb_kernel(int64_t n, int ncols, const T* __restrict__ M, int64_t ld, const T* __restrict__ x,
+                                                           int64_t rows_per_block, int nblocks, double* partials, int ldp, unsigned int* ticket,
+                                                           T alpha, T beta, T* y, T* y2) {
+    constexpr int VEC = 16 / sizeof(T);
+    using V4 = typename std::conditional<sizeof(T) == 4, float4, double2>::type;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __shared__ double red[8][NC];
+    for (int rb = blockIdx.x; rb < nblocks; rb += gridDim.x) {
+        const int64_t r0 = (int64_t)rb * rows_per_block;
+        const int64_t r1 = min(n, r0 + rows_per_block);
+        for (int j0 = 0; j0 < ncols; j0 += NC) {
+            const int nc = min(NC, ncols - j0);
+            T acc[NC];
+#pragma unroll
+            for (int c = 0; c < NC; ++c) acc[c] = T(0);
+            for (int64_t i = r0 + (int64_t)threadIdx.x * VEC; i < r1; i += 256 * VEC) {
+                T xv[VEC];
+                if (i + VEC <= n) {
+                    const V4 t = *reinterpret_cast<const V4*>(x + i);
+                    const T* pt = reinterpret_cast<const T*>(&t);
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) xv[e] = pt[e];
+                } else {
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) xv[e] = (i + e < n) ? x[i + e] : T(0);
+                }
+                V4 buf[NC];
+#pragma unroll
+                for (int c = 0; c < NC; ++c)
+                    if (c < nc) buf[c] = ldg_stream(reinterpret_cast<const V4*>(M + (size_t)(j0 + c) * ld + i));
+#pragma unroll
+                for (int c = 0; c < NC; ++c)
+                    if (c < nc) {
+                        const T* pb = reinterpret_cast<const T*>(&buf[c]);
+#pragma unroll
+                        for (int e = 0; e < VEC; ++e) acc[c] = (i + e < n) ? fma(pb[e], xv[e], acc[c]) : acc[c];
+                    }
+            }
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                const double sred = warp_sum((double)acc[c]);
+                if (lane == 0) red[wid][c] = sred;
+            }
+            __syncthreads();
+            if (threadIdx.x < nc) {
+                double t = 0.0;
+#pragma unroll
+                for (int w8 = 0; w8 < 8; ++w8) t += red[w8][threadIdx.x];
+                partials[(size_t)rb * ldp + j0 + threadIdx.x] = t;
+            }
+            __syncthreads();
+        }
+    }
+    if (grid_last_block(ticket)) {
+        for (int j = wid; j < ncols; j += 8) {
+            const double sred = reduce_partials_column(partials, ldp, nblocks, j);
+            if (lane == 0) {
+                const T v = (beta == T(0)) ? alpha * (T)sred : fma(alpha, (T)sred, beta * y[j]);
+                y[j] = v;
+                if (y2) y2[j] = v;
+            }
+        }
+    }
+}
+
 template <class T>
 bool aligned16(const T* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-constexpr size_t kMaxDynSmem = 227 * 1024;
+constexpr size_t kMaxDynSmem = 227 * 1024 - 1024;  // opt-in limit is 227 KB INCLUDING the kernel's static shared memory
 
-template <class T, int TR, int MAXJ, bool BULK>
-int launch_vpass_inst(mpg_ctx* ctx, int64_t n, int k1, const T* V, int64_t ldv, T* w, const T* h_in, int fin, T* coef_out, T* hcol) {
-    const size_t stage_bytes = (size_t)(k1 + 1) * TR * sizeof(T);
-    const size_t extra = sizeof(T) * (size_t)(((k1 + 3) & ~3) + 4) + 8 * 16 + 16;
-    int stages = BULK ? (int)std::min<size_t>(8, (kMaxDynSmem - extra) / stage_bytes) : 1;
-    if (BULK && ctx->tune.vpass_stages > 0) stages = std::min(stages, ctx->tune.vpass_stages);
-    if (stages < 1) return fail(ctx, MPG_ERR_ARG, "vpass: tile does not fit in shared memory");
-    // small k1: do not hog the SM with one CTA; aim for <= ~110 KB per CTA so two can be resident
-    if (BULK && stages > 2 && stage_bytes * stages > 110 * 1024) stages = std::max<int>(2, (int)((110 * 1024) / stage_bytes));
-    const size_t smem = stage_bytes * stages + extra;
-    const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, kMaxDynSmem / (smem + 1024)));
-    const int64_t ntiles = cdiv(n, TR);
-    const int grid = (int)std::min<int64_t>(std::min<int64_t>(ntiles, (int64_t)ctx->num_sms * ctas_per_sm), kMaxPartBlocks);
-    auto kern = vpass_kernel<T, TR, MAXJ, BULK>;
-    MPG_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
-    // algorithmic bytes (SURVEY.md §8d, fused CGS2 = 3 k1 n s + 4 n s): pass A reads V only (w was just written by the
-    // SpMV and is counted there), pass B reads V, reads w, writes w'
-    ProfScope prof(ctx, MPG_PROF_VPASS, (double)k1 * n * sizeof(T) + (h_in ? 2.0 * n * sizeof(T) : 0.0));
-    const int reverse = ctx->tune.vpass_serpentine ? (ctx->vpass_parity & 1) : 0;
-    ctx->vpass_parity ^= 1;
-    kern<<<grid, TR, smem, ctx->stream>>>(n, k1, V, ldv, w, h_in, stages, reverse, ctx->partials, kMaxCols + 8, ctx->ticket, fin, coef_out, hcol);
-    MPG_CHECK_LAUNCH(ctx);
-    return MPG_OK;
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda link dependency)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// returns 0 on success, else 1000*which + CUresult
+template <class T>
+int make_maps(const T* V, int64_t ldv, const T* w, int64_t n, int k1, int TR, CUtensorMap* mapV, CUtensorMap* mapW) {
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) return -1;
+    const CUtensorMapDataType dt = sizeof(T) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64;
+    cuuint64_t gdim[2] = {(cuuint64_t)n, (cuuint64_t)k1};
+    cuuint64_t gstr[1] = {(cuuint64_t)ldv * sizeof(T)};
+    cuuint32_t box[2] = {(cuuint32_t)TR, (cuuint32_t)k1};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(mapV, dt, 2, const_cast<T*>(V), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return 1000 + (int)r;
+    // w as an n x 1 matrix (same 2-D load path; rows past n are zero-filled)
+    cuuint64_t gdim1[2] = {(cuuint64_t)n, 1};
+    cuuint64_t gstr1[1] = {(((cuuint64_t)n * sizeof(T) + 15) / 16) * 16};
+    cuuint32_t box1[2] = {(cuuint32_t)TR, 1};
+    r = enc(mapW, dt, 2, const_cast<T*>(w), gdim1, gstr1, box1, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+            CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return 2000 + (int)r;
+    return 0;
 }
 
 template <class T>
@@ -397,14 +482,47 @@ struct VpassCfg;
 template <> struct VpassCfg<float> { static constexpr int TR = 256; };
 template <> struct VpassCfg<double> { static constexpr int TR = 128; };
 
-template <class T, bool BULK>
-int launch_vpass_maxj(mpg_ctx* ctx, int64_t n, int k1, const T* V, int64_t ldv, T* w, const T* h_in, int fin, T* coef_out, T* hcol) {
+template <class T, int TR, int MAXJ>
+int launch_vpass_inst(mpg_ctx* ctx, int64_t n, int k1, const T* V, int64_t ldv, T* w, const T* h_in, int fin, T* coef_out, T* hcol) {
+    CUtensorMap mapV, mapW;
+    const int mrc = make_maps<T>(V, ldv, w, n, k1, TR, &mapV, &mapW);
+    if (mrc != 0)
+        return fail(ctx, MPG_ERR_CUDA, "vpass: cuTensorMapEncodeTiled failed, code " + std::to_string(mrc) + " (n=" + std::to_string(n) + " k1=" +
+                                           std::to_string(k1) + " ldv=" + std::to_string(ldv) + ")");
+    const size_t stage_bytes = (size_t)(k1 + 2) * TR * sizeof(T);
+    const size_t extra = sizeof(T) * (size_t)(((k1 + 3) & ~3) + 4) + 8 * 2 * 8 + 32;
+    int stages = (int)std::min<size_t>(8, (kMaxDynSmem - extra) / stage_bytes);
+    if (ctx->tune.vpass_stages > 0) stages = std::min(stages, ctx->tune.vpass_stages);
+    if (stages < 1) return fail(ctx, MPG_ERR_ARG, "vpass: tile does not fit in shared memory");
+    // 544 threads x ~75-100 registers: one CTA per SM; the producer warp keeps up to `stages` tiles in flight
+    const size_t smem = stage_bytes * stages + extra;
+    const int ctas_per_sm = 1;
+    const int64_t ntiles = cdiv(n, TR);
+    const int grid = (int)std::min<int64_t>(std::min<int64_t>(ntiles, (int64_t)ctx->num_sms * ctas_per_sm), kMaxPartBlocks);
+    auto kern = vpass_kernel<T, TR, MAXJ>;
+    MPG_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
+    // algorithmic bytes (SURVEY.md §8d, fused CGS2 = 3 k1 n s + 4 n s): pass A reads V only (w was just written by the
+    // SpMV and is counted there), pass B reads V, reads w, writes w'
+    ProfScope prof(ctx, MPG_PROF_VPASS, (double)k1 * n * sizeof(T) + (h_in ? 2.0 * n * sizeof(T) : 0.0));
+    // traversal direction is a function of the pass, never of call history (bit-reproducible results): the plain
+    // gemv-T pass runs forward, the fused update+gemv-T pass runs backward so it starts on the part of V the previous
+    // pass left in L2, and the following gemv-N pass (forward) starts on the part this one leaves there
+    const int reverse = (ctx->tune.vpass_serpentine && h_in) ? 1 : 0;
+    kern<<<grid, 2 * TR + 32, smem, ctx->stream>>>(mapV, mapW, n, k1, w, h_in, stages, reverse, ctx->partials, kMaxCols + 8, ctx->ticket, fin,
+                                                   coef_out, hcol);
+    MPG_CHECK_LAUNCH(ctx);
+    return MPG_OK;
+}
+
+template <class T>
+int launch_vpass(mpg_ctx* ctx, int64_t n, int k1, const T* V, int64_t ldv, T* w, const T* h_in, int fin, T* coef_out, T* hcol) {
     constexpr int TR = VpassCfg<T>::TR;
-    constexpr int NW = TR / 32;
+    constexpr int NW = 2 * TR / 32;
     const int need = (k1 + NW - 1) / NW;
-    if (need <= 4) return launch_vpass_inst<T, TR, 4, BULK>(ctx, n, k1, V, ldv, w, h_in, fin, coef_out, hcol);
-    if (need <= 13) return launch_vpass_inst<T, TR, 13, BULK>(ctx, n, k1, V, ldv, w, h_in, fin, coef_out, hcol);
-    if (need <= 26) return launch_vpass_inst<T, TR, 26, BULK>(ctx, n, k1, V, ldv, w, h_in, fin, coef_out, hcol);
+    if (need <= 2) return launch_vpass_inst<T, TR, 2>(ctx, n, k1, V, ldv, w, h_in, fin, coef_out, hcol);
+    if (need <= 4) return launch_vpass_inst<T, TR, 4>(ctx, n, k1, V, ldv, w, h_in, fin, coef_out, hcol);
+    if (need <= 7) return launch_vpass_inst<T, TR, 7>(ctx, n, k1, V, ldv, w, h_in, fin, coef_out, hcol);
+    if (need <= 13) return launch_vpass_inst<T, TR, 13>(ctx, n, k1, V, ldv, w, h_in, fin, coef_out, hcol);
     return fail(ctx, MPG_ERR_ARG, "vpass: too many columns");
 }
 
@@ -412,28 +530,34 @@ int launch_vpass_maxj(mpg_ctx* ctx, int64_t n, int k1, const T* V, int64_t ldv, 
 
 namespace mpg {
 
-// max k1 the fused vpass supports for T (shared memory: one stage must fit twice; registers: MAXJ <= 26)
+// widest basis block the fused vpass accepts for T: two stages of [TR x (k1+2)] must fit in shared memory and each
+// compute warp owns at most 13 columns
 template <class T>
 int vpass_max_cols() {
     constexpr int TR = VpassCfg<T>::TR;
-    const int by_regs = 26 * (TR / 32);
-    const int by_smem = (int)((kMaxDynSmem - 4096) / 2 / (TR * sizeof(T))) - 1;
-    return std::min(by_regs, by_smem);
+    const int by_regs = 13 * (2 * TR / 32);
+    const int by_smem = (int)((kMaxDynSmem - 4096) / 2 / (TR * sizeof(T))) - 2;
+    return std::min(std::min(by_regs, by_smem), 256);
 }
 template int vpass_max_cols<float>();
 template int vpass_max_cols<double>();
 
-// `padded`: caller guarantees V columns and w can be read up to the next 16-byte boundary past row n
+// TMA needs 16-byte aligned base addresses and a 16-byte multiple column stride; callers fall back to the
+// unfused gemv-T / gemv-N kernels otherwise
 template <class T>
-int vpass(mpg_ctx* ctx, int64_t n, int k1, const T* V, int64_t ldv, T* w, const T* h_in, int accumulate, T* coef_out, T* hcol, bool padded) {
-    const bool bulk_ok = ctx->tune.vpass_bulk && aligned16(V) && aligned16(w) && ((ldv * sizeof(T)) % 16 == 0) &&
-                         (padded || (n * sizeof(T)) % 16 == 0);
-    const int fin = accumulate ? FIN_COEF_ACCUM : FIN_COEF;
-    if (bulk_ok) return launch_vpass_maxj<T, true>(ctx, n, k1, V, ldv, w, h_in, fin, coef_out, hcol);
-    return launch_vpass_maxj<T, false>(ctx, n, k1, V, ldv, w, h_in, fin, coef_out, hcol);
+bool vpass_ok(const T* V, int64_t ldv, const T* w, int64_t n, int k1) {
+    return aligned16(V) && aligned16(w) && ((ldv * sizeof(T)) % 16 == 0) && k1 >= 1 && k1 <= vpass_max_cols<T>() && n < (int64_t)2147483647 &&
+           encode_tiled() != nullptr;
 }
-template int vpass<float>(mpg_ctx*, int64_t, int, const float*, int64_t, float*, const float*, int, float*, float*, bool);
-template int vpass<double>(mpg_ctx*, int64_t, int, const double*, int64_t, double*, const double*, int, double*, double*, bool);
+template bool vpass_ok<float>(const float*, int64_t, const float*, int64_t, int);
+template bool vpass_ok<double>(const double*, int64_t, const double*, int64_t, int);
+
+template <class T>
+int vpass(mpg_ctx* ctx, int64_t n, int k1, const T* V, int64_t ldv, T* w, const T* h_in, int accumulate, T* coef_out, T* hcol) {
+    return launch_vpass<T>(ctx, n, k1, V, ldv, w, h_in, accumulate ? FIN_COEF_ACCUM : FIN_COEF, coef_out, hcol);
+}
+template int vpass<float>(mpg_ctx*, int64_t, int, const float*, int64_t, float*, const float*, int, float*, float*);
+template int vpass<double>(mpg_ctx*, int64_t, int, const double*, int64_t, double*, const double*, int, double*, double*);
 
 template <class T>
 int gemvn(mpg_ctx* ctx, int64_t n, int k1, const T* M, int64_t ld, T alpha, const T* x, T beta, T* y, bool want_norm, T* norm_out, T* inv_out,
@@ -470,6 +594,19 @@ template <class T>
 int gemvt(mpg_ctx* ctx, int64_t n, int ncols, const T* M, int64_t ld, T alpha, const T* x, T beta, T* y) {
     if (ncols <= 0) return MPG_OK;
     if (ncols > kMaxCols) return fail(ctx, MPG_ERR_ARG, "gemv-T: more than 256 columns");
+    constexpr int VEC = 16 / sizeof(T);
+    // fast path: 16-byte aligned columns whose vector loads cannot run past the allocation (ld >= n rounded up)
+    if (ctx->tune.gemvt_rb && n >= 4096 && aligned16(M) && aligned16(x) && ((ld * sizeof(T)) % 16 == 0) && ld >= ((n + VEC - 1) / VEC) * VEC) {
+        int64_t rpb = std::max<int64_t>(ctx->tune.gemvt_rows_per_block, cdiv(n, kMaxPartBlocks));
+        rpb = ((rpb + 256 * VEC - 1) / (256 * VEC)) * (256 * VEC);
+        const int nblocks = (int)cdiv(n, rpb);
+        const int grid = std::min(nblocks, ctx->num_sms * 2);
+        ProfScope prof(ctx, MPG_PROF_GEMVT, (double)ncols * n * sizeof(T) + (double)n * sizeof(T));
+        constexpr int NC = sizeof(T) == 4 ? 16 : 8;
+        gemvt_rb_kernel<T, NC><<<grid, 256, 0, ctx->stream>>>(n, ncols, M, ld, x, rpb, nblocks, ctx->partials, kMaxCols + 8, ctx->ticket, alpha, beta, y, nullptr);
+        MPG_CHECK_LAUNCH(ctx);
+        return MPG_OK;
+    }
     int grid = (int)std::min<int64_t>(std::max<int64_t>(1, cdiv(n, 256 * 4)), (int64_t)ctx->num_sms * 4);
     grid = std::min(grid, kMaxPartBlocks);
     ProfScope prof(ctx, MPG_PROF_GEMVT, (double)ncols * n * sizeof(T) + (double)n * sizeof(T));
@@ -497,11 +634,14 @@ int add_vector(mpg_ctx* ctx, int orth, int64_t n, int64_t k, T* V, int64_t ldv, 
         // nrm2(w, h(k+1,k)) as a gemv-N with zero columns would be wasteful: reuse the NORM epilogue with k1 = 0
         MPG_TRY(gemvn<T>(ctx, n, 0, V, ldv, T(0), hcol, T(1), w, true, hcol + k1, inv, nullptr));
     } else {
-        const bool fused = k1 <= vpass_max_cols<T>();
+        // narrow bases (k1 < fuse_min_cols) are dominated by the staged kernel's per-tile cost: the register kernels
+        // (gemv-T row-block sweep + gemv-N) are faster there even though they read V four times instead of three
+        const bool fused = ctx->tune.cgs2_fused && k1 >= ctx->tune.fuse_min_cols && vpass_ok<T>(V, ldv, w, n, k1);
         if (fused) {
-            MPG_TRY(vpass<T>(ctx, n, k1, V, ldv, w, nullptr, 0, hcol, hcol, padded));                       // h = V'w          :82,:126
+            if (ctx->tune.passA_rb) MPG_TRY(gemvt<T>(ctx, n, k1, V, ldv, T(1), w, T(0), hcol));
+            else MPG_TRY(vpass<T>(ctx, n, k1, V, ldv, w, nullptr, 0, hcol, hcol));                          // h = V'w          :82,:126
             if (orth == MPG_ORTH_CGSR) {
-                MPG_TRY(vpass<T>(ctx, n, k1, V, ldv, w, hcol, 1, weights, hcol, padded));                   // w-=Vh; c=V'w; h+=c :127-133
+                MPG_TRY(vpass<T>(ctx, n, k1, V, ldv, w, hcol, 1, weights, hcol));                           // w-=Vh; c=V'w; h+=c :127-133
                 MPG_TRY(gemvn<T>(ctx, n, k1, V, ldv, T(-1), weights, T(1), w, true, hcol + k1, inv, nullptr));  // w-=Vc; ||w||   :131,:55
             } else {
                 MPG_TRY(gemvn<T>(ctx, n, k1, V, ldv, T(-1), hcol, T(1), w, true, hcol + k1, inv, nullptr));     // w-=Vh; ||w||   :87,:55

@@ -42,7 +42,10 @@ typedef struct mpg_csr mpg_csr; /* CSR structure + SpMV plan; replaces cusparseM
 const char* mpg_version(void);
 int mpg_ctx_create(int device, mpg_ctx** out);
 int mpg_ctx_destroy(mpg_ctx* ctx);
-int mpg_ctx_set_stream(mpg_ctx* ctx, void* cuda_stream); /* NULL = the context's own stream */
+/* A new context runs on its own non-blocking stream.  set_stream takes any cudaStream_t; NULL is the CUDA legacy
+ * default stream, which is what the reference runs everything on. */
+int mpg_ctx_set_stream(mpg_ctx* ctx, void* cuda_stream);
+int mpg_ctx_use_own_stream(mpg_ctx* ctx);
 void* mpg_ctx_stream(mpg_ctx* ctx);
 int mpg_sync(mpg_ctx* ctx); /* Device::execution_space().fence(), gmres.cpp:113,225 */
 const char* mpg_last_error(mpg_ctx* ctx);

@@ -23,11 +23,11 @@ def test_library_builds_and_exports_every_declared_symbol(g):
     assert b"sm_100a" in L.mpg_version()
 
 
-def test_binary_is_sm100a_and_uses_tma_bulk_copies(g):
+def test_binary_is_sm100a_and_uses_tma(g):
     out = subprocess.run(["cuobjdump", "-lelf", g.library_path()], capture_output=True, text=True).stdout
     assert "sm_100a" in out and "sm_90" not in out and "sm_80" not in out
     sass = subprocess.run(["cuobjdump", "-sass", g.library_path()], capture_output=True, text=True).stdout
-    assert "UBLKCP" in sass, "the V-pass kernel must stage its tiles with TMA bulk copies"
+    assert "UTMALDG" in sass, "the V-pass kernel must stage its tiles with TMA tensor loads"
     assert "SYNCS" in sass
 
 

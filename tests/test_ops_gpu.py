@@ -111,7 +111,7 @@ def test_rotations_and_trsv_bit_exact(ctx, orc, dt):
     s[0] = 2.5
     csd, snd, sd = dev(cs), dev(sn), dev(s)
     resid = torch.zeros(m, dtype=torch.float64, device="cuda:0")
-    Ho = H.copy()
+    Ho = H.copy(order="F")
     res_o = []
     for k in range(m):
         ctx.givens_step(k, Hd, m + 1, csd, snd, sd, resid[k:k + 1])

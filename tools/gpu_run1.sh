@@ -9,6 +9,4 @@ timeout 900 python -m pytest tests/test_solver_gpu.py -m gpu -q --timeout 600 -p
 timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1
 timeout 600 python bench.py --workload cd27:64 --steps 2 --warmup 1 --cpu-sample cd27:32 > gpurun_out/bench_small.log 2>&1
 timeout 900 python bench.py --steps 3 --warmup 2 --cpu-sample cd27:96 > gpurun_out/bench_full.log 2>&1
-timeout 600 compute-sanitizer --tool memcheck python __graft_entry__.py smoke > gpurun_out/memcheck.log 2>&1
-tail -5 gpurun_out/pytest_ops.log gpurun_out/pytest_solver.log gpurun_out/smoke.log gpurun_out/bench_small.log gpurun_out/bench_full.log
-tail -15 gpurun_out/memcheck.log
+for f in pytest_ops pytest_solver smoke bench_small bench_full; do echo "== $f"; tail -n 4 gpurun_out/$f.log; done
