@@ -9,6 +9,9 @@
 #ifndef ORACLE_SHIM_KOKKOS_CORE_HPP
 #define ORACLE_SHIM_KOKKOS_CORE_HPP
 
+#include <algorithm>
+#include <cassert>
+#include <cmath>
 #include <cstddef>
 #include <cstdio>
 #include <cstdlib>
@@ -110,6 +113,11 @@ public:
     // unmanaged view over caller-owned memory (Kokkos: View(pointer, extents...))
     View(value_type* p, size_t n0) : ptr_(p), e0_(n0), e1_(1), s1_(n0) {}
     View(value_type* p, size_t n0, size_t n1) : ptr_(p), e0_(n0), e1_(n1), s1_(n0) {}
+
+    // compatible views convert implicitly (same value type and rank, e.g. default layout -> LayoutLeft)
+    template <class DT2, class... P2,
+              class = typename std::enable_if<View<DT2, P2...>::rank == rank && std::is_same<typename View<DT2, P2...>::value_type, value_type>::value>::type>
+    View(const View<DT2, P2...>& o) : alloc_(o.alloc_), ptr_(o.ptr_), e0_(o.e0_), e1_(o.e1_), s1_(o.s1_) {}
 
     // sub-views: one argument per source dimension; integral = fix, pair = range, ALL = whole extent
     template <class DT2, class... P2, class A0>

@@ -1,6 +1,20 @@
-"""GPU parity of the GMRES drivers (gmres_singleUpdate / gmres_baseline behind mpg_gmres_solve) against the oracle:
-same stopping decision, same restart count, inner iterations within +-5 %, residual histories inside a stated
-fp32-rounding envelope, post-solve fp64 resNorm/errNorm as the reference prints them (gmres_perf_test.cpp:169-178)."""
+"""GPU parity of the GMRES drivers (gmres_singleUpdate / gmres_baseline behind mpg_gmres_solve).
+
+Every case of tests/golden/gmres_cases.json (produced by the reference itself, see tests/golden/make_goldens.py) is
+solved on the GPU through the C ABI and compared with (a) the reference's recorded results and (b) the oracle run
+live on the same inputs:
+  * status, outer index i and restart count: equal; inner iterations: equal (base policy) or within +-5 % (policies
+    whose restart decision depends on a residual);
+  * residual history |s(k+1)|/||M^-1 b||: relative difference, while the residual is above 1e-4 of its start, at most
+        max(HIST_RTOL[mode], 4 x dev_oracle_vs_ref)
+    where dev_oracle_vs_ref is the recorded difference between the reference (MKL) and the oracle on that case - two
+    correct implementations of the same algorithm.  Well-conditioned cases sit at 1e-6..1e-4; the badly row-scaled
+    power-law matrix amplifies fp32 rounding to 5e-2..3e-1 for the reference as well, and the envelope follows it;
+  * post-solve fp64 resNorm / errNorm (gmres_perf_test.cpp:169-178): same size as the reference's, or inside the
+    stopping criterion."""
+import json
+import os
+
 import numpy as np
 import pytest
 
@@ -8,97 +22,73 @@ from util import dev, host, problem
 
 pytestmark = pytest.mark.gpu
 
-# Residual-history envelope.  |s(k+1)|/||M^-1 b|| is a smooth function of the Arnoldi data; two correct fp32
-# implementations differ by rounding amplified by the conditioning of the small least-squares problem.  We accept
-# a relative difference of HIST_RTOL while the residual is above HIST_FLOOR x its starting value (below that the
-# fp32 Arnoldi process has lost the digits the comparison would need).
-HIST_RTOL = {"mixed": 5e-3, "single": 5e-3, "single-prec": 5e-3, "baseline": 1e-8}
-HIST_FLOOR = {"mixed": 1e-4, "single": 1e-4, "single-prec": 1e-4, "baseline": 1e-10}
+GOLD = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "gmres_cases.json")))
+CASES = GOLD["cases"]
+FLOOR = GOLD["hist_floor"]
+HIST_RTOL = {"mixed": 5e-3, "single": 5e-3, "single-prec": 1e-4, "baseline": 1e-9}
 
 
-def run_both(ctx, g, orc, spec, **kw):
+def case_id(c):
+    extra = "".join(f"-{k}={c[k]}" for k in ("conv", "prec") if k in c)
+    return f"{c['spec']}-{c['mode']}-{c['orth']}{extra}"
+
+
+def solver_kwargs(c):
+    return {k: c[k] for k in ("mode", "orth", "rlen", "tol", "conv", "rtol", "prec") if k in c}
+
+
+def deviation(h, h0):
+    m = min(len(h), len(h0))
+    a, b = np.asarray(h[:m]), np.asarray(h0[:m])
+    live = b >= FLOOR * b[0]
+    return float((np.abs(a - b) / np.maximum(b, 1e-300))[live].max()) if m and live.any() else 0.0
+
+
+def gpu_solve(ctx, g, rm, ind, val, b, **kw):
     import torch
-    rm, ind, val, xt, b = problem(orc, spec)
-    ro = orc.gmres(rm, ind, val, b, **kw)
     A = g.CSR(ctx, dev(rm), dev(ind))
     x = torch.zeros(len(b), dtype=torch.float64, device="cuda:0")
-    rg = ctx.gmres(A, dev(val), dev(b), x, **kw)
-    rg["x"] = host(x)
-    return (rm, ind, val, xt, b), ro, rg
+    r = ctx.gmres(A, dev(val), dev(b), x, **kw)
+    r["x"] = host(x)
+    return r
 
 
-def check_parity(data, ro, rg, mode, rlen, exact_counts=True):
+@pytest.mark.parametrize("c", CASES, ids=case_id)
+def test_parity_with_reference_and_oracle(ctx, g, orc, c):
     import scipy.sparse as sp
-    rm, ind, val, xt, b = data
-    n = len(b)
-    A = sp.csr_matrix((val, ind, rm), shape=(n, n))
-    assert rg["status"] == ro["status"] == 1
-    assert rg["total_restarts"] == ro["total_restarts"], (rg["total_restarts"], ro["total_restarts"])
-    if exact_counts:
-        assert rg["total_iters"] == ro["total_iters"]
+    rm, ind, val, xt, b = problem(orc, c["spec"])
+    kw = solver_kwargs(c)
+    rg = gpu_solve(ctx, g, rm, ind, val, b, max_restarts=5000, **kw)
+    ro = orc.gmres(rm, ind, val, b, max_restarts=5000, **kw)
+    ref = c["ref"]
+    data_driven = "conv" in c
+    assert rg["status"] == ref["status"] == ro["status"] == 1
+    if data_driven:
+        assert abs(rg["total_iters"] - ref["total_iters"]) <= 0.05 * ref["total_iters"] + 1
+        assert abs(rg["total_restarts"] - ref["total_restarts"]) <= 0.05 * ref["total_restarts"] + 1
     else:
-        assert abs(rg["total_iters"] - ro["total_iters"]) <= 0.05 * ro["total_iters"] + 1
-    assert rg["outer_i"] == ro["outer_i"]
+        assert (rg["total_iters"], rg["total_restarts"], rg["outer_i"]) == (ref["total_iters"], ref["total_restarts"], ref["outer_i"])
     for f in ("b_norm", "Minvb_norm", "A_norm"):
         assert abs(rg[f] - ro[f]) <= 1e-6 * abs(ro[f])
-    # residual histories
-    m = min(len(rg["hist_inner"]), len(ro["hist_inner"]))
-    hg, ho = rg["hist_inner"][:m], ro["hist_inner"][:m]
-    # compare cycle by cycle relative to each cycle's starting residual
-    rel = np.abs(hg - ho) / np.maximum(ho, 1e-300)
-    live = ho >= HIST_FLOOR[mode] * np.maximum.accumulate(ho[::1])[0]
-    if live.any():
-        assert rel[live].max() <= HIST_RTOL[mode], f"history rel diff {rel[live].max():.3e} at {np.argmax(rel * live)}"
-    og, oo = rg["hist_outer"], ro["hist_outer"]
-    assert og.shape == oo.shape
-    # backward error at each restart boundary (what the stopping rule sees)
-    # (well above the fp32 noise floor of an IR cycle the two must agree closely; at the floor only in magnitude)
-    beg, beo = og[:, 0] / og[:, 1], oo[:, 0] / oo[:, 1]
-    for i in range(len(beo)):
-        if beo[i] > 1e-4:
-            assert abs(beg[i] - beo[i]) <= 5e-2 * beo[i], (i, beg[i], beo[i])
-        else:
-            assert beo[i] / 4 <= beg[i] <= beo[i] * 4 or beg[i] < 1e-14, (i, beg[i], beo[i])
-    # post-solve quantities the reference prints
-    res_g, res_o = np.linalg.norm(b - A @ rg["x"]), np.linalg.norm(b - A @ ro["x"])
-    err_g, err_o = np.linalg.norm(rg["x"] - xt), np.linalg.norm(ro["x"] - xt)
-    assert res_g <= 4 * res_o + 1e-12 * np.linalg.norm(b)
-    assert err_g <= 4 * err_o + 1e-12 * np.linalg.norm(xt)
-
-
-@pytest.mark.parametrize("spec,rlen", [("lap2d:64", 50), ("cd27:16", 100), ("powerlaw:5000", 50), ("lap2d:7", 10), ("cd27:3", 5)])
-@pytest.mark.parametrize("orth", ["cgsr", "cgs", "mgs"])
-def test_gmres_ir_parity(ctx, g, orc, spec, rlen, orth):
-    data, ro, rg = run_both(ctx, g, orc, spec, mode="mixed", orth=orth, rlen=rlen, tol=1e-9, max_restarts=500)
-    check_parity(data, ro, rg, "mixed", rlen)
-
-
-@pytest.mark.parametrize("mode", ["baseline", "single-prec", "single"])
-@pytest.mark.parametrize("spec,rlen", [("lap2d:48", 50), ("cd27:12", 30)])
-def test_uniform_precision_parity(ctx, g, orc, mode, spec, rlen):
-    tol = 1e-10 if mode == "baseline" else 1e-6
-    data, ro, rg = run_both(ctx, g, orc, spec, mode=mode, orth="cgsr", rlen=rlen, tol=tol, max_restarts=500)
-    check_parity(data, ro, rg, mode, rlen)
-
-
-@pytest.mark.parametrize("conv,rtol", [("relprecres", 1e-2), ("repeat", 1e-2), ("orthloss", 1e-3)])
-def test_restart_policies_parity(ctx, g, orc, conv, rtol):
-    data, ro, rg = run_both(ctx, g, orc, "lap2d:40", mode="mixed", orth="cgsr", conv=conv, rtol=rtol, rlen=40, tol=1e-9, max_restarts=5000)
-    assert rg["status"] == ro["status"] == 1
-    # data-dependent restart decisions may flip on a rounding difference: +-5 % on iterations and restarts
-    assert abs(rg["total_iters"] - ro["total_iters"]) <= 0.05 * ro["total_iters"] + 2
-    assert abs(rg["total_restarts"] - ro["total_restarts"]) <= 0.05 * ro["total_restarts"] + 1
-    import scipy.sparse as sp
-    rm, ind, val, xt, b = data
-    A = sp.csr_matrix((val, ind, rm), shape=(len(b), len(b)))
-    assert np.linalg.norm(b - A @ rg["x"]) <= 4 * np.linalg.norm(b - A @ ro["x"])
-
-
-def test_jacobi_parity(ctx, g, orc):
-    for mode in ("mixed", "baseline", "single-prec"):
-        tol = 1e-9 if mode != "single-prec" else 1e-6
-        data, ro, rg = run_both(ctx, g, orc, "powerlaw:4000", mode=mode, orth="cgsr", prec="jacobi", rlen=20, tol=tol, max_restarts=500)
-        check_parity(data, ro, rg, mode, 20)
+    env = max(HIST_RTOL[c["mode"]], 4 * c["dev_oracle_vs_ref"])
+    d_or, d_ref = deviation(rg["hist_inner"], ro["hist_inner"]), deviation(rg["hist_inner"], ref["hist_inner"])
+    if not data_driven or rg["total_iters"] == ro["total_iters"]:
+        assert d_or <= env, f"history vs oracle {d_or:.3e} > envelope {env:.3e}"
+    if not data_driven or rg["total_iters"] == ref["total_iters"]:
+        assert d_ref <= env, f"history vs reference {d_ref:.3e} > envelope {env:.3e}"
+    # what check_initial sees at each restart boundary
+    hg, hr = rg["hist_outer"], np.asarray(ref["hist_outer"])
+    k = min(len(hg), len(hr))
+    np.testing.assert_allclose(hg[0, :2], hr[0, :2], rtol=1e-4)
+    above = hr[:k, 0] >= 1e-5 * hr[0, 0]
+    if not data_driven:
+        assert np.all(np.abs(np.log10(hg[:k, 0][above] / hr[:k, 0][above])) <= 0.5)
+    # post-solve fp64 quantities the reference prints
+    n = len(b)
+    A = sp.csr_matrix((val, ind, rm), shape=(n, n))
+    res, err = np.linalg.norm(b - A @ rg["x"]), np.linalg.norm(rg["x"] - xt)
+    assert res <= max(8 * ref["res_norm"], c["tol"] * hr[0, 1])
+    assert err <= max(8 * ref["err_norm"], 100 * c["tol"] * np.linalg.norm(xt))
 
 
 def test_abort_and_x0(ctx, g, orc):
@@ -109,7 +99,7 @@ def test_abort_and_x0(ctx, g, orc):
     r = ctx.gmres(A, dev(val), dev(b), x, mode="mixed", rlen=5, tol=1e-14, max_restarts=3)
     ro = orc.gmres(rm, ind, val, b, mode="mixed", rlen=5, tol=1e-14, max_restarts=3)
     assert r["status"] == ro["status"] == 3 and r["total_restarts"] == ro["total_restarts"] == 4 and r["total_iters"] == ro["total_iters"]
-    # starting from the exact solution: converged at the first check, zero iterations
+    # starting from the exact solution: converged at the first check, zero iterations, x untouched
     x = dev(xt)
     r = ctx.gmres(A, dev(val), dev(b), x, mode="mixed", rlen=20, tol=1e-6)
     assert r["status"] == 1 and r["total_iters"] == 0 and r["total_restarts"] == 1
@@ -129,10 +119,27 @@ def test_host_entry_point_matches_device_entry_point(ctx, g, orc):
     np.testing.assert_array_equal(r1["hist_inner"], r2["hist_inner"])
 
 
-@pytest.mark.parametrize("spec,rlen", [("lap2d:1024", 50), ("cd27:96", 100)])
+def test_kernel_variants_agree(ctx, g, orc):
+    """the tuning knobs select different kernels for the same arithmetic: 3-pass fused vs 4-pass, staged vs register
+    gemv-T.  Reduction grouping differs, so results agree to rounding, not bitwise."""
+    rm, ind, val, xt, b = problem(orc, "cd27:20")
+    base = gpu_solve(ctx, g, rm, ind, val, b, mode="mixed", rlen=40, tol=1e-9)
+    try:
+        for key, value in [("cgs2_fused", 0), ("passA_rb", 1), ("fuse_min_cols", 1), ("vpass_serpentine", 0), ("gemvt_rb", 0)]:
+            ctx.set_tuning(key, value)
+            r = gpu_solve(ctx, g, rm, ind, val, b, mode="mixed", rlen=40, tol=1e-9)
+            ctx.set_tuning(key, {"cgs2_fused": 1, "passA_rb": 0, "fuse_min_cols": 16, "vpass_serpentine": 1, "gemvt_rb": 1}[key])
+            assert r["total_iters"] == base["total_iters"] and r["total_restarts"] == base["total_restarts"]
+            assert deviation(r["hist_inner"], base["hist_inner"]) <= 5e-3, key
+    finally:
+        for key, value in [("cgs2_fused", 1), ("passA_rb", 0), ("fuse_min_cols", 16), ("vpass_serpentine", 1), ("gemvt_rb", 1)]:
+            ctx.set_tuning(key, value)
+
+
+@pytest.mark.parametrize("spec,rlen", [("lap2d:1024", 50), ("cd27:96", 100), ("powerlaw:400000", 50)])
 def test_size_independent_properties_at_scale(ctx, g, spec, rlen):
     """sizes the oracle cannot finish quickly: check what must hold at any size — the reference's own stopping rule
-    recomputed from scratch in fp64 on the device, monotone Arnoldi residuals, orthonormal basis, determinism"""
+    recomputed from scratch in fp64 on the device, non-increasing Arnoldi residuals inside a cycle, bitwise determinism"""
     import torch
     rm, ind, val = ctx.gen(spec)
     n = rm.numel() - 1
@@ -142,7 +149,7 @@ def test_size_independent_properties_at_scale(ctx, g, spec, rlen):
     ctx.spmv(A, val, 1.0, xt, 0.0, b)
     x = torch.zeros(n, dtype=torch.float64, device="cuda:0")
     tol = 1e-8
-    r = ctx.gmres(A, val, b, x, mode="mixed", orth="cgsr", rlen=rlen, tol=tol, max_restarts=200)
+    r = ctx.gmres(A, val, b, x, mode="mixed", orth="cgsr", rlen=rlen, tol=tol, max_restarts=400)
     assert r["status"] == 1
     res = b.clone(); ctx.spmv(A, val, -1.0, x, 1.0, res)
     crit = ctx.nrm2(res) / (ctx.nrm2(b) + ctx.nrm2(val.float()) * ctx.nrm2(x))
@@ -152,5 +159,5 @@ def test_size_independent_properties_at_scale(ctx, g, spec, rlen):
         cyc = hi[c * rlen:(c + 1) * rlen]
         assert np.all(np.diff(cyc) <= 1e-6 * cyc[0])
     x2 = torch.zeros(n, dtype=torch.float64, device="cuda:0")
-    r2 = ctx.gmres(A, val, b, x2, mode="mixed", orth="cgsr", rlen=rlen, tol=tol, max_restarts=200)
+    r2 = ctx.gmres(A, val, b, x2, mode="mixed", orth="cgsr", rlen=rlen, tol=tol, max_restarts=400)
     assert torch.equal(x, x2) and np.array_equal(r["hist_inner"], r2["hist_inner"])
