@@ -8,5 +8,7 @@ importing works anywhere, but every compute call needs the CUDA library and a CU
 from .binding import (Context, CSR, GmresParams, GmresStats, MODES, ORTHS, CONVS, PRECS, load_library, library_path,
                       exported_symbols, header_symbols, MpgError)
 
-__all__ = ["Context", "CSR", "GmresParams", "GmresStats", "MODES", "ORTHS", "CONVS", "PRECS", "load_library",
+from . import dist  # noqa: E402,F401  (multi-GPU plumbing: partition builder + DistContext)
+
+__all__ = ["dist", "Context", "CSR", "GmresParams", "GmresStats", "MODES", "ORTHS", "CONVS", "PRECS", "load_library",
            "library_path", "exported_symbols", "header_symbols", "MpgError"]

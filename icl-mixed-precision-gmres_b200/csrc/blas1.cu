@@ -35,6 +35,7 @@ extern "C" int mpg_ctx_create(int device, mpg_ctx** out) {
     MPG_CUDA(ctx, cudaMalloc(&ctx->dscal, sizeof(double) * 1024));
     MPG_CUDA(ctx, cudaMemset(ctx->dscal, 0, sizeof(double) * 1024));
     MPG_CUDA(ctx, cudaMallocHost(&ctx->hscal, sizeof(double) * 64));
+    MPG_CUDA(ctx, cudaMalloc(&ctx->red_raw, sizeof(double) * (kMaxCols + 8)));
     *out = ctx;
     return MPG_OK;
 }
@@ -46,6 +47,8 @@ extern "C" int mpg_ctx_destroy(mpg_ctx* ctx) {
     if (ctx->ws && ctx->ws_free) ctx->ws_free(ctx->ws);
     for (auto& r : ctx->prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto e : ctx->prof_pool) cudaEventDestroy(e);
+    cudaFree(ctx->arena);
+    cudaFree(ctx->red_raw);
     cudaFree(ctx->partials);
     cudaFree(ctx->ticket);
     cudaFree(ctx->dscal);
@@ -179,7 +182,7 @@ constexpr int RED_THREADS = 256;
 
 template <class T, bool IS_NRM2>
 __global__ void __launch_bounds__(RED_THREADS) reduce_kernel(int64_t n, const T* __restrict__ x, const T* __restrict__ y,
-                                                              double* partials, unsigned int* ticket, T* out) {
+                                                              double* partials, unsigned int* ticket, Epi epi) {
     constexpr int VEC = 16 / sizeof(T);
     using V = typename std::conditional<sizeof(T) == 4, float4, double2>::type;
     const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -223,7 +226,7 @@ __global__ void __launch_bounds__(RED_THREADS) reduce_kernel(int64_t n, const T*
     if (grid_last_block(ticket)) {
         if (threadIdx.x < 32) {
             const double t = reduce_partials_column(partials, 1, gridDim.x, 0);
-            if (threadIdx.x == 0) *out = IS_NRM2 ? (T)sqrt(t) : (T)t;
+            if (threadIdx.x == 0) apply_epi<T>(epi, 0, t);
         }
     }
 }
@@ -234,9 +237,10 @@ int launch_reduce(mpg_ctx* ctx, int64_t n, const T* x, const T* y, T* out_dev) {
     int grid = (int)std::min<int64_t>(std::max<int64_t>(1, cdiv(n, per_block)), (int64_t)ctx->num_sms * ctx->tune.red_ctas_per_sm);
     grid = std::min(grid, kMaxPartBlocks);
     ProfScope prof(ctx, MPG_PROF_REDUCE, (double)n * sizeof(T) * (IS_NRM2 ? 1 : 2));
-    reduce_kernel<T, IS_NRM2><<<grid, RED_THREADS, 0, ctx->stream>>>(n, x, y, ctx->partials, ctx->ticket, out_dev);
+    const Epi epi{IS_NRM2 ? EPI_NRM2 : EPI_DOT, out_dev, nullptr, 0.0, 0.0, dist_raw(ctx)};
+    reduce_kernel<T, IS_NRM2><<<grid, RED_THREADS, 0, ctx->stream>>>(n, x, y, ctx->partials, ctx->ticket, epi);
     MPG_CHECK_LAUNCH(ctx);
-    return MPG_OK;
+    return dist_finish_reduction(ctx, epi, 1, (int)sizeof(T));
 }
 
 template <class T>
@@ -544,6 +548,33 @@ __global__ void trsv_kernel(int upper, int trans, int64_t n, const T* A, int64_t
     }
 }
 
+// Upper / NoTrans / NonUnit (the solution_update case, gmres.cpp:288,300) with the whole triangle staged in shared
+// memory: same column sweep and the same per-element operation order as the netlib loop above (bit-identical
+// results), but the i-loop of each column runs across the block and the matrix is read with coalesced loads.
+template <class T>
+__global__ void __launch_bounds__(128) trsv_upper_smem_kernel(int n, const T* __restrict__ A, int64_t ld, T* x) {
+    extern __shared__ __align__(16) unsigned char smem_trsv[];
+    T* As = reinterpret_cast<T*>(smem_trsv);  // n x n, column-major, ld = n
+    T* xs = As + (size_t)n * n;
+    for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
+        const int i = idx % n, j = idx / n;
+        As[idx] = (i <= j) ? A[i + (int64_t)j * ld] : T(0);
+    }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) xs[i] = x[i];
+    __syncthreads();
+    for (int j = n - 1; j >= 0; --j) {
+        if (xs[j] != T(0)) {   // uniform branch: every thread reads the same shared value
+            __syncthreads();
+            if (threadIdx.x == 0) xs[j] = div_rn(xs[j], As[j + j * n]);
+            __syncthreads();
+            const T t = xs[j];
+            for (int i = threadIdx.x; i < j; i += blockDim.x) xs[i] = fma(-t, As[i + j * n], xs[i]);
+        }
+        __syncthreads();
+    }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) x[i] = xs[i];
+}
+
 }  // namespace
 
 namespace mpg {
@@ -560,6 +591,15 @@ template int givens_step<double>(mpg_ctx*, int64_t, double*, int64_t, double*, d
 template <class T>
 int trsv(mpg_ctx* ctx, int upper, int trans, int64_t n, const T* A, int64_t ld, T* x) {
     if (n <= 0) return MPG_OK;
+    ProfScope prof(ctx, MPG_PROF_SMALL, 0.0);
+    const size_t smem = sizeof(T) * ((size_t)n * n + n);
+    if (upper && !trans && smem <= 200 * 1024) {
+        auto kern = trsv_upper_smem_kernel<T>;
+        if (smem > 48 * 1024) MPG_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<1, 128, smem, ctx->stream>>>((int)n, A, ld, x);
+        MPG_CHECK_LAUNCH(ctx);
+        return MPG_OK;
+    }
     trsv_kernel<T><<<1, 1, 0, ctx->stream>>>(upper, trans, n, A, ld, x);
     MPG_CHECK_LAUNCH(ctx);
     return MPG_OK;

@@ -60,6 +60,14 @@ struct mpg_ctx {
     double prof_bytes[MPG_PROF_NCLASS] = {0};
     int64_t prof_launches[MPG_PROF_NCLASS] = {0};
 
+    // grow-only device staging arena of the host-buffer entry point (no cudaMalloc/cudaFree per call)
+    void* arena = nullptr;
+    size_t arena_bytes = 0;
+
+    // multi-GPU (dist.cu): communicator + partition attached to this context, raw reduction buffer
+    struct mpg_dist* dist = nullptr;
+    double* red_raw = nullptr;   // kMaxCols + 8 doubles
+
     // cached solver workspace (see solver.cu)
     void* ws = nullptr;
     void (*ws_free)(void*) = nullptr;
@@ -116,6 +124,10 @@ inline int fail(mpg_ctx* ctx, int code, const std::string& msg) {
     } while (0)
 
 inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// dist.cu: all-reduce `count` raw sums over the ranks and apply the epilogue (no-op when no communicator is attached)
+int dist_finish_reduction(mpg_ctx* ctx, const struct Epi& e, int count, int tbytes);
+inline double* dist_raw(mpg_ctx* ctx);
 
 // RAII timer for one kernel (or a kernel + its fix-up) of class `cls`, carrying its ALGORITHMIC bytes
 // (compulsory traffic).  No-op unless mpg_prof_enable(ctx, 1).
@@ -208,6 +220,33 @@ __device__ __forceinline__ bool grid_last_block(unsigned int* ticket) {
     return is_last;
 }
 
+// Epilogue of a grid-wide reduction: what happens to the reduced value(s).  On one GPU the last CTA applies it in the
+// reducing kernel itself; with a communicator attached (dist.cu) the kernel stores the raw local sums instead, they are
+// all-reduced over the ranks (fp64), and epilogue_kernel applies the same function afterwards.
+enum EpiKind { EPI_DOT = 0, EPI_NRM2 = 1, EPI_COEF = 2, EPI_COEF_ACCUM = 3, EPI_NORM_INV = 4, EPI_GEMVT = 5, EPI_MAX = 6 };
+struct Epi {
+    int kind;
+    void* p0;      // DOT/NRM2/MAX: out | COEF*: coef_out | NORM_INV: norm_out | GEMVT: y
+    void* p1;      // COEF*: hcol | NORM_INV: inv_out
+    double alpha, beta;
+    double* raw;   // non-null: store the raw fp64 sums here and skip the epilogue (multi-GPU)
+};
+template <class T>
+__device__ __forceinline__ void apply_epi(const Epi& e, int j, double s) {
+    if (e.raw) { e.raw[j] = s; return; }
+    T* p0 = static_cast<T*>(e.p0);
+    T* p1 = static_cast<T*>(e.p1);
+    switch (e.kind) {
+        case EPI_DOT: p0[j] = (T)s; break;
+        case EPI_MAX: p0[j] = (T)s; break;
+        case EPI_NRM2: p0[j] = (T)sqrt(s); break;
+        case EPI_COEF: { const T c = (T)s; p0[j] = c; if (p1 && p1 != p0) p1[j] = c; } break;
+        case EPI_COEF_ACCUM: { const T c = (T)s; p0[j] = c; p1[j] = p1[j] + c; } break;   // axpy(1, weights, h_col) Orthogonalization.hpp:133
+        case EPI_NORM_INV: { const T nrm = (T)sqrt(s); p0[j] = nrm; p1[j] = T(1) / nrm; } break;   // Orthogonalization.hpp:55,59
+        case EPI_GEMVT: { const T a = (T)e.alpha, b = (T)e.beta; p0[j] = (b == T(0)) ? a * (T)s : fma(a, (T)s, b * p0[j]); } break;
+    }
+}
+
 // sum over blocks of partials[b*ld + j] for the calling warp's column j (all lanes get the result)
 __device__ __forceinline__ double reduce_partials_column(const double* partials, int ld, int nblocks, int j) {
     const int lane = threadIdx.x & 31;
@@ -215,5 +254,7 @@ __device__ __forceinline__ double reduce_partials_column(const double* partials,
     for (int b = lane; b < nblocks; b += 32) acc += __ldcg(partials + (size_t)b * ld + j);
     return warp_sum(acc);
 }
+
+inline double* dist_raw(mpg_ctx* ctx) { return ctx->dist ? ctx->red_raw : nullptr; }
 
 }  // namespace mpg

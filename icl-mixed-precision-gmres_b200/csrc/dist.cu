@@ -1,0 +1,210 @@
+// dist.cu — 1-D row-partitioned multi-GPU layer (one process per GPU).  New functionality: the reference is single
+// device.  Rank r owns rows [floor(r n/P), floor((r+1) n/P)); every vector on the path is split by
+// the same row map; h, s, cos, sin and the Givens / least-squares state are replicated, so every rank takes identical
+// control decisions.
+//   * SpMV: the local slab's columns are renumbered [local | halo]; x lives in a buffer with the halo appended
+//     (the tail of each basis column), filled by mpg_halo_exchange: pack kernel (gather of the rows each peer needs)
+//     + grouped ncclSend/ncclRecv over NVLink, received straight into the halo tail.
+//   * dot / nrm2 / gemv-T / the fused passes: kernels store their raw fp64 local sums, one ncclAllReduce(sum, fp64) of
+//     <= 257 values combines them, and epilogue_kernel applies the same epilogue the single-GPU kernel applies in its
+//     last CTA (common.cuh Epi).  gemv-N / axpy / scal / casts are purely local.
+// NCCL is loaded at run time (dlopen "libnccl.so.2": the copy torch already mapped), so the library has no link-time
+// NCCL dependency and single-GPU use never touches it.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <vector>
+
+#include "common.cuh"
+
+using namespace mpg;
+
+namespace {
+
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+};
+
+NcclApi& nccl() {
+    static NcclApi api;
+    if (api.handle) return api;
+    for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+        api.handle = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+        if (api.handle) break;
+    }
+    if (!api.handle) return api;
+#define MPG_SYM(f) api.f = reinterpret_cast<decltype(api.f)>(dlsym(api.handle, "nccl" #f))
+    MPG_SYM(GetUniqueId); MPG_SYM(CommInitRank); MPG_SYM(CommDestroy); MPG_SYM(AllReduce); MPG_SYM(Send); MPG_SYM(Recv);
+    MPG_SYM(GroupStart); MPG_SYM(GroupEnd); MPG_SYM(GetErrorString);
+#undef MPG_SYM
+    api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.Send && api.Recv && api.GroupStart && api.GroupEnd;
+    return api;
+}
+
+#define MPG_NCCL(ctx, expr)                                                                                              \
+    do {                                                                                                                 \
+        ncclResult_t _r = (expr);                                                                                        \
+        if (_r != ncclSuccess)                                                                                           \
+            return mpg::fail(ctx, MPG_ERR_NCCL, std::string(#expr) + ": " + (nccl().GetErrorString ? nccl().GetErrorString(_r) : "nccl error")); \
+    } while (0)
+
+template <class T>
+__global__ void epilogue_kernel(Epi e, int count) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= count) return;
+    const double s = e.raw[j];
+    e.raw = nullptr;
+    apply_epi<T>(e, j, s);
+}
+
+template <class T>
+__global__ void pack_kernel(int64_t count, const int* __restrict__ idx, const T* __restrict__ x, T* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) out[i] = x[idx[i]];
+}
+
+}  // namespace
+
+struct mpg_dist {
+    int rank = 0, world = 1;
+    ncclComm_t comm = nullptr;
+    int device = 0;
+    // partition (rows are local; columns [0, n_local) local, [n_local, n_local + n_halo) halo)
+    int64_t n_global = 0, n_local = 0, n_halo = 0;
+    struct Peer {
+        int rank;
+        int64_t send_count, send_offset;   // offset into the packed send buffer
+        int64_t recv_count, recv_offset;   // offset into the halo tail
+        const int* send_idx;               // device, local row indices (ascending), not owned
+    };
+    std::vector<Peer> peers;
+    int64_t send_total = 0;
+    void* send_buf = nullptr;              // send_total doubles
+};
+
+extern "C" int mpg_nccl_unique_id(void* id128) {
+    if (!id128) return MPG_ERR_ARG;
+    if (!nccl().ok) return MPG_ERR_NCCL;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    return nccl().GetUniqueId(static_cast<ncclUniqueId*>(id128)) == ncclSuccess ? MPG_OK : MPG_ERR_NCCL;
+}
+
+extern "C" int mpg_dist_create(mpg_ctx* ctx, const void* id128, int rank, int world, mpg_dist** out) {
+    MPG_REQUIRE(ctx, id128 && out && world >= 1 && rank >= 0 && rank < world, "dist_create: bad argument");
+    if (!nccl().ok) return fail(ctx, MPG_ERR_NCCL, "libnccl.so.2 could not be loaded");
+    mpg_dist* d = new mpg_dist();
+    d->rank = rank; d->world = world; d->device = ctx->device;
+    MPG_CUDA(ctx, cudaSetDevice(ctx->device));
+    ncclUniqueId id;
+    memcpy(&id, id128, sizeof(id));
+    MPG_NCCL(ctx, nccl().CommInitRank(&d->comm, world, id, rank));
+    *out = d;
+    return MPG_OK;
+}
+
+extern "C" int mpg_dist_destroy(mpg_dist* d) {
+    if (!d) return MPG_OK;
+    cudaSetDevice(d->device);
+    if (d->comm && nccl().ok) nccl().CommDestroy(d->comm);
+    cudaFree(d->send_buf);
+    delete d;
+    return MPG_OK;
+}
+
+extern "C" int mpg_dist_set_partition(mpg_ctx* ctx, mpg_dist* d, int64_t n_global, int64_t n_local, int64_t n_halo, int npeers,
+                                      const int* peer_ranks, const int64_t* send_counts, const int* const* send_idx_dev,
+                                      const int64_t* recv_offsets, const int64_t* recv_counts) {
+    MPG_REQUIRE(ctx, d && n_global >= 0 && n_local >= 0 && n_halo >= 0 && npeers >= 0, "dist_set_partition: bad argument");
+    d->n_global = n_global; d->n_local = n_local; d->n_halo = n_halo;
+    d->peers.clear();
+    int64_t off = 0;
+    for (int i = 0; i < npeers; ++i) {
+        MPG_REQUIRE(ctx, peer_ranks[i] >= 0 && peer_ranks[i] < d->world && peer_ranks[i] != d->rank, "dist_set_partition: bad peer rank");
+        MPG_REQUIRE(ctx, recv_offsets[i] >= 0 && recv_offsets[i] + recv_counts[i] <= n_halo, "dist_set_partition: halo range out of bounds");
+        d->peers.push_back({peer_ranks[i], send_counts[i], off, recv_counts[i], recv_offsets[i], send_idx_dev[i]});
+        off += send_counts[i];
+    }
+    d->send_total = off;
+    cudaFree(d->send_buf);
+    d->send_buf = nullptr;
+    if (off > 0) MPG_CUDA(ctx, cudaMalloc(&d->send_buf, sizeof(double) * (size_t)off));
+    return MPG_OK;
+}
+
+extern "C" int mpg_ctx_attach_dist(mpg_ctx* ctx, mpg_dist* d) {
+    if (!ctx) return MPG_ERR_ARG;
+    ctx->dist = (d && d->world > 1) ? d : nullptr;   // a single-rank communicator behaves exactly like no communicator
+    return MPG_OK;
+}
+
+extern "C" int mpg_dist_info(const mpg_dist* d, int* rank, int* world, int64_t* n_global, int64_t* n_local, int64_t* n_halo) {
+    if (!d) return MPG_ERR_ARG;
+    if (rank) *rank = d->rank;
+    if (world) *world = d->world;
+    if (n_global) *n_global = d->n_global;
+    if (n_local) *n_local = d->n_local;
+    if (n_halo) *n_halo = d->n_halo;
+    return MPG_OK;
+}
+
+namespace mpg {
+
+int dist_finish_reduction(mpg_ctx* ctx, const Epi& e, int count, int tbytes) {
+    if (!ctx->dist || !e.raw || count <= 0) return MPG_OK;
+    mpg_dist* d = ctx->dist;
+    ProfScope prof(ctx, MPG_PROF_SMALL, 0.0);
+    const ncclRedOp_t op = (e.kind == EPI_MAX) ? ncclMax : ncclSum;
+    MPG_NCCL(ctx, nccl().AllReduce(e.raw, e.raw, (size_t)count, ncclDouble, op, d->comm, ctx->stream));
+    const int grid = (count + 127) / 128;
+    if (tbytes == 4) epilogue_kernel<float><<<grid, 128, 0, ctx->stream>>>(e, count);
+    else epilogue_kernel<double><<<grid, 128, 0, ctx->stream>>>(e, count);
+    MPG_CHECK_LAUNCH(ctx);
+    return MPG_OK;
+}
+
+// x_ext: n_local owned values followed by n_halo halo slots
+template <class T>
+int halo_exchange(mpg_ctx* ctx, T* x_ext) {
+    mpg_dist* d = ctx->dist;
+    if (!d || d->peers.empty()) return MPG_OK;
+    ProfScope prof(ctx, MPG_PROF_SMALL, 0.0);
+    T* sbuf = static_cast<T*>(d->send_buf);
+    for (const auto& p : d->peers) {
+        if (p.send_count == 0) continue;
+        pack_kernel<T><<<(int)cdiv(p.send_count, 256), 256, 0, ctx->stream>>>(p.send_count, p.send_idx, x_ext, sbuf + p.send_offset);
+        MPG_CHECK_LAUNCH(ctx);
+    }
+    const ncclDataType_t dt = sizeof(T) == 4 ? ncclFloat : ncclDouble;
+    MPG_NCCL(ctx, nccl().GroupStart());
+    for (const auto& p : d->peers) {
+        if (p.send_count > 0) MPG_NCCL(ctx, nccl().Send(sbuf + p.send_offset, (size_t)p.send_count, dt, p.rank, d->comm, ctx->stream));
+        if (p.recv_count > 0) MPG_NCCL(ctx, nccl().Recv(x_ext + d->n_local + p.recv_offset, (size_t)p.recv_count, dt, p.rank, d->comm, ctx->stream));
+    }
+    MPG_NCCL(ctx, nccl().GroupEnd());
+    return MPG_OK;
+}
+template int halo_exchange<float>(mpg_ctx*, float*);
+template int halo_exchange<double>(mpg_ctx*, double*);
+
+int64_t dist_halo(mpg_ctx* ctx) { return ctx->dist ? ctx->dist->n_halo : 0; }
+int64_t dist_nlocal(mpg_ctx* ctx) { return ctx->dist ? ctx->dist->n_local : -1; }
+
+}  // namespace mpg
+
+extern "C" int mpg_halo_exchange_f32(mpg_ctx* ctx, float* x_ext) { return mpg::halo_exchange<float>(ctx, x_ext); }
+extern "C" int mpg_halo_exchange_f64(mpg_ctx* ctx, double* x_ext) { return mpg::halo_exchange<double>(ctx, x_ext); }
+extern "C" int mpg_allreduce_sum_f64(mpg_ctx* ctx, double* buf, int64_t count) {
+    if (!ctx->dist) return MPG_OK;
+    MPG_NCCL(ctx, nccl().AllReduce(buf, buf, (size_t)count, ncclDouble, ncclSum, ctx->dist->comm, ctx->stream));
+    return MPG_OK;
+}

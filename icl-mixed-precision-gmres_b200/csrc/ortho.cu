@@ -88,7 +88,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volat
 template <class T, int TR, int MAXJ>
 __global__ void __launch_bounds__(2 * TR + 32, 1)
 vpass_kernel(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapW, int64_t n, int k1, T* w, const T* h_in,
-             int stages, int reverse, double* partials, int ldp, unsigned int* ticket, int fin, T* coef_out, T* hcol) {
+             int stages, int reverse, double* partials, int ldp, unsigned int* ticket, Epi epi) {
     constexpr int CT = 2 * TR;         // compute threads
     constexpr int NW = CT / 32;        // compute warps
     constexpr int RPL = TR / 32;       // rows per lane in the dot phase
@@ -194,12 +194,7 @@ vpass_kernel(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ C
     if (grid_last_block(ticket)) {
         for (int j = wid; j < k1; j += NW + 1) {
             const double sred = reduce_partials_column(partials, ldp, gridDim.x, j);
-            if (lane == 0) {
-                const T c = (T)sred;
-                coef_out[j] = c;
-                if (fin == FIN_COEF_ACCUM) hcol[j] = hcol[j] + c;   // axpy(1, weights, h_col) Orthogonalization.hpp:133
-                else if (hcol != coef_out) hcol[j] = c;
-            }
+            if (lane == 0) apply_epi<T>(epi, j, sred);
         }
     }
 }
@@ -212,7 +207,7 @@ vpass_kernel(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ C
 // ---------------------------------------------------------------------------------------------------------
 template <class T, int VEC, bool NORM, bool XUPD>
 __global__ void __launch_bounds__(256) gemvn_kernel(int64_t n, int k1, const T* __restrict__ M, int64_t ld, T alpha, const T* x, T beta,
-                                                     T* y, double* x64, double* partials, unsigned int* ticket, T* norm_out, T* inv_out) {
+                                                     T* y, double* x64, double* partials, unsigned int* ticket, Epi epi) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     T* ax = reinterpret_cast<T*>(smem_raw);
     for (int j = threadIdx.x; j < k1; j += blockDim.x) ax[j] = alpha * x[j];
@@ -309,11 +304,7 @@ __global__ void __launch_bounds__(256) gemvn_kernel(int64_t n, int k1, const T* 
         if (grid_last_block(ticket)) {
             if (threadIdx.x < 32) {
                 const double t = reduce_partials_column(partials, 1, gridDim.x, 0);
-                if (threadIdx.x == 0) {
-                    const T nrm = (T)sqrt(t);
-                    norm_out[0] = nrm;            // h(k+1,k) = nrm2(w)            Orthogonalization.hpp:55
-                    inv_out[0] = T(1) / nrm;      // 1/h_final formed in Type      Orthogonalization.hpp:59
-                }
+                if (threadIdx.x == 0) apply_epi<T>(epi, 0, t);   // h(k+1,k) = nrm2(w), 1/h_final in Type  Orthogonalization.hpp:55,59
             }
         }
     }
@@ -325,7 +316,7 @@ __global__ void __launch_bounds__(256) gemvn_kernel(int64_t n, int k1, const T* 
 // ---------------------------------------------------------------------------------------------------------
 template <class T, int NC>
 __global__ void __launch_bounds__(256) gemvt_kernel(int64_t n, int ncols, const T* __restrict__ M, int64_t ld, T alpha, const T* __restrict__ x,
-                                                     T beta, T* y, double* partials, int ldp, unsigned int* ticket) {
+                                                     T beta, T* y, double* partials, int ldp, unsigned int* ticket, Epi epi) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     __shared__ double red[8][NC];
     for (int j0 = 0; j0 < ncols; j0 += NC) {
@@ -357,7 +348,7 @@ __global__ void __launch_bounds__(256) gemvt_kernel(int64_t n, int ncols, const 
     if (grid_last_block(ticket)) {
         for (int j = wid; j < ncols; j += 8) {
             const double s = reduce_partials_column(partials, ldp, gridDim.x, j);
-            if (lane == 0) y[j] = (beta == T(0)) ? alpha * (T)s : fma(alpha, (T)s, beta * y[j]);
+            if (lane == 0) apply_epi<T>(epi, j, s);
         }
     }
 }
@@ -372,7 +363,7 @@ __global__ void __launch_bounds__(256) gemvt_kernel(int64_t n, int ncols, const 
 template <class T, int NC>
 __global__ void __launch_bounds__(256, 2) gemvt_rb_kernel(int64_t n, int ncols, const T* __restrict__ M, int64_t ld, const T* __restrict__ x,
                                                            int64_t rows_per_block, int nblocks, double* partials, int ldp, unsigned int* ticket,
-                                                           T alpha, T beta, T* y, T* y2) {
+                                                           Epi epi) {
     constexpr int VEC = 16 / sizeof(T);
     using V4 = typename std::conditional<sizeof(T) == 4, float4, double2>::type;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -426,11 +417,7 @@ __global__ void __launch_bounds__(256, 2) gemvt_rb_kernel(int64_t n, int ncols, 
     if (grid_last_block(ticket)) {
         for (int j = wid; j < ncols; j += 8) {
             const double sred = reduce_partials_column(partials, ldp, nblocks, j);
-            if (lane == 0) {
-                const T v = (beta == T(0)) ? alpha * (T)sred : fma(alpha, (T)sred, beta * y[j]);
-                y[j] = v;
-                if (y2) y2[j] = v;
-            }
+            if (lane == 0) apply_epi<T>(epi, j, sred);
         }
     }
 }
@@ -508,10 +495,10 @@ int launch_vpass_inst(mpg_ctx* ctx, int64_t n, int k1, const T* V, int64_t ldv, 
     // gemv-T pass runs forward, the fused update+gemv-T pass runs backward so it starts on the part of V the previous
     // pass left in L2, and the following gemv-N pass (forward) starts on the part this one leaves there
     const int reverse = (ctx->tune.vpass_serpentine && h_in) ? 1 : 0;
-    kern<<<grid, 2 * TR + 32, smem, ctx->stream>>>(mapV, mapW, n, k1, w, h_in, stages, reverse, ctx->partials, kMaxCols + 8, ctx->ticket, fin,
-                                                   coef_out, hcol);
+    const Epi epi{fin == FIN_COEF_ACCUM ? EPI_COEF_ACCUM : EPI_COEF, coef_out, hcol, 0.0, 0.0, dist_raw(ctx)};
+    kern<<<grid, 2 * TR + 32, smem, ctx->stream>>>(mapV, mapW, n, k1, w, h_in, stages, reverse, ctx->partials, kMaxCols + 8, ctx->ticket, epi);
     MPG_CHECK_LAUNCH(ctx);
-    return MPG_OK;
+    return dist_finish_reduction(ctx, epi, k1, (int)sizeof(T));
 }
 
 template <class T>
@@ -571,9 +558,9 @@ int gemvn(mpg_ctx* ctx, int64_t n, int k1, const T* M, int64_t ld, T alpha, cons
     grid = std::max(1, std::min(grid, kMaxPartBlocks));
     // gemv-N: k1 n s + 2 n s (read y, write y) [+ 16 n for the fp64 x read-modify-write of the mixed update]
     ProfScope prof(ctx, MPG_PROF_GEMVN, (double)k1 * n * sizeof(T) + (beta != T(0) ? 2.0 : 1.0) * n * sizeof(T) + (x64 ? 16.0 * n : 0.0));
+    const Epi epi{EPI_NORM_INV, norm_out, inv_out, 0.0, 0.0, want_norm ? dist_raw(ctx) : nullptr};
 #define MPG_GEMVN(VV, NN, XX)                                                                                                   \
-    gemvn_kernel<T, VV, NN, XX><<<grid, 256, smem, ctx->stream>>>(n, k1, M, ld, alpha, x, beta, y, x64, ctx->partials, ctx->ticket, \
-                                                                  norm_out, inv_out)
+    gemvn_kernel<T, VV, NN, XX><<<grid, 256, smem, ctx->stream>>>(n, k1, M, ld, alpha, x, beta, y, x64, ctx->partials, ctx->ticket, epi)
     if (vec_ok) {
         if (want_norm) MPG_GEMVN(VEC, true, false);
         else if (x64) MPG_GEMVN(VEC, false, true);
@@ -585,6 +572,7 @@ int gemvn(mpg_ctx* ctx, int64_t n, int k1, const T* M, int64_t ld, T alpha, cons
     }
 #undef MPG_GEMVN
     MPG_CHECK_LAUNCH(ctx);
+    if (want_norm) return dist_finish_reduction(ctx, epi, 1, (int)sizeof(T));
     return MPG_OK;
 }
 template int gemvn<float>(mpg_ctx*, int64_t, int, const float*, int64_t, float, const float*, float, float*, bool, float*, float*, double*);
@@ -603,16 +591,18 @@ int gemvt(mpg_ctx* ctx, int64_t n, int ncols, const T* M, int64_t ld, T alpha, c
         const int grid = std::min(nblocks, ctx->num_sms * 2);
         ProfScope prof(ctx, MPG_PROF_GEMVT, (double)ncols * n * sizeof(T) + (double)n * sizeof(T));
         constexpr int NC = sizeof(T) == 4 ? 16 : 8;
-        gemvt_rb_kernel<T, NC><<<grid, 256, 0, ctx->stream>>>(n, ncols, M, ld, x, rpb, nblocks, ctx->partials, kMaxCols + 8, ctx->ticket, alpha, beta, y, nullptr);
+        const Epi epi{EPI_GEMVT, y, nullptr, (double)alpha, (double)beta, dist_raw(ctx)};
+        gemvt_rb_kernel<T, NC><<<grid, 256, 0, ctx->stream>>>(n, ncols, M, ld, x, rpb, nblocks, ctx->partials, kMaxCols + 8, ctx->ticket, epi);
         MPG_CHECK_LAUNCH(ctx);
-        return MPG_OK;
+        return dist_finish_reduction(ctx, epi, ncols, (int)sizeof(T));
     }
     int grid = (int)std::min<int64_t>(std::max<int64_t>(1, cdiv(n, 256 * 4)), (int64_t)ctx->num_sms * 4);
     grid = std::min(grid, kMaxPartBlocks);
     ProfScope prof(ctx, MPG_PROF_GEMVT, (double)ncols * n * sizeof(T) + (double)n * sizeof(T));
-    gemvt_kernel<T, 8><<<grid, 256, 0, ctx->stream>>>(n, ncols, M, ld, alpha, x, beta, y, ctx->partials, kMaxCols + 8, ctx->ticket);
+    const Epi epi{EPI_GEMVT, y, nullptr, (double)alpha, (double)beta, dist_raw(ctx)};
+    gemvt_kernel<T, 8><<<grid, 256, 0, ctx->stream>>>(n, ncols, M, ld, alpha, x, beta, y, ctx->partials, kMaxCols + 8, ctx->ticket, epi);
     MPG_CHECK_LAUNCH(ctx);
-    return MPG_OK;
+    return dist_finish_reduction(ctx, epi, ncols, (int)sizeof(T));
 }
 template int gemvt<float>(mpg_ctx*, int64_t, int, const float*, int64_t, float, const float*, float, float*);
 template int gemvt<double>(mpg_ctx*, int64_t, int, const double*, int64_t, double, const double*, double, double*);

@@ -43,6 +43,8 @@ template <class T> int spmv(mpg_ctx*, const mpg_csr*, const T*, T, const T*, T, 
 template <class T> int gemvn(mpg_ctx*, int64_t, int, const T*, int64_t, T, const T*, T, T*, bool, T*, T*, double*);
 template <class T> int gemvt(mpg_ctx*, int64_t, int, const T*, int64_t, T, const T*, T, T*);
 template <class T> int add_vector(mpg_ctx*, int, int64_t, int64_t, T*, int64_t, T*, T*, T*, bool);
+template <class T> int halo_exchange(mpg_ctx*, T*);
+int64_t dist_halo(mpg_ctx*);
 }  // namespace mpg
 
 namespace {
@@ -120,8 +122,16 @@ struct Workspace {
     void* S = nullptr;        // (m+1)^2 of T, ORTHLOSS   IterUtil.hpp:178,185
     void* u = nullptr;        // m+1 of T
     float* tmp32 = nullptr;   // n floats: single-prec preconditioner bridge (typesafe_apply, gmres.cpp:12-17)
-    double* x_norm_in = nullptr;
-    size_t bytes = 0;
+    int64_t halo = 0;         // multi-GPU: halo slots appended to every SpMV input (tail of each basis column)
+    void* xext = nullptr;     // multi-GPU: [x_local ; halo] copy of the iterate for the outer residual
+};
+
+// replicated (not row-distributed) data: reductions over it must not be all-reduced
+struct LocalScope {
+    mpg_ctx* ctx;
+    mpg_dist* saved;
+    explicit LocalScope(mpg_ctx* c) : ctx(c), saved(c->dist) { c->dist = nullptr; }
+    ~LocalScope() { ctx->dist = saved; }
 };
 
 void ws_release(void* p) {
@@ -129,20 +139,22 @@ void ws_release(void* p) {
     if (!ws) return;
     cudaFree(ws->V); cudaFree(ws->w); cudaFree(ws->h); cudaFree(ws->cs); cudaFree(ws->sn); cudaFree(ws->s);
     cudaFree(ws->scratch); cudaFree(ws->hist); cudaFreeHost(ws->hist_host); cudaFree(ws->S); cudaFree(ws->u); cudaFree(ws->tmp32);
+    cudaFree(ws->xext);
     delete ws;
 }
 
 int get_workspace(mpg_ctx* ctx, int64_t n, int64_t m, int tsize, bool need_S, bool need_tmp32, Workspace** out) {
     Workspace* ws = static_cast<Workspace*>(ctx->ws);
-    if (ws && (ws->n != n || ws->m != m || ws->tsize != tsize)) {
+    const int64_t halo = dist_halo(ctx);
+    if (ws && (ws->n != n || ws->m != m || ws->tsize != tsize || ws->halo != halo)) {
         MPG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         ws_release(ws);
         ctx->ws = ws = nullptr;
     }
     if (!ws) {
         ws = new Workspace();
-        ws->n = n; ws->m = m; ws->tsize = tsize;
-        ws->ldv = (n + 31) & ~int64_t(31);  // 128-byte aligned columns, readable to the next 16 B past row n
+        ws->n = n; ws->m = m; ws->tsize = tsize; ws->halo = halo;
+        ws->ldv = (n + halo + 31) & ~int64_t(31);  // 128-byte aligned columns; rows [n, n+halo) of a column hold its SpMV halo
         ctx->ws = ws;
         ctx->ws_free = ws_release;
         const size_t ts = (size_t)tsize;
@@ -160,6 +172,7 @@ int get_workspace(mpg_ctx* ctx, int64_t n, int64_t m, int tsize, bool need_S, bo
         MPG_CUDA(ctx, cudaMemsetAsync(ws->V, 0, ts * (size_t)ws->ldv * (size_t)(m + 1), ctx->stream));
         MPG_CUDA(ctx, cudaMemsetAsync(ws->w, 0, ts * (size_t)(ws->ldv + 32), ctx->stream));
         MPG_CUDA(ctx, cudaMemsetAsync(ws->h, 0, ts * (size_t)(m + 1) * (size_t)std::max<int64_t>(m, 1), ctx->stream));
+        if (halo > 0) MPG_CUDA(ctx, cudaMalloc(&ws->xext, sizeof(double) * (size_t)(n + halo)));
     }
     if (need_S && !ws->S) {
         MPG_CUDA(ctx, cudaMalloc(&ws->S, (size_t)tsize * (size_t)(m + 1) * (size_t)(m + 1)));
@@ -233,6 +246,7 @@ int run_cycle(mpg_ctx* ctx, const mpg_gmres_params& p, Policy& pol, Workspace* w
     int64_t flushed = 0;
     for (k = 0;; ++k) {
         // w = A v_k ; M(w)            gmres.cpp:98-102,210-215
+        MPG_TRY(halo_exchange<T>(ctx, V + (size_t)k * ldv));   // multi-GPU: fill the halo tail of v_k (no-op on one GPU)
         MPG_TRY(spmv<T>(ctx, A, vals, T(1), V + (size_t)k * ldv, T(0), w, w, nullptr));
         MPG_TRY(apply_prec<T>(ctx, n, w, jac, jac32, bridge, ws->tmp32));
         // orth.add_vector(k, w, h)     gmres.cpp:104,217
@@ -258,6 +272,7 @@ int run_cycle(mpg_ctx* ctx, const mpg_gmres_params& p, Policy& pol, Workspace* w
             const int k1 = (int)kk + 1;
             T* scol = S + (size_t)(kk + 1) * ldS;
             rc_loss = gemvt<T>(ctx, n, k1, V, ldv, T(1), V + (size_t)(kk + 1) * ldv, T(0), u);
+            LocalScope replicated(ctx);   // S, u, s_col are replicated on every rank
             if (rc_loss == MPG_OK) rc_loss = cast_copy(ctx, k1, u, scol);
             if (rc_loss == MPG_OK) rc_loss = gemvn<T>(ctx, k1, k1, S, ldS, T(-1), u, T(1), scol, false, nullptr, nullptr, nullptr);
             if (rc_loss == MPG_OK) rc_loss = dot_dev(ctx, k1, scol, scol, ds<T>(ctx, 16));
@@ -311,7 +326,14 @@ int solve_mixed(mpg_ctx* ctx, const mpg_gmres_params& p, const mpg_csr* A, const
 
     for (int64_t i = 0;; ++i) {
         // r = b - A x (fp64), w = (float) r : one fused kernel  (gmres.cpp:173-175)
-        MPG_TRY(spmv<double>(ctx, A, vals64, -1.0, x, 1.0, b, nullptr, w));
+        const double* xin = x;
+        if (ws->halo > 0) {   // multi-GPU: [x_local ; halo]
+            double* xe = static_cast<double*>(ws->xext);
+            MPG_TRY(cast_copy(ctx, n, x, xe));
+            MPG_TRY(halo_exchange<double>(ctx, xe));
+            xin = xe;
+        }
+        MPG_TRY(spmv<double>(ctx, A, vals64, -1.0, xin, 1.0, b, nullptr, w));
         MPG_TRY(nrm2_dev(ctx, n, w, ds<float>(ctx, 0)));                       // r_norm   :176
         MPG_TRY(apply_prec<float>(ctx, n, w, jac32, nullptr, false, nullptr)); // M(w)     :177
         if (jac32) MPG_TRY(nrm2_dev(ctx, n, w, ds<float>(ctx, 1)));            // beta     :179 (same vector when M = I)
@@ -368,7 +390,14 @@ int solve_uniform(mpg_ctx* ctx, const mpg_gmres_params& p, const mpg_csr* A, con
 
     for (int64_t i = 0;; ++i) {
         // w = b - A x in Type: one kernel (gmres.cpp:62-63)
-        MPG_TRY(spmv<T>(ctx, A, vals, T(-1), x, T(1), b, w, nullptr));
+        const T* xin = x;
+        if (ws->halo > 0) {
+            T* xe = static_cast<T*>(ws->xext);
+            MPG_TRY(cast_copy(ctx, n, x, xe));
+            MPG_TRY(halo_exchange<T>(ctx, xe));
+            xin = xe;
+        }
+        MPG_TRY(spmv<T>(ctx, A, vals, T(-1), xin, T(1), b, w, nullptr));
         MPG_TRY(nrm2_dev(ctx, n, w, ds<T>(ctx, 0)));                           // r_norm :67
         MPG_TRY(apply_prec<T>(ctx, n, w, jac, jac32, bridge, ws->tmp32));      //        :68
         if (have_prec) MPG_TRY(nrm2_dev(ctx, n, w, ds<T>(ctx, 1)));            // beta   :70
@@ -407,7 +436,7 @@ extern "C" int mpg_gmres_solve(mpg_ctx* ctx, const mpg_gmres_params* pp, const m
     MPG_REQUIRE(ctx, p.restart_length >= 1 && p.restart_length + 1 <= kMaxCols, "gmres_solve: restart length must be in [1, 255]");
     MPG_REQUIRE(ctx, p.mode >= 0 && p.mode <= 3 && p.orth >= 0 && p.orth <= 2 && p.conv >= 0 && p.conv <= 3 && p.prec >= 0 && p.prec <= 1,
                 "gmres_solve: bad enum");
-    MPG_REQUIRE(ctx, A->nrows == A->ncols, "gmres_solve: matrix must be square");
+    MPG_REQUIRE(ctx, (int64_t)A->ncols == (int64_t)A->nrows + dist_halo(ctx), "gmres_solve: matrix must be square (local slab: nrows + halo columns)");
     memset(st, 0, sizeof(*st));
     History hist{hist_inner, cap_inner, hist_outer, cap_outer};
     const int64_t n = A->nrows, nnz = A->nnz;
@@ -484,7 +513,30 @@ extern "C" int mpg_gmres_solve_host(mpg_ctx* ctx, const mpg_gmres_params* p, int
                                     const double* vals64_h, const double* b_h, double* x_h, mpg_gmres_stats* st, double* hist_inner,
                                     int64_t cap_inner, double* hist_outer, int64_t cap_outer) {
     MPG_REQUIRE(ctx, p && row_map_h && inds_h && vals64_h && b_h && x_h && st && nrows >= 0 && nnz >= 0, "gmres_solve_host: bad argument");
-    int* row_map = nullptr; int* inds = nullptr; double* vals = nullptr; double* b = nullptr; double* x = nullptr;
+    MPG_REQUIRE(ctx, ctx->dist == nullptr, "gmres_solve_host: takes a global matrix; with a communicator attached use mpg_gmres_solve on the local slab");
+    // carve the operands out of the context's grow-only arena: repeated solves pay no allocation cost
+    auto up = [](size_t v) { return (v + 255) & ~size_t(255); };
+    const size_t o_rm = 0;
+    const size_t o_in = o_rm + up(sizeof(int) * (size_t)(nrows + 1));
+    const size_t o_v64 = o_in + up(sizeof(int) * (size_t)nnz);
+    const size_t o_v32 = o_v64 + up(sizeof(double) * (size_t)nnz);
+    const size_t o_b = o_v32 + up(sizeof(float) * (size_t)nnz);
+    const size_t o_x = o_b + up(sizeof(double) * (size_t)nrows);
+    const size_t total = o_x + up(sizeof(double) * (size_t)nrows) + 256;
+    if (total > ctx->arena_bytes) {
+        MPG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->arena);
+        ctx->arena = nullptr; ctx->arena_bytes = 0;
+        MPG_CUDA(ctx, cudaMalloc(&ctx->arena, total));
+        ctx->arena_bytes = total;
+    }
+    char* base = static_cast<char*>(ctx->arena);
+    int* row_map = reinterpret_cast<int*>(base + o_rm);
+    int* inds = reinterpret_cast<int*>(base + o_in);
+    double* vals = reinterpret_cast<double*>(base + o_v64);
+    float* vals32 = reinterpret_cast<float*>(base + o_v32);
+    double* b = reinterpret_cast<double*>(base + o_b);
+    double* x = reinterpret_cast<double*>(base + o_x);
     mpg_csr* A = nullptr;
     cudaEvent_t e0, e1, e2, e3;
     cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2); cudaEventCreate(&e3);
@@ -492,14 +544,8 @@ extern "C" int mpg_gmres_solve_host(mpg_ctx* ctx, const mpg_gmres_params* p, int
     auto cleanup = [&]() {
         cudaStreamSynchronize(ctx->stream);
         if (A) mpg_csr_destroy(A);
-        cudaFree(row_map); cudaFree(inds); cudaFree(vals); cudaFree(b); cudaFree(x);
         cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); cudaEventDestroy(e3);
     };
-    MPG_CUDA_C(cudaMalloc(&row_map, sizeof(int) * (size_t)(nrows + 1)));
-    MPG_CUDA_C(cudaMalloc(&inds, sizeof(int) * (size_t)std::max<int64_t>(nnz, 1)));
-    MPG_CUDA_C(cudaMalloc(&vals, sizeof(double) * (size_t)std::max<int64_t>(nnz, 1)));
-    MPG_CUDA_C(cudaMalloc(&b, sizeof(double) * (size_t)std::max(nrows, 1)));
-    MPG_CUDA_C(cudaMalloc(&x, sizeof(double) * (size_t)std::max(nrows, 1)));
     MPG_CUDA_C(cudaEventRecord(e0, ctx->stream));
     MPG_CUDA_C(cudaMemcpyAsync(row_map, row_map_h, sizeof(int) * (size_t)(nrows + 1), cudaMemcpyHostToDevice, ctx->stream));
     MPG_CUDA_C(cudaMemcpyAsync(inds, inds_h, sizeof(int) * (size_t)nnz, cudaMemcpyHostToDevice, ctx->stream));
@@ -508,7 +554,8 @@ extern "C" int mpg_gmres_solve_host(mpg_ctx* ctx, const mpg_gmres_params* p, int
     MPG_CUDA_C(cudaMemcpyAsync(x, x_h, sizeof(double) * (size_t)nrows, cudaMemcpyHostToDevice, ctx->stream));
     MPG_CUDA_C(cudaEventRecord(e1, ctx->stream));
     MPG_TRY_C(mpg_csr_create(ctx, nrows, nrows, nnz, row_map, inds, &A));
-    MPG_TRY_C(mpg_gmres_solve(ctx, p, A, vals, nullptr, b, x, st, hist_inner, cap_inner, hist_outer, cap_outer));
+    MPG_TRY_C(cast_copy(ctx, nnz, vals, vals32));   // SparseMatrix<float>(A), gmres_perf_test.cpp:136
+    MPG_TRY_C(mpg_gmres_solve(ctx, p, A, vals, vals32, b, x, st, hist_inner, cap_inner, hist_outer, cap_outer));
     MPG_CUDA_C(cudaEventRecord(e2, ctx->stream));
     MPG_CUDA_C(cudaMemcpyAsync(x_h, x, sizeof(double) * (size_t)nrows, cudaMemcpyDeviceToHost, ctx->stream));
     MPG_CUDA_C(cudaEventRecord(e3, ctx->stream));

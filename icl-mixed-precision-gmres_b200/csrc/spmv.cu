@@ -265,7 +265,7 @@ extern "C" int mpg_residual_f64_cast_f32(mpg_ctx* ctx, const mpg_csr* A, const d
 namespace {
 template <class T>
 __global__ void rowabs_max_kernel(int nrows, const int* __restrict__ row_map, const T* __restrict__ vals, double* partials,
-                                  unsigned int* ticket, T* out) {
+                                  unsigned int* ticket, Epi epi) {
     T m = T(0);
     for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += gridDim.x * blockDim.x) {
         T s = T(0);
@@ -284,7 +284,7 @@ __global__ void rowabs_max_kernel(int nrows, const int* __restrict__ row_map, co
         if (threadIdx.x == 0) {
             double g = 0;
             for (unsigned b = 0; b < gridDim.x; ++b) g = max(g, __ldcg(partials + b));
-            *out = (T)g;
+            apply_epi<T>(epi, 0, g);
         }
     }
 }
@@ -294,8 +294,11 @@ __global__ void jacobi_diag_kernel(int nrows, const int* __restrict__ row_map, c
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nrows) return;
     const T alpha = *amax * (T)1.1920928955078125e-07f;  // numeric_limits<float>::epsilon(), types.hpp:416
+    // the diagonal entry: LoadMatrix-canonical rows always hold it (LoadMatrix.hpp:62-66).  types.hpp:424-427 scans
+    // for the first column >= i, which is the same entry on a sorted row; an equality scan also works on a
+    // partitioned slab whose remote columns are renumbered past the local ones.
     int j = row_map[i];
-    while (inds[j] < i) ++j;
+    while (inds[j] != i) ++j;
     const T v = vals[j];
     if (v >= 0) diag[i] = T(1) / ((v < alpha) ? alpha : v);
     else diag[i] = T(1) / ((v > -alpha) ? -alpha : v);
@@ -305,8 +308,10 @@ int jacobi_diag(mpg_ctx* ctx, const mpg_csr* A, const T* vals, T* diag) {
     if (A->nrows == 0) return MPG_OK;
     T* amax = reinterpret_cast<T*>(ctx->dscal + 8);
     const int grid = std::min<int>((int)cdiv(A->nrows, 256), ctx->num_sms * 8);
-    rowabs_max_kernel<T><<<grid, 256, 0, ctx->stream>>>(A->nrows, A->row_map, vals, ctx->partials, ctx->ticket, amax);
+    const Epi epi{EPI_MAX, amax, nullptr, 0.0, 0.0, dist_raw(ctx)};
+    rowabs_max_kernel<T><<<grid, 256, 0, ctx->stream>>>(A->nrows, A->row_map, vals, ctx->partials, ctx->ticket, epi);
     MPG_CHECK_LAUNCH(ctx);
+    MPG_TRY(dist_finish_reduction(ctx, epi, 1, (int)sizeof(T)));
     jacobi_diag_kernel<T><<<(int)cdiv(A->nrows, 256), 256, 0, ctx->stream>>>(A->nrows, A->row_map, A->inds, vals, amax, diag);
     MPG_CHECK_LAUNCH(ctx);
     return MPG_OK;

@@ -1,0 +1,129 @@
+"""Host-side plumbing of the multi-GPU path (one process per GPU, torch.distributed for rendezvous and set-up only).
+
+build_partition() turns a global CSR into this rank's slab + halo plan with torch tensor ops (any device, so the
+world_size-2 gloo tests exercise exactly this code on CPU); the index sets it produces are the bit-exact artefacts
+defined by the oracle: rows [floor(r n/P), floor((r+1) n/P)), local columns -> c - lo, remote columns
+-> n_local + rank in the ascending list of distinct remote globals.  DistContext hands the plan and an NCCL
+communicator to the C library; after attach the solver's reductions are all-reduced and SpMV inputs are halo-filled."""
+import ctypes as C
+
+from .binding import Context, CSR, _ptr
+
+
+def bounds(n, world):
+    return [(r * n) // world for r in range(world + 1)]
+
+
+class Partition:
+    """this rank's share of a 1-D row-partitioned CSR matrix"""
+
+    def __init__(self, n_global, rank, world, row_map, inds, vals, halo_cols, peers):
+        self.n_global, self.rank, self.world = n_global, rank, world
+        self.row_map, self.inds, self.vals = row_map, inds, vals      # local slab, columns renumbered [local | halo]
+        self.halo_cols = halo_cols                                    # int64 global ids, ascending
+        self.peers = peers                                            # list of dict(rank, send_idx, recv_offset, recv_count)
+        b = bounds(n_global, world)
+        self.lo, self.hi = b[rank], b[rank + 1]
+        self.n_local, self.n_halo = self.hi - self.lo, int(halo_cols.numel())
+
+
+def local_slab(row_map, inds, vals, n_global, rank, world):
+    """(row_map_local, local_inds, vals_local, halo_cols) for rank `rank`; pure tensor ops on the inputs' device"""
+    import torch
+    b = bounds(n_global, world)
+    lo, hi = b[rank], b[rank + 1]
+    p0, p1 = int(row_map[lo]), int(row_map[hi])
+    rm = (row_map[lo:hi + 1] - row_map[lo]).to(torch.int32)
+    c = inds[p0:p1].to(torch.int64)
+    remote = (c < lo) | (c >= hi)
+    halo_cols = torch.unique(c[remote])  # sorted ascending, distinct
+    li = torch.where(remote, (hi - lo) + torch.searchsorted(halo_cols, c), c - lo).to(torch.int32)
+    return rm.contiguous(), li.contiguous(), vals[p0:p1].contiguous(), halo_cols
+
+
+def build_partition(row_map, inds, vals, n_global, rank, world, group=None):
+    """slab + halo plan.  Collective: every rank calls it (the send lists come from the peers' halo lists)."""
+    import torch
+    import torch.distributed as dist
+    rm, li, v, halo_cols = local_slab(row_map, inds, vals, n_global, rank, world)
+    b = bounds(n_global, world)
+    owner_lo = torch.tensor(b[:-1], dtype=torch.int64, device=halo_cols.device)
+    owner = torch.searchsorted(owner_lo, halo_cols, right=True) - 1 if halo_cols.numel() else halo_cols
+    need = {}
+    for q in range(world):
+        if q == rank or halo_cols.numel() == 0:
+            continue
+        sel = halo_cols[owner == q]
+        if sel.numel():
+            need[q] = (sel - b[q]).to(torch.int32).cpu().numpy()   # row indices local to the owner, ascending
+    if world > 1:
+        all_need = [None] * world
+        dist.all_gather_object(all_need, need, group=group)
+    else:
+        all_need = [need]
+    peers = []
+    recv_off = 0
+    for q in range(world):
+        if q == rank:
+            continue
+        send = all_need[q].get(rank) if all_need[q] else None
+        recv_cnt = len(need[q]) if q in need else 0
+        if send is None and recv_cnt == 0:
+            continue
+        send_idx = torch.from_numpy(send).to(halo_cols.device) if send is not None else torch.empty(0, dtype=torch.int32, device=halo_cols.device)
+        peers.append(dict(rank=q, send_idx=send_idx, recv_offset=recv_off, recv_count=recv_cnt))
+        recv_off += recv_cnt
+    assert recv_off == halo_cols.numel()
+    return Partition(n_global, rank, world, rm, li, v, halo_cols, peers)
+
+
+class DistContext:
+    """NCCL communicator + halo plan attached to a Context (C ABI: mpg_dist_*)."""
+
+    def __init__(self, ctx: Context, rank, world, group=None):
+        import torch
+        import torch.distributed as dist
+        self.ctx, self.rank, self.world = ctx, rank, world
+        self.h = C.c_void_p()
+        idbuf = (C.c_ubyte * 128)()
+        if rank == 0:
+            ctx._chk(ctx.L.mpg_nccl_unique_id(idbuf))
+        payload = [bytes(idbuf)]
+        if world > 1:
+            dist.broadcast_object_list(payload, src=0, group=group)
+        idbuf = (C.c_ubyte * 128).from_buffer_copy(payload[0])
+        ctx._chk(ctx.L.mpg_dist_create(ctx.h, idbuf, C.c_int(rank), C.c_int(world), C.byref(self.h)))
+        self._keep = None
+
+    def set_partition(self, part: Partition):
+        ctx = self.ctx
+        n = len(part.peers)
+        ranks = (C.c_int * max(n, 1))(*[p["rank"] for p in part.peers])
+        scount = (C.c_int64 * max(n, 1))(*[int(p["send_idx"].numel()) for p in part.peers])
+        sptr = (C.c_void_p * max(n, 1))(*[p["send_idx"].data_ptr() for p in part.peers])
+        roff = (C.c_int64 * max(n, 1))(*[p["recv_offset"] for p in part.peers])
+        rcount = (C.c_int64 * max(n, 1))(*[p["recv_count"] for p in part.peers])
+        ctx._chk(ctx.L.mpg_dist_set_partition(ctx.h, self.h, C.c_int64(part.n_global), C.c_int64(part.n_local), C.c_int64(part.n_halo), C.c_int(n),
+                                              ranks, scount, sptr, roff, rcount))
+        self._keep = part  # the send index tensors must outlive the plan
+
+    def attach(self):
+        self.ctx._chk(self.ctx.L.mpg_ctx_attach_dist(self.ctx.h, self.h))
+
+    def detach(self):
+        self.ctx._chk(self.ctx.L.mpg_ctx_attach_dist(self.ctx.h, None))
+
+    def halo_exchange(self, x_ext):
+        import torch
+        fn = self.ctx.L.mpg_halo_exchange_f32 if x_ext.dtype == torch.float32 else self.ctx.L.mpg_halo_exchange_f64
+        self.ctx._chk(fn(self.ctx.h, _ptr(x_ext)))
+
+    def close(self):
+        if self.h:
+            self.detach()
+            self.ctx.L.mpg_dist_destroy(self.h)
+            self.h = None
+
+
+def local_csr(ctx: Context, part: Partition):
+    return CSR(ctx, part.row_map, part.inds, ncols=part.n_local + part.n_halo)

@@ -195,6 +195,26 @@ int mpg_gen_powerlaw_fill(mpg_ctx*, int64_t n, uint64_t seed, int lmin, int gmax
 /* gmres_perf_test.cpp:39-51 rand_vect (host; libstdc++ mt19937 + uniform_real_distribution<float>) */
 int mpg_rand_vect_host(int64_t n, uint32_t seed, double* out_host);
 
+/* ---- multi-GPU: one process per GPU, 1-D row blocks (new functionality) --------------------------
+ * NCCL is loaded at run time.  Rank 0 makes a 128-byte unique id, the host plumbing (torch.distributed) broadcasts it,
+ * every rank creates its communicator, describes its halo plan and attaches it to its context.  From then on the
+ * reductions behind dot / nrm2 / gemv-T / add_vector are all-reduced over the ranks, and mpg_halo_exchange fills the
+ * halo tail of an SpMV input; mpg_gmres_solve takes the LOCAL slab (nrows = n_local, ncols = n_local + n_halo). */
+typedef struct mpg_dist mpg_dist;
+int mpg_nccl_unique_id(void* id128_host);
+int mpg_dist_create(mpg_ctx*, const void* id128_host, int rank, int world, mpg_dist** out);
+int mpg_dist_destroy(mpg_dist* d);
+/* peers: for each neighbour, the ascending local row indices it needs from us (device array, not owned) and the
+ * [offset, offset+count) range of our halo that it owns. */
+int mpg_dist_set_partition(mpg_ctx*, mpg_dist* d, int64_t n_global, int64_t n_local, int64_t n_halo, int npeers, const int* peer_ranks_host,
+                           const int64_t* send_counts_host, const int* const* send_idx_dev_ptrs_host, const int64_t* recv_offsets_host,
+                           const int64_t* recv_counts_host);
+int mpg_ctx_attach_dist(mpg_ctx*, mpg_dist* d); /* NULL detaches */
+int mpg_dist_info(const mpg_dist* d, int* rank, int* world, int64_t* n_global, int64_t* n_local, int64_t* n_halo);
+int mpg_halo_exchange_f32(mpg_ctx*, float* x_ext);  /* x_ext = [n_local owned | n_halo halo slots] */
+int mpg_halo_exchange_f64(mpg_ctx*, double* x_ext);
+int mpg_allreduce_sum_f64(mpg_ctx*, double* buf_dev, int64_t count);
+
 /* ---- 1-D row partition (new functionality, host-side, bit-exact vs the oracle) ------------- */
 int mpg_partition_bounds(int64_t n, int P, int64_t* bounds_host /* P+1 */);
 /* halo_cols_host/local_inds_host may be NULL to query sizes.  Returns the halo count through *n_halo. */

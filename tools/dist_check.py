@@ -1,0 +1,79 @@
+"""torchrun target: multi-rank correctness of the partitioned path against a single-GPU solve of the same system."""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import torch
+import torch.distributed as dist
+
+import gmres_b200 as g
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dev = f"cuda:{local}"
+dist.init_process_group("nccl", device_id=torch.device(dev))
+ctx = g.Context(local)
+report = {"ok": True, "cases": []}
+for spec, rlen, orth in [("cd27:32", 60, "cgsr"), ("lap2d:200", 50, "cgsr"), ("powerlaw:20000", 30, "cgsr"), ("cd27:24", 40, "mgs"), ("cd27:24", 40, "cgs")]:
+    rm, ind, val = ctx.gen(spec)
+    n = rm.numel() - 1
+    xt_host = ctx.rand_vect(n, 42)
+    xt = torch.from_numpy(xt_host).to(dev)
+    # single-GPU reference on every rank (detached)
+    A = g.CSR(ctx, rm, ind)
+    b = torch.zeros(n, dtype=torch.float64, device=dev)
+    ctx.spmv(A, val, 1.0, xt, 0.0, b)
+    x1 = torch.zeros(n, dtype=torch.float64, device=dev)
+    kw = dict(mode="mixed", orth=orth, rlen=rlen, tol=1e-9, max_restarts=300)
+    r1 = ctx.gmres(A, val, b, x1, **kw)
+    # partitioned
+    part = g.dist.build_partition(rm, ind, val, n, rank, world)
+    dctx = g.dist.DistContext(ctx, rank, world)
+    dctx.set_partition(part)
+    Al = g.dist.local_csr(ctx, part)
+    dctx.attach()
+    # halo exchange delivers exactly the remote entries
+    xe = torch.cat([xt[part.lo:part.hi], torch.zeros(part.n_halo, dtype=torch.float64, device=dev)])
+    dctx.halo_exchange(xe)
+    halo_ok = bool(torch.equal(xe[part.n_local:], xt[part.halo_cols]))
+    xe32 = xe.float(); xe32[part.n_local:] = 0
+    dctx.halo_exchange(xe32)
+    halo_ok = halo_ok and bool(torch.equal(xe32[part.n_local:], xt[part.halo_cols].float()))
+    # distributed reductions equal the global ones to rounding
+    nb = ctx.nrm2(b[part.lo:part.hi].contiguous())
+    dctx.detach(); nb1 = ctx.nrm2(b); dctx.attach()
+    bl = b[part.lo:part.hi].contiguous()
+    xl = torch.zeros(part.n_local, dtype=torch.float64, device=dev)
+    r2 = ctx.gmres(Al, part.vals, bl, xl, **kw)
+    dctx.detach()
+    # gather x and compare
+    xs = [torch.zeros(int(c), dtype=torch.float64, device=dev) for c in np.diff(g.dist.bounds(n, world))]
+    dist.all_gather(xs, xl)
+    xg = torch.cat(xs)
+    err1, err2 = float((x1 - xt).norm()), float((xg - xt).norm())
+    m = min(len(r1["hist_inner"]), len(r2["hist_inner"]))
+    h1, h2 = r1["hist_inner"][:m], r2["hist_inner"][:m]
+    live = h1 >= 1e-4 * h1[0]
+    dev_hist = float((np.abs(h1 - h2) / h1)[live].max())
+    # replicated scalars identical on all ranks
+    t = torch.tensor(list(r2["hist_inner"][:50]) + [r2["total_iters"], r2["total_restarts"]], dtype=torch.float64, device=dev)
+    tmax, tmin = t.clone(), t.clone()
+    dist.all_reduce(tmax, op=dist.ReduceOp.MAX); dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+    replicated = bool(torch.equal(tmax, tmin))
+    env = 0.5 if spec.startswith("powerlaw") else 5e-3
+    ok = (halo_ok and replicated and r1["status"] == r2["status"] == 1 and r1["total_iters"] == r2["total_iters"] and r1["total_restarts"] == r2["total_restarts"]
+          and dev_hist <= env and abs(nb - nb1) <= 1e-12 * nb1 and err2 <= 4 * err1 + 1e-10)
+    report["cases"].append(dict(spec=spec, orth=orth, ok=ok, halo_ok=halo_ok, replicated=replicated, iters=(r1["total_iters"], r2["total_iters"]),
+                                dev_hist=dev_hist, err=(err1, err2), n_halo=part.n_halo, peers=len(part.peers)))
+    report["ok"] = report["ok"] and ok
+    dctx.close()
+ok_t = torch.tensor([1.0 if report["ok"] else 0.0], device=dev)
+dist.all_reduce(ok_t, op=dist.ReduceOp.MIN)
+report["ok"] = bool(ok_t.item() == 1.0)
+if rank == 0:
+    print(json.dumps(report), flush=True)
+dist.destroy_process_group()
+sys.exit(0 if report["ok"] else 1)
