@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(SPMV_THREADS) spmv_tile_kernel(int nrows, int6
                                                                   const int* __restrict__ inds, const T* __restrict__ vals,
                                                                   const int* __restrict__ tile_row, const T* __restrict__ x,
                                                                   T alpha, T beta, const T* y_in, T* y_out, float* out32,
-                                                                  T* carry_in, T* carry_out) {
+                                                                  T* carry_in, T* carry_out, int vec_ok) {
     __shared__ T prod[SPMV_TILE];
     __shared__ int rm_s[SPMV_TILE + 2];
 
@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(SPMV_THREADS) spmv_tile_kernel(int nrows, int6
     // ---- stream indices + values, gather x, form products ----
     constexpr int VPT = 16 / sizeof(T);          // values per 16-byte load (4 fp32 / 2 fp64)
     const int tid = threadIdx.x;
-    if (cnt == SPMV_TILE) {
+    if (cnt == SPMV_TILE && vec_ok) {
         const int4* ip = reinterpret_cast<const int4*>(inds + base);
         int4 c0 = ldg_stream(ip + tid);
         int4 c1 = ldg_stream(ip + SPMV_THREADS + tid);
@@ -175,8 +175,10 @@ int launch_spmv(mpg_ctx* ctx, const mpg_csr* A, const T* vals, T alpha, const T*
     const double bytes = (double)A->nnz * (s_ + 4) + 4 * (n_ + 1) + n_ * s_ + (y_out ? n_ * s_ : 0) + (beta != T(0) ? n_ * s_ : 0) + (out32 ? 4 * n_ : 0);
     ProfScope prof(ctx, sizeof(T) == 4 ? MPG_PROF_SPMV_F32 : MPG_PROF_SPMV_F64, bytes);
     if (A->ntiles > 0) {
+        // 16-byte vector loads need aligned index / value arrays; sub-views fall back to scalar streaming loads
+        const int vec_ok = ((reinterpret_cast<uintptr_t>(A->inds) | reinterpret_cast<uintptr_t>(vals)) & 15) == 0;
         spmv_tile_kernel<T><<<A->ntiles, SPMV_THREADS, 0, ctx->stream>>>(A->nrows, A->nnz, A->row_map, A->inds, vals, A->tile_row, x,
-                                                                        alpha, beta, y_in, y_out, out32, carry_in, carry_out);
+                                                                        alpha, beta, y_in, y_out, out32, carry_in, carry_out, vec_ok);
         MPG_CHECK_LAUNCH(ctx);
         if (A->ntiles > 1) {
             spmv_fixup_kernel<T><<<(int)cdiv(A->ntiles - 1, 256), 256, 0, ctx->stream>>>(A->nrows, A->nnz, A->ntiles, A->row_map, A->tile_row,

@@ -38,7 +38,7 @@ def local_slab(row_map, inds, vals, n_global, rank, world):
     remote = (c < lo) | (c >= hi)
     halo_cols = torch.unique(c[remote])  # sorted ascending, distinct
     li = torch.where(remote, (hi - lo) + torch.searchsorted(halo_cols, c), c - lo).to(torch.int32)
-    return rm.contiguous(), li.contiguous(), vals[p0:p1].contiguous(), halo_cols
+    return rm.contiguous(), li.contiguous(), vals[p0:p1].clone(), halo_cols   # clone: a slice keeps the parent's (possibly odd) offset
 
 
 def build_partition(row_map, inds, vals, n_global, rank, world, group=None):

@@ -1,0 +1,148 @@
+// types_b200.hpp — what a maintainer of iamsonderr/icl-mixed-precision-gmres adds next to types_cuda.hpp to get a
+// `B200` device backed by libmpgmres_b200.so.  It is written against the REFERENCE's own headers
+// (types.hpp, kernels.hpp, Orthogonalization.hpp) and Kokkos, exactly like types_cuda.hpp (types_cuda.hpp:1-255):
+//   * B200Backend          replaces CudaLibSingleton            types_cuda.hpp:9-36   (one mpg_ctx per process)
+//   * struct B200          replaces struct Cuda                 types_cuda.hpp:39-44
+//   * SparseMatrix<T,B200> replaces SparseMatrix<T,Cuda>        types_cuda.hpp:47-152 (+ the SpMV plan, shared between
+//                                                               the fp64 matrix and its fp32 copy like row_map/inds)
+//   * ILU<T,B200>, ILU_Jacobi_handles<B200>: declared so the harness compiles; out of scope
+// The operator surface itself is specialised in kernels_b200.cpp.
+#ifndef TYPES_B200_HPP
+#define TYPES_B200_HPP
+
+#include <cstdio>
+#include <cstdlib>
+#include <memory>
+
+#include "kernels.hpp"
+#include "Orthogonalization.hpp"
+#include "mpgmres_b200.h"
+
+struct B200Backend {
+    mpg_ctx* ctx = nullptr;
+    B200Backend() {
+        if (mpg_ctx_create(0, &ctx) != MPG_OK) Kokkos::abort("mpgmres_b200 initialization failed (no CUDA device?)\n");
+        // Kokkos::Cuda's default instance and the reference's cuBLAS/cuSPARSE handles run on the legacy default stream
+        mpg_ctx_set_stream(ctx, nullptr);
+    }
+    static B200Backend& singleton() {
+        static B200Backend s;
+        return s;
+    }
+    static mpg_ctx* context() { return singleton().ctx; }
+    static void check(int rc, const char* what) {
+        if (rc != MPG_OK) {
+            std::fprintf(stderr, "mpgmres_b200: %s failed (%d): %s\n", what, rc, mpg_last_error(singleton().ctx));
+            std::abort();
+        }
+    }
+};
+#define B200_CHECK(expr) B200Backend::check((expr), #expr)
+
+struct B200 {
+public:
+    typedef Kokkos::CudaSpace memory_space;
+    typedef Kokkos::Cuda execution_space;
+};
+
+template <class Type>
+class SparseMatrix<Type, B200> {
+private:
+    std::shared_ptr<mpg_csr> plan_;  // SpMV plan over (row_map_, inds_); shared with precision-cast copies
+    bool transposed_ = false;
+
+    void create_plan() {
+        mpg_csr* p = nullptr;
+        B200_CHECK(mpg_csr_create(B200Backend::context(), m_, n_, nnz_, row_map_.data(), inds_.data(), &p));
+        plan_ = std::shared_ptr<mpg_csr>(p, [](mpg_csr* q) { mpg_csr_destroy(q); });
+    }
+
+    template <class, class>
+    friend class SparseMatrix;
+
+public:
+    int m_, n_, nnz_;
+
+    Kokkos::View<int*, typename B200::memory_space> row_map_;
+    Kokkos::View<int*, typename B200::memory_space> inds_;
+    Kokkos::View<Type*, typename B200::memory_space> vals_;
+
+    SparseMatrix(int m, int n, Kokkos::View<int*, typename B200::memory_space> row_map, Kokkos::View<int*, typename B200::memory_space> inds,
+                 Kokkos::View<Type*, typename B200::memory_space> vals)
+        : m_(m), n_(n), nnz_(inds.extent(0)), row_map_(row_map), inds_(inds), vals_(vals) {
+        create_plan();
+    }
+
+    // precision cast: shares row_map / inds / plan, converts the values (types_cuda.hpp:82-101)
+    template <class OldType>
+    SparseMatrix(SparseMatrix<OldType, B200> old)
+        : plan_(old.plan_), transposed_(old.is_transposed()), m_(old.m_), n_(old.n_), nnz_(old.inds_.extent(0)), row_map_(old.row_map_),
+          inds_(old.inds_), vals_("vals", old.vals_.extent(0)) {
+        copy(Vect<OldType, B200>(old.vals_), Vect<Type, B200>(vals_));
+    }
+
+    // host -> device (types_cuda.hpp:103-114)
+    template <class OldDevice>
+    SparseMatrix(SparseMatrix<Type, OldDevice> old)
+        : transposed_(old.is_transposed()), m_(old.nrows()), n_(old.ncols()), nnz_(old.inds_.extent(0)), row_map_("row_map", old.row_map_.extent(0)),
+          inds_("inds", old.inds_.extent(0)), vals_("vals", old.vals_.extent(0)) {
+        Kokkos::deep_copy(row_map_, old.row_map_);
+        Kokkos::deep_copy(inds_, old.inds_);
+        Kokkos::deep_copy(vals_, old.vals_);
+        create_plan();
+    }
+
+    int nrows() const { return m_; }
+    int ncols() const { return n_; }
+    int nnz() const { return nnz_; }
+    int* row_map_data() { return row_map_.data(); }
+    int* inds_data() { return inds_.data(); }
+    Type* vals_data() { return vals_.data(); }
+    Vect<Type, B200> vals_vect() { return Vect<Type, B200>(vals_); }
+    const mpg_csr* plan() const { return plan_.get(); }
+    void set_transpose(bool new_trans) { this->transposed_ = new_trans; }  // only condest.cpp uses it (out of scope)
+    bool is_transposed() { return this->transposed_; }
+};
+
+// ILU(0) and its triangular solves are out of scope for this backend (cusparse csrilu02 / csrsv2 in the reference,
+// kernels_cuda.cpp:13-107,617-791; csrsv2 no longer exists in CUDA 12).  The types exist so gmres_perf_test.cpp compiles;
+// selecting --prec ilu / ilu_jacobi with this device aborts with a message.
+template <class Type>
+class ILU<Type, B200> : public LinearOperator<Type, B200> {
+public:
+    int n_ = 0, nnz_ = 0;
+    Kokkos::View<int*, typename B200::memory_space> row_map_;
+    Kokkos::View<int*, typename B200::memory_space> inds_;
+    Kokkos::View<Type*, typename B200::memory_space> vals_;
+    int n() const { return n_; }
+    int nnz() const { return nnz_; }
+    void apply(Vect<Type, B200>) { Kokkos::abort("ILU preconditioning is not provided by the B200 backend (use --prec identity or jacobi)\n"); }
+};
+template <>
+class ILU_Jacobi_handles<B200> {
+public:
+    template <class Type>
+    ILU_Jacobi_handles(const ILU_Jacobi<Type, B200>&) {}
+};
+
+// ---- specialisations of the header-inline generic operators (kernels.hpp:11-20,131-146) -------------------------------
+// declared here, before the driver uses them; defined in kernels_b200.cpp
+template <> void copy<double, float, B200>(Vect<double, B200> x, Vect<float, B200> y);
+template <> void copy<float, double, B200>(Vect<float, B200> x, Vect<double, B200> y);
+template <> void copy<float, float, B200>(Vect<float, B200> x, Vect<float, B200> y);
+template <> void copy<double, double, B200>(Vect<double, B200> x, Vect<double, B200> y);
+template <> void gdmv<float, B200>(float alpha, Vect<float, B200> diag, Vect<float, B200> x, float beta, Vect<float, B200> y);
+template <> void gdmv<double, B200>(double alpha, Vect<double, B200> diag, Vect<double, B200> x, double beta, Vect<double, B200> y);
+
+// ---- fused Arnoldi step behind the unchanged class API of Orthogonalization.hpp:51-60 ---------------------------------
+// (orthogonalise + norm + normalise in 3 passes over the basis and no host read-back of h(k+1,k))
+namespace Orthogonalization {
+template <> void GS<float, CGS_Kernel<float, B200>, B200>::add_vector(const size_t k, Vect<float, B200> w, MultiVect<float, B200> h);
+template <> void GS<float, MGS_Kernel<float, B200>, B200>::add_vector(const size_t k, Vect<float, B200> w, MultiVect<float, B200> h);
+template <> void GS<float, CGSR_Kernel<float, B200, 2>, B200>::add_vector(const size_t k, Vect<float, B200> w, MultiVect<float, B200> h);
+template <> void GS<double, CGS_Kernel<double, B200>, B200>::add_vector(const size_t k, Vect<double, B200> w, MultiVect<double, B200> h);
+template <> void GS<double, MGS_Kernel<double, B200>, B200>::add_vector(const size_t k, Vect<double, B200> w, MultiVect<double, B200> h);
+template <> void GS<double, CGSR_Kernel<double, B200, 2>, B200>::add_vector(const size_t k, Vect<double, B200> w, MultiVect<double, B200> h);
+}  // namespace Orthogonalization
+
+#endif  // TYPES_B200_HPP

@@ -197,6 +197,25 @@ def test_spmv(ctx, g, orc, spec, dt):
     np.testing.assert_array_equal(host(y1), host(y2))
 
 
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_spmv_unaligned_value_and_index_views(ctx, g, orc, dt):
+    """index / value arrays that are sub-views (not 16-byte aligned) take the scalar-load path: same results"""
+    import torch
+    rm, ind, val = orc.gen("cd27:18")
+    n = len(rm) - 1
+    x = _rng(3).standard_normal(n).astype(dt)
+    v = val.astype(dt)
+    xd = dev(x)
+    A0 = g.CSR(ctx, dev(rm), dev(ind))
+    y0 = torch.empty_like(xd); ctx.spmv(A0, dev(v), 1.0, xd, 0.0, y0)
+    ind_pad = dev(np.concatenate([[0], ind]).astype(np.int32))[1:]      # data_ptr offset by 4 bytes
+    val_pad = dev(np.concatenate([[0], v]).astype(dt))[1:]              # offset by 4 / 8 bytes
+    assert ind_pad.data_ptr() % 16 != 0
+    A1 = g.CSR(ctx, dev(rm), ind_pad)
+    y1 = torch.empty_like(xd); ctx.spmv(A1, val_pad, 1.0, xd, 0.0, y1)
+    np.testing.assert_array_equal(host(y1), host(y0))
+
+
 @pytest.mark.parametrize("spec", ["lap2d:50", "cd27:15", "powerlaw:30000"])
 def test_fused_residual_cast(ctx, g, orc, spec):
     """r = b - A x (fp64) and w = (float) r in one kernel == the reference's copy + spmv + copy (gmres.cpp:173-175)"""
