@@ -37,7 +37,8 @@ def parse():
     ap.add_argument("--tol", type=float, default=1e-6)
     ap.add_argument("--orth", default="cgsr")
     ap.add_argument("--max-restarts", type=int, default=1000)
-    ap.add_argument("--cpu-sample", default="cd27:96", help="bounded sample of the workload for the CPU baseline")
+    ap.add_argument("--cpu-sample", default="auto", help="bounded sample of the workload for the CPU baseline (auto: cd27:128 with "
+                    "oracle/_ref's MKL build, cd27:96 with the slower oracle port)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=2)
@@ -106,6 +107,8 @@ def cpu_reference_run(sample, rlen, tol, orth, max_restarts, full_rows):
         have_ref = oracle_ref.available()
     except Exception:
         have_ref = False
+    if sample == "auto":
+        sample = "cd27:128" if have_ref else "cd27:96"
     rm, ind, val = orc.gen(sample)
     n = len(rm) - 1
     xt = orc.rand_vect(n, 42)

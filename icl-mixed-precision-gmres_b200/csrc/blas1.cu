@@ -81,6 +81,7 @@ extern "C" int mpg_set_tuning(mpg_ctx* ctx, const char* key, int value) {
     if (!ctx || !key) return MPG_ERR_ARG;
     const std::string k(key);
     if (k == "spmv_ctas_per_sm") ctx->tune.spmv_ctas_per_sm = value;
+    else if (k == "spmv_variant") ctx->tune.spmv_variant = value;
     else if (k == "vpass_stages") ctx->tune.vpass_stages = value;
     else if (k == "fuse_min_cols") ctx->tune.fuse_min_cols = value;
     else if (k == "gemvt_rb") ctx->tune.gemvt_rb = value;
