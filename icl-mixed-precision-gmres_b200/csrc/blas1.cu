@@ -82,6 +82,7 @@ extern "C" int mpg_set_tuning(mpg_ctx* ctx, const char* key, int value) {
     const std::string k(key);
     if (k == "spmv_ctas_per_sm") ctx->tune.spmv_ctas_per_sm = value;
     else if (k == "spmv_variant") ctx->tune.spmv_variant = value;
+    else if (k == "dist_peer_reduce") ctx->tune.dist_peer_reduce = value;
     else if (k == "vpass_stages") ctx->tune.vpass_stages = value;
     else if (k == "fuse_min_cols") ctx->tune.fuse_min_cols = value;
     else if (k == "gemvt_rb") ctx->tune.gemvt_rb = value;
@@ -224,12 +225,7 @@ __global__ void __launch_bounds__(RED_THREADS) reduce_kernel(int64_t n, const T*
         for (int w = 0; w < RED_THREADS / 32; ++w) t += wsum[w];
         partials[blockIdx.x] = t;
     }
-    if (grid_last_block(ticket)) {
-        if (threadIdx.x < 32) {
-            const double t = reduce_partials_column(partials, 1, gridDim.x, 0);
-            if (threadIdx.x == 0) apply_epi<T>(epi, 0, t);
-        }
-    }
+    if (grid_last_block(ticket)) last_block_finish<T>(epi, partials, 1, gridDim.x, 1);
 }
 
 template <class T, bool IS_NRM2>
@@ -238,7 +234,7 @@ int launch_reduce(mpg_ctx* ctx, int64_t n, const T* x, const T* y, T* out_dev) {
     int grid = (int)std::min<int64_t>(std::max<int64_t>(1, cdiv(n, per_block)), (int64_t)ctx->num_sms * ctx->tune.red_ctas_per_sm);
     grid = std::min(grid, kMaxPartBlocks);
     ProfScope prof(ctx, MPG_PROF_REDUCE, (double)n * sizeof(T) * (IS_NRM2 ? 1 : 2));
-    const Epi epi{IS_NRM2 ? EPI_NRM2 : EPI_DOT, out_dev, nullptr, 0.0, 0.0, dist_raw(ctx)};
+    const Epi epi = make_epi(ctx, IS_NRM2 ? EPI_NRM2 : EPI_DOT, out_dev, nullptr, 0.0, 0.0);
     reduce_kernel<T, IS_NRM2><<<grid, RED_THREADS, 0, ctx->stream>>>(n, x, y, ctx->partials, ctx->ticket, epi);
     MPG_CHECK_LAUNCH(ctx);
     return dist_finish_reduction(ctx, epi, 1, (int)sizeof(T));

@@ -31,6 +31,7 @@ struct Tuning {
     int gemvn_ctas_per_sm = 4;
     int red_ctas_per_sm = 4;
     int use_graph = 0;
+    int dist_peer_reduce = 1; // multi-GPU reductions inside the kernels over peer memory (0: NCCL all-reduce + epilogue kernel)
 };
 
 }  // namespace mpg
@@ -128,7 +129,9 @@ inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // dist.cu: all-reduce `count` raw sums over the ranks and apply the epilogue (no-op when no communicator is attached)
 int dist_finish_reduction(mpg_ctx* ctx, const struct Epi& e, int count, int tbytes);
-inline double* dist_raw(mpg_ctx* ctx);
+// epilogue descriptor for the next reducing kernel of this context: plain on one GPU; with a communicator attached it
+// carries either the peer-memory mailboxes (default) or the raw buffer for the NCCL path
+struct Epi make_epi(mpg_ctx* ctx, int kind, void* p0, void* p1, double alpha, double beta);
 
 // RAII timer for one kernel (or a kernel + its fix-up) of class `cls`, carrying its ALGORITHMIC bytes
 // (compulsory traffic).  No-op unless mpg_prof_enable(ctx, 1).
@@ -224,13 +227,31 @@ __device__ __forceinline__ bool grid_last_block(unsigned int* ticket) {
 // Epilogue of a grid-wide reduction: what happens to the reduced value(s).  On one GPU the last CTA applies it in the
 // reducing kernel itself; with a communicator attached (dist.cu) the kernel stores the raw local sums instead, they are
 // all-reduced over the ranks (fp64), and epilogue_kernel applies the same function afterwards.
+// In-kernel all-reduce over NVLink peer memory (multi-GPU, dist.cu): every rank owns a mailbox
+// [slot][source rank][kMaxCols+8] doubles + one 64-bit flag per (slot, source); the peers' mailboxes are mapped into
+// this process (CUDA IPC).  The last CTA of a reducing kernel pushes its local sums into every rank's mailbox with
+// plain stores over NVLink, publishes a sequence number (release, system scope), waits for the other ranks' flags
+// (acquire) and adds the contributions in rank order - identical bits on every rank - before running the epilogue.
+// One kernel = local reduction + cross-GPU combine + epilogue; no NCCL launch, no separate epilogue launch.
+constexpr int kMaxPeers = 8;
+constexpr int kMboxSlots = 4;
+constexpr int kMboxStride = 256 + 8;
+struct PeerComm {
+    int world = 0;   // 0: disabled
+    int rank = 0;
+    unsigned long long seq = 0;
+    double* mbox[kMaxPeers];
+    unsigned long long* flag[kMaxPeers];
+};
+
 enum EpiKind { EPI_DOT = 0, EPI_NRM2 = 1, EPI_COEF = 2, EPI_COEF_ACCUM = 3, EPI_NORM_INV = 4, EPI_GEMVT = 5, EPI_MAX = 6 };
 struct Epi {
     int kind;
     void* p0;      // DOT/NRM2/MAX: out | COEF*: coef_out | NORM_INV: norm_out | GEMVT: y
     void* p1;      // COEF*: hcol | NORM_INV: inv_out
     double alpha, beta;
-    double* raw;   // non-null: store the raw fp64 sums here and skip the epilogue (multi-GPU)
+    double* raw;   // non-null: store the raw fp64 sums here and skip the epilogue (multi-GPU through NCCL)
+    PeerComm peer; // world > 1: combine over peer memory inside the kernel (multi-GPU, default)
 };
 template <class T>
 __device__ __forceinline__ void apply_epi(const Epi& e, int j, double s) {
@@ -256,6 +277,55 @@ __device__ __forceinline__ double reduce_partials_column(const double* partials,
     return warp_sum(acc);
 }
 
-inline double* dist_raw(mpg_ctx* ctx) { return ctx->dist ? ctx->red_raw : nullptr; }
+// Called by ALL threads of the last CTA with the `count` locally reduced values in shared memory: cross-GPU combine
+// over peer memory when a PeerComm is attached, then the epilogue.
+template <class T>
+__device__ __forceinline__ void finish_reduction(const Epi& e, int count, double* red_s) {
+    if (e.peer.world > 1) {
+        const int P = e.peer.world, r = e.peer.rank;
+        const int slot = (int)(e.peer.seq % kMboxSlots);
+        for (int idx = threadIdx.x; idx < count * P; idx += blockDim.x) {
+            const int q = idx / count, j = idx - q * count;
+            volatile double* dst = e.peer.mbox[q] + ((size_t)slot * P + r) * kMboxStride + j;
+            *dst = red_s[j];
+        }
+        __threadfence_system();
+        __syncthreads();
+        if ((int)threadIdx.x < P) {
+            unsigned long long* f = e.peer.flag[threadIdx.x] + slot * P + r;
+            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(e.peer.seq) : "memory");
+            const unsigned long long* mine = e.peer.flag[r] + slot * P + threadIdx.x;
+            unsigned long long v;
+            do {
+                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
+            } while (v < e.peer.seq);
+        }
+        __syncthreads();
+        for (int j = threadIdx.x; j < count; j += blockDim.x) {
+            const double* src = e.peer.mbox[r] + (size_t)slot * P * kMboxStride + j;
+            double t = __ldcv(src);
+            for (int q = 1; q < P; ++q) {
+                const double c = __ldcv(src + (size_t)q * kMboxStride);
+                t = (e.kind == EPI_MAX) ? fmax(t, c) : t + c;
+            }
+            red_s[j] = t;
+        }
+        __syncthreads();
+    }
+    for (int j = threadIdx.x; j < count; j += blockDim.x) apply_epi<T>(e, j, red_s[j]);
+}
+
+// last CTA: fixed-order sum of the per-CTA partials of `count` columns, then finish_reduction
+template <class T>
+__device__ __forceinline__ void last_block_finish(const Epi& e, const double* partials, int ldp, int nblocks, int count) {
+    __shared__ double red_s[kMaxCols + 8];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int j = wid; j < count; j += nw) {
+        const double sred = reduce_partials_column(partials, ldp, nblocks, j);
+        if (lane == 0) red_s[j] = sred;
+    }
+    __syncthreads();
+    finish_reduction<T>(e, count, red_s);
+}
 
 }  // namespace mpg

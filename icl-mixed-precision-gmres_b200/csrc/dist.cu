@@ -5,9 +5,13 @@
 //   * SpMV: the local slab's columns are renumbered [local | halo]; x lives in a buffer with the halo appended
 //     (the tail of each basis column), filled by mpg_halo_exchange: pack kernel (gather of the rows each peer needs)
 //     + grouped ncclSend/ncclRecv over NVLink, received straight into the halo tail.
-//   * dot / nrm2 / gemv-T / the fused passes: kernels store their raw fp64 local sums, one ncclAllReduce(sum, fp64) of
-//     <= 257 values combines them, and epilogue_kernel applies the same epilogue the single-GPU kernel applies in its
-//     last CTA (common.cuh Epi).  gemv-N / axpy / scal / casts are purely local.
+//   * dot / nrm2 / gemv-T / the fused passes: ONE kernel does the local reduction, the cross-GPU combine and the
+//     epilogue.  Its last CTA pushes the <= 257 local fp64 sums into every rank's mailbox with stores over NVLink peer
+//     memory (CUDA IPC mapped), publishes a sequence number, waits for the peers' and adds the contributions in rank
+//     order (common.cuh finish_reduction) - identical bits on all ranks, no collective launch, no epilogue launch.
+//     Fallback / comparison path (tuning knob dist_peer_reduce = 0, or more than 8 ranks): the kernel stores the raw
+//     sums, ncclAllReduce(sum, fp64) combines them and epilogue_kernel applies the epilogue.
+//     gemv-N / axpy / scal / casts are purely local.
 // NCCL is loaded at run time (dlopen "libnccl.so.2": the copy torch already mapped), so the library has no link-time
 // NCCL dependency and single-GPU use never touches it.
 #include <dlfcn.h>
@@ -90,6 +94,13 @@ struct mpg_dist {
     std::vector<Peer> peers;
     int64_t send_total = 0;
     void* send_buf = nullptr;              // send_total doubles
+    // peer-memory mailboxes for the in-kernel all-reduce (common.cuh PeerComm)
+    void* mbox_own = nullptr;              // [kMboxSlots][world][kMboxStride] doubles, then [kMboxSlots][world] u64 flags
+    void* mbox_map[kMaxPeers] = {nullptr}; // every rank's mailbox mapped into this process (own pointer for self)
+    bool peer_ready = false;
+    unsigned long long seq = 0;
+    size_t mbox_data_bytes() const { return sizeof(double) * (size_t)kMboxSlots * world * kMboxStride; }
+    size_t mbox_bytes() const { return mbox_data_bytes() + sizeof(unsigned long long) * (size_t)kMboxSlots * world; }
 };
 
 extern "C" int mpg_nccl_unique_id(void* id128) {
@@ -116,6 +127,9 @@ extern "C" int mpg_dist_destroy(mpg_dist* d) {
     if (!d) return MPG_OK;
     cudaSetDevice(d->device);
     if (d->comm && nccl().ok) nccl().CommDestroy(d->comm);
+    for (int q = 0; q < d->world && q < kMaxPeers; ++q)
+        if (d->mbox_map[q] && q != d->rank) cudaIpcCloseMemHandle(d->mbox_map[q]);
+    cudaFree(d->mbox_own);
     cudaFree(d->send_buf);
     delete d;
     return MPG_OK;
@@ -141,6 +155,34 @@ extern "C" int mpg_dist_set_partition(mpg_ctx* ctx, mpg_dist* d, int64_t n_globa
     return MPG_OK;
 }
 
+// ---- peer-memory mailboxes (CUDA IPC; one process per GPU) ---------------------------------------------------------------
+extern "C" int mpg_dist_mailbox_handle(mpg_ctx* ctx, mpg_dist* d, void* handle64) {
+    MPG_REQUIRE(ctx, d && handle64, "dist_mailbox_handle: bad argument");
+    MPG_REQUIRE(ctx, d->world <= kMaxPeers, "dist_mailbox_handle: at most 8 ranks");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    if (!d->mbox_own) {
+        MPG_CUDA(ctx, cudaMalloc(&d->mbox_own, d->mbox_bytes()));
+        MPG_CUDA(ctx, cudaMemset(d->mbox_own, 0, d->mbox_bytes()));
+    }
+    cudaIpcMemHandle_t h;
+    MPG_CUDA(ctx, cudaIpcGetMemHandle(&h, d->mbox_own));
+    memcpy(handle64, &h, sizeof(h));
+    return MPG_OK;
+}
+// handles: world x 64 bytes, in rank order (all-gathered by the host plumbing)
+extern "C" int mpg_dist_open_mailboxes(mpg_ctx* ctx, mpg_dist* d, const void* handles) {
+    MPG_REQUIRE(ctx, d && handles && d->mbox_own, "dist_open_mailboxes: bad argument");
+    for (int q = 0; q < d->world; ++q) {
+        if (q == d->rank) { d->mbox_map[q] = d->mbox_own; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, static_cast<const char*>(handles) + (size_t)q * 64, sizeof(h));
+        MPG_CUDA(ctx, cudaIpcOpenMemHandle(&d->mbox_map[q], h, cudaIpcMemLazyEnablePeerAccess));
+    }
+    d->peer_ready = true;
+    d->seq = 0;
+    return MPG_OK;
+}
+
 extern "C" int mpg_ctx_attach_dist(mpg_ctx* ctx, mpg_dist* d) {
     if (!ctx) return MPG_ERR_ARG;
     ctx->dist = (d && d->world > 1) ? d : nullptr;   // a single-rank communicator behaves exactly like no communicator
@@ -158,6 +200,24 @@ extern "C" int mpg_dist_info(const mpg_dist* d, int* rank, int* world, int64_t* 
 }
 
 namespace mpg {
+
+Epi make_epi(mpg_ctx* ctx, int kind, void* p0, void* p1, double alpha, double beta) {
+    Epi e{kind, p0, p1, alpha, beta, nullptr, PeerComm()};
+    mpg_dist* d = ctx->dist;
+    if (!d) return e;
+    if (d->peer_ready && ctx->tune.dist_peer_reduce) {
+        e.peer.world = d->world;
+        e.peer.rank = d->rank;
+        e.peer.seq = ++d->seq;   // every rank issues the same sequence of reductions
+        for (int q = 0; q < d->world; ++q) {
+            e.peer.mbox[q] = static_cast<double*>(d->mbox_map[q]);
+            e.peer.flag[q] = reinterpret_cast<unsigned long long*>(static_cast<char*>(d->mbox_map[q]) + d->mbox_data_bytes());
+        }
+    } else {
+        e.raw = ctx->red_raw;
+    }
+    return e;
+}
 
 int dist_finish_reduction(mpg_ctx* ctx, const Epi& e, int count, int tbytes) {
     if (!ctx->dist || !e.raw || count <= 0) return MPG_OK;

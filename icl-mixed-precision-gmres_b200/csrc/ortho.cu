@@ -191,12 +191,7 @@ vpass_kernel(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ C
             }
         }
     }
-    if (grid_last_block(ticket)) {
-        for (int j = wid; j < k1; j += NW + 1) {
-            const double sred = reduce_partials_column(partials, ldp, gridDim.x, j);
-            if (lane == 0) apply_epi<T>(epi, j, sred);
-        }
-    }
+    if (grid_last_block(ticket)) last_block_finish<T>(epi, partials, ldp, gridDim.x, k1);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -301,12 +296,7 @@ __global__ void __launch_bounds__(256) gemvn_kernel(int64_t n, int k1, const T* 
             for (int w = 0; w < 8; ++w) t += wsum[w];
             partials[blockIdx.x] = t;
         }
-        if (grid_last_block(ticket)) {
-            if (threadIdx.x < 32) {
-                const double t = reduce_partials_column(partials, 1, gridDim.x, 0);
-                if (threadIdx.x == 0) apply_epi<T>(epi, 0, t);   // h(k+1,k) = nrm2(w), 1/h_final in Type  Orthogonalization.hpp:55,59
-            }
-        }
+        if (grid_last_block(ticket)) last_block_finish<T>(epi, partials, 1, gridDim.x, 1);   // h(k+1,k) = nrm2(w), 1/h_final in Type  Orthogonalization.hpp:55,59
     }
 }
 
@@ -345,12 +335,7 @@ __global__ void __launch_bounds__(256) gemvt_kernel(int64_t n, int ncols, const 
         }
         __syncthreads();
     }
-    if (grid_last_block(ticket)) {
-        for (int j = wid; j < ncols; j += 8) {
-            const double s = reduce_partials_column(partials, ldp, gridDim.x, j);
-            if (lane == 0) apply_epi<T>(epi, j, s);
-        }
-    }
+    if (grid_last_block(ticket)) last_block_finish<T>(epi, partials, ldp, gridDim.x, ncols);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -414,18 +399,13 @@ __global__ void __launch_bounds__(256, 2) gemvt_rb_kernel(int64_t n, int ncols, 
             __syncthreads();
         }
     }
-    if (grid_last_block(ticket)) {
-        for (int j = wid; j < ncols; j += 8) {
-            const double sred = reduce_partials_column(partials, ldp, nblocks, j);
-            if (lane == 0) apply_epi<T>(epi, j, sred);
-        }
-    }
+    if (grid_last_block(ticket)) last_block_finish<T>(epi, partials, ldp, nblocks, ncols);
 }
 
 template <class T>
 bool aligned16(const T* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-constexpr size_t kMaxDynSmem = 227 * 1024 - 1024;  // opt-in limit is 227 KB INCLUDING the kernel's static shared memory
+constexpr size_t kMaxDynSmem = 227 * 1024 - 4096;  // opt-in limit is 227 KB INCLUDING the kernel's static shared memory (~2.3 KB here)
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda link dependency)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -495,7 +475,7 @@ int launch_vpass_inst(mpg_ctx* ctx, int64_t n, int k1, const T* V, int64_t ldv, 
     // gemv-T pass runs forward, the fused update+gemv-T pass runs backward so it starts on the part of V the previous
     // pass left in L2, and the following gemv-N pass (forward) starts on the part this one leaves there
     const int reverse = (ctx->tune.vpass_serpentine && h_in) ? 1 : 0;
-    const Epi epi{fin == FIN_COEF_ACCUM ? EPI_COEF_ACCUM : EPI_COEF, coef_out, hcol, 0.0, 0.0, dist_raw(ctx)};
+    const Epi epi = make_epi(ctx, fin == FIN_COEF_ACCUM ? EPI_COEF_ACCUM : EPI_COEF, coef_out, hcol, 0.0, 0.0);
     kern<<<grid, 2 * TR + 32, smem, ctx->stream>>>(mapV, mapW, n, k1, w, h_in, stages, reverse, ctx->partials, kMaxCols + 8, ctx->ticket, epi);
     MPG_CHECK_LAUNCH(ctx);
     return dist_finish_reduction(ctx, epi, k1, (int)sizeof(T));
@@ -558,7 +538,7 @@ int gemvn(mpg_ctx* ctx, int64_t n, int k1, const T* M, int64_t ld, T alpha, cons
     grid = std::max(1, std::min(grid, kMaxPartBlocks));
     // gemv-N: k1 n s + 2 n s (read y, write y) [+ 16 n for the fp64 x read-modify-write of the mixed update]
     ProfScope prof(ctx, MPG_PROF_GEMVN, (double)k1 * n * sizeof(T) + (beta != T(0) ? 2.0 : 1.0) * n * sizeof(T) + (x64 ? 16.0 * n : 0.0));
-    const Epi epi{EPI_NORM_INV, norm_out, inv_out, 0.0, 0.0, want_norm ? dist_raw(ctx) : nullptr};
+    const Epi epi = want_norm ? make_epi(ctx, EPI_NORM_INV, norm_out, inv_out, 0.0, 0.0) : Epi{EPI_NORM_INV, norm_out, inv_out, 0.0, 0.0, nullptr, PeerComm()};
 #define MPG_GEMVN(VV, NN, XX)                                                                                                   \
     gemvn_kernel<T, VV, NN, XX><<<grid, 256, smem, ctx->stream>>>(n, k1, M, ld, alpha, x, beta, y, x64, ctx->partials, ctx->ticket, epi)
     if (vec_ok) {
@@ -591,7 +571,7 @@ int gemvt(mpg_ctx* ctx, int64_t n, int ncols, const T* M, int64_t ld, T alpha, c
         const int grid = std::min(nblocks, ctx->num_sms * 2);
         ProfScope prof(ctx, MPG_PROF_GEMVT, (double)ncols * n * sizeof(T) + (double)n * sizeof(T));
         constexpr int NC = sizeof(T) == 4 ? 16 : 8;
-        const Epi epi{EPI_GEMVT, y, nullptr, (double)alpha, (double)beta, dist_raw(ctx)};
+        const Epi epi = make_epi(ctx, EPI_GEMVT, y, nullptr, (double)alpha, (double)beta);
         gemvt_rb_kernel<T, NC><<<grid, 256, 0, ctx->stream>>>(n, ncols, M, ld, x, rpb, nblocks, ctx->partials, kMaxCols + 8, ctx->ticket, epi);
         MPG_CHECK_LAUNCH(ctx);
         return dist_finish_reduction(ctx, epi, ncols, (int)sizeof(T));
@@ -599,7 +579,7 @@ int gemvt(mpg_ctx* ctx, int64_t n, int ncols, const T* M, int64_t ld, T alpha, c
     int grid = (int)std::min<int64_t>(std::max<int64_t>(1, cdiv(n, 256 * 4)), (int64_t)ctx->num_sms * 4);
     grid = std::min(grid, kMaxPartBlocks);
     ProfScope prof(ctx, MPG_PROF_GEMVT, (double)ncols * n * sizeof(T) + (double)n * sizeof(T));
-    const Epi epi{EPI_GEMVT, y, nullptr, (double)alpha, (double)beta, dist_raw(ctx)};
+    const Epi epi = make_epi(ctx, EPI_GEMVT, y, nullptr, (double)alpha, (double)beta);
     gemvt_kernel<T, 8><<<grid, 256, 0, ctx->stream>>>(n, ncols, M, ld, alpha, x, beta, y, ctx->partials, kMaxCols + 8, ctx->ticket, epi);
     MPG_CHECK_LAUNCH(ctx);
     return dist_finish_reduction(ctx, epi, ncols, (int)sizeof(T));

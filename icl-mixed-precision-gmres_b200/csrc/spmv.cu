@@ -364,11 +364,14 @@ __global__ void rowabs_max_kernel(int nrows, const int* __restrict__ row_map, co
         partials[blockIdx.x] = (double)m;
     }
     if (grid_last_block(ticket)) {
+        __shared__ double gmax_s[1];
         if (threadIdx.x == 0) {
             double g = 0;
             for (unsigned b = 0; b < gridDim.x; ++b) g = max(g, __ldcg(partials + b));
-            apply_epi<T>(epi, 0, g);
+            gmax_s[0] = g;
         }
+        __syncthreads();
+        finish_reduction<T>(epi, 1, gmax_s);
     }
 }
 template <class T>
@@ -391,7 +394,7 @@ int jacobi_diag(mpg_ctx* ctx, const mpg_csr* A, const T* vals, T* diag) {
     if (A->nrows == 0) return MPG_OK;
     T* amax = reinterpret_cast<T*>(ctx->dscal + 8);
     const int grid = std::min<int>((int)cdiv(A->nrows, 256), ctx->num_sms * 8);
-    const Epi epi{EPI_MAX, amax, nullptr, 0.0, 0.0, dist_raw(ctx)};
+    const Epi epi = make_epi(ctx, EPI_MAX, amax, nullptr, 0.0, 0.0);
     rowabs_max_kernel<T><<<grid, 256, 0, ctx->stream>>>(A->nrows, A->row_map, vals, ctx->partials, ctx->ticket, epi);
     MPG_CHECK_LAUNCH(ctx);
     MPG_TRY(dist_finish_reduction(ctx, epi, 1, (int)sizeof(T)));

@@ -80,7 +80,7 @@ def build_partition(row_map, inds, vals, n_global, rank, world, group=None):
 class DistContext:
     """NCCL communicator + halo plan attached to a Context (C ABI: mpg_dist_*)."""
 
-    def __init__(self, ctx: Context, rank, world, group=None):
+    def __init__(self, ctx: Context, rank, world, group=None, peer_reduce=True):
         import torch
         import torch.distributed as dist
         self.ctx, self.rank, self.world = ctx, rank, world
@@ -94,6 +94,17 @@ class DistContext:
         idbuf = (C.c_ubyte * 128).from_buffer_copy(payload[0])
         ctx._chk(ctx.L.mpg_dist_create(ctx.h, idbuf, C.c_int(rank), C.c_int(world), C.byref(self.h)))
         self._keep = None
+        # peer-memory mailboxes for the in-kernel all-reduce (CUDA IPC handles all-gathered in rank order)
+        self.peer_reduce = False
+        if world > 1 and world <= 8 and peer_reduce:
+            hb = (C.c_ubyte * 64)()
+            ctx._chk(ctx.L.mpg_dist_mailbox_handle(ctx.h, self.h, hb))
+            handles = [None] * world
+            dist.all_gather_object(handles, bytes(hb), group=group)
+            allh = (C.c_ubyte * (64 * world)).from_buffer_copy(b"".join(handles))
+            ctx._chk(ctx.L.mpg_dist_open_mailboxes(ctx.h, self.h, allh))
+            dist.barrier(group=group)
+            self.peer_reduce = True
 
     def set_partition(self, part: Partition):
         ctx = self.ctx

@@ -209,6 +209,10 @@ int mpg_dist_destroy(mpg_dist* d);
 int mpg_dist_set_partition(mpg_ctx*, mpg_dist* d, int64_t n_global, int64_t n_local, int64_t n_halo, int npeers, const int* peer_ranks_host,
                            const int64_t* send_counts_host, const int* const* send_idx_dev_ptrs_host, const int64_t* recv_offsets_host,
                            const int64_t* recv_counts_host);
+/* Peer-memory mailboxes for the in-kernel all-reduce: every rank exports a 64-byte CUDA IPC handle, the host plumbing
+ * all-gathers them (rank order) and every rank maps its peers.  Without this step reductions go through ncclAllReduce. */
+int mpg_dist_mailbox_handle(mpg_ctx*, mpg_dist* d, void* handle64_host);
+int mpg_dist_open_mailboxes(mpg_ctx*, mpg_dist* d, const void* handles_world_x_64_host);
 int mpg_ctx_attach_dist(mpg_ctx*, mpg_dist* d); /* NULL detaches */
 int mpg_dist_info(const mpg_dist* d, int* rank, int* world, int64_t* n_global, int64_t* n_local, int64_t* n_halo);
 int mpg_halo_exchange_f32(mpg_ctx*, float* x_ext);  /* x_ext = [n_local owned | n_halo halo slots] */

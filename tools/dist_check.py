@@ -17,7 +17,8 @@ dev = f"cuda:{local}"
 dist.init_process_group("nccl", device_id=torch.device(dev))
 ctx = g.Context(local)
 report = {"ok": True, "cases": []}
-for spec, rlen, orth in [("cd27:32", 60, "cgsr"), ("lap2d:200", 50, "cgsr"), ("powerlaw:20000", 30, "cgsr"), ("cd27:24", 40, "mgs"), ("cd27:24", 40, "cgs")]:
+for spec, rlen, orth, peer in [("cd27:32", 60, "cgsr", True), ("cd27:32", 60, "cgsr", False), ("lap2d:200", 50, "cgsr", True), ("powerlaw:20000", 30, "cgsr", True),
+                               ("cd27:24", 40, "mgs", True), ("cd27:24", 40, "cgs", True), ("cd27:24", 40, "cgs", False)]:
     rm, ind, val = ctx.gen(spec)
     n = rm.numel() - 1
     xt_host = ctx.rand_vect(n, 42)
@@ -31,7 +32,7 @@ for spec, rlen, orth in [("cd27:32", 60, "cgsr"), ("lap2d:200", 50, "cgsr"), ("p
     r1 = ctx.gmres(A, val, b, x1, **kw)
     # partitioned
     part = g.dist.build_partition(rm, ind, val, n, rank, world)
-    dctx = g.dist.DistContext(ctx, rank, world)
+    dctx = g.dist.DistContext(ctx, rank, world, peer_reduce=peer)
     dctx.set_partition(part)
     Al = g.dist.local_csr(ctx, part)
     dctx.attach()
@@ -66,7 +67,7 @@ for spec, rlen, orth in [("cd27:32", 60, "cgsr"), ("lap2d:200", 50, "cgsr"), ("p
     env = 0.5 if spec.startswith("powerlaw") else 5e-3
     ok = (halo_ok and replicated and r1["status"] == r2["status"] == 1 and r1["total_iters"] == r2["total_iters"] and r1["total_restarts"] == r2["total_restarts"]
           and dev_hist <= env and abs(nb - nb1) <= 1e-12 * nb1 and err2 <= 4 * err1 + 1e-10)
-    report["cases"].append(dict(spec=spec, orth=orth, ok=ok, halo_ok=halo_ok, replicated=replicated, iters=(r1["total_iters"], r2["total_iters"]),
+    report["cases"].append(dict(spec=spec, orth=orth, peer_reduce=dctx.peer_reduce, ok=ok, halo_ok=halo_ok, replicated=replicated, iters=(r1["total_iters"], r2["total_iters"]),
                                 dev_hist=dev_hist, err=(err1, err2), n_halo=part.n_halo, peers=len(part.peers)))
     report["ok"] = report["ok"] and ok
     dctx.close()
