@@ -36,6 +36,7 @@ def parse():
     ap.add_argument("--rlen", type=int, default=100)
     ap.add_argument("--tol", type=float, default=1e-6)
     ap.add_argument("--orth", default="cgsr")
+    ap.add_argument("--mode", default="mixed", choices=["mixed", "baseline", "single-prec", "single"])
     ap.add_argument("--max-restarts", type=int, default=1000)
     ap.add_argument("--cpu-sample", default="auto", help="bounded sample of the workload for the CPU baseline (auto: cd27:128 with "
                     "oracle/_ref's MKL build, cd27:96 with the slower oracle port)")
@@ -95,7 +96,7 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_reference_run(sample, rlen, tol, orth, max_restarts, full_rows):
+def cpu_reference_run(sample, rlen, tol, orth, max_restarts, full_rows, mode="mixed"):
     """The reference's CPU implementation of the path on this box's host cores, on a bounded sample of the workload.
     Uses oracle/_ref (the reference's own sources built against the MKL inside libtorch) when present, else the oracle
     port.  Returns dict(value=<it/s scaled to the full workload>, ...)."""
@@ -116,10 +117,10 @@ def cpu_reference_run(sample, rlen, tol, orth, max_restarts, full_rows):
     orc.spmv(rm, ind, val, 1.0, xt, 0.0, b)
     t0 = time.perf_counter()
     if have_ref:
-        r = oracle_ref.gmres(rm, ind, val, b, mode="mixed", orth=orth, rlen=rlen, tol=tol, max_restarts=max_restarts)
+        r = oracle_ref.gmres(rm, ind, val, b, mode=mode, orth=orth, rlen=rlen, tol=tol, max_restarts=max_restarts)
         kind, cores = "reference", oracle_ref.num_threads()
     else:
-        r = orc.gmres(rm, ind, val, b, mode="mixed", orth=orth, rlen=rlen, tol=tol, max_restarts=max_restarts)
+        r = orc.gmres(rm, ind, val, b, mode=mode, orth=orth, rlen=rlen, tol=tol, max_restarts=max_restarts)
         kind, cores = "port", orc.num_threads()
     dt = r.get("gmres_seconds", time.perf_counter() - t0)
     its = int(r["total_iters"])
@@ -137,7 +138,7 @@ def run_reference(args, rank, world):
     vals, total_it, total_t = [], 0, 0.0
     last = None
     for i in range(args.warmup + args.steps):
-        last = cpu_reference_run(args.cpu_sample, args.rlen, args.tol, args.orth, args.max_restarts, full_rows)
+        last = cpu_reference_run(args.cpu_sample, args.rlen, args.tol, args.orth, args.max_restarts, full_rows, args.mode)
         if i >= args.warmup:
             total_it += last["iters"]; total_t += last["seconds"]
     scale = last["value"] / (last["iters"] / last["seconds"])
@@ -186,7 +187,7 @@ def main():
     val32 = torch.empty(nnz, dtype=torch.float32, device=dev)
     ctx.copy(val, val32)  # SparseMatrix<float>(A): the reference's "prec" window, gmres_perf_test.cpp:135-136
     x = torch.zeros(n, dtype=torch.float64, device=dev)
-    kw = dict(mode="mixed", orth=args.orth, conv="base", prec="identity", rlen=args.rlen, tol=args.tol, max_restarts=args.max_restarts)
+    kw = dict(mode=args.mode, orth=args.orth, conv="base", prec="identity", rlen=args.rlen, tol=args.tol, max_restarts=args.max_restarts)
 
     def solve():
         x.zero_()
@@ -196,23 +197,31 @@ def main():
         r = solve()
     torch.cuda.synchronize()
 
+    # working set of one solve: matrix (fp32 + fp64 values, indices) + Krylov basis.  When it does not dwarf the 126 MB
+    # L2, L2 is flushed (a 512 MB buffer is overwritten) between timed steps and each step is timed with its own events.
+    ws_bytes = nnz * 16 + (n + 1) * 4 + n * (args.rlen + 1) * (8 if args.mode in ("baseline", "single-prec") else 4)
+    flush = ws_bytes < 8 * 126e6
+    flush_buf = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev) if flush else None
+
     # ---- timed region: K solves, device time from CUDA events; per-kernel-class timers on ----
     ctx.prof_enable(True)
     ctx.prof_reset()
     sampler = ClockSampler(local_rank)
     launches0 = ctx.launches()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     torch.cuda.synchronize()
-    e0.record()
     iters = restarts = 0
     status = 1
-    for _ in range(args.steps):
+    for i in range(args.steps):
+        if flush:
+            flush_buf.fill_(i & 0xFF)
+        evs[i][0].record()
         r = solve()
+        evs[i][1].record()
         iters += r["total_iters"]; restarts += r["total_restarts"]; status = r["status"]
-    e1.record()
     torch.cuda.synchronize()
     clocks = sampler.stop()
-    total_ms = e0.elapsed_time(e1)
+    total_ms = sum(a.elapsed_time(b) for a, b in evs)
     launches = ctx.launches() - launches0
     prof = ctx.prof_get()
     ctx.prof_enable(False)
@@ -233,13 +242,13 @@ def main():
         kernels[name] = {"ms_total": round(p["ms"], 3), "share": round(p["ms"] / total_ms, 4), "launches": p["launches"],
                          "avg_ms": round(p["ms"] / p["launches"], 4), "algorithmic_GB_per_launch": round(p["bytes"] / p["launches"] / 1e9, 5),
                          "achieved_GBps": round(gbs, 1), "frac_of_peak": round(gbs / peak, 4)}
-    dom = max((k for k in kernels if k in ("vpass", "spmv_f32", "gemvn", "spmv_f64")), key=lambda k: kernels[k]["ms_total"])
+    dom = max((k for k in kernels if k in ("vpass", "spmv_f32", "gemvn", "spmv_f64", "gemvt")), key=lambda k: kernels[k]["ms_total"])
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_GBps"], "peak": peak, "unit": "GB/s",
                 "frac": kernels[dom]["frac_of_peak"], "traffic": None, "peak_source": peak_src,
                 "note": "achieved = algorithmic bytes (SURVEY.md §8d / DESIGN.md §4) of all launches of this kernel class in the timed region / "
                         "their CUDA-event time on the launching stream"}
     prof_path = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(prof_path):
+    if os.path.exists(prof_path) and args.workload == "cd27:256":
         try:
             roofline["traffic"] = json.load(open(prof_path)).get(dom)
         except Exception:
@@ -271,17 +280,19 @@ def main():
     # ---- CPU baseline on this box's host cores (bounded sample) ----
     cpu = None
     if not args.no_cpu_baseline:
-        c = cpu_reference_run(args.cpu_sample, args.rlen, args.tol, args.orth, args.max_restarts, n)
+        c = cpu_reference_run(args.cpu_sample, args.rlen, args.tol, args.orth, args.max_restarts, n, args.mode)
         cpu = {k: c[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f32 inner / f64 outer", "data": "synthetic",
-            "config": {"workload": args.workload, "n_rows": n, "nnz": nnz, "restart_length": args.rlen, "tol": args.tol, "orth": args.orth,
+            "dtype": {"mixed": "f32 inner / f64 outer", "baseline": "f64", "single-prec": "f64 (f32 preconditioner)", "single": "f32"}[args.mode],
+            "data": "synthetic",
+            "config": {"workload": args.workload, "mode": args.mode, "n_rows": n, "nnz": nnz, "restart_length": args.rlen, "tol": args.tol, "orth": args.orth,
                        "prec": "identity", "iters_per_solve": iters // max(args.steps, 1), "restarts_per_solve": restarts // max(args.steps, 1),
                        "time_to_solution_s": total_ms * 1e-3 / args.steps, "status": int(status),
                        "resNorm": res_norm, "errNorm": err_norm, "rel_res": res_norm / b_norm,
-                       "l2": "working set (matrix 7.2 GB + basis 6.8 GB) >> 126 MB L2; no flush needed"},
+                       "l2": (f"working set {ws_bytes / 1e9:.2f} GB: L2 flushed (512 MB overwrite) between timed steps" if flush else
+                              f"working set {ws_bytes / 1e9:.1f} GB (matrix + basis) >> 126 MB L2; no flush needed")},
             "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
     print(json.dumps(line), flush=True)
 
