@@ -72,8 +72,30 @@ def load_library():
     L.mpg_cd27_nnz.restype = C.c_int64
     L.mpg_lap2d_nnz.argtypes = [C.c_int64]
     L.mpg_cd27_nnz.argtypes = [C.c_int64]
+    L.mpg_host_free.argtypes = [C.c_void_p]
+    L.mpg_host_free.restype = None
     _LIB = L
     return L
+
+
+def read_matrix_market(path):
+    """MatrixMarket file -> (row_map int32[n+1], inds int32[nnz], vals float64[nnz]) numpy arrays in the reference's
+    LoadMatrix-canonical CSR form (mpg_mm_read_host).  Raises MpgError with the reference's exception text."""
+    import numpy as np
+    L = load_library()
+    n, m, nnz = C.c_int(), C.c_int(), C.c_int64()
+    prm, pin, pv = C.POINTER(C.c_int)(), C.POINTER(C.c_int)(), C.POINTER(C.c_double)()
+    err = C.create_string_buffer(256)
+    rc = L.mpg_mm_read_host(str(path).encode(), C.byref(n), C.byref(m), C.byref(nnz), C.byref(prm), C.byref(pin), C.byref(pv), err, 256)
+    if rc != 0:
+        raise MpgError(err.value.decode() or f"mpg_mm_read_host failed ({rc})")
+    try:
+        rm = np.ctypeslib.as_array(prm, shape=(m.value + 1,)).copy()
+        ind = np.ctypeslib.as_array(pin, shape=(max(nnz.value, 1),))[:nnz.value].copy()
+        val = np.ctypeslib.as_array(pv, shape=(max(nnz.value, 1),))[:nnz.value].copy()
+    finally:
+        L.mpg_host_free(prm); L.mpg_host_free(pin); L.mpg_host_free(pv)
+    return rm, ind, val
 
 
 def _ptr(t):

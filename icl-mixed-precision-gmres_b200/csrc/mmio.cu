@@ -1,0 +1,109 @@
+// mmio.cu — MatrixMarket ingest into LoadMatrix-canonical CSR (host code).  SURVEY.md §8f-2 ("next" row).
+// Restates LoadMatrix<S>() of the reference (LoadMatrix.hpp:17-154) without its quadratic parts:
+//   * coordinate, real|integer, general|symmetric only (LoadMatrix.hpp:48-54); anything else is an error;
+//   * every row gets a diagonal entry, explicit 0 if the file has none (:62-66,94-101); a file diagonal overwrites it,
+//     the last one wins (:110-111);
+//   * symmetric files are mirrored (:79-82,118-124); duplicates are NOT merged;
+//   * columns ascending within a row; the reference's bubble sort (:128-145) is stable, so is the sort used here:
+//     equal columns keep insertion order (diagonal slot first, then file order with mirrored entries interleaved as read).
+// The reference parses with fscanf and sorts each row in O(len^2); here the file is read in one block, parsed with
+// strtol/strtod, and rows are sorted with std::stable_sort — same result, usable at 10^8 nonzeros.
+#include <algorithm>
+#include <cctype>
+#include <cstdlib>
+#include <numeric>
+#include <vector>
+
+#include "common.cuh"
+
+namespace {
+struct Entry { int col; int seq; double val; };
+}
+
+extern "C" int mpg_mm_read_host(const char* path, int* nrows_out, int* ncols_out, int64_t* nnz_out, int** row_map_out, int** inds_out,
+                                double** vals_out, char* errbuf, int errlen) {
+    auto fail_msg = [&](const char* m) {
+        if (errbuf && errlen > 0) { std::snprintf(errbuf, (size_t)errlen, "%s", m); }
+        return MPG_ERR_ARG;
+    };
+    if (!path || !nrows_out || !ncols_out || !nnz_out || !row_map_out || !inds_out || !vals_out) return fail_msg("null argument");
+    FILE* f = std::fopen(path, "rb");
+    if (!f) return fail_msg("Could not access file");                                  // LoadMatrix.hpp:22-25
+    std::fseek(f, 0, SEEK_END);
+    const long sz = std::ftell(f);
+    std::fseek(f, 0, SEEK_SET);
+    std::vector<char> buf((size_t)sz + 1);
+    const size_t got = std::fread(buf.data(), 1, (size_t)sz, f);
+    std::fclose(f);
+    buf[got] = 0;
+    char* p = buf.data();
+    // ---- banner (mmio.c mm_read_banner semantics: "%%MatrixMarket matrix <format> <field> <symmetry>") ----
+    char* eol = std::strchr(p, '\n');
+    if (!eol) return fail_msg("Missing values in banner");
+    std::string banner(p, eol);
+    for (auto& c : banner) c = (char)std::tolower((unsigned char)c);
+    char b0[64], b1[64], b2[64], b3[64], b4[64];
+    if (std::sscanf(banner.c_str(), "%63s %63s %63s %63s %63s", b0, b1, b2, b3, b4) != 5) return fail_msg("Missing values in banner");
+    if (std::string(b0) != "%%matrixmarket") return fail_msg("Banner is missing");
+    if (std::string(b1) != "matrix") return fail_msg("Unrecognized description");
+    const bool coordinate = std::string(b2) == "coordinate";
+    const bool real_or_int = std::string(b3) == "real" || std::string(b3) == "integer";
+    const bool general = std::string(b4) == "general", symmetric = std::string(b4) == "symmetric";
+    if (!(coordinate && real_or_int && (general || symmetric))) return fail_msg("Unsupported matrix type");   // :48-54
+    p = eol + 1;
+    while (*p == '%') { eol = std::strchr(p, '\n'); if (!eol) return fail_msg("Malformed matrix size information"); p = eol + 1; }
+    char* q;
+    const long M = std::strtol(p, &q, 10); p = q;
+    const long N = std::strtol(p, &q, 10); p = q;
+    const long nz = std::strtol(p, &q, 10);
+    if (q == p || M <= 0 || N <= 0 || nz < 0) return fail_msg("Malformed matrix size information");
+    p = q;
+    // ---- entries: count, then place ----
+    std::vector<int> I((size_t)nz), J((size_t)nz);
+    std::vector<double> V((size_t)nz);
+    std::vector<int64_t> cnt((size_t)N + 1, 1);   // one diagonal per row (:62-64)
+    cnt[0] = 0;
+    for (long e = 0; e < nz; ++e) {
+        const long i = std::strtol(p, &q, 10); if (q == p) return fail_msg("premature end of entries"); p = q;
+        const long j = std::strtol(p, &q, 10); if (q == p) return fail_msg("premature end of entries"); p = q;
+        const double v = std::strtod(p, &q); if (q == p) return fail_msg("premature end of entries"); p = q;
+        if (i < 1 || i > N || j < 1 || j > N) return fail_msg("entry index out of range");
+        I[(size_t)e] = (int)(i - 1); J[(size_t)e] = (int)(j - 1); V[(size_t)e] = v;
+        if (i != j) { cnt[(size_t)i] += 1; if (symmetric) cnt[(size_t)j] += 1; }
+    }
+    for (long r = 0; r < N; ++r) cnt[(size_t)r + 1] += cnt[(size_t)r];
+    const int64_t nnz = cnt[(size_t)N];
+    if (nnz >= 2147483647LL) return fail_msg("nnz overflows int32 (types_cuda.hpp:66-70)");
+    int* row_map = (int*)std::malloc(sizeof(int) * ((size_t)N + 1));
+    int* inds = (int*)std::malloc(sizeof(int) * (size_t)std::max<int64_t>(nnz, 1));
+    double* vals = (double*)std::malloc(sizeof(double) * (size_t)std::max<int64_t>(nnz, 1));
+    if (!row_map || !inds || !vals) { std::free(row_map); std::free(inds); std::free(vals); return fail_msg("out of memory"); }
+    for (long r = 0; r <= N; ++r) row_map[r] = (int)cnt[(size_t)r];
+    std::vector<int> fill((size_t)N, 1);
+    for (long r = 0; r < N; ++r) { inds[row_map[r]] = (int)r; vals[row_map[r]] = 0.0; }   // base diagonal (:94-101)
+    for (long e = 0; e < nz; ++e) {
+        const int row = I[(size_t)e], col = J[(size_t)e];
+        const double v = V[(size_t)e];
+        if (row == col) { vals[row_map[row]] = v; continue; }                              // :110-111
+        int k = fill[(size_t)row]++;
+        inds[row_map[row] + k] = col; vals[row_map[row] + k] = v;
+        if (symmetric) { k = fill[(size_t)col]++; inds[row_map[col] + k] = row; vals[row_map[col] + k] = v; }
+    }
+    // ---- stable sort of every row by column (:128-145) ----
+    std::vector<Entry> tmp;
+    for (long r = 0; r < N; ++r) {
+        const int s = row_map[r], len = row_map[r + 1] - s;
+        bool sorted = true;
+        for (int k = 1; k < len && sorted; ++k) sorted = inds[s + k - 1] <= inds[s + k];
+        if (sorted) continue;
+        tmp.resize((size_t)len);
+        for (int k = 0; k < len; ++k) tmp[(size_t)k] = {inds[s + k], k, vals[s + k]};
+        std::stable_sort(tmp.begin(), tmp.end(), [](const Entry& a, const Entry& b) { return a.col < b.col; });
+        for (int k = 0; k < len; ++k) { inds[s + k] = tmp[(size_t)k].col; vals[s + k] = tmp[(size_t)k].val; }
+    }
+    *nrows_out = (int)M; *ncols_out = (int)N; *nnz_out = nnz;
+    *row_map_out = row_map; *inds_out = inds; *vals_out = vals;
+    return MPG_OK;
+}
+
+extern "C" void mpg_host_free(void* p) { std::free(p); }

@@ -219,6 +219,12 @@ int mpg_halo_exchange_f32(mpg_ctx*, float* x_ext);  /* x_ext = [n_local owned | 
 int mpg_halo_exchange_f64(mpg_ctx*, double* x_ext);
 int mpg_allreduce_sum_f64(mpg_ctx*, double* buf_dev, int64_t count);
 
+/* ---- MatrixMarket ingest: LoadMatrix<S>(), LoadMatrix.hpp:17-154, into canonical CSR (host).  Arrays are malloc'ed by
+ * the library and released with mpg_host_free.  errbuf receives the reference's exception text on failure. ------------ */
+int mpg_mm_read_host(const char* path, int* nrows, int* ncols, int64_t* nnz, int** row_map_host, int** inds_host, double** vals_host,
+                     char* errbuf, int errlen);
+void mpg_host_free(void* p);
+
 /* ---- 1-D row partition (new functionality, host-side, bit-exact vs the oracle) ------------- */
 int mpg_partition_bounds(int64_t n, int P, int64_t* bounds_host /* P+1 */);
 /* halo_cols_host/local_inds_host may be NULL to query sizes.  Returns the halo count through *n_halo. */

@@ -63,3 +63,14 @@ def gmres(rm, ind, val64, b, x0=None, true_x=None, mode="mixed", orth="cgsr", co
     res["hist_outer"] = ho[:4 * min(st.n_hist_outer, cap_outer)].reshape(-1, 4).copy()
     res["x"] = x
     return res
+
+
+def load_matrix(path):
+    """the reference's own LoadMatrix<double>() -> (row_map, inds, vals); raises ValueError with its exception text"""
+    n, nnz = C.c_int(), C.c_long()
+    err = C.create_string_buffer(256)
+    if lib().ref_load_matrix(str(path).encode(), C.byref(n), C.byref(nnz), None, None, None, err, 256) != 0:
+        raise ValueError(err.value.decode())
+    rm, ind, val = np.empty(n.value + 1, np.int32), np.empty(nnz.value, np.int32), np.empty(nnz.value, np.float64)
+    lib().ref_load_matrix(str(path).encode(), C.byref(n), C.byref(nnz), _p(rm), _p(ind), _p(val), err, 256)
+    return rm, ind, val

@@ -35,9 +35,9 @@ $(OUT)/mmio.o: $(FARM)/.linked
 $(OUT)/mkl_shim.o: shim/mkl_shim.cpp shim/mkl.h
 	$(CXX) $(CXXFLAGS) -c shim/mkl_shim.cpp -o $@
 $(OUT)/ref_driver.o: ref_driver.cpp $(FARM)/.linked shim/Kokkos_Core.hpp
-	$(CXX) $(CXXFLAGS) -I $(FARM) -c ref_driver.cpp -o $@
+	$(CXX) $(CXXFLAGS) -include cstring -include sstream -I $(FARM) -c ref_driver.cpp -o $@
 
-$(OUT)/libref.so: $(OUT)/gmres.o $(OUT)/kernels_mkl.o $(OUT)/mkl_shim.o $(OUT)/ref_driver.o
+$(OUT)/libref.so: $(OUT)/gmres.o $(OUT)/kernels_mkl.o $(OUT)/mkl_shim.o $(OUT)/ref_driver.o $(OUT)/mmio.o
 	$(CXX) -shared -o $@ $^ $(LDLIBS)
 $(OUT)/gmres_perf_test: $(OUT)/gmres_perf_test.o $(OUT)/gmres.o $(OUT)/kernels_mkl.o $(OUT)/mkl_shim.o $(OUT)/mmio.o
 	$(CXX) -o $@ $^ $(LDLIBS)

@@ -19,6 +19,7 @@
 #include "gmres.hpp"
 #include "IterUtil.hpp"
 #include "Orthogonalization.hpp"
+#include "LoadMatrix.hpp"
 
 namespace {
 
@@ -166,6 +167,22 @@ void export_hist(L* c, RefStats* st, double* hi, int64_t cap_i, double* ho, int6
 }  // namespace
 
 extern "C" {
+
+// the reference's own LoadMatrix<double>() (LoadMatrix.hpp:17-154).  Call with null arrays to get the sizes.
+// returns 0, or 1 with the exception text in err
+int ref_load_matrix(const char* path, int* n, long* nnz, int* row_map, int* inds, double* vals, char* err, int errlen) {
+    try {
+        SparseMatrix<double, MKL> A = LoadMatrix<double>(const_cast<char*>(path));
+        *n = A.nrows();
+        *nnz = (long)A.inds_.extent(0);
+        if (row_map) for (int i = 0; i <= *n; ++i) row_map[i] = A.row_map_(i);
+        if (inds) for (long k = 0; k < *nnz; ++k) { inds[k] = A.inds_(k); vals[k] = A.vals_(k); }
+        return 0;
+    } catch (const std::exception& e) {
+        if (err && errlen > 0) std::snprintf(err, (size_t)errlen, "%s", e.what());
+        return 1;
+    }
+}
 
 int ref_num_threads() { return MKL_Get_Max_Threads(); }
 

@@ -77,3 +77,23 @@ def test_reference_cli_restart_policies_on_b200_backend(orc, tmp_path):
         gpu = run_cli(mtx, True, "mixed", "cgsr", "identity", 40, 1e-9, extra)
         assert abs(gpu["iters"] - host["iters"]) <= 0.05 * host["iters"] + 2, (extra, gpu["iters"], host["iters"])
         assert abs(gpu["i"] - host["i"]) <= 0.05 * host["i"] + 1
+
+
+def test_python_harness_prints_the_reference_stdout_contract(orc, tmp_path):
+    """gmres_perf_test.py (native device-resident driver) vs the reference CLI's MKL path on the same .mtx: same fields"""
+    import sys
+    if not os.path.exists(EXE):
+        pytest.skip("oracle/_ref/gmres_perf_test_b200 not built")
+    rm, ind, val, xt, b = problem(orc, "cd27:10")
+    mtx = tmp_path / "a.mtx"
+    write_mtx(mtx, rm, ind, val)
+    host = run_cli(mtx, False, "mixed", "cgsr", "identity", 30, 1e-9)
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "gmres_perf_test.py"), "--Apath", str(mtx), "--mode", "mixed", "--orth", "cgsr",
+                          "--prec", "identity", "--rlen", "30", "--tol", "1e-9", "--gpu"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout + out.stderr
+    m = re.search(r"Found solution with rel prec res norm = (\S+) when k = (\d+) and i = (\d+)\s+total iterations = (\d+)", out.stdout)
+    assert m and (int(m.group(3)), int(m.group(4))) == (host["i"], host["iters"]), out.stdout
+    assert re.search(r"  ilu took \S+s; gmres took \S+s\n  resNorm = \S+; errNorm = \S+", out.stdout)
+    assert out.stdout.startswith("||x|| = ")
+    bad = subprocess.run([sys.executable, os.path.join(ROOT, "gmres_perf_test.py"), "--bogus"], capture_output=True, text=True)
+    assert bad.returncode == 1 and "Unknown flag" in bad.stdout      # gmres_perf_test.cpp:390-393
