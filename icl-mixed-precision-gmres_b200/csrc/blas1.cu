@@ -477,7 +477,7 @@ __global__ void rot_vec_kernel(int64_t k, T* a, const T* c, const T* s) {
 // gmres.cpp:219-226 in one launch.  One warp: lanes prefetch c/s/h into shared memory, lane 0 runs the
 // dependent rotation chain from shared memory.
 template <class T>
-__global__ void __launch_bounds__(32) givens_step_kernel(int64_t k, T* h, int64_t ldh, T* cs, T* sn, T* s, double* resid) {
+__global__ void __launch_bounds__(32) givens_step_kernel(int64_t k, T* h, int64_t ldh, T* cs, T* sn, T* s, double* resid, double* resid_host) {
     extern __shared__ unsigned char smem_raw[];
     T* sh = reinterpret_cast<T*>(smem_raw);        // k+2
     T* sc = sh + (k + 2);                          // k
@@ -505,6 +505,10 @@ __global__ void __launch_bounds__(32) givens_step_kernel(int64_t k, T* h, int64_
         s[k] = s0;
         s[k + 1] = s1;
         if (resid) *resid = fabs((double)s1);
+        if (resid_host) {   // mapped pinned memory: lets the host follow the residual without synchronising the stream
+            *reinterpret_cast<volatile double*>(resid_host) = fabs((double)s1);
+            __threadfence_system();
+        }
     }
     __syncwarp();
     for (int64_t j = threadIdx.x; j < k + 2; j += 32) hcol[j] = sh[j];
@@ -576,15 +580,15 @@ __global__ void __launch_bounds__(128) trsv_upper_smem_kernel(int n, const T* __
 
 namespace mpg {
 template <class T>
-int givens_step(mpg_ctx* ctx, int64_t k, T* h, int64_t ldh, T* cs, T* sn, T* s, double* resid) {
+int givens_step(mpg_ctx* ctx, int64_t k, T* h, int64_t ldh, T* cs, T* sn, T* s, double* resid, double* resid_host) {
     const size_t smem = sizeof(T) * (size_t)(3 * k + 2);
     ProfScope prof(ctx, MPG_PROF_SMALL, 0.0);
-    givens_step_kernel<T><<<1, 32, smem, ctx->stream>>>(k, h, ldh, cs, sn, s, resid);
+    givens_step_kernel<T><<<1, 32, smem, ctx->stream>>>(k, h, ldh, cs, sn, s, resid, resid_host);
     MPG_CHECK_LAUNCH(ctx);
     return MPG_OK;
 }
-template int givens_step<float>(mpg_ctx*, int64_t, float*, int64_t, float*, float*, float*, double*);
-template int givens_step<double>(mpg_ctx*, int64_t, double*, int64_t, double*, double*, double*, double*);
+template int givens_step<float>(mpg_ctx*, int64_t, float*, int64_t, float*, float*, float*, double*, double*);
+template int givens_step<double>(mpg_ctx*, int64_t, double*, int64_t, double*, double*, double*, double*, double*);
 template <class T>
 int trsv(mpg_ctx* ctx, int upper, int trans, int64_t n, const T* A, int64_t ld, T* x) {
     if (n <= 0) return MPG_OK;
@@ -627,7 +631,7 @@ template int trsv<double>(mpg_ctx*, int, int, int64_t, const double*, int64_t, d
     }                                                                                                          \
     extern "C" int mpg_givens_step_##SFX(mpg_ctx* ctx, int64_t k, T* h, int64_t ldh, T* cs, T* sn, T* s, double* r) { \
         MPG_REQUIRE(ctx, k >= 0 && k + 2 <= kMaxCols + 2, "givens_step: bad k");                               \
-        return mpg::givens_step<T>(ctx, k, h, ldh, cs, sn, s, r);                                              \
+        return mpg::givens_step<T>(ctx, k, h, ldh, cs, sn, s, r, nullptr);                                              \
     }
 MPG_DEF_LS(f32, float)
 MPG_DEF_LS(f64, double)

@@ -37,7 +37,7 @@ int fill_host(mpg_ctx*, int64_t, float, float*);
 int fill_host(mpg_ctx*, int64_t, double, double*);
 int gdmv_host(mpg_ctx*, int64_t, float, const float*, const float*, float, float*);
 int gdmv_host(mpg_ctx*, int64_t, double, const double*, const double*, double, double*);
-template <class T> int givens_step(mpg_ctx*, int64_t, T*, int64_t, T*, T*, T*, double*);
+template <class T> int givens_step(mpg_ctx*, int64_t, T*, int64_t, T*, T*, T*, double*, double*);
 template <class T> int trsv(mpg_ctx*, int, int, int64_t, const T*, int64_t, T*);
 template <class T> int spmv(mpg_ctx*, const mpg_csr*, const T*, T, const T*, T, const T*, T*, float*);
 template <class T> int gemvn(mpg_ctx*, int64_t, int, const T*, int64_t, T, const T*, T, T*, bool, T*, T*, double*);
@@ -240,56 +240,93 @@ int run_cycle(mpg_ctx* ctx, const mpg_gmres_params& p, Policy& pol, Workspace* w
     MPG_TRY(fill_host(ctx, m + 1, T(0), s));
     MPG_TRY(fill_host(ctx, 1, beta, s));
 
-    const bool per_iter_sync = pol.needs_residual() || pol.kind == MPG_CONV_ORTHLOSS;
-    int64_t k = 0;
-    Action act = NEXT;
-    int64_t flushed = 0;
-    for (k = 0;; ++k) {
+    // one Arnoldi step, enqueued asynchronously
+    auto enqueue_iteration = [&](int64_t kk, double* resid_host) -> int {
         // w = A v_k ; M(w)            gmres.cpp:98-102,210-215
-        MPG_TRY(halo_exchange<T>(ctx, V + (size_t)k * ldv));   // multi-GPU: fill the halo tail of v_k (no-op on one GPU)
-        MPG_TRY(spmv<T>(ctx, A, vals, T(1), V + (size_t)k * ldv, T(0), w, w, nullptr));
+        MPG_TRY(halo_exchange<T>(ctx, V + (size_t)kk * ldv));   // multi-GPU: fill the halo tail of v_k (no-op on one GPU)
+        MPG_TRY(spmv<T>(ctx, A, vals, T(1), V + (size_t)kk * ldv, T(0), w, w, nullptr));
         MPG_TRY(apply_prec<T>(ctx, n, w, jac, jac32, bridge, ws->tmp32));
         // orth.add_vector(k, w, h)     gmres.cpp:104,217
-        MPG_TRY(add_vector<T>(ctx, p.orth, n, k, V, ldv, w, h + (size_t)k * ldh, scratch, true));
+        MPG_TRY(add_vector<T>(ctx, p.orth, n, kk, V, ldv, w, h + (size_t)kk * ldh, scratch, true));
         // rot / rotg / rot             gmres.cpp:106-110,219-222 ; |s(k+1)| stays on the device
-        MPG_TRY(givens_step<T>(ctx, k, h, ldh, cs, sn, s, ws->hist + k));
+        return givens_step<T>(ctx, kk, h, ldh, cs, sn, s, ws->hist + kk, resid_host);
+    };
+    auto no_loss = [](int64_t) -> double { return 0.0; };
 
-        double ares = 0.0;
-        if (per_iter_sync) {
-            MPG_CUDA(ctx, cudaMemcpyAsync(ws->hist_host + k, ws->hist + k, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-            MPG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-            ares = ws->hist_host[k];
-            hist.push_inner(ares / Minvb_norm);
-            flushed = k + 1;
+    int64_t k = 0;
+    Action act = NEXT;
+    if (pol.kind == MPG_CONV_BASE) {
+        // Convergence::check only counts (IterUtil.hpp:57-65): the whole cycle is enqueued without a read-back
+        for (k = 0;; ++k) {
+            MPG_TRY(enqueue_iteration(k, nullptr));
+            act = pol.check(k + 1, 0.0, Minvb_norm, no_loss);   // gmres.cpp:115,227
+            if (act != NEXT) { ++k; break; }
         }
-        int rc_loss = MPG_OK;
-        auto loss_inc = [&](int64_t kk) -> double {
-            // LostOrthogonality_Convergence::check, IterUtil.hpp:205-216 (kk = k+1).  Note the reference reads basis
-            // column kk+1, which add_vector has not written yet in this cycle; reproduced as is.
-            T* S = static_cast<T*>(ws->S);
-            T* u = static_cast<T*>(ws->u);
-            const int64_t ldS = m + 1;
-            const int k1 = (int)kk + 1;
-            T* scol = S + (size_t)(kk + 1) * ldS;
-            rc_loss = gemvt<T>(ctx, n, k1, V, ldv, T(1), V + (size_t)(kk + 1) * ldv, T(0), u);
-            LocalScope replicated(ctx);   // S, u, s_col are replicated on every rank
-            if (rc_loss == MPG_OK) rc_loss = cast_copy(ctx, k1, u, scol);
-            if (rc_loss == MPG_OK) rc_loss = gemvn<T>(ctx, k1, k1, S, ldS, T(-1), u, T(1), scol, false, nullptr, nullptr, nullptr);
-            if (rc_loss == MPG_OK) rc_loss = dot_dev(ctx, k1, scol, scol, ds<T>(ctx, 16));
-            if (rc_loss != MPG_OK) return 0.0;
-            cudaMemcpyAsync(ctx->hscal + 16, ctx->dscal + 16, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
-            cudaStreamSynchronize(ctx->stream);
-            return (double)hs<T>(ctx, 16);
-        };
-        act = pol.check(k + 1, ares, Minvb_norm, loss_inc);   // gmres.cpp:115,227
-        MPG_TRY(rc_loss);
-        if (act != NEXT) { ++k; break; }
-    }
-    if (!per_iter_sync && k > 0) {
-        // base policy: the whole cycle ran without a readback; fetch the residual history in one copy
         MPG_CUDA(ctx, cudaMemcpyAsync(ws->hist_host, ws->hist, sizeof(double) * (size_t)k, cudaMemcpyDeviceToHost, ctx->stream));
         MPG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        for (int64_t j = flushed; j < k; ++j) hist.push_inner(ws->hist_host[j] / Minvb_norm);
+        for (int64_t j = 0; j < k; ++j) hist.push_inner(ws->hist_host[j] / Minvb_norm);
+    } else if (pol.needs_residual()) {
+        // RelPrecRes_ / RepeatIteration_ (IterUtil.hpp:84-169) restart on the Arnoldi residual.  Instead of the
+        // reference's blocking read per iteration (gmres.cpp:225-226) the Givens kernel also writes |s(k+1)| to mapped
+        // pinned memory and the host follows it while up to kLookahead further iterations are already enqueued.  A
+        // restart decided at step k* leaves at most kLookahead-1 speculative steps behind; they only touch basis columns
+        // > k*, Hessenberg columns >= k* and s[k*..], none of which solution_update(k*) reads.  The issue order is a
+        // function of the decisions alone, so all ranks of a multi-GPU run enqueue the same sequence.
+        // Speculation wastes up to kLookahead-1 steps per restart; it pays when a step is short compared with the
+        // ~30-50 us the GPU idles across a blocking read-back, so the depth follows a bandwidth estimate of the step time.
+        const double step_us = ((double)A->nnz * (sizeof(T) + 4) + 1.5 * (double)m * (double)n * sizeof(T)) / 6.0e6;
+        const int64_t kLookahead = step_us < 200.0 ? 3 : (step_us < 1000.0 ? 2 : 1);
+        volatile double* hh = ws->hist_host;
+        for (int64_t j = 0; j <= m; ++j) hh[j] = -1.0;   // |s| >= 0: negative = not written yet (stream is idle here)
+        int64_t issued = 0, checked = 0;
+        while (issued < std::min<int64_t>(m, kLookahead)) { MPG_TRY(enqueue_iteration(issued, ws->hist_host + issued)); ++issued; }
+        for (;;) {
+            int64_t spins = 0;
+            while (hh[checked] < 0.0) {
+                if ((++spins & 0xFFFF) == 0) {   // surface a device fault instead of spinning forever
+                    const cudaError_t e = cudaStreamQuery(ctx->stream);
+                    if (e != cudaSuccess && e != cudaErrorNotReady) return fail(ctx, MPG_ERR_CUDA, std::string("stream error: ") + cudaGetErrorString(e));
+                }
+            }
+            const double ares = hh[checked];
+            hist.push_inner(ares / Minvb_norm);
+            act = pol.check(checked + 1, ares, Minvb_norm, no_loss);
+            ++checked;
+            if (act != NEXT) break;
+            if (issued < m) { MPG_TRY(enqueue_iteration(issued, ws->hist_host + issued)); ++issued; }
+        }
+        k = checked;
+    } else {
+        // LostOrthogonality_ (IterUtil.hpp:172-227) needs a gemv-T on the basis per check: one read-back per iteration
+        for (k = 0;; ++k) {
+            MPG_TRY(enqueue_iteration(k, nullptr));
+            MPG_CUDA(ctx, cudaMemcpyAsync(ws->hist_host + k, ws->hist + k, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+            MPG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            const double ares = ws->hist_host[k];
+            hist.push_inner(ares / Minvb_norm);
+            int rc_loss = MPG_OK;
+            auto loss_inc = [&](int64_t kk) -> double {
+                // LostOrthogonality_Convergence::check, IterUtil.hpp:205-216 (kk = k+1).  Note the reference reads basis
+                // column kk+1, which add_vector has not written yet in this cycle; reproduced as is.
+                T* S = static_cast<T*>(ws->S);
+                T* u = static_cast<T*>(ws->u);
+                const int64_t ldS = m + 1;
+                const int k1 = (int)kk + 1;
+                T* scol = S + (size_t)(kk + 1) * ldS;
+                rc_loss = gemvt<T>(ctx, n, k1, V, ldv, T(1), V + (size_t)(kk + 1) * ldv, T(0), u);
+                LocalScope replicated(ctx);   // S, u, s_col are replicated on every rank
+                if (rc_loss == MPG_OK) rc_loss = cast_copy(ctx, k1, u, scol);
+                if (rc_loss == MPG_OK) rc_loss = gemvn<T>(ctx, k1, k1, S, ldS, T(-1), u, T(1), scol, false, nullptr, nullptr, nullptr);
+                if (rc_loss == MPG_OK) rc_loss = dot_dev(ctx, k1, scol, scol, ds<T>(ctx, 16));
+                if (rc_loss != MPG_OK) return 0.0;
+                cudaMemcpyAsync(ctx->hscal + 16, ctx->dscal + 16, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+                cudaStreamSynchronize(ctx->stream);
+                return (double)hs<T>(ctx, 16);
+            };
+            act = pol.check(k + 1, ares, Minvb_norm, loss_inc);   // gmres.cpp:115,227
+            MPG_TRY(rc_loss);
+            if (act != NEXT) { ++k; break; }
+        }
     }
     *k_out = k;
     *act_out = act;
