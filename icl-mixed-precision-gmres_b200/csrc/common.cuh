@@ -31,6 +31,7 @@ struct Tuning {
     int gemvn_ctas_per_sm = 4;
     int red_ctas_per_sm = 4;
     int use_graph = 0;
+    int dist_peer_halo = 1;   // multi-GPU halo exchange by stores into the neighbours' memory (0: pack + ncclSend/ncclRecv)
     int dist_peer_reduce = 1; // multi-GPU reductions inside the kernels over peer memory (0: NCCL all-reduce + epilogue kernel)
 };
 

@@ -77,6 +77,43 @@ __global__ void pack_kernel(int64_t count, const int* __restrict__ idx, const T*
     if (i < count) out[i] = x[idx[i]];
 }
 
+// ---- halo exchange over NVLink peer memory (push model) ---------------------------------------------------------------
+// Every rank owns an IPC-shared inbox: [2 slots][n_halo] 8-byte cells + one flag per (slot, source rank).  The sender
+// gathers the rows a neighbour needs and stores them straight into that neighbour's inbox, then publishes the exchange
+// number; the receiver waits for its neighbours' flags and moves the inbox into the halo tail of the SpMV input.
+struct PushArgs {
+    int npeers;
+    const int* send_idx[kMaxPeers];
+    long long count[kMaxPeers];
+    void* dst[kMaxPeers];                   // neighbour's inbox + slot offset + where our rows go (bytes resolved per type)
+    unsigned long long* flag[kMaxPeers];    // neighbour's flag for (slot, this rank)
+};
+template <class T>
+__global__ void __launch_bounds__(1024) halo_push_kernel(PushArgs a, const T* __restrict__ x, unsigned long long seq) {
+    const int q = blockIdx.x;
+    T* dst = static_cast<T*>(a.dst[q]);
+    const int* idx = a.send_idx[q];
+    for (long long i = threadIdx.x; i < a.count[q]; i += blockDim.x) dst[i] = x[idx[i]];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.flag[q]), "l"(seq) : "memory");
+}
+struct WaitArgs {
+    int npeers;
+    const unsigned long long* flag[kMaxPeers];   // own flags for (slot, neighbour)
+};
+template <class T>
+__global__ void __launch_bounds__(256) halo_wait_copy_kernel(WaitArgs a, unsigned long long seq, const T* inbox, T* tail, long long n_halo) {
+    if ((int)threadIdx.x < a.npeers) {
+        unsigned long long v;
+        do {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(a.flag[threadIdx.x]) : "memory");
+        } while (v < seq);
+    }
+    __syncthreads();
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_halo; i += (long long)gridDim.x * blockDim.x) tail[i] = __ldcv(inbox + i);
+}
+
 }  // namespace
 
 struct mpg_dist {
@@ -99,6 +136,15 @@ struct mpg_dist {
     void* mbox_map[kMaxPeers] = {nullptr}; // every rank's mailbox mapped into this process (own pointer for self)
     bool peer_ready = false;
     unsigned long long seq = 0;
+    // peer-memory halo inboxes: [2][n_halo] 8-byte cells, then [2][kMaxPeers] u64 flags
+    void* inbox_own = nullptr;
+    void* inbox_map[kMaxPeers] = {nullptr};
+    int64_t remote_off[kMaxPeers] = {0};     // per peer (index into `peers`): where our rows land in that peer's halo
+    int64_t remote_nhalo[kMaxPeers] = {0};   // per peer: that peer's n_halo (slot stride)
+    bool halo_ready = false;
+    unsigned long long halo_seq = 0;
+    size_t inbox_data_bytes() const { return 2 * (size_t)std::max<int64_t>(n_halo, 1) * 8; }
+    size_t inbox_bytes() const { return inbox_data_bytes() + sizeof(unsigned long long) * 2 * kMaxPeers; }
     size_t mbox_data_bytes() const { return sizeof(double) * (size_t)kMboxSlots * world * kMboxStride; }
     size_t mbox_bytes() const { return mbox_data_bytes() + sizeof(unsigned long long) * (size_t)kMboxSlots * world; }
 };
@@ -127,8 +173,11 @@ extern "C" int mpg_dist_destroy(mpg_dist* d) {
     if (!d) return MPG_OK;
     cudaSetDevice(d->device);
     if (d->comm && nccl().ok) nccl().CommDestroy(d->comm);
-    for (int q = 0; q < d->world && q < kMaxPeers; ++q)
+    for (int q = 0; q < d->world && q < kMaxPeers; ++q) {
         if (d->mbox_map[q] && q != d->rank) cudaIpcCloseMemHandle(d->mbox_map[q]);
+        if (d->inbox_map[q] && q != d->rank) cudaIpcCloseMemHandle(d->inbox_map[q]);
+    }
+    cudaFree(d->inbox_own);
     cudaFree(d->mbox_own);
     cudaFree(d->send_buf);
     delete d;
@@ -180,6 +229,38 @@ extern "C" int mpg_dist_open_mailboxes(mpg_ctx* ctx, mpg_dist* d, const void* ha
     }
     d->peer_ready = true;
     d->seq = 0;
+    return MPG_OK;
+}
+
+// halo inbox (after mpg_dist_set_partition: its size is this rank's halo)
+extern "C" int mpg_dist_halo_handle(mpg_ctx* ctx, mpg_dist* d, void* handle64) {
+    MPG_REQUIRE(ctx, d && handle64 && d->world <= kMaxPeers, "dist_halo_handle: bad argument");
+    if (d->inbox_own) { cudaFree(d->inbox_own); d->inbox_own = nullptr; d->halo_ready = false; }
+    MPG_CUDA(ctx, cudaMalloc(&d->inbox_own, d->inbox_bytes()));
+    MPG_CUDA(ctx, cudaMemset(d->inbox_own, 0, d->inbox_bytes()));
+    cudaIpcMemHandle_t h;
+    MPG_CUDA(ctx, cudaIpcGetMemHandle(&h, d->inbox_own));
+    memcpy(handle64, &h, sizeof(h));
+    return MPG_OK;
+}
+// handles: world x 64 bytes (rank order); per peer of the plan (same order as mpg_dist_set_partition): the offset of our
+// rows inside that peer's halo and that peer's halo length
+extern "C" int mpg_dist_open_halo(mpg_ctx* ctx, mpg_dist* d, const void* handles, const int64_t* remote_offsets, const int64_t* remote_nhalo) {
+    MPG_REQUIRE(ctx, d && handles && d->inbox_own && remote_offsets && remote_nhalo, "dist_open_halo: bad argument");
+    MPG_REQUIRE(ctx, (int)d->peers.size() <= kMaxPeers, "dist_open_halo: too many neighbours");
+    for (int q = 0; q < d->world; ++q) {
+        if (q == d->rank) { d->inbox_map[q] = d->inbox_own; continue; }
+        if (d->inbox_map[q]) { cudaIpcCloseMemHandle(d->inbox_map[q]); d->inbox_map[q] = nullptr; }
+        bool needed = false;
+        for (const auto& p : d->peers) needed = needed || p.rank == q;
+        if (!needed) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, static_cast<const char*>(handles) + (size_t)q * 64, sizeof(h));
+        MPG_CUDA(ctx, cudaIpcOpenMemHandle(&d->inbox_map[q], h, cudaIpcMemLazyEnablePeerAccess));
+    }
+    for (size_t i = 0; i < d->peers.size(); ++i) { d->remote_off[i] = remote_offsets[i]; d->remote_nhalo[i] = remote_nhalo[i]; }
+    d->halo_ready = true;
+    d->halo_seq = 0;
     return MPG_OK;
 }
 
@@ -238,6 +319,31 @@ int halo_exchange(mpg_ctx* ctx, T* x_ext) {
     mpg_dist* d = ctx->dist;
     if (!d || d->peers.empty()) return MPG_OK;
     ProfScope prof(ctx, MPG_PROF_SMALL, 0.0);
+    if (d->halo_ready && ctx->tune.dist_peer_halo) {
+        // push over peer memory: one gather-and-store kernel (a block per neighbour), one wait-and-move kernel
+        const unsigned long long seq = ++d->halo_seq;
+        const int slot = (int)(seq & 1);
+        PushArgs pa;
+        WaitArgs wa;
+        pa.npeers = wa.npeers = (int)d->peers.size();
+        for (size_t i = 0; i < d->peers.size(); ++i) {
+            const auto& p = d->peers[i];
+            char* inbox = static_cast<char*>(d->inbox_map[p.rank]);
+            const size_t their_data = 2 * (size_t)std::max<int64_t>(d->remote_nhalo[i], 1) * 8;
+            pa.send_idx[i] = p.send_idx;
+            pa.count[i] = p.send_count;
+            pa.dst[i] = inbox + (size_t)slot * (size_t)std::max<int64_t>(d->remote_nhalo[i], 1) * 8 + (size_t)d->remote_off[i] * sizeof(T);
+            pa.flag[i] = reinterpret_cast<unsigned long long*>(inbox + their_data) + slot * kMaxPeers + d->rank;
+            wa.flag[i] = reinterpret_cast<const unsigned long long*>(static_cast<char*>(d->inbox_own) + d->inbox_data_bytes()) + slot * kMaxPeers + p.rank;
+        }
+        halo_push_kernel<T><<<pa.npeers, 1024, 0, ctx->stream>>>(pa, x_ext, seq);
+        MPG_CHECK_LAUNCH(ctx);
+        const T* inbox = reinterpret_cast<const T*>(static_cast<char*>(d->inbox_own) + (size_t)slot * (size_t)std::max<int64_t>(d->n_halo, 1) * 8);
+        const int grid = (int)std::min<int64_t>(32, std::max<int64_t>(1, cdiv(d->n_halo, 256 * 8)));
+        halo_wait_copy_kernel<T><<<grid, 256, 0, ctx->stream>>>(wa, seq, inbox, x_ext + d->n_local, (long long)d->n_halo);
+        MPG_CHECK_LAUNCH(ctx);
+        return MPG_OK;
+    }
     T* sbuf = static_cast<T*>(d->send_buf);
     for (const auto& p : d->peers) {
         if (p.send_count == 0) continue;

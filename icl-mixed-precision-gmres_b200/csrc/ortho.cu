@@ -451,8 +451,21 @@ template <> struct VpassCfg<double> { static constexpr int TR = 128; };
 
 template <class T, int TR, int MAXJ>
 int launch_vpass_inst(mpg_ctx* ctx, int64_t n, int k1, const T* V, int64_t ldv, T* w, const T* h_in, int fin, T* coef_out, T* hcol) {
-    CUtensorMap mapV, mapW;
-    const int mrc = make_maps<T>(V, ldv, w, n, k1, TR, &mapV, &mapW);
+    // tensor maps are pure functions of (pointer, n, ldv, k1): keep the last few (one Arnoldi cycle re-uses one per width)
+    struct MapKey { const void* V; const void* w; int64_t n, ldv; int k1, tr, ts; };
+    struct MapSlot { MapKey key; CUtensorMap mapV, mapW; bool valid; };
+    static MapSlot cache[512];   // contexts are single-threaded by contract
+    MapSlot& slot = cache[((size_t)k1 * 2 + (sizeof(T) == 8)) & 511];
+    const MapKey key{V, w, n, ldv, k1, TR, (int)sizeof(T)};
+    int mrc = 0;
+    if (!slot.valid || memcmp(&slot.key, &key, sizeof(MapKey)) != 0) {
+        memset(&slot.key, 0, sizeof(MapKey));
+        mrc = make_maps<T>(V, ldv, w, n, k1, TR, &slot.mapV, &slot.mapW);
+        slot.key = key;
+        slot.valid = (mrc == 0);
+    }
+    const CUtensorMap& mapV = slot.mapV;
+    const CUtensorMap& mapW = slot.mapW;
     if (mrc != 0)
         return fail(ctx, MPG_ERR_CUDA, "vpass: cuTensorMapEncodeTiled failed, code " + std::to_string(mrc) + " (n=" + std::to_string(n) + " k1=" +
                                            std::to_string(k1) + " ldv=" + std::to_string(ldv) + ")");
@@ -467,7 +480,11 @@ int launch_vpass_inst(mpg_ctx* ctx, int64_t n, int k1, const T* V, int64_t ldv, 
     const int64_t ntiles = cdiv(n, TR);
     const int grid = (int)std::min<int64_t>(std::min<int64_t>(ntiles, (int64_t)ctx->num_sms * ctas_per_sm), kMaxPartBlocks);
     auto kern = vpass_kernel<T, TR, MAXJ>;
-    MPG_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
+    static bool attr_set = false;   // per instantiation; one device per process
+    if (!attr_set) {
+        MPG_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
+        attr_set = true;
+    }
     // algorithmic bytes (fused CGS2 = 3 k1 n s + 4 n s): pass A reads V only (w was just written by the
     // SpMV and is counted there), pass B reads V, reads w, writes w'
     ProfScope prof(ctx, MPG_PROF_VPASS, (double)k1 * n * sizeof(T) + (h_in ? 2.0 * n * sizeof(T) : 0.0));

@@ -84,6 +84,7 @@ class DistContext:
         import torch
         import torch.distributed as dist
         self.ctx, self.rank, self.world = ctx, rank, world
+        self._group = group
         self.h = C.c_void_p()
         idbuf = (C.c_ubyte * 128)()
         if rank == 0:
@@ -117,6 +118,19 @@ class DistContext:
         ctx._chk(ctx.L.mpg_dist_set_partition(ctx.h, self.h, C.c_int64(part.n_global), C.c_int64(part.n_local), C.c_int64(part.n_halo), C.c_int(n),
                                               ranks, scount, sptr, roff, rcount))
         self._keep = part  # the send index tensors must outlive the plan
+        # peer-memory halo inboxes: exchange IPC handles and, for every neighbour, where our rows land in its halo
+        if self.peer_reduce and self.world > 1:
+            import torch.distributed as dist
+            hb = (C.c_ubyte * 64)()
+            ctx._chk(ctx.L.mpg_dist_halo_handle(ctx.h, self.h, hb))
+            mine = dict(handle=bytes(hb), n_halo=part.n_halo, recv={p["rank"]: p["recv_offset"] for p in part.peers})
+            allinfo = [None] * self.world
+            dist.all_gather_object(allinfo, mine, group=self._group)
+            allh = (C.c_ubyte * (64 * self.world)).from_buffer_copy(b"".join(i["handle"] for i in allinfo))
+            roff = (C.c_int64 * max(n, 1))(*[allinfo[p["rank"]]["recv"].get(self.rank, 0) for p in part.peers])
+            rnh = (C.c_int64 * max(n, 1))(*[allinfo[p["rank"]]["n_halo"] for p in part.peers])
+            ctx._chk(ctx.L.mpg_dist_open_halo(ctx.h, self.h, allh, roff, rnh))
+            dist.barrier(group=self._group)
 
     def attach(self):
         self.ctx._chk(self.ctx.L.mpg_ctx_attach_dist(self.ctx.h, self.h))

@@ -213,6 +213,12 @@ int mpg_dist_set_partition(mpg_ctx*, mpg_dist* d, int64_t n_global, int64_t n_lo
  * all-gathers them (rank order) and every rank maps its peers.  Without this step reductions go through ncclAllReduce. */
 int mpg_dist_mailbox_handle(mpg_ctx*, mpg_dist* d, void* handle64_host);
 int mpg_dist_open_mailboxes(mpg_ctx*, mpg_dist* d, const void* handles_world_x_64_host);
+/* Peer-memory halo inboxes (after mpg_dist_set_partition).  remote_offsets / remote_nhalo: for each neighbour of the plan,
+ * where this rank's rows land in that neighbour's halo and that neighbour's halo length.  Without this step the halo goes
+ * through pack + ncclSend/ncclRecv. */
+int mpg_dist_halo_handle(mpg_ctx*, mpg_dist* d, void* handle64_host);
+int mpg_dist_open_halo(mpg_ctx*, mpg_dist* d, const void* handles_world_x_64_host, const int64_t* remote_offsets_host,
+                       const int64_t* remote_nhalo_host);
 int mpg_ctx_attach_dist(mpg_ctx*, mpg_dist* d); /* NULL detaches */
 int mpg_dist_info(const mpg_dist* d, int* rank, int* world, int64_t* n_global, int64_t* n_local, int64_t* n_halo);
 int mpg_halo_exchange_f32(mpg_ctx*, float* x_ext);  /* x_ext = [n_local owned | n_halo halo slots] */

@@ -18,7 +18,7 @@ dist.init_process_group("nccl", device_id=torch.device(dev))
 ctx = g.Context(local)
 report = {"ok": True, "cases": []}
 for spec, rlen, orth, peer in [("cd27:32", 60, "cgsr", True), ("cd27:32", 60, "cgsr", False), ("lap2d:200", 50, "cgsr", True), ("powerlaw:20000", 30, "cgsr", True),
-                               ("cd27:24", 40, "mgs", True), ("cd27:24", 40, "cgs", True), ("cd27:24", 40, "cgs", False)]:
+                               ("cd27:24", 40, "mgs", True), ("cd27:24", 40, "cgs", True), ("cd27:24", 40, "cgs", False), ("lap2d:120", 40, "relprecres", True)]:
     rm, ind, val = ctx.gen(spec)
     n = rm.numel() - 1
     xt_host = ctx.rand_vect(n, 42)
@@ -29,6 +29,8 @@ for spec, rlen, orth, peer in [("cd27:32", 60, "cgsr", True), ("cd27:32", 60, "c
     ctx.spmv(A, val, 1.0, xt, 0.0, b)
     x1 = torch.zeros(n, dtype=torch.float64, device=dev)
     kw = dict(mode="mixed", orth=orth, rlen=rlen, tol=1e-9, max_restarts=300)
+    if orth == "relprecres":   # residual-driven restart policy: the look-ahead issue order must be identical on all ranks
+        kw = dict(mode="mixed", orth="cgsr", conv="relprecres", rtol=1e-2, rlen=rlen, tol=1e-9, max_restarts=3000)
     r1 = ctx.gmres(A, val, b, x1, **kw)
     # partitioned
     part = g.dist.build_partition(rm, ind, val, n, rank, world)
@@ -65,8 +67,15 @@ for spec, rlen, orth, peer in [("cd27:32", 60, "cgsr", True), ("cd27:32", 60, "c
     dist.all_reduce(tmax, op=dist.ReduceOp.MAX); dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
     replicated = bool(torch.equal(tmax, tmin))
     env = 0.5 if spec.startswith("powerlaw") else 5e-3
-    ok = (halo_ok and replicated and r1["status"] == r2["status"] == 1 and r1["total_iters"] == r2["total_iters"] and r1["total_restarts"] == r2["total_restarts"]
-          and dev_hist <= env and abs(nb - nb1) <= 1e-12 * nb1 and err2 <= 4 * err1 + 1e-10)
+    data_driven = "conv" in kw
+    if data_driven:   # restart decisions depend on rounding: counts within 5 %, histories comparable only if the counts agree
+        counts_ok = abs(r1["total_iters"] - r2["total_iters"]) <= 0.05 * r1["total_iters"] + 2
+        hist_ok = dev_hist <= env or r1["total_iters"] != r2["total_iters"]
+    else:
+        counts_ok = r1["total_iters"] == r2["total_iters"] and r1["total_restarts"] == r2["total_restarts"]
+        hist_ok = dev_hist <= env
+    ok = (halo_ok and replicated and r1["status"] == r2["status"] == 1 and counts_ok and hist_ok and abs(nb - nb1) <= 1e-12 * nb1
+          and err2 <= 4 * err1 + 1e-10)
     report["cases"].append(dict(spec=spec, orth=orth, peer_reduce=dctx.peer_reduce, ok=ok, halo_ok=halo_ok, replicated=replicated, iters=(r1["total_iters"], r2["total_iters"]),
                                 dev_hist=dev_hist, err=(err1, err2), n_halo=part.n_halo, peers=len(part.peers)))
     report["ok"] = report["ok"] and ok
