@@ -88,15 +88,23 @@ struct PushArgs {
     void* dst[kMaxPeers];                   // neighbour's inbox + slot offset + where our rows go (bytes resolved per type)
     unsigned long long* flag[kMaxPeers];    // neighbour's flag for (slot, this rank)
 };
+constexpr int kPushBlocksPerPeer = 32;   // one SM cannot keep an NVLink busy with stores; spread every neighbour's rows
 template <class T>
-__global__ void __launch_bounds__(1024) halo_push_kernel(PushArgs a, const T* __restrict__ x, unsigned long long seq) {
-    const int q = blockIdx.x;
+__global__ void __launch_bounds__(256) halo_push_kernel(PushArgs a, const T* __restrict__ x, unsigned long long seq, unsigned int* counters) {
+    const int q = blockIdx.x / kPushBlocksPerPeer, part = blockIdx.x % kPushBlocksPerPeer;
     T* dst = static_cast<T*>(a.dst[q]);
     const int* idx = a.send_idx[q];
-    for (long long i = threadIdx.x; i < a.count[q]; i += blockDim.x) dst[i] = x[idx[i]];
+    for (long long i = (long long)part * blockDim.x + threadIdx.x; i < a.count[q]; i += (long long)kPushBlocksPerPeer * blockDim.x) dst[i] = x[idx[i]];
     __threadfence_system();
     __syncthreads();
-    if (threadIdx.x == 0) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.flag[q]), "l"(seq) : "memory");
+    if (threadIdx.x == 0) {
+        // the last block of this neighbour publishes the exchange number (its fence + the counter chain order all stores)
+        if (atomicAdd(counters + q, 1u) == kPushBlocksPerPeer - 1) {
+            counters[q] = 0u;
+            __threadfence_system();
+            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.flag[q]), "l"(seq) : "memory");
+        }
+    }
 }
 struct WaitArgs {
     int npeers;
@@ -143,6 +151,7 @@ struct mpg_dist {
     int64_t remote_nhalo[kMaxPeers] = {0};   // per peer: that peer's n_halo (slot stride)
     bool halo_ready = false;
     unsigned long long halo_seq = 0;
+    unsigned int* push_counters = nullptr;   // kMaxPeers, device
     size_t inbox_data_bytes() const { return 2 * (size_t)std::max<int64_t>(n_halo, 1) * 8; }
     size_t inbox_bytes() const { return inbox_data_bytes() + sizeof(unsigned long long) * 2 * kMaxPeers; }
     size_t mbox_data_bytes() const { return sizeof(double) * (size_t)kMboxSlots * world * kMboxStride; }
@@ -178,6 +187,7 @@ extern "C" int mpg_dist_destroy(mpg_dist* d) {
         if (d->inbox_map[q] && q != d->rank) cudaIpcCloseMemHandle(d->inbox_map[q]);
     }
     cudaFree(d->inbox_own);
+    cudaFree(d->push_counters);
     cudaFree(d->mbox_own);
     cudaFree(d->send_buf);
     delete d;
@@ -259,6 +269,10 @@ extern "C" int mpg_dist_open_halo(mpg_ctx* ctx, mpg_dist* d, const void* handles
         MPG_CUDA(ctx, cudaIpcOpenMemHandle(&d->inbox_map[q], h, cudaIpcMemLazyEnablePeerAccess));
     }
     for (size_t i = 0; i < d->peers.size(); ++i) { d->remote_off[i] = remote_offsets[i]; d->remote_nhalo[i] = remote_nhalo[i]; }
+    if (!d->push_counters) {
+        MPG_CUDA(ctx, cudaMalloc(&d->push_counters, sizeof(unsigned int) * kMaxPeers));
+        MPG_CUDA(ctx, cudaMemset(d->push_counters, 0, sizeof(unsigned int) * kMaxPeers));
+    }
     d->halo_ready = true;
     d->halo_seq = 0;
     return MPG_OK;
@@ -336,7 +350,7 @@ int halo_exchange(mpg_ctx* ctx, T* x_ext) {
             pa.flag[i] = reinterpret_cast<unsigned long long*>(inbox + their_data) + slot * kMaxPeers + d->rank;
             wa.flag[i] = reinterpret_cast<const unsigned long long*>(static_cast<char*>(d->inbox_own) + d->inbox_data_bytes()) + slot * kMaxPeers + p.rank;
         }
-        halo_push_kernel<T><<<pa.npeers, 1024, 0, ctx->stream>>>(pa, x_ext, seq);
+        halo_push_kernel<T><<<pa.npeers * kPushBlocksPerPeer, 256, 0, ctx->stream>>>(pa, x_ext, seq, d->push_counters);
         MPG_CHECK_LAUNCH(ctx);
         const T* inbox = reinterpret_cast<const T*>(static_cast<char*>(d->inbox_own) + (size_t)slot * (size_t)std::max<int64_t>(d->n_halo, 1) * 8);
         const int grid = (int)std::min<int64_t>(32, std::max<int64_t>(1, cdiv(d->n_halo, 256 * 8)));
