@@ -81,7 +81,6 @@ extern "C" int mpg_set_tuning(mpg_ctx* ctx, const char* key, int value) {
     if (!ctx || !key) return MPG_ERR_ARG;
     const std::string k(key);
     if (k == "spmv_ctas_per_sm") ctx->tune.spmv_ctas_per_sm = value;
-    else if (k == "spmv_variant") ctx->tune.spmv_variant = value;
     else if (k == "dist_peer_reduce") ctx->tune.dist_peer_reduce = value;
     else if (k == "dist_peer_halo") ctx->tune.dist_peer_halo = value;
     else if (k == "vpass_stages") ctx->tune.vpass_stages = value;

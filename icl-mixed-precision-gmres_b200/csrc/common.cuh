@@ -20,7 +20,6 @@ constexpr int kMaxPartBlocks = 2048;   // upper bound on the grid of a reducing 
 
 struct Tuning {
     int spmv_ctas_per_sm = 8;
-    int spmv_variant = 0;     // 0: products first (gather per nonzero) - default; 1: row-gather from staged indices (slower: profiles/r01_tune_spmv_variants.txt)
     int vpass_stages = 0;     // 0 = auto
     int vpass_serpentine = 1; // alternate traversal direction between consecutive V passes (L2 reuse)
     int gemvt_rb = 1;         // register row-block kernel for gemv-T

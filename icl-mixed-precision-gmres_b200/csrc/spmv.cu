@@ -144,83 +144,6 @@ __global__ void __launch_bounds__(SPMV_THREADS) spmv_tile_kernel(int nrows, int6
     }
 }
 
-// Variant 2 ("row-gather"): the tile's indices and values are staged in shared memory first (same aligned streaming
-// loads), then rows are reduced straight from there with the x gather done per ROW: lane <-> row, step <-> position in
-// the row.  For stencil-like rows 32 consecutive rows read 32 consecutive x entries at each step, so a gather
-// instruction touches 1-2 cache lines instead of ~10 (ncu: the product-first variant is bound by L1TEX tag lookups of
-// the gathers, 79 % busy, and pulls 1.6x the matrix bytes from L2 for x).  Per-row arithmetic is a sequential fma chain.
-template <class T>
-__global__ void __launch_bounds__(SPMV_THREADS) spmv_tile2_kernel(int nrows, int64_t nnz, const int* __restrict__ row_map,
-                                                                   const int* __restrict__ inds, const T* __restrict__ vals,
-                                                                   const int* __restrict__ tile_row, const T* __restrict__ x,
-                                                                   T alpha, T beta, const T* y_in, T* y_out, float* out32,
-                                                                   T* carry_in, T* carry_out, int vec_ok) {
-    __shared__ __align__(16) T val_s[SPMV_TILE];
-    __shared__ __align__(16) int ind_s[SPMV_TILE];
-    __shared__ int rm_s[SPMV_TILE + 2];
-
-    const int t = blockIdx.x;
-    const int tid = threadIdx.x;
-    const int64_t base = (int64_t)t * SPMV_TILE;
-    const int64_t end = min(nnz, base + SPMV_TILE);
-    const int cnt = (int)(end - base);
-    const int r_lo = tile_row[t];
-    int r_hi = tile_row[t + 1];
-    if (r_hi >= nrows) r_hi = nrows - 1;
-    else if ((int64_t)__ldg(row_map + r_hi) >= end) r_hi -= 1;
-    const int nr = r_hi - r_lo + 1;
-
-    for (int i = tid; i <= nr; i += SPMV_THREADS) rm_s[i] = __ldg(row_map + r_lo + i);
-    if (cnt == SPMV_TILE && vec_ok) {
-        const int4* ip = reinterpret_cast<const int4*>(inds + base);
-        reinterpret_cast<int4*>(ind_s)[tid] = ldg_stream(ip + tid);
-        reinterpret_cast<int4*>(ind_s)[SPMV_THREADS + tid] = ldg_stream(ip + SPMV_THREADS + tid);
-        if (sizeof(T) == 4) {
-            const float4* vp = reinterpret_cast<const float4*>(vals + base);
-            reinterpret_cast<float4*>(val_s)[tid] = ldg_stream(vp + tid);
-            reinterpret_cast<float4*>(val_s)[SPMV_THREADS + tid] = ldg_stream(vp + SPMV_THREADS + tid);
-        } else {
-            const double2* vp = reinterpret_cast<const double2*>(vals + base);
-            double2* vs = reinterpret_cast<double2*>(val_s);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) vs[q * SPMV_THREADS + tid] = ldg_stream(vp + q * SPMV_THREADS + tid);
-        }
-    } else {
-        for (int e = tid; e < cnt; e += SPMV_THREADS) { ind_s[e] = ldg_stream(inds + base + e); val_s[e] = ldg_stream(vals + base + e); }
-    }
-    __syncthreads();
-
-    const bool many_rows = nr > (SPMV_THREADS / 8);
-    if (many_rows) {
-        for (int lr = tid; lr < nr; lr += SPMV_THREADS) {
-            const int64_t rs = rm_s[lr], re = rm_s[lr + 1];
-            const int s = (int)(max(rs, base) - base), e = (int)(min(re, end) - base);
-            T sum = T(0);
-#pragma unroll 4
-            for (int p = s; p < e; ++p) sum = fma(val_s[p], __ldg(x + ind_s[p]), sum);
-            const bool head_cut = rs < base, tail_cut = re > end;
-            if (!head_cut && !tail_cut) spmv_store<T>(r_lo + lr, sum, alpha, beta, y_in, y_out, out32);
-            else if (head_cut) carry_in[t] = sum;
-            else carry_out[t] = sum;
-        }
-    } else {
-        const int warp = tid >> 5, lane = tid & 31;
-        for (int lr = warp; lr < nr; lr += SPMV_THREADS / 32) {
-            const int64_t rs = rm_s[lr], re = rm_s[lr + 1];
-            const int s = (int)(max(rs, base) - base), e = (int)(min(re, end) - base);
-            T sum = T(0);
-            for (int p = s + lane; p < e; p += 32) sum = fma(val_s[p], __ldg(x + ind_s[p]), sum);
-            sum = warp_sum(sum);
-            if (lane == 0) {
-                const bool head_cut = rs < base, tail_cut = re > end;
-                if (!head_cut && !tail_cut) spmv_store<T>(r_lo + lr, sum, alpha, beta, y_in, y_out, out32);
-                else if (head_cut) carry_in[t] = sum;
-                else carry_out[t] = sum;
-            }
-        }
-    }
-}
-
 // One thread per tile: if a row BEGINS in tile t and is cut by its end, gather the pieces in tile order.
 template <class T>
 __global__ void spmv_fixup_kernel(int nrows, int64_t nnz, int ntiles, const int* __restrict__ row_map,
@@ -254,12 +177,10 @@ int launch_spmv(mpg_ctx* ctx, const mpg_csr* A, const T* vals, T alpha, const T*
     if (A->ntiles > 0) {
         // 16-byte vector loads need aligned index / value arrays; sub-views fall back to scalar streaming loads
         const int vec_ok = ((reinterpret_cast<uintptr_t>(A->inds) | reinterpret_cast<uintptr_t>(vals)) & 15) == 0;
-        if (ctx->tune.spmv_variant == 1)
-            spmv_tile2_kernel<T><<<A->ntiles, SPMV_THREADS, 0, ctx->stream>>>(A->nrows, A->nnz, A->row_map, A->inds, vals, A->tile_row, x,
-                                                                             alpha, beta, y_in, y_out, out32, carry_in, carry_out, vec_ok);
-        else
-            spmv_tile_kernel<T><<<A->ntiles, SPMV_THREADS, 0, ctx->stream>>>(A->nrows, A->nnz, A->row_map, A->inds, vals, A->tile_row, x,
-                                                                            alpha, beta, y_in, y_out, out32, carry_in, carry_out, vec_ok);
+        // (two "gather x per row from staged indices" variants were measured and dropped: 0.93 / 1.10 ms against 0.75 ms
+        //  on cd27:256 - profiles/r01_tune_spmv_variants.txt)
+        spmv_tile_kernel<T><<<A->ntiles, SPMV_THREADS, 0, ctx->stream>>>(A->nrows, A->nnz, A->row_map, A->inds, vals, A->tile_row, x,
+                                                                        alpha, beta, y_in, y_out, out32, carry_in, carry_out, vec_ok);
         MPG_CHECK_LAUNCH(ctx);
         if (A->ntiles > 1) {
             spmv_fixup_kernel<T><<<(int)cdiv(A->ntiles - 1, 256), 256, 0, ctx->stream>>>(A->nrows, A->nnz, A->ntiles, A->row_map, A->tile_row,

@@ -161,3 +161,30 @@ def test_size_independent_properties_at_scale(ctx, g, spec, rlen):
     x2 = torch.zeros(n, dtype=torch.float64, device="cuda:0")
     r2 = ctx.gmres(A, val, b, x2, mode="mixed", orth="cgsr", rlen=rlen, tol=tol, max_restarts=400)
     assert torch.equal(x, x2) and np.array_equal(r["hist_inner"], r2["hist_inner"])
+
+
+def test_argument_validation_returns_errors_not_crashes(ctx, g, orc):
+    """the C ABI reports bad arguments through its status code + mpg_last_error (the reference asserts or ignores)"""
+    import ctypes as C
+    import torch
+    rm, ind, val, xt, b = problem(orc, "lap2d:8")
+    A = g.CSR(ctx, dev(rm), dev(ind))
+    x = torch.zeros(len(b), dtype=torch.float64, device="cuda:0")
+    for kw, msg in [(dict(rlen=0), "restart length"), (dict(rlen=300), "restart length")]:
+        with pytest.raises(g.MpgError, match=msg):
+            ctx.gmres(A, dev(val), dev(b), x, mode="mixed", tol=1e-6, **kw)
+    p = ctx.params(rlen=10)
+    p.orth = 7
+    st = g.GmresStats()
+    rc = ctx.L.mpg_gmres_solve(ctx.h, C.byref(p), A.h, C.c_void_p(dev(val).data_ptr()), None, C.c_void_p(dev(b).data_ptr()), C.c_void_p(x.data_ptr()),
+                               C.byref(st), None, C.c_int64(0), None, C.c_int64(0))
+    assert rc == 2 and b"bad enum" in ctx.L.mpg_last_error(ctx.h)
+    # non-square structure
+    A2 = g.CSR(ctx, dev(rm), dev(ind), ncols=len(b) + 3)
+    with pytest.raises(g.MpgError, match="square"):
+        ctx.gmres(A2, dev(val), dev(b), x, mode="mixed", rlen=10)
+    with pytest.raises(g.MpgError, match="unknown tuning key"):
+        ctx.set_tuning("no_such_knob", 1)
+    # the context is still usable afterwards
+    r = ctx.gmres(A, dev(val), dev(b), x, mode="mixed", rlen=10, tol=1e-9)
+    assert r["status"] == 1
