@@ -302,6 +302,9 @@ class Context:
     def spmv(self, A, vals, alpha, x, beta, y):
         self._chk(getattr(self.L, "mpg_spmv_" + _sfx(vals))(self.h, A.h, _ptr(vals), _sc(vals, alpha), _ptr(x), _sc(vals, beta), _ptr(y)))
 
+    def spmv_jacobi(self, A, vals, diag, x, y):
+        self._chk(getattr(self.L, "mpg_spmv_jacobi_" + _sfx(vals))(self.h, A.h, _ptr(vals), _ptr(diag), _ptr(x), _ptr(y)))
+
     def residual_cast(self, A, vals64, b, x, r64, w32):
         self._chk(self.L.mpg_residual_f64_cast_f32(self.h, A.h, _ptr(vals64), _ptr(b), _ptr(x), _ptr(r64), _ptr(w32)))
 

@@ -83,6 +83,7 @@ extern "C" int mpg_set_tuning(mpg_ctx* ctx, const char* key, int value) {
     if (k == "spmv_ctas_per_sm") ctx->tune.spmv_ctas_per_sm = value;
     else if (k == "dist_peer_reduce") ctx->tune.dist_peer_reduce = value;
     else if (k == "dist_peer_halo") ctx->tune.dist_peer_halo = value;
+    else if (k == "dist_overlap") ctx->tune.dist_overlap = value;
     else if (k == "vpass_stages") ctx->tune.vpass_stages = value;
     else if (k == "fuse_min_cols") ctx->tune.fuse_min_cols = value;
     else if (k == "gemvt_rb") ctx->tune.gemvt_rb = value;

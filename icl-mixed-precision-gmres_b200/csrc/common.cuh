@@ -18,6 +18,8 @@ namespace mpg {
 constexpr int kMaxCols = 256;          // widest basis block any fused kernel accepts (restart length + 1)
 constexpr int kMaxPartBlocks = 2048;   // upper bound on the grid of a reducing kernel
 
+enum SpmvPart { SPMV_ALL = 0, SPMV_INTERIOR = 1, SPMV_BOUNDARY = 2 };
+
 struct Tuning {
     int spmv_ctas_per_sm = 8;
     int vpass_stages = 0;     // 0 = auto
@@ -31,6 +33,7 @@ struct Tuning {
     int red_ctas_per_sm = 4;
     int use_graph = 0;
     int dist_peer_halo = 1;   // multi-GPU halo exchange by stores into the neighbours' memory (0: pack + ncclSend/ncclRecv)
+    int dist_overlap = 1;     // multi-GPU SpMV: rows without halo columns run between the halo push and the wait for the neighbours' data
     int dist_peer_reduce = 1; // multi-GPU reductions inside the kernels over peer memory (0: NCCL all-reduce + epilogue kernel)
 };
 
@@ -86,6 +89,11 @@ struct mpg_csr {
     int* tile_row = nullptr;       // [ntiles+1] row containing the first nonzero of each tile
     void* carry = nullptr;         // [2*ntiles] doubles: carry_in / carry_out partial row sums
     int device = 0;
+    int has_empty_rows = 0;        // non-canonical input: SpMV takes the warp-per-row kernel
+    // local slab of a partitioned matrix (ncols > nrows, columns >= nrows are halo slots): tiles that touch no halo
+    // column first, then the others - lets the solver run the former while the halo is in flight
+    int* tile_list = nullptr;      // [ntiles] or null
+    int n_interior_tiles = 0;
 };
 
 namespace mpg {

@@ -327,19 +327,20 @@ int dist_finish_reduction(mpg_ctx* ctx, const Epi& e, int count, int tbytes) {
     return MPG_OK;
 }
 
-// x_ext: n_local owned values followed by n_halo halo slots
+// x_ext: n_local owned values followed by n_halo halo slots.
+// halo_begin sends this rank's rows to the neighbours; halo_finish makes the neighbours' rows visible in the halo
+// tail.  Work that does not read the tail (the SpMV tiles without halo columns) goes between the two.
 template <class T>
-int halo_exchange(mpg_ctx* ctx, T* x_ext) {
+int halo_begin(mpg_ctx* ctx, T* x_ext) {
     mpg_dist* d = ctx->dist;
     if (!d || d->peers.empty()) return MPG_OK;
     ProfScope prof(ctx, MPG_PROF_SMALL, 0.0);
     if (d->halo_ready && ctx->tune.dist_peer_halo) {
-        // push over peer memory: one gather-and-store kernel (a block per neighbour), one wait-and-move kernel
+        // push over peer memory: gather-and-store kernel, kPushBlocksPerPeer blocks per neighbour
         const unsigned long long seq = ++d->halo_seq;
         const int slot = (int)(seq & 1);
         PushArgs pa;
-        WaitArgs wa;
-        pa.npeers = wa.npeers = (int)d->peers.size();
+        pa.npeers = (int)d->peers.size();
         for (size_t i = 0; i < d->peers.size(); ++i) {
             const auto& p = d->peers[i];
             char* inbox = static_cast<char*>(d->inbox_map[p.rank]);
@@ -348,13 +349,8 @@ int halo_exchange(mpg_ctx* ctx, T* x_ext) {
             pa.count[i] = p.send_count;
             pa.dst[i] = inbox + (size_t)slot * (size_t)std::max<int64_t>(d->remote_nhalo[i], 1) * 8 + (size_t)d->remote_off[i] * sizeof(T);
             pa.flag[i] = reinterpret_cast<unsigned long long*>(inbox + their_data) + slot * kMaxPeers + d->rank;
-            wa.flag[i] = reinterpret_cast<const unsigned long long*>(static_cast<char*>(d->inbox_own) + d->inbox_data_bytes()) + slot * kMaxPeers + p.rank;
         }
         halo_push_kernel<T><<<pa.npeers * kPushBlocksPerPeer, 256, 0, ctx->stream>>>(pa, x_ext, seq, d->push_counters);
-        MPG_CHECK_LAUNCH(ctx);
-        const T* inbox = reinterpret_cast<const T*>(static_cast<char*>(d->inbox_own) + (size_t)slot * (size_t)std::max<int64_t>(d->n_halo, 1) * 8);
-        const int grid = (int)std::min<int64_t>(32, std::max<int64_t>(1, cdiv(d->n_halo, 256 * 8)));
-        halo_wait_copy_kernel<T><<<grid, 256, 0, ctx->stream>>>(wa, seq, inbox, x_ext + d->n_local, (long long)d->n_halo);
         MPG_CHECK_LAUNCH(ctx);
         return MPG_OK;
     }
@@ -373,6 +369,36 @@ int halo_exchange(mpg_ctx* ctx, T* x_ext) {
     MPG_NCCL(ctx, nccl().GroupEnd());
     return MPG_OK;
 }
+
+template <class T>
+int halo_finish(mpg_ctx* ctx, T* x_ext) {
+    mpg_dist* d = ctx->dist;
+    if (!d || d->peers.empty()) return MPG_OK;
+    if (!(d->halo_ready && ctx->tune.dist_peer_halo)) return MPG_OK;   // NCCL path: the receive was enqueued by halo_begin
+    ProfScope prof(ctx, MPG_PROF_SMALL, 0.0);
+    // wait-and-move kernel: spin on the neighbours' exchange numbers, then inbox -> halo tail
+    const unsigned long long seq = d->halo_seq;
+    const int slot = (int)(seq & 1);
+    WaitArgs wa;
+    wa.npeers = (int)d->peers.size();
+    for (size_t i = 0; i < d->peers.size(); ++i)
+        wa.flag[i] = reinterpret_cast<const unsigned long long*>(static_cast<char*>(d->inbox_own) + d->inbox_data_bytes()) + slot * kMaxPeers + d->peers[i].rank;
+    const T* inbox = reinterpret_cast<const T*>(static_cast<char*>(d->inbox_own) + (size_t)slot * (size_t)std::max<int64_t>(d->n_halo, 1) * 8);
+    const int grid = (int)std::min<int64_t>(32, std::max<int64_t>(1, cdiv(d->n_halo, 256 * 8)));
+    halo_wait_copy_kernel<T><<<grid, 256, 0, ctx->stream>>>(wa, seq, inbox, x_ext + d->n_local, (long long)d->n_halo);
+    MPG_CHECK_LAUNCH(ctx);
+    return MPG_OK;
+}
+
+template <class T>
+int halo_exchange(mpg_ctx* ctx, T* x_ext) {
+    MPG_TRY(halo_begin<T>(ctx, x_ext));
+    return halo_finish<T>(ctx, x_ext);
+}
+template int halo_begin<float>(mpg_ctx*, float*);
+template int halo_begin<double>(mpg_ctx*, double*);
+template int halo_finish<float>(mpg_ctx*, float*);
+template int halo_finish<double>(mpg_ctx*, double*);
 template int halo_exchange<float>(mpg_ctx*, float*);
 template int halo_exchange<double>(mpg_ctx*, double*);
 

@@ -39,11 +39,13 @@ int gdmv_host(mpg_ctx*, int64_t, float, const float*, const float*, float, float
 int gdmv_host(mpg_ctx*, int64_t, double, const double*, const double*, double, double*);
 template <class T> int givens_step(mpg_ctx*, int64_t, T*, int64_t, T*, T*, T*, double*, double*);
 template <class T> int trsv(mpg_ctx*, int, int, int64_t, const T*, int64_t, T*);
-template <class T> int spmv(mpg_ctx*, const mpg_csr*, const T*, T, const T*, T, const T*, T*, float*);
+template <class T> int spmv(mpg_ctx*, const mpg_csr*, const T*, T, const T*, T, const T*, T*, float*, const T* rowscale = nullptr, int part = SPMV_ALL);
 template <class T> int gemvn(mpg_ctx*, int64_t, int, const T*, int64_t, T, const T*, T, T*, bool, T*, T*, double*);
 template <class T> int gemvt(mpg_ctx*, int64_t, int, const T*, int64_t, T, const T*, T, T*);
 template <class T> int add_vector(mpg_ctx*, int, int64_t, int64_t, T*, int64_t, T*, T*, T*, bool);
 template <class T> int halo_exchange(mpg_ctx*, T*);
+template <class T> int halo_begin(mpg_ctx*, T*);
+template <class T> int halo_finish(mpg_ctx*, T*);
 int64_t dist_halo(mpg_ctx*);
 }  // namespace mpg
 
@@ -243,9 +245,20 @@ int run_cycle(mpg_ctx* ctx, const mpg_gmres_params& p, Policy& pol, Workspace* w
     // one Arnoldi step, enqueued asynchronously
     auto enqueue_iteration = [&](int64_t kk, double* resid_host) -> int {
         // w = A v_k ; M(w)            gmres.cpp:98-102,210-215
-        MPG_TRY(halo_exchange<T>(ctx, V + (size_t)kk * ldv));   // multi-GPU: fill the halo tail of v_k (no-op on one GPU)
-        MPG_TRY(spmv<T>(ctx, A, vals, T(1), V + (size_t)kk * ldv, T(0), w, w, nullptr));
-        MPG_TRY(apply_prec<T>(ctx, n, w, jac, jac32, bridge, ws->tmp32));
+        // Jacobi in the working precision rides in the SpMV store (same rounding as the separate gdmv pass)
+        const T* rowscale = (jac && !bridge) ? jac : nullptr;
+        T* vk = V + (size_t)kk * ldv;
+        if (A->tile_list && ctx->tune.dist_overlap) {
+            // multi-GPU: send v_k's boundary rows, multiply the rows that need no halo while they travel, then the rest
+            MPG_TRY(halo_begin<T>(ctx, vk));
+            MPG_TRY(spmv<T>(ctx, A, vals, T(1), vk, T(0), w, w, nullptr, rowscale, SPMV_INTERIOR));
+            MPG_TRY(halo_finish<T>(ctx, vk));
+            MPG_TRY(spmv<T>(ctx, A, vals, T(1), vk, T(0), w, w, nullptr, rowscale, SPMV_BOUNDARY));
+        } else {
+            MPG_TRY(halo_exchange<T>(ctx, vk));   // fill the halo tail of v_k (no-op on one GPU)
+            MPG_TRY(spmv<T>(ctx, A, vals, T(1), vk, T(0), w, w, nullptr, rowscale));
+        }
+        if (!rowscale) MPG_TRY(apply_prec<T>(ctx, n, w, jac, jac32, bridge, ws->tmp32));
         // orth.add_vector(k, w, h)     gmres.cpp:104,217
         MPG_TRY(add_vector<T>(ctx, p.orth, n, kk, V, ldv, w, h + (size_t)kk * ldh, scratch, true));
         // rot / rotg / rot             gmres.cpp:106-110,219-222 ; |s(k+1)| stays on the device

@@ -15,6 +15,8 @@
 // The plan (tile -> first row) is built once per matrix structure on the device (mpg_csr_create), the
 // analogue of the reference's create_cuda_handles (types_cuda.hpp:53-60); fp32 and fp64 value arrays
 // share it exactly as SparseMatrix<float,Cuda> aliases row_map/inds (types_cuda.hpp:82-91).
+#include <vector>
+
 #include "common.cuh"
 
 using namespace mpg;
@@ -44,10 +46,16 @@ __global__ void plan_kernel(int nrows, int64_t nnz, const int* __restrict__ row_
 
 template <class T> struct Carry { using type = T; };
 
-// Epilogue: y_out[r] = alpha*sum + beta*y_in[r]  (beta == 0: y_in never read), optional fp32 copy.
+// gdmv(1, d, v, 0, v) of kernels.hpp:143-145 with the same rounding sequence as the stand-alone kernel in blas1.cu
+__device__ __forceinline__ float rowscale_apply(float d, float v) { return __fadd_rn(__fmul_rn(0.f, v), __fmul_rn(__fmul_rn(1.f, d), v)); }
+__device__ __forceinline__ double rowscale_apply(double d, double v) { return __dadd_rn(__dmul_rn(0.0, v), __dmul_rn(__dmul_rn(1.0, d), v)); }
+
+// Epilogue: y_out[r] = alpha*sum + beta*y_in[r]  (beta == 0: y_in never read), optional Jacobi row scaling
+// (the preconditioner application M(w) = diag .* w of types.hpp:444-446 folded into the store), optional fp32 copy.
 template <class T>
-__device__ __forceinline__ void spmv_store(int r, T sum, T alpha, T beta, const T* y_in, T* y_out, float* out32) {
+__device__ __forceinline__ void spmv_store(int r, T sum, T alpha, T beta, const T* y_in, T* y_out, float* out32, const T* rowscale) {
     T v = (beta == T(0)) ? alpha * sum : fma(alpha, sum, beta * y_in[r]);
+    if (rowscale) v = rowscale_apply(__ldg(rowscale + r), v);
     if (y_out) y_out[r] = v;
     if (out32) out32[r] = (float)v;
 }
@@ -57,11 +65,12 @@ __global__ void __launch_bounds__(SPMV_THREADS) spmv_tile_kernel(int nrows, int6
                                                                   const int* __restrict__ inds, const T* __restrict__ vals,
                                                                   const int* __restrict__ tile_row, const T* __restrict__ x,
                                                                   T alpha, T beta, const T* y_in, T* y_out, float* out32,
-                                                                  T* carry_in, T* carry_out, int vec_ok) {
+                                                                  T* carry_in, T* carry_out, int vec_ok, const T* rowscale,
+                                                                  const int* __restrict__ tile_list) {
     __shared__ T prod[SPMV_TILE];
     __shared__ int rm_s[SPMV_TILE + 2];
 
-    const int t = blockIdx.x;
+    const int t = tile_list ? __ldg(tile_list + blockIdx.x) : blockIdx.x;
     const int64_t base = (int64_t)t * SPMV_TILE;
     const int64_t end = min(nnz, base + SPMV_TILE);
     const int cnt = (int)(end - base);
@@ -122,7 +131,7 @@ __global__ void __launch_bounds__(SPMV_THREADS) spmv_tile_kernel(int nrows, int6
             T sum = T(0);
             for (int p = s; p < e; ++p) sum += prod[p];
             const bool head_cut = rs < base, tail_cut = re > end;
-            if (!head_cut && !tail_cut) spmv_store<T>(r_lo + lr, sum, alpha, beta, y_in, y_out, out32);
+            if (!head_cut && !tail_cut) spmv_store<T>(r_lo + lr, sum, alpha, beta, y_in, y_out, out32, rowscale);
             else if (head_cut) carry_in[t] = sum;       // continues a row begun in an earlier tile
             else carry_out[t] = sum;                    // row begins here, finishes later
         }
@@ -136,7 +145,7 @@ __global__ void __launch_bounds__(SPMV_THREADS) spmv_tile_kernel(int nrows, int6
             sum = warp_sum(sum);
             if (lane == 0) {
                 const bool head_cut = rs < base, tail_cut = re > end;
-                if (!head_cut && !tail_cut) spmv_store<T>(r_lo + lr, sum, alpha, beta, y_in, y_out, out32);
+                if (!head_cut && !tail_cut) spmv_store<T>(r_lo + lr, sum, alpha, beta, y_in, y_out, out32, rowscale);
                 else if (head_cut) carry_in[t] = sum;
                 else carry_out[t] = sum;
             }
@@ -148,7 +157,7 @@ __global__ void __launch_bounds__(SPMV_THREADS) spmv_tile_kernel(int nrows, int6
 template <class T>
 __global__ void spmv_fixup_kernel(int nrows, int64_t nnz, int ntiles, const int* __restrict__ row_map,
                                   const int* __restrict__ tile_row, T alpha, T beta, const T* y_in, T* y_out, float* out32,
-                                  const T* carry_in, const T* carry_out) {
+                                  const T* carry_in, const T* carry_out, const T* rowscale) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= ntiles - 1) return;  // the last tile cannot be cut at its end
     const int64_t end = (int64_t)(t + 1) * SPMV_TILE;
@@ -162,45 +171,80 @@ __global__ void spmv_fixup_kernel(int nrows, int64_t nnz, int ntiles, const int*
         sum += carry_in[t2];
         if (re <= (int64_t)(t2 + 1) * SPMV_TILE) break;
     }
-    spmv_store<T>(r, sum, alpha, beta, y_in, y_out, out32);
+    spmv_store<T>(r, sum, alpha, beta, y_in, y_out, out32, rowscale);
+}
+
+// Non-canonical input (rows with no stored entry at all; LoadMatrix-canonical matrices always hold the diagonal,
+// LoadMatrix.hpp:98-100): the tile plan assumes every row owns at least one nonzero, so such matrices take this
+// plain warp-per-row kernel instead.
+template <class T>
+__global__ void __launch_bounds__(256) spmv_rows_kernel(int nrows, const int* __restrict__ row_map, const int* __restrict__ inds,
+                                                         const T* __restrict__ vals, const T* __restrict__ x, T alpha, T beta,
+                                                         const T* y_in, T* y_out, float* out32, const T* rowscale) {
+    const int lane = threadIdx.x & 31;
+    for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < nrows; r += ((int64_t)gridDim.x * blockDim.x) >> 5) {
+        const int rs = __ldg(row_map + r), re = __ldg(row_map + r + 1);
+        T sum = T(0);
+        for (int p = rs + lane; p < re; p += 32) sum += ldg_stream(vals + p) * __ldg(x + ldg_stream(inds + p));
+        sum = warp_sum(sum);
+        if (lane == 0) spmv_store<T>((int)r, sum, alpha, beta, y_in, y_out, out32, rowscale);
+    }
 }
 
 template <class T>
-int launch_spmv(mpg_ctx* ctx, const mpg_csr* A, const T* vals, T alpha, const T* x, T beta, const T* y_in, T* y_out, float* out32) {
+int launch_spmv(mpg_ctx* ctx, const mpg_csr* A, const T* vals, T alpha, const T* x, T beta, const T* y_in, T* y_out, float* out32,
+                const T* rowscale = nullptr, int part = SPMV_ALL) {
     if (A->nrows == 0) return MPG_OK;
+    // part: the solver splits a partitioned SpMV into the tiles without halo columns (SPMV_INTERIOR, may run before the
+    // halo has arrived) and the rest + the cut-row fix-up (SPMV_BOUNDARY); without a tile list the second call does it all
+    if (part != SPMV_ALL && (!A->tile_list || A->has_empty_rows)) {
+        if (part == SPMV_INTERIOR) return MPG_OK;
+        part = SPMV_ALL;
+    }
+    const int t_first = part == SPMV_BOUNDARY ? A->n_interior_tiles : 0;
+    const int t_count = part == SPMV_INTERIOR ? A->n_interior_tiles : A->ntiles - t_first;
+    const int* tile_list = part == SPMV_ALL ? nullptr : A->tile_list + t_first;
+    const double share = A->ntiles > 0 ? (double)t_count / A->ntiles : 1.0;
     T* carry_in = reinterpret_cast<T*>(A->carry);
     T* carry_out = carry_in + A->ntiles;
     // algorithmic bytes, SURVEY.md §8d: nnz*(s+4) + 4(n+1) + n*s (x) + n*s (y)  [+ n*s for y_in when beta != 0, + 4n for the fp32 copy]
     const double n_ = A->nrows, s_ = sizeof(T);
-    const double bytes = (double)A->nnz * (s_ + 4) + 4 * (n_ + 1) + n_ * s_ + (y_out ? n_ * s_ : 0) + (beta != T(0) ? n_ * s_ : 0) + (out32 ? 4 * n_ : 0);
-    ProfScope prof(ctx, sizeof(T) == 4 ? MPG_PROF_SPMV_F32 : MPG_PROF_SPMV_F64, bytes);
-    if (A->ntiles > 0) {
+    const double bytes = (double)A->nnz * (s_ + 4) + 4 * (n_ + 1) + n_ * s_ + (y_out ? n_ * s_ : 0) + (beta != T(0) ? n_ * s_ : 0) + (out32 ? 4 * n_ : 0) +
+                         (rowscale ? n_ * s_ : 0);
+    if (part == SPMV_INTERIOR && t_count == 0) return MPG_OK;
+    ProfScope prof(ctx, sizeof(T) == 4 ? MPG_PROF_SPMV_F32 : MPG_PROF_SPMV_F64, bytes * share);
+    if (A->has_empty_rows) {
+        const int grid = (int)std::min<int64_t>(cdiv((int64_t)A->nrows * 32, 256), (int64_t)ctx->num_sms * 32);
+        spmv_rows_kernel<T><<<grid, 256, 0, ctx->stream>>>(A->nrows, A->row_map, A->inds, vals, x, alpha, beta, y_in, y_out, out32, rowscale);
+        MPG_CHECK_LAUNCH(ctx);
+    } else if (A->ntiles > 0) {
         // 16-byte vector loads need aligned index / value arrays; sub-views fall back to scalar streaming loads
         const int vec_ok = ((reinterpret_cast<uintptr_t>(A->inds) | reinterpret_cast<uintptr_t>(vals)) & 15) == 0;
         // (two "gather x per row from staged indices" variants were measured and dropped: 0.93 / 1.10 ms against 0.75 ms
         //  on cd27:256 - profiles/r01_tune_spmv_variants.txt)
-        spmv_tile_kernel<T><<<A->ntiles, SPMV_THREADS, 0, ctx->stream>>>(A->nrows, A->nnz, A->row_map, A->inds, vals, A->tile_row, x,
-                                                                        alpha, beta, y_in, y_out, out32, carry_in, carry_out, vec_ok);
-        MPG_CHECK_LAUNCH(ctx);
-        if (A->ntiles > 1) {
+        if (t_count > 0) {
+            spmv_tile_kernel<T><<<t_count, SPMV_THREADS, 0, ctx->stream>>>(A->nrows, A->nnz, A->row_map, A->inds, vals, A->tile_row, x, alpha, beta,
+                                                                          y_in, y_out, out32, carry_in, carry_out, vec_ok, rowscale, tile_list);
+            MPG_CHECK_LAUNCH(ctx);
+        }
+        if (A->ntiles > 1 && part != SPMV_INTERIOR) {
             spmv_fixup_kernel<T><<<(int)cdiv(A->ntiles - 1, 256), 256, 0, ctx->stream>>>(A->nrows, A->nnz, A->ntiles, A->row_map, A->tile_row,
-                                                                                      alpha, beta, y_in, y_out, out32, carry_in, carry_out);
+                                                                                      alpha, beta, y_in, y_out, out32, carry_in, carry_out, rowscale);
             MPG_CHECK_LAUNCH(ctx);
         }
     }
     return MPG_OK;
 }
 
-// rows with no nonzeros at all never appear in a tile; give them y = beta*y (only needed for non-canonical input)
-template <class T>
-__global__ void empty_rows_kernel(int nrows, const int* __restrict__ row_map, T beta, const T* y_in, T* y_out, float* out32) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= nrows) return;
-    if (row_map[r] == row_map[r + 1]) {
-        const T v = (beta == T(0)) ? T(0) : beta * y_in[r];
-        if (y_out) y_out[r] = v;
-        if (out32) out32[r] = (float)v;
-    }
+// one warp per tile: does the tile reference a halo column (index >= nrows)?
+__global__ void tile_halo_flag_kernel(int ntiles, int64_t nnz, int nrows, const int* __restrict__ inds, int* __restrict__ flag) {
+    const int t = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (t >= ntiles) return;
+    const int64_t base = (int64_t)t * SPMV_TILE, end = min(nnz, base + SPMV_TILE);
+    int any = 0;
+    for (int64_t p = base + lane; p < end; p += 32) any |= __ldg(inds + p) >= nrows;
+    any = __any_sync(0xffffffffu, any);
+    if (lane == 0) flag[t] = any;
 }
 
 __global__ void count_empty_kernel(int nrows, const int* __restrict__ row_map, int* count) {
@@ -209,10 +253,6 @@ __global__ void count_empty_kernel(int nrows, const int* __restrict__ row_map, i
 }
 
 }  // namespace
-
-struct mpg_csr_priv {
-    int has_empty_rows;
-};
 
 extern "C" int mpg_csr_create(mpg_ctx* ctx, int nrows, int ncols, int64_t nnz, const int* row_map, const int* inds, mpg_csr** out) {
     MPG_REQUIRE(ctx, out != nullptr, "csr_create: null out");
@@ -228,6 +268,31 @@ extern "C" int mpg_csr_create(mpg_ctx* ctx, int nrows, int ncols, int64_t nnz, c
     MPG_CUDA(ctx, cudaMemsetAsync(A->carry, 0, sizeof(double) * 2 * (size_t)(A->ntiles + 1), ctx->stream));
     plan_kernel<<<(int)cdiv(A->ntiles + 1, 256), 256, 0, ctx->stream>>>(nrows, nnz, row_map, SPMV_TILE, A->ntiles, A->tile_row);
     MPG_CHECK_LAUNCH(ctx);
+    if (nrows > 0) {   // the scratch slot after the plan doubles as the empty-row counter
+        int* cnt = A->tile_row + A->ntiles + 1;
+        MPG_CUDA(ctx, cudaMemsetAsync(cnt, 0, sizeof(int), ctx->stream));
+        count_empty_kernel<<<(int)cdiv(nrows, 256), 256, 0, ctx->stream>>>(nrows, row_map, cnt);
+        MPG_CHECK_LAUNCH(ctx);
+        int h = 0;
+        MPG_CUDA(ctx, cudaMemcpyAsync(&h, cnt, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        MPG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        A->has_empty_rows = h > 0;
+    }
+    if (ncols > nrows && A->ntiles > 0 && !A->has_empty_rows) {
+        // local slab of a partitioned matrix: order the tiles [no halo column | some halo column]
+        std::vector<int> flag((size_t)A->ntiles), list((size_t)A->ntiles);
+        MPG_CUDA(ctx, cudaMalloc(&A->tile_list, sizeof(int) * (size_t)A->ntiles));
+        tile_halo_flag_kernel<<<(int)cdiv((int64_t)A->ntiles * 32, 256), 256, 0, ctx->stream>>>(A->ntiles, nnz, nrows, inds, A->tile_list);
+        MPG_CHECK_LAUNCH(ctx);
+        MPG_CUDA(ctx, cudaMemcpyAsync(flag.data(), A->tile_list, sizeof(int) * flag.size(), cudaMemcpyDeviceToHost, ctx->stream));
+        MPG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        int ni = 0;
+        for (int t = 0; t < A->ntiles; ++t) if (!flag[(size_t)t]) list[(size_t)ni++] = t;
+        A->n_interior_tiles = ni;
+        for (int t = 0; t < A->ntiles; ++t) if (flag[(size_t)t]) list[(size_t)ni++] = t;
+        MPG_CUDA(ctx, cudaMemcpyAsync(A->tile_list, list.data(), sizeof(int) * list.size(), cudaMemcpyHostToDevice, ctx->stream));
+        MPG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
     *out = A;
     return MPG_OK;
 }
@@ -237,26 +302,36 @@ extern "C" int mpg_csr_destroy(mpg_csr* A) {
     cudaSetDevice(A->device);
     cudaFree(A->tile_row);
     cudaFree(A->carry);
+    cudaFree(A->tile_list);
     delete A;
     return MPG_OK;
 }
 
 namespace mpg {
 template <class T>
-int spmv(mpg_ctx* ctx, const mpg_csr* A, const T* vals, T alpha, const T* x, T beta, const T* y_in, T* y_out, float* out32) {
-    return launch_spmv<T>(ctx, A, vals, alpha, x, beta, y_in, y_out, out32);
+int spmv(mpg_ctx* ctx, const mpg_csr* A, const T* vals, T alpha, const T* x, T beta, const T* y_in, T* y_out, float* out32, const T* rowscale,
+         int part) {
+    return launch_spmv<T>(ctx, A, vals, alpha, x, beta, y_in, y_out, out32, rowscale, part);
 }
-template int spmv<float>(mpg_ctx*, const mpg_csr*, const float*, float, const float*, float, const float*, float*, float*);
-template int spmv<double>(mpg_ctx*, const mpg_csr*, const double*, double, const double*, double, const double*, double*, float*);
+template int spmv<float>(mpg_ctx*, const mpg_csr*, const float*, float, const float*, float, const float*, float*, float*, const float*, int);
+template int spmv<double>(mpg_ctx*, const mpg_csr*, const double*, double, const double*, double, const double*, double*, float*, const double*, int);
 }  // namespace mpg
 
 extern "C" int mpg_spmv_f32(mpg_ctx* ctx, const mpg_csr* A, const float* vals, float alpha, const float* x, float beta, float* y) {
-    MPG_REQUIRE(ctx, A && vals && x && y, "spmv: null argument");
+    MPG_REQUIRE(ctx, A && (vals || A->nnz == 0) && x && y, "spmv: null argument");
     return launch_spmv<float>(ctx, A, vals, alpha, x, beta, y, y, nullptr);
 }
 extern "C" int mpg_spmv_f64(mpg_ctx* ctx, const mpg_csr* A, const double* vals, double alpha, const double* x, double beta, double* y) {
-    MPG_REQUIRE(ctx, A && vals && x && y, "spmv: null argument");
+    MPG_REQUIRE(ctx, A && (vals || A->nnz == 0) && x && y, "spmv: null argument");
     return launch_spmv<double>(ctx, A, vals, alpha, x, beta, y, y, nullptr);
+}
+extern "C" int mpg_spmv_jacobi_f32(mpg_ctx* ctx, const mpg_csr* A, const float* vals, const float* diag, const float* x, float* y) {
+    MPG_REQUIRE(ctx, A && vals && diag && x && y, "spmv_jacobi: null argument");
+    return launch_spmv<float>(ctx, A, vals, 1.f, x, 0.f, y, y, nullptr, diag);
+}
+extern "C" int mpg_spmv_jacobi_f64(mpg_ctx* ctx, const mpg_csr* A, const double* vals, const double* diag, const double* x, double* y) {
+    MPG_REQUIRE(ctx, A && vals && diag && x && y, "spmv_jacobi: null argument");
+    return launch_spmv<double>(ctx, A, vals, 1.0, x, 0.0, y, y, nullptr, diag);
 }
 extern "C" int mpg_residual_f64_cast_f32(mpg_ctx* ctx, const mpg_csr* A, const double* vals, const double* b, const double* x,
                                          double* r64, float* w32) {

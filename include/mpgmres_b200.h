@@ -131,6 +131,10 @@ int mpg_csr_create(mpg_ctx*, int nrows, int ncols, int64_t nnz, const int* row_m
 int mpg_csr_destroy(mpg_csr* A);
 int mpg_spmv_f32(mpg_ctx*, const mpg_csr* A, const float* vals, float alpha, const float* x, float beta, float* y);
 int mpg_spmv_f64(mpg_ctx*, const mpg_csr* A, const double* vals, double alpha, const double* x, double beta, double* y);
+/* Jacobi-preconditioned operator in one kernel: y = diag .* (A*x), i.e. spmv (gmres.cpp:100,212) followed by
+ * Jacobi::apply = gdmv(1, diag, y, 0, y) (types.hpp:444-446), bit-identical to the two separate calls. */
+int mpg_spmv_jacobi_f32(mpg_ctx*, const mpg_csr* A, const float* vals, const float* diag, const float* x, float* y);
+int mpg_spmv_jacobi_f64(mpg_ctx*, const mpg_csr* A, const double* vals, const double* diag, const double* x, double* y);
 /* Fused outer residual, replaces gmres.cpp:173-175 (copy + fp64 SpMV + cast kernel):
  * r = b - A*x in fp64; w32 = (float) r; r64 may be NULL (then r is never stored). */
 int mpg_residual_f64_cast_f32(mpg_ctx*, const mpg_csr* A, const double* vals, const double* b, const double* x,

@@ -295,3 +295,51 @@ def test_jacobi_diag_bit_exact(ctx, g, orc):
             dd = torch.empty(n, dtype=torch.float32 if dt == np.float32 else torch.float64, device="cuda:0")
             ctx.jacobi_diag(A, dev(v), dd)
             np.testing.assert_array_equal(host(dd), do)
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_spmv_rows_without_entries(ctx, g, orc, dt):
+    """non-canonical CSR (rows with no stored entry: leading, trailing, long runs in the middle, all rows) - the reference's
+    loader never produces these (LoadMatrix.hpp:98-100) but the operator must not read or write out of bounds"""
+    import scipy.sparse as sp
+    r = _rng(11)
+    n = 9000
+    M = sp.random(n, n, density=2e-3, format="lil", random_state=5, dtype=np.float64)
+    for lo, hi in [(0, 40), (100, 3200), (n - 25, n)]:
+        M[lo:hi, :] = 0
+    M = M.tocsr(); M.eliminate_zeros(); M.sort_indices()
+    assert np.diff(M.indptr)[:40].sum() == 0 and M.nnz > 2048
+    x = r.standard_normal(n).astype(dt)
+    y = r.standard_normal(n).astype(dt)
+    rm, ind, v = M.indptr.astype(np.int32), M.indices.astype(np.int32), M.data.astype(np.float32).astype(dt)
+    A = g.CSR(ctx, dev(rm), dev(ind))
+    for alpha, beta in [(1.0, 0.0), (-1.0, 1.0)]:
+        yd = dev(y if beta != 0 else np.full(n, np.nan, dt))
+        ctx.spmv(A, dev(v), alpha, dev(x), beta, yd)
+        yo = orc.spmv(rm, ind, v, alpha, x, beta, y.copy())
+        np.testing.assert_allclose(host(yd), yo, rtol=0, atol=64 * np.finfo(dt).eps * max(1.0, np.abs(yo).max()))
+        empty = np.diff(rm) == 0
+        np.testing.assert_array_equal(host(yd)[empty], (beta * y)[empty] if beta != 0 else np.zeros(empty.sum(), dt))
+    # a matrix with no entries at all
+    rm0 = np.zeros(n + 1, np.int32)
+    A0 = g.CSR(ctx, dev(rm0), dev(np.zeros(0, np.int32)))
+    yd = dev(np.full(n, np.nan, dt))
+    ctx.spmv(A0, dev(np.zeros(0, dt)), 1.0, dev(x), 0.0, yd)
+    np.testing.assert_array_equal(host(yd), np.zeros(n, dt))
+
+
+@pytest.mark.parametrize("spec", ["lap2d:40", "cd27:17", "powerlaw:20000"])
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_spmv_jacobi_fused_equals_spmv_then_gdmv(ctx, g, orc, spec, dt):
+    import torch
+    rm, ind, val = orc.gen(spec)
+    n = len(rm) - 1
+    v = val.astype(dt)
+    x = _rng(n).standard_normal(n).astype(dt)
+    A = g.CSR(ctx, dev(rm), dev(ind))
+    vd, xd = dev(v), dev(x)
+    diag = torch.empty(n, dtype=vd.dtype, device="cuda:0")
+    ctx.jacobi_diag(A, vd, diag)
+    y_sep = torch.empty_like(xd); ctx.spmv(A, vd, 1.0, xd, 0.0, y_sep); ctx.gdmv(1.0, diag, y_sep, 0.0, y_sep)
+    y_fused = torch.full_like(xd, float("nan")); ctx.spmv_jacobi(A, vd, diag, xd, y_fused)
+    np.testing.assert_array_equal(host(y_fused), host(y_sep))
