@@ -140,6 +140,29 @@ class CSR:
             pass
 
 
+class Packed:
+    """mpg_packed handle: sliced-ELL copy of a CSR matrix + values (None-like when the structure does not pack well: .h is null)"""
+
+    def __init__(self, ctx, A, vals):
+        self.ctx, self.A, self.sfx = ctx, A, _sfx(vals)
+        self.h = C.c_void_p()
+        ctx._chk(getattr(ctx.L, "mpg_pack_create_" + self.sfx)(ctx.h, A.h, _ptr(vals), C.byref(self.h)))
+
+    def __bool__(self):
+        return bool(self.h)
+
+    def update(self, vals):
+        self.ctx._chk(getattr(self.ctx.L, "mpg_pack_update_" + self.sfx)(self.ctx.h, self.h, _ptr(vals)))
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.ctx.L.mpg_pack_destroy(self.h)
+                self.h = C.c_void_p()
+        except Exception:
+            pass
+
+
 class Context:
     def __init__(self, device=0):
         import torch
@@ -301,6 +324,9 @@ class Context:
 
     def spmv(self, A, vals, alpha, x, beta, y):
         self._chk(getattr(self.L, "mpg_spmv_" + _sfx(vals))(self.h, A.h, _ptr(vals), _sc(vals, alpha), _ptr(x), _sc(vals, beta), _ptr(y)))
+
+    def spmv_packed(self, P, alpha, x, beta, y):
+        self._chk(getattr(self.L, "mpg_spmv_packed_" + P.sfx)(self.h, P.h, _sc(x, alpha), _ptr(x), _sc(x, beta), _ptr(y)))
 
     def spmv_jacobi(self, A, vals, diag, x, y):
         self._chk(getattr(self.L, "mpg_spmv_jacobi_" + _sfx(vals))(self.h, A.h, _ptr(vals), _ptr(diag), _ptr(x), _ptr(y)))

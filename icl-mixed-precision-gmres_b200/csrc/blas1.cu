@@ -36,6 +36,14 @@ extern "C" int mpg_ctx_create(int device, mpg_ctx** out) {
     MPG_CUDA(ctx, cudaMemset(ctx->dscal, 0, sizeof(double) * 1024));
     MPG_CUDA(ctx, cudaMallocHost(&ctx->hscal, sizeof(double) * 64));
     MPG_CUDA(ctx, cudaMalloc(&ctx->red_raw, sizeof(double) * (kMaxCols + 8)));
+    {   // keep freed pool memory cached (see pool_alloc)
+        cudaMemPool_t pool = nullptr;
+        if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess && pool) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+    }
     *out = ctx;
     return MPG_OK;
 }
@@ -84,8 +92,13 @@ extern "C" int mpg_set_tuning(mpg_ctx* ctx, const char* key, int value) {
     else if (k == "dist_peer_reduce") ctx->tune.dist_peer_reduce = value;
     else if (k == "dist_peer_halo") ctx->tune.dist_peer_halo = value;
     else if (k == "dist_overlap") ctx->tune.dist_overlap = value;
+    else if (k == "spmv_packed") ctx->tune.spmv_packed = value;
     else if (k == "vpass_stages") ctx->tune.vpass_stages = value;
     else if (k == "fuse_min_cols") ctx->tune.fuse_min_cols = value;
+    else if (k == "vdirect_max_cols_a") ctx->tune.vdirect_max_cols_a = value;
+    else if (k == "vdirect_max_cols_b") ctx->tune.vdirect_max_cols_b = value;
+    else if (k == "vrow_max_cols") ctx->tune.vrow_max_cols = std::max(0, std::min(value, 64));
+    else if (k == "vrow_max_cols_a") ctx->tune.vrow_max_cols_a = std::max(0, std::min(value, 64));
     else if (k == "gemvt_rb") ctx->tune.gemvt_rb = value;
     else if (k == "gemvt_rows_per_block") ctx->tune.gemvt_rows_per_block = value;
     else if (k == "passA_rb") ctx->tune.passA_rb = value;

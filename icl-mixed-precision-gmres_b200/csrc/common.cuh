@@ -27,12 +27,17 @@ struct Tuning {
     int gemvt_rb = 1;         // register row-block kernel for gemv-T
     int gemvt_rows_per_block = 8192;
     int passA_rb = 0;         // use gemvt_rb for the first CGS pass (h = V'w) instead of the staged vpass kernel
-    int fuse_min_cols = 16;   // basis width from which the staged fused kernel beats the register kernels (tools/tune.py)
+    int vdirect_max_cols_a = 8;   // widest basis for the register-resident fused kernel, pass A (h = V'w)
+    int vdirect_max_cols_b = 8;   //   ... and pass B (w -= V h; c = V'w)
+    int vrow_max_cols_a = 32;     // pass A: widest basis for the row-owner staged kernel
+    int vrow_max_cols = 56;   // pass B: widest basis handled by the row-owner staged kernel (vrow); wider ones take the column-owner vpass
+    int fuse_min_cols = 1;    // basis width from which the fused 3-pass kernels are used (below: gemv-T / gemv-N register kernels, 4 passes)
     int cgs2_fused = 1;       // fused update + gemv-T second pass (3 passes) vs separate gemv-N, gemv-T (4 passes)
     int gemvn_ctas_per_sm = 4;
     int red_ctas_per_sm = 4;
     int use_graph = 0;
     int dist_peer_halo = 1;   // multi-GPU halo exchange by stores into the neighbours' memory (0: pack + ncclSend/ncclRecv)
+    int spmv_packed = 1;      // solver: run the inner SpMV on the packed (sliced-ELL) copy of the matrix when it packs well (sell.cu)
     int dist_overlap = 1;     // multi-GPU SpMV: rows without halo columns run between the halo push and the wait for the neighbours' data
     int dist_peer_reduce = 1; // multi-GPU reductions inside the kernels over peer memory (0: NCCL all-reduce + epilogue kernel)
 };
@@ -78,6 +83,8 @@ struct mpg_ctx {
     void (*ws_free)(void*) = nullptr;
 };
 
+struct mpg_sell_plan;   // sell.cu: packed (sliced-ELL) structure of a matrix
+
 struct mpg_csr {
     int nrows = 0, ncols = 0;
     int64_t nnz = 0;
@@ -94,9 +101,20 @@ struct mpg_csr {
     // column first, then the others - lets the solver run the former while the halo is in flight
     int* tile_list = nullptr;      // [ntiles] or null
     int n_interior_tiles = 0;
+    // packed structure per group size (slot 0: 4 = fp32, slot 1: 2 = fp64), built on first use (sell.cu)
+    mpg_sell_plan* sell[2] = {nullptr, nullptr};
+    int sell_tried[2] = {0, 0};
 };
 
 namespace mpg {
+
+void sell_plan_free(mpg_sell_plan* p);
+
+// Plan / packed-matrix / per-solve temporaries come from the device's stream-ordered memory pool (release threshold
+// raised in mpg_ctx_create): building and dropping a multi-GB plan per call then re-uses the same physical memory
+// instead of mapping and unmapping it.  Freed with plain cudaFree (synchronising, returns the block to the pool).
+inline cudaError_t pool_alloc(mpg_ctx* ctx, void** p, size_t bytes) { return cudaMallocAsync(p, bytes, ctx->stream); }
+template <class P> inline cudaError_t pool_alloc(mpg_ctx* ctx, P** p, size_t bytes) { return pool_alloc(ctx, reinterpret_cast<void**>(p), bytes); }
 
 inline int fail(mpg_ctx* ctx, int code, const std::string& msg) {
     if (ctx) ctx->last_error = msg;

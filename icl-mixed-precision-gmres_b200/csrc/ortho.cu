@@ -402,6 +402,233 @@ __global__ void __launch_bounds__(256, 2) gemvt_rb_kernel(int64_t n, int ncols, 
     if (grid_last_block(ticket)) last_block_finish<T>(epi, partials, ldp, nblocks, ncols);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// vrow: the same operation as vpass for NARROW bases (k1 <= 32), where vpass's per-tile barriers dominate.
+// Every compute thread owns RPT rows of a tile for ALL columns: it reads its V entries from shared memory once
+// into registers, forms w' = w - sum_j h_j V[r,j] (sequential j), stores w', and adds V[r,j]*w'[r] into its
+// k1 private accumulators - no communication between threads inside a tile, so the only synchronisation per
+// tile is the full/empty mbarrier pair and the warps drift freely over the stages.  A tile is CT*RPT rows,
+// brought in by the producer warp as CT*RPT/256 boxes of [256 rows x k1 columns] (+ the matching w boxes).
+// After the last tile: warp xor-tree per column, cross-warp sum in warp order through shared memory, one set
+// of partials per CTA, then the same last-CTA finish as vpass.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int VROW_BOX = 256;
+
+template <class T, int CT, int RPT, int MAXK>
+__global__ void __launch_bounds__(CT + 32, 1)
+vrow_kernel(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapW, int64_t n, int k1, T* w, const T* h_in,
+            int stages, int reverse, double* partials, int ldp, unsigned int* ticket, Epi epi) {
+    constexpr int NW = CT / 32;
+    constexpr int TRW = CT * RPT;             // rows per tile
+    constexpr int NB = TRW / VROW_BOX;        // boxes per tile
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ double red[NW][MAXK];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const size_t box_elems = (size_t)(k1 + 1) * VROW_BOX;   // k1 columns of V, then the w column
+    const size_t stage_elems = box_elems * NB;
+    T* tiles = reinterpret_cast<T*>(smem_raw);
+    T* h_s = tiles + stage_elems * stages;
+    uint64_t* full = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(h_s + MAXK + 4) + 7) & ~uintptr_t(7));
+    uint64_t* empty = full + stages;
+
+    const int64_t ntiles = (n + TRW - 1) / TRW;
+    const int64_t my_count = (ntiles > blockIdx.x) ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    auto tile_row0 = [&](int64_t it) -> int64_t {
+        int64_t tix = blockIdx.x + it * gridDim.x;
+        if (reverse) tix = ntiles - 1 - tix;
+        return tix * TRW;
+    };
+
+    if (tid < MAXK) h_s[tid] = (h_in && tid < k1) ? h_in[tid] : T(0);
+    if (tid == 0) {
+        for (int s = 0; s < stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, NW); }
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    T acc[MAXK];
+#pragma unroll
+    for (int j = 0; j < MAXK; ++j) acc[j] = T(0);
+
+    if (wid == NW) {
+        // ===== producer warp =====
+        if (lane == 0) {
+            const uint32_t bytes = (uint32_t)(stage_elems * sizeof(T));
+            for (int64_t it = 0; it < my_count; ++it) {
+                const int s = (int)(it % stages);
+                if (it >= stages) mbar_wait(empty + s, (uint32_t)(((it / stages) - 1) & 1));
+                T* st = tiles + stage_elems * s;
+                const int64_t row0 = tile_row0(it);
+                mbar_arrive_expect_tx(full + s, bytes);
+#pragma unroll
+                for (int b = 0; b < NB; ++b) {
+                    // boxes that start past n are zero-filled by the hardware like any other out-of-range element
+                    const int r0 = (int)min(row0 + (int64_t)b * VROW_BOX, (int64_t)2147483000);
+                    tma_load_2d(st + box_elems * b, &mapV, r0, 0, full + s);
+                    tma_load_2d(st + box_elems * b + (size_t)k1 * VROW_BOX, &mapW, r0, 0, full + s);
+                }
+            }
+        }
+    } else {
+        // ===== consumers: thread owns rows tid + i*CT of the tile =====
+        const int b0 = tid / VROW_BOX, r = tid % VROW_BOX;
+        for (int64_t it = 0; it < my_count; ++it) {
+            const int s = (int)(it % stages);
+            const int64_t row0 = tile_row0(it);
+            const T* st = tiles + stage_elems * s;
+            mbar_wait(full + s, (uint32_t)((it / stages) & 1));
+#pragma unroll
+            for (int i = 0; i < RPT; ++i) {
+                const T* base = st + box_elems * (b0 + i * (CT / VROW_BOX)) + r;
+                T v[MAXK];
+#pragma unroll
+                for (int j = 0; j < MAXK; ++j) v[j] = (j < k1) ? base[(size_t)j * VROW_BOX] : T(0);
+                T a = base[(size_t)k1 * VROW_BOX];
+                if (h_in) {
+#pragma unroll
+                    for (int j = 0; j < MAXK; ++j) a = fma(-h_s[j], v[j], a);      // h_s is zero past k1
+                    const int64_t row = row0 + tid + (int64_t)i * CT;
+                    if (row < n) w[row] = a;
+                }
+#pragma unroll
+                for (int j = 0; j < MAXK; ++j) acc[j] = fma(v[j], a, acc[j]);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty + s);
+        }
+#pragma unroll
+        for (int j = 0; j < MAXK; ++j) {
+            const double sred = warp_sum((double)acc[j]);
+            if (lane == 0) red[wid][j] = sred;
+        }
+    }
+    __syncthreads();
+    if (tid < k1) {
+        double t = 0.0;
+#pragma unroll
+        for (int q = 0; q < NW; ++q) t += red[q][tid];
+        partials[(size_t)blockIdx.x * ldp + tid] = t;
+    }
+    if (grid_last_block(ticket)) last_block_finish<T>(epi, partials, ldp, gridDim.x, k1);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// vdirect: the fused update + gemv-T with NO shared-memory staging.  A thread owns 16 bytes worth of consecutive
+// rows (4 fp32 / 2 fp64) and one private accumulator per column: it loads its piece of every column straight
+// from global memory into registers (coalesced 16-byte streaming loads, all k1 of them in flight together),
+// forms w' = w - sum_j h_j V[r,j] (sequential j, HAS_H only), stores w', and adds V[r,j] * w'[r] into acc[j].
+// Same access pattern as gemv-N, which is the fastest kernel of the path; the price is k1 accumulators (and,
+// with HAS_H, the k1 loaded vectors) in registers, so it serves the widths where they fit:
+//   HAS_H (pass B): k1 <= 32;   !HAS_H (pass A, h = V'w): k1 <= 104.
+// After the grid-stride loop: warp xor-tree per column (fp64), cross-warp sum in warp order, per-CTA partials,
+// last-CTA finish as in vpass.
+// ---------------------------------------------------------------------------------------------------------
+template <class T, int MAXK, bool HAS_H>
+__global__ void __launch_bounds__(256) vdirect_kernel(int64_t n, int k1, const T* __restrict__ V, int64_t ldv, T* w, const T* __restrict__ h_in,
+                                                      int reverse, double* partials, int ldp, unsigned int* ticket, Epi epi) {
+    constexpr int VEC = 16 / sizeof(T);
+    using V4 = typename std::conditional<sizeof(T) == 4, float4, double2>::type;
+    __shared__ double red[8][MAXK];
+    __shared__ T h_s[MAXK];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (HAS_H && tid < MAXK) h_s[tid] = (tid < k1) ? h_in[tid] : T(0);
+    __syncthreads();
+
+    T acc[MAXK];
+#pragma unroll
+    for (int j = 0; j < MAXK; ++j) acc[j] = T(0);
+
+    const int64_t nv = n / VEC;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t iv0 = (int64_t)blockIdx.x * blockDim.x + tid; iv0 < nv; iv0 += stride) {
+        const int64_t i = (reverse ? nv - 1 - iv0 : iv0) * VEC;
+        T a[VEC];
+        {
+            const V4 t = *reinterpret_cast<const V4*>(w + i);
+            const T* pt = reinterpret_cast<const T*>(&t);
+#pragma unroll
+            for (int c = 0; c < VEC; ++c) a[c] = pt[c];
+        }
+        if (HAS_H) {
+            V4 v[MAXK];
+#pragma unroll
+            for (int j = 0; j < MAXK; ++j)
+                if (j < k1) v[j] = ldg_stream(reinterpret_cast<const V4*>(V + (size_t)j * ldv + i));
+#pragma unroll
+            for (int j = 0; j < MAXK; ++j)
+                if (j < k1) {
+                    const T* pv = reinterpret_cast<const T*>(&v[j]);
+                    const T hj = h_s[j];
+#pragma unroll
+                    for (int c = 0; c < VEC; ++c) a[c] = fma(-hj, pv[c], a[c]);
+                }
+            V4 o;
+            T* po = reinterpret_cast<T*>(&o);
+#pragma unroll
+            for (int c = 0; c < VEC; ++c) po[c] = a[c];
+            *reinterpret_cast<V4*>(w + i) = o;
+#pragma unroll
+            for (int j = 0; j < MAXK; ++j)
+                if (j < k1) {
+                    const T* pv = reinterpret_cast<const T*>(&v[j]);
+                    T q = T(0);
+#pragma unroll
+                    for (int c = 0; c < VEC; ++c) q = fma(pv[c], a[c], q);
+                    acc[j] += q;
+                }
+        } else {
+            constexpr int UN = 8;
+#pragma unroll
+            for (int j0 = 0; j0 < MAXK; j0 += UN) {
+                if (j0 < k1) {
+                    V4 b[UN];
+#pragma unroll
+                    for (int u = 0; u < UN; ++u)
+                        if (j0 + u < MAXK && j0 + u < k1) b[u] = ldg_stream(reinterpret_cast<const V4*>(V + (size_t)(j0 + u) * ldv + i));
+#pragma unroll
+                    for (int u = 0; u < UN; ++u)
+                        if (j0 + u < MAXK && j0 + u < k1) {
+                            const T* pb = reinterpret_cast<const T*>(&b[u]);
+                            T q = T(0);
+#pragma unroll
+                            for (int c = 0; c < VEC; ++c) q = fma(pb[c], a[c], q);
+                            acc[j0 + u] += q;
+                        }
+                }
+            }
+        }
+    }
+    // rows past the last full 16-byte group: one thread each, same arithmetic
+    if (blockIdx.x == 0 && tid < (int)(n - nv * VEC)) {
+        const int64_t r = nv * VEC + tid;
+        T a = w[r];
+        if (HAS_H) {
+#pragma unroll
+            for (int j = 0; j < MAXK; ++j)
+                if (j < k1) a = fma(-h_s[j], V[(size_t)j * ldv + r], a);
+            w[r] = a;
+        }
+#pragma unroll
+        for (int j = 0; j < MAXK; ++j)
+            if (j < k1) acc[j] = fma(V[(size_t)j * ldv + r], a, acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < MAXK; ++j) {
+        if (j < k1) {
+            const double sred = warp_sum((double)acc[j]);
+            if (lane == 0) red[wid][j] = sred;
+        }
+    }
+    __syncthreads();
+    if (tid < k1) {
+        double t = 0.0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) t += red[q][tid];
+        partials[(size_t)blockIdx.x * ldp + tid] = t;
+    }
+    if (grid_last_block(ticket)) last_block_finish<T>(epi, partials, ldp, gridDim.x, k1);
+}
+
 template <class T>
 bool aligned16(const T* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
@@ -498,8 +725,117 @@ int launch_vpass_inst(mpg_ctx* ctx, int64_t n, int k1, const T* V, int64_t ldv, 
     return dist_finish_reduction(ctx, epi, k1, (int)sizeof(T));
 }
 
+// tensor maps are pure functions of (pointer, n, ldv, k1, box rows): keep the last few (one Arnoldi cycle re-uses one per width)
+template <class T>
+int cached_maps(mpg_ctx* ctx, const T* V, int64_t ldv, const T* w, int64_t n, int k1, int box_rows, const CUtensorMap** mapV, const CUtensorMap** mapW) {
+    struct MapKey { const void* V; const void* w; int64_t n, ldv; int k1, tr, ts; };
+    struct MapSlot { MapKey key; CUtensorMap mapV, mapW; bool valid; };
+    static MapSlot cache[1024];   // contexts are single-threaded by contract
+    MapSlot& slot = cache[(((size_t)k1 * 2 + (sizeof(T) == 8)) * 2 + (box_rows == VROW_BOX)) & 1023];
+    MapKey key;
+    memset(&key, 0, sizeof(MapKey));
+    key.V = V; key.w = w; key.n = n; key.ldv = ldv; key.k1 = k1; key.tr = box_rows; key.ts = (int)sizeof(T);
+    if (!slot.valid || memcmp(&slot.key, &key, sizeof(MapKey)) != 0) {
+        const int mrc = make_maps<T>(V, ldv, w, n, k1, box_rows, &slot.mapV, &slot.mapW);
+        memcpy(&slot.key, &key, sizeof(MapKey));
+        slot.valid = (mrc == 0);
+        if (mrc != 0)
+            return fail(ctx, MPG_ERR_CUDA, "vpass: cuTensorMapEncodeTiled failed, code " + std::to_string(mrc) + " (n=" + std::to_string(n) + " k1=" +
+                                               std::to_string(k1) + " ldv=" + std::to_string(ldv) + ")");
+    }
+    *mapV = &slot.mapV;
+    *mapW = &slot.mapW;
+    return MPG_OK;
+}
+
+template <class T, int CT, int RPT, int MAXK>
+int launch_vrow_inst(mpg_ctx* ctx, int64_t n, int k1, const T* V, int64_t ldv, T* w, const T* h_in, int fin, T* coef_out, T* hcol) {
+    const CUtensorMap *mapV, *mapW;
+    MPG_TRY(cached_maps<T>(ctx, V, ldv, w, n, k1, VROW_BOX, &mapV, &mapW));
+    constexpr int TRW = CT * RPT;
+    const size_t stage_bytes = (size_t)(k1 + 1) * TRW * sizeof(T);
+    const size_t extra = sizeof(T) * (size_t)(MAXK + 4) + 8 * 2 * 8 + 32 + 128;
+    const size_t budget = kMaxDynSmem - sizeof(double) * (CT / 32) * MAXK;   // the cross-warp buffer is static shared memory
+    int stages = (int)std::min<size_t>(8, (budget - extra) / stage_bytes);
+    if (ctx->tune.vpass_stages > 0) stages = std::min(stages, ctx->tune.vpass_stages);
+    if (stages < 1) return fail(ctx, MPG_ERR_ARG, "vrow: tile does not fit in shared memory");
+    const size_t smem = stage_bytes * stages + extra;
+    const int64_t ntiles = cdiv(n, TRW);
+    const int grid = (int)std::min<int64_t>(std::min<int64_t>(ntiles, (int64_t)ctx->num_sms), kMaxPartBlocks);
+    auto kern = vrow_kernel<T, CT, RPT, MAXK>;
+    static bool attr_set = false;   // per instantiation; one device per process
+    if (!attr_set) {
+        MPG_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+        attr_set = true;
+    }
+    ProfScope prof(ctx, MPG_PROF_VPASS, (double)k1 * n * sizeof(T) + (h_in ? 2.0 * n * sizeof(T) : 0.0));
+    const int reverse = (ctx->tune.vpass_serpentine && h_in) ? 1 : 0;   // same rule as vpass: a function of the pass only
+    const Epi epi = make_epi(ctx, fin == FIN_COEF_ACCUM ? EPI_COEF_ACCUM : EPI_COEF, coef_out, hcol, 0.0, 0.0);
+    kern<<<grid, CT + 32, smem, ctx->stream>>>(*mapV, *mapW, n, k1, w, h_in, stages, reverse, ctx->partials, kMaxCols + 8, ctx->ticket, epi);
+    MPG_CHECK_LAUNCH(ctx);
+    return dist_finish_reduction(ctx, epi, k1, (int)sizeof(T));
+}
+
+template <class T>
+int launch_vrow(mpg_ctx* ctx, int64_t n, int k1, const T* V, int64_t ldv, T* w, const T* h_in, int fin, T* coef_out, T* hcol) {
+    constexpr int CT = sizeof(T) == 4 ? 512 : 256;
+    if (k1 <= 8) return launch_vrow_inst<T, CT, 4, 8>(ctx, n, k1, V, ldv, w, h_in, fin, coef_out, hcol);
+    if (k1 <= 16) return launch_vrow_inst<T, CT, 2, 16>(ctx, n, k1, V, ldv, w, h_in, fin, coef_out, hcol);
+    if (k1 <= 32) return launch_vrow_inst<T, CT, 1, 32>(ctx, n, k1, V, ldv, w, h_in, fin, coef_out, hcol);
+    if constexpr (sizeof(T) == 4) {
+        if (k1 <= 48) return launch_vrow_inst<T, 256, 1, 48>(ctx, n, k1, V, ldv, w, h_in, fin, coef_out, hcol);
+        if (k1 <= 64) return launch_vrow_inst<T, 256, 1, 64>(ctx, n, k1, V, ldv, w, h_in, fin, coef_out, hcol);
+    }
+    return fail(ctx, MPG_ERR_ARG, "vrow: too many columns");
+}
+
+template <class T, int MAXK, bool HAS_H>
+int launch_vdirect_inst(mpg_ctx* ctx, int64_t n, int k1, const T* V, int64_t ldv, T* w, const T* h_in, int fin, T* coef_out, T* hcol) {
+    constexpr int VEC = 16 / sizeof(T);
+    auto kern = vdirect_kernel<T, MAXK, HAS_H>;
+    static int ctas_per_sm = 0;   // per instantiation; one device per process
+    if (ctas_per_sm == 0) {
+        MPG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, 256, 0));
+        ctas_per_sm = std::max(1, std::min(ctas_per_sm, 4));
+    }
+    const int64_t groups = std::max<int64_t>(1, n / VEC);
+    int grid = (int)std::min<int64_t>(cdiv(groups, 256), (int64_t)ctx->num_sms * ctas_per_sm);
+    grid = std::max(1, std::min(grid, kMaxPartBlocks));
+    ProfScope prof(ctx, MPG_PROF_VPASS, (double)k1 * n * sizeof(T) + (h_in ? 2.0 * n * sizeof(T) : 0.0));
+    const int reverse = (ctx->tune.vpass_serpentine && h_in) ? 1 : 0;   // same rule as vpass: a function of the pass only
+    const Epi epi = make_epi(ctx, fin == FIN_COEF_ACCUM ? EPI_COEF_ACCUM : EPI_COEF, coef_out, hcol, 0.0, 0.0);
+    kern<<<grid, 256, 0, ctx->stream>>>(n, k1, V, ldv, w, h_in, reverse, ctx->partials, kMaxCols + 8, ctx->ticket, epi);
+    MPG_CHECK_LAUNCH(ctx);
+    return dist_finish_reduction(ctx, epi, k1, (int)sizeof(T));
+}
+
+// widest basis the register-resident kernel is built for.  Measured (profiles/r01_tune_vdirect.txt): it wins up to 8
+// columns; from 9 on the k1 accumulators (+ k1 live 16-byte vectors in pass B) cost too much occupancy and the
+// shared-memory staged kernels are faster.
+constexpr int kVdirectCap = 16;
+
+template <class T>
+int launch_vdirect(mpg_ctx* ctx, int64_t n, int k1, const T* V, int64_t ldv, T* w, const T* h_in, int fin, T* coef_out, T* hcol) {
+#define MPG_VD(K, H) return launch_vdirect_inst<T, K, H>(ctx, n, k1, V, ldv, w, h_in, fin, coef_out, hcol)
+    if (h_in) {
+        if (k1 <= 8) MPG_VD(8, true);
+        if (k1 <= 16) MPG_VD(16, true);
+    } else {
+        if (k1 <= 8) MPG_VD(8, false);
+        if (k1 <= 16) MPG_VD(16, false);
+    }
+#undef MPG_VD
+    return fail(ctx, MPG_ERR_ARG, "vdirect: too many columns");
+}
+
 template <class T>
 int launch_vpass(mpg_ctx* ctx, int64_t n, int k1, const T* V, int64_t ldv, T* w, const T* h_in, int fin, T* coef_out, T* hcol) {
+    {
+        const int cap = std::min(h_in ? ctx->tune.vdirect_max_cols_b : ctx->tune.vdirect_max_cols_a, kVdirectCap);
+        if (k1 <= cap && (ldv * sizeof(T)) % 16 == 0) return launch_vdirect<T>(ctx, n, k1, V, ldv, w, h_in, fin, coef_out, hcol);
+    }
+    if (k1 <= (h_in ? ctx->tune.vrow_max_cols : std::min(ctx->tune.vrow_max_cols, ctx->tune.vrow_max_cols_a)) && k1 <= (sizeof(T) == 4 ? 64 : 32))
+        return launch_vrow<T>(ctx, n, k1, V, ldv, w, h_in, fin, coef_out, hcol);
     constexpr int TR = VpassCfg<T>::TR;
     constexpr int NW = 2 * TR / 32;
     const int need = (k1 + NW - 1) / NW;

@@ -43,6 +43,11 @@ template <class T> int spmv(mpg_ctx*, const mpg_csr*, const T*, T, const T*, T, 
 template <class T> int gemvn(mpg_ctx*, int64_t, int, const T*, int64_t, T, const T*, T, T*, bool, T*, T*, double*);
 template <class T> int gemvt(mpg_ctx*, int64_t, int, const T*, int64_t, T, const T*, T, T*);
 template <class T> int add_vector(mpg_ctx*, int, int64_t, int64_t, T*, int64_t, T*, T*, T*, bool);
+template <class T> int pack_create(mpg_ctx*, const mpg_csr*, const T*, mpg_packed**);
+template <class T> int pack_update(mpg_ctx*, mpg_packed*, const T*);
+void pack_free(mpg_packed*);
+bool pack_matches(const mpg_packed*, const mpg_csr*, int tsize);
+template <class T> int spmv_packed(mpg_ctx*, const mpg_packed*, T, const T*, T, const T*, T*, float*, const T*, int);
 template <class T> int halo_exchange(mpg_ctx*, T*);
 template <class T> int halo_begin(mpg_ctx*, T*);
 template <class T> int halo_finish(mpg_ctx*, T*);
@@ -126,6 +131,7 @@ struct Workspace {
     float* tmp32 = nullptr;   // n floats: single-prec preconditioner bridge (typesafe_apply, gmres.cpp:12-17)
     int64_t halo = 0;         // multi-GPU: halo slots appended to every SpMV input (tail of each basis column)
     void* xext = nullptr;     // multi-GPU: [x_local ; halo] copy of the iterate for the outer residual
+    mpg_packed* packed = nullptr;  // packed copy of the inner-precision matrix (sell.cu); values refreshed at every solve
 };
 
 // replicated (not row-distributed) data: reductions over it must not be all-reduced
@@ -142,6 +148,7 @@ void ws_release(void* p) {
     cudaFree(ws->V); cudaFree(ws->w); cudaFree(ws->h); cudaFree(ws->cs); cudaFree(ws->sn); cudaFree(ws->s);
     cudaFree(ws->scratch); cudaFree(ws->hist); cudaFreeHost(ws->hist_host); cudaFree(ws->S); cudaFree(ws->u); cudaFree(ws->tmp32);
     cudaFree(ws->xext);
+    pack_free(ws->packed);
     delete ws;
 }
 
@@ -206,6 +213,24 @@ int read_scalars(mpg_ctx* ctx, int count) {
 template <class T> T hs(mpg_ctx* ctx, int slot) { T v; memcpy(&v, ctx->hscal + slot, sizeof(T)); return v; }
 template <class T> T* ds(mpg_ctx* ctx, int slot) { return reinterpret_cast<T*>(ctx->dscal + slot); }
 
+// Packed copy of the matrix the inner iterations multiply with (T = the inner precision).  The structure is cached in
+// the mpg_csr plan, the values are re-packed at every solve (one pass over the matrix; the caller may have changed them).
+// *out stays null when packing is switched off or the structure does not pack well: the CSR kernel is used then.
+template <class T>
+int get_packed(mpg_ctx* ctx, Workspace* ws, const mpg_csr* A, const T* vals, const mpg_packed** out) {
+    *out = nullptr;
+    if (!ctx->tune.spmv_packed) return MPG_OK;
+    if (ws->packed && !pack_matches(ws->packed, A, (int)sizeof(T))) {
+        MPG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        pack_free(ws->packed);
+        ws->packed = nullptr;
+    }
+    if (!ws->packed) MPG_TRY(pack_create<T>(ctx, A, vals, &ws->packed));
+    else MPG_TRY(pack_update<T>(ctx, ws->packed, vals));
+    *out = ws->packed;
+    return MPG_OK;
+}
+
 // Preconditioner application M(w) in the working type T.
 //   jac != null: Jacobi, gdmv(1, diag, w, 0, w)  (types.hpp:444-446)
 //   bridge:      typesafe_apply with PrecType = float and Type = double (gmres.cpp:12-17): cast, apply, cast back
@@ -224,7 +249,7 @@ int apply_prec(mpg_ctx* ctx, int64_t n, T* w, const T* jac, const float* jac32, 
 // One restart cycle shared by both drivers: first_vector, s init, Arnoldi loop.  On return *k_out is the
 // number of inner iterations performed (the `k` handed to solution_update).
 template <class T>
-int run_cycle(mpg_ctx* ctx, const mpg_gmres_params& p, Policy& pol, Workspace* ws, const mpg_csr* A, const T* vals, const T* jac,
+int run_cycle(mpg_ctx* ctx, const mpg_gmres_params& p, Policy& pol, Workspace* ws, const mpg_csr* A, const T* vals, const mpg_packed* P, const T* jac,
               const float* jac32, bool bridge, T beta, double Minvb_norm, History& hist, int64_t* k_out, Action* act_out) {
     const int64_t n = ws->n, m = ws->m, ldv = ws->ldv, ldh = m + 1;
     T* V = static_cast<T*>(ws->V);
@@ -248,15 +273,19 @@ int run_cycle(mpg_ctx* ctx, const mpg_gmres_params& p, Policy& pol, Workspace* w
         // Jacobi in the working precision rides in the SpMV store (same rounding as the separate gdmv pass)
         const T* rowscale = (jac && !bridge) ? jac : nullptr;
         T* vk = V + (size_t)kk * ldv;
-        if (A->tile_list && ctx->tune.dist_overlap) {
+        auto mult = [&](int part) -> int {
+            if (P) return spmv_packed<T>(ctx, P, T(1), vk, T(0), w, w, nullptr, rowscale, part);
+            return spmv<T>(ctx, A, vals, T(1), vk, T(0), w, w, nullptr, rowscale, part);
+        };
+        if (A->ncols > A->nrows && ctx->tune.dist_overlap) {
             // multi-GPU: send v_k's boundary rows, multiply the rows that need no halo while they travel, then the rest
             MPG_TRY(halo_begin<T>(ctx, vk));
-            MPG_TRY(spmv<T>(ctx, A, vals, T(1), vk, T(0), w, w, nullptr, rowscale, SPMV_INTERIOR));
+            MPG_TRY(mult(SPMV_INTERIOR));
             MPG_TRY(halo_finish<T>(ctx, vk));
-            MPG_TRY(spmv<T>(ctx, A, vals, T(1), vk, T(0), w, w, nullptr, rowscale, SPMV_BOUNDARY));
+            MPG_TRY(mult(SPMV_BOUNDARY));
         } else {
             MPG_TRY(halo_exchange<T>(ctx, vk));   // fill the halo tail of v_k (no-op on one GPU)
-            MPG_TRY(spmv<T>(ctx, A, vals, T(1), vk, T(0), w, w, nullptr, rowscale));
+            MPG_TRY(mult(SPMV_ALL));
         }
         if (!rowscale) MPG_TRY(apply_prec<T>(ctx, n, w, jac, jac32, bridge, ws->tmp32));
         // orth.add_vector(k, w, h)     gmres.cpp:104,217
@@ -356,6 +385,8 @@ int solve_mixed(mpg_ctx* ctx, const mpg_gmres_params& p, const mpg_csr* A, const
     float* h = static_cast<float*>(ws->h);
     float* s = static_cast<float*>(ws->s);
     float* V = static_cast<float*>(ws->V);
+    const mpg_packed* packed = nullptr;
+    MPG_TRY(get_packed<float>(ctx, ws, A, vals32, &packed));
     Policy pol(p);
     if (p.conv == MPG_CONV_ORTHLOSS) {
         MPG_TRY(fill_host(ctx, (m + 1) * (m + 1), 0.f, static_cast<float*>(ws->S)));  // IterUtil.hpp:191
@@ -399,7 +430,7 @@ int solve_mixed(mpg_ctx* ctx, const mpg_gmres_params& p, const mpg_csr* A, const
 
         int64_t k = 0;
         Action act = NEXT;
-        MPG_TRY(run_cycle<float>(ctx, p, pol, ws, A, vals32, jac32, nullptr, false, beta, Minvb_norm, hist, &k, &act));
+        MPG_TRY(run_cycle<float>(ctx, p, pol, ws, A, vals32, packed, jac32, nullptr, false, beta, Minvb_norm, hist, &k, &act));
         if (act == ABORTED) { st->status = 3; st->outer_i = i; break; }
 
         // solution_update, gmres.cpp:276-290: y = triu(H)^-1 s ; x += (double)(V_k y)  (Orthogonalization.hpp:67-73)
@@ -422,6 +453,8 @@ int solve_uniform(mpg_ctx* ctx, const mpg_gmres_params& p, const mpg_csr* A, con
     T* h = static_cast<T*>(ws->h);
     T* s = static_cast<T*>(ws->s);
     T* V = static_cast<T*>(ws->V);
+    const mpg_packed* packed = nullptr;
+    MPG_TRY(get_packed<T>(ctx, ws, A, vals, &packed));
     Policy pol(p);
     if (p.conv == MPG_CONV_ORTHLOSS) {
         MPG_TRY(fill_host(ctx, (m + 1) * (m + 1), T(0), static_cast<T*>(ws->S)));
@@ -464,7 +497,7 @@ int solve_uniform(mpg_ctx* ctx, const mpg_gmres_params& p, const mpg_csr* A, con
 
         int64_t k = 0;
         Action act = NEXT;
-        MPG_TRY(run_cycle<T>(ctx, p, pol, ws, A, vals, jac, jac32, bridge, beta, (double)Minvb_norm, hist, &k, &act));
+        MPG_TRY(run_cycle<T>(ctx, p, pol, ws, A, vals, packed, jac, jac32, bridge, beta, (double)Minvb_norm, hist, &k, &act));
         if (act == ABORTED) { st->status = 3; st->outer_i = i; break; }
 
         // solution_update, gmres.cpp:291-303: y = triu(H)^-1 s ; x = 1*V_k y + 1*x (Orthogonalization.hpp:62-65)
@@ -512,13 +545,13 @@ extern "C" int mpg_gmres_solve(mpg_ctx* ctx, const mpg_gmres_params* pp, const m
 
     const float* vals32 = vals32_in;
     if (!vals32) {  // SparseMatrix<float,Device>(A): cast values, share structure (types_cuda.hpp:82-101)
-        MPG_CUDA_C(cudaMalloc(&vals32_own, sizeof(float) * (size_t)std::max<int64_t>(nnz, 1)));
+        MPG_CUDA_C(pool_alloc(ctx, &vals32_own, sizeof(float) * (size_t)std::max<int64_t>(nnz, 1)));
         MPG_TRY_C(cast_copy(ctx, nnz, vals64, vals32_own));
         vals32 = vals32_own;
     }
     if (p.mode == MPG_MODE_MIXED) {
         if (p.prec == MPG_PREC_JACOBI) {  // Jacobi<float>(A) on the fp32-cast matrix, gmres_perf_test.cpp:149
-            MPG_CUDA_C(cudaMalloc(&jac32, sizeof(float) * (size_t)n));
+            MPG_CUDA_C(pool_alloc(ctx, &jac32, sizeof(float) * (size_t)n));
             MPG_TRY_C(mpg_jacobi_diag_f32(ctx, A, vals32, jac32));
         }
         MPG_CUDA_C(cudaEventRecord(e0, ctx->stream));
@@ -526,19 +559,19 @@ extern "C" int mpg_gmres_solve(mpg_ctx* ctx, const mpg_gmres_params* pp, const m
     } else if (p.mode == MPG_MODE_BASELINE || p.mode == MPG_MODE_SINGLE_PREC) {
         // DoBaselineProblem hands the solver the fp32-rounded matrix converted back to double
         // (gmres_perf_test.cpp:66,101 + implicit conversion)
-        MPG_CUDA_C(cudaMalloc(&vals_rt, sizeof(double) * (size_t)std::max<int64_t>(nnz, 1)));
+        MPG_CUDA_C(pool_alloc(ctx, &vals_rt, sizeof(double) * (size_t)std::max<int64_t>(nnz, 1)));
         MPG_TRY_C(cast_copy(ctx, nnz, vals32, vals_rt));
         const bool bridge = (p.mode == MPG_MODE_SINGLE_PREC);
         if (p.prec == MPG_PREC_JACOBI) {
-            if (bridge) { MPG_CUDA_C(cudaMalloc(&jac32, sizeof(float) * (size_t)n)); MPG_TRY_C(mpg_jacobi_diag_f32(ctx, A, vals32, jac32)); }
-            else { MPG_CUDA_C(cudaMalloc(&jac64, sizeof(double) * (size_t)n)); MPG_TRY_C(mpg_jacobi_diag_f64(ctx, A, vals64, jac64)); }
+            if (bridge) { MPG_CUDA_C(pool_alloc(ctx, &jac32, sizeof(float) * (size_t)n)); MPG_TRY_C(mpg_jacobi_diag_f32(ctx, A, vals32, jac32)); }
+            else { MPG_CUDA_C(pool_alloc(ctx, &jac64, sizeof(double) * (size_t)n)); MPG_TRY_C(mpg_jacobi_diag_f64(ctx, A, vals64, jac64)); }
         }
         MPG_CUDA_C(cudaEventRecord(e0, ctx->stream));
         MPG_TRY_C(solve_uniform<double>(ctx, p, A, vals_rt, jac64, jac32, bridge, b, x, st, hist));
     } else {
-        if (p.prec == MPG_PREC_JACOBI) { MPG_CUDA_C(cudaMalloc(&jac32, sizeof(float) * (size_t)n)); MPG_TRY_C(mpg_jacobi_diag_f32(ctx, A, vals32, jac32)); }
-        MPG_CUDA_C(cudaMalloc(&b32, sizeof(float) * (size_t)n));
-        MPG_CUDA_C(cudaMalloc(&x32, sizeof(float) * (size_t)n));
+        if (p.prec == MPG_PREC_JACOBI) { MPG_CUDA_C(pool_alloc(ctx, &jac32, sizeof(float) * (size_t)n)); MPG_TRY_C(mpg_jacobi_diag_f32(ctx, A, vals32, jac32)); }
+        MPG_CUDA_C(pool_alloc(ctx, &b32, sizeof(float) * (size_t)n));
+        MPG_CUDA_C(pool_alloc(ctx, &x32, sizeof(float) * (size_t)n));
         MPG_TRY_C(cast_copy(ctx, n, b, b32));   // copy(b, b_type)  gmres_perf_test.cpp:97-98
         MPG_TRY_C(cast_copy(ctx, n, x, x32));
         MPG_CUDA_C(cudaEventRecord(e0, ctx->stream));

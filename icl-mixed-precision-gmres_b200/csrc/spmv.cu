@@ -263,8 +263,8 @@ extern "C" int mpg_csr_create(mpg_ctx* ctx, int nrows, int ncols, int64_t nnz, c
     A->tile_nnz = SPMV_TILE;
     A->ntiles = (int)cdiv(nnz, SPMV_TILE);
     A->device = ctx->device;
-    MPG_CUDA(ctx, cudaMalloc(&A->tile_row, sizeof(int) * (size_t)(A->ntiles + 2)));
-    MPG_CUDA(ctx, cudaMalloc(&A->carry, sizeof(double) * 2 * (size_t)(A->ntiles + 1)));
+    MPG_CUDA(ctx, pool_alloc(ctx, &A->tile_row, sizeof(int) * (size_t)(A->ntiles + 2)));
+    MPG_CUDA(ctx, pool_alloc(ctx, &A->carry, sizeof(double) * 2 * (size_t)(A->ntiles + 1)));
     MPG_CUDA(ctx, cudaMemsetAsync(A->carry, 0, sizeof(double) * 2 * (size_t)(A->ntiles + 1), ctx->stream));
     plan_kernel<<<(int)cdiv(A->ntiles + 1, 256), 256, 0, ctx->stream>>>(nrows, nnz, row_map, SPMV_TILE, A->ntiles, A->tile_row);
     MPG_CHECK_LAUNCH(ctx);
@@ -281,7 +281,7 @@ extern "C" int mpg_csr_create(mpg_ctx* ctx, int nrows, int ncols, int64_t nnz, c
     if (ncols > nrows && A->ntiles > 0 && !A->has_empty_rows) {
         // local slab of a partitioned matrix: order the tiles [no halo column | some halo column]
         std::vector<int> flag((size_t)A->ntiles), list((size_t)A->ntiles);
-        MPG_CUDA(ctx, cudaMalloc(&A->tile_list, sizeof(int) * (size_t)A->ntiles));
+        MPG_CUDA(ctx, pool_alloc(ctx, &A->tile_list, sizeof(int) * (size_t)A->ntiles));
         tile_halo_flag_kernel<<<(int)cdiv((int64_t)A->ntiles * 32, 256), 256, 0, ctx->stream>>>(A->ntiles, nnz, nrows, inds, A->tile_list);
         MPG_CHECK_LAUNCH(ctx);
         MPG_CUDA(ctx, cudaMemcpyAsync(flag.data(), A->tile_list, sizeof(int) * flag.size(), cudaMemcpyDeviceToHost, ctx->stream));
@@ -303,6 +303,8 @@ extern "C" int mpg_csr_destroy(mpg_csr* A) {
     cudaFree(A->tile_row);
     cudaFree(A->carry);
     cudaFree(A->tile_list);
+    mpg::sell_plan_free(A->sell[0]);
+    mpg::sell_plan_free(A->sell[1]);
     delete A;
     return MPG_OK;
 }

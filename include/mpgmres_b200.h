@@ -135,6 +135,20 @@ int mpg_spmv_f64(mpg_ctx*, const mpg_csr* A, const double* vals, double alpha, c
  * Jacobi::apply = gdmv(1, diag, y, 0, y) (types.hpp:444-446), bit-identical to the two separate calls. */
 int mpg_spmv_jacobi_f32(mpg_ctx*, const mpg_csr* A, const float* vals, const float* diag, const float* x, float* y);
 int mpg_spmv_jacobi_f64(mpg_ctx*, const mpg_csr* A, const double* vals, const double* diag, const double* x, double* y);
+/* Packed operator (sell.cu): the same matrix re-laid as 32-row slices stored position-major (sliced ELLPACK), the
+ * analogue of the per-matrix library handles the reference builds once per SparseMatrix (create_cuda_handles,
+ * types_cuda.hpp:53-60).  One lane per row: the gathers of x coalesce for stencil-like matrices.  mpg_pack_create
+ * returns MPG_OK with *out == NULL when the structure does not pack well (row lengths too uneven: > 25 % padding);
+ * keep using mpg_spmv_* then.  The packed object refers to A (destroy it before A); mpg_pack_update re-packs the
+ * values after the caller changed them.  mpg_gmres_solve packs the inner-precision matrix itself. */
+typedef struct mpg_packed mpg_packed;
+int mpg_pack_create_f32(mpg_ctx*, const mpg_csr* A, const float* vals, mpg_packed** out);
+int mpg_pack_create_f64(mpg_ctx*, const mpg_csr* A, const double* vals, mpg_packed** out);
+int mpg_pack_update_f32(mpg_ctx*, mpg_packed* P, const float* vals);
+int mpg_pack_update_f64(mpg_ctx*, mpg_packed* P, const double* vals);
+int mpg_pack_destroy(mpg_packed* P);
+int mpg_spmv_packed_f32(mpg_ctx*, const mpg_packed* P, float alpha, const float* x, float beta, float* y);
+int mpg_spmv_packed_f64(mpg_ctx*, const mpg_packed* P, double alpha, const double* x, double beta, double* y);
 /* Fused outer residual, replaces gmres.cpp:173-175 (copy + fp64 SpMV + cast kernel):
  * r = b - A*x in fp64; w32 = (float) r; r64 may be NULL (then r is never stored). */
 int mpg_residual_f64_cast_f32(mpg_ctx*, const mpg_csr* A, const double* vals, const double* b, const double* x,

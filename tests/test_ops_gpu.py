@@ -243,7 +243,8 @@ def test_fused_residual_cast(ctx, g, orc, spec):
 
 @pytest.mark.parametrize("dt", [np.float32, np.float64])
 @pytest.mark.parametrize("orth", ["cgsr", "cgs", "mgs"])
-@pytest.mark.parametrize("n,k", [(4, 0), (1000, 0), (1000, 3), (4099, 12), (65536, 31), (100003, 50), (30000, 100)])
+@pytest.mark.parametrize("n,k", [(4, 0), (1000, 0), (1000, 3), (4099, 12), (65536, 31), (100003, 50), (30000, 100),
+                                 (70000, 7), (300004, 2), (200000, 15), (200000, 16), (150000, 32)])
 def test_add_vector(ctx, orc, dt, orth, n, k):
     """GS::add_vector (Orthogonalization.hpp:51-60) fused on the device vs the oracle's gemv-by-gemv restatement"""
     import torch
@@ -343,3 +344,67 @@ def test_spmv_jacobi_fused_equals_spmv_then_gdmv(ctx, g, orc, spec, dt):
     y_sep = torch.empty_like(xd); ctx.spmv(A, vd, 1.0, xd, 0.0, y_sep); ctx.gdmv(1.0, diag, y_sep, 0.0, y_sep)
     y_fused = torch.full_like(xd, float("nan")); ctx.spmv_jacobi(A, vd, diag, xd, y_fused)
     np.testing.assert_array_equal(host(y_fused), host(y_sep))
+
+
+@pytest.mark.parametrize("spec", ["lap2d:3", "lap2d:64", "lap2d:300", "cd27:2", "cd27:20", "cd27:40"])
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_spmv_packed(ctx, g, orc, spec, dt):
+    """packed (sliced-ELL) operator == the CSR operator: same products, per-row sums in nonzero order"""
+    import scipy.sparse as sp
+    import torch
+    rm, ind, val = orc.gen(spec)
+    n = len(rm) - 1
+    r = _rng(n + 1)
+    x = r.standard_normal(n).astype(dt)
+    y = r.standard_normal(n).astype(dt)
+    v = val.astype(dt)
+    A = g.CSR(ctx, dev(rm), dev(ind))
+    vd, xd = dev(v), dev(x)
+    P = g.Packed(ctx, A, vd)
+    assert P, "stencil matrices must pack"
+    As = sp.csr_matrix((val, ind, rm), shape=(n, n))
+    absrow = abs(As) @ np.abs(x.astype(np.float64))
+    maxlen = int(np.diff(rm).max())
+    for alpha, beta in [(1.0, 0.0), (-1.0, 1.0), (0.5, -2.0)]:
+        yd = dev(y if beta != 0 else np.full(n, np.nan, dt))
+        ctx.spmv_packed(P, alpha, xd, beta, yd)
+        exact = alpha * (As @ x.astype(np.float64)) + (beta * y.astype(np.float64) if beta != 0 else 0)
+        bound = summation_bound(abs(alpha) * absrow + abs(beta) * np.abs(y), maxlen, dt)
+        assert np.all(np.abs(host(yd) - exact) <= bound)
+        yo = orc.spmv(rm, ind, v, alpha, x, beta, y.copy())
+        assert np.all(np.abs(host(yd) - yo) <= 2 * bound)
+    # values changed in place -> update
+    v2 = (v * dt(0.5)).astype(dt)
+    vd.copy_(dev(v2)); P.update(vd)
+    y1 = torch.empty_like(xd); ctx.spmv_packed(P, 1.0, xd, 0.0, y1)
+    y2 = torch.empty_like(xd); ctx.spmv(A, vd, 1.0, xd, 0.0, y2)
+    b2 = summation_bound(0.5 * absrow, maxlen, dt)
+    assert np.all(np.abs(host(y1) - host(y2)) <= 2 * b2)
+
+
+def test_pack_refuses_uneven_rows_and_handles_rows_without_entries(ctx, g, orc):
+    import scipy.sparse as sp
+    import torch
+    # power-law rows: too much padding inside 32-row slices -> no packed form, callers keep the CSR kernel
+    rm, ind, val = orc.gen("powerlaw:20000")
+    A = g.CSR(ctx, dev(rm), dev(ind))
+    P = g.Packed(ctx, A, dev(val.astype(np.float32)))
+    pad = float((np.diff(rm).reshape(-1, 32).max(axis=1) * 32).sum()) / len(ind) if (len(rm) - 1) % 32 == 0 else None
+    if pad is not None and pad > 1.3:
+        assert not P
+    # rows without entries pack (length 0) and give y = beta*y
+    n = 4096
+    M = sp.random(n, n, density=4e-3, format="lil", random_state=7, dtype=np.float64)
+    M[0:70, :] = 0; M[n - 5:, :] = 0
+    M = (M + sp.eye(n, format="lil") * 0).tocsr(); M.eliminate_zeros(); M.sort_indices()
+    lens = np.diff(M.indptr)
+    rm2, ind2, v2 = M.indptr.astype(np.int32), M.indices.astype(np.int32), M.data.astype(np.float32)
+    A2 = g.CSR(ctx, dev(rm2), dev(ind2))
+    P2 = g.Packed(ctx, A2, dev(v2))
+    x = _rng(2).standard_normal(n).astype(np.float32)
+    if P2:
+        yd = dev(np.full(n, np.nan, np.float32))
+        ctx.spmv_packed(P2, 1.0, dev(x), 0.0, yd)
+        yo = orc.spmv(rm2, ind2, v2, 1.0, x, 0.0, np.zeros(n, np.float32))
+        np.testing.assert_allclose(host(yd), yo, rtol=0, atol=64 * np.finfo(np.float32).eps * max(1.0, np.abs(yo).max()))
+        np.testing.assert_array_equal(host(yd)[lens == 0], 0)

@@ -188,3 +188,25 @@ def test_argument_validation_returns_errors_not_crashes(ctx, g, orc):
     # the context is still usable afterwards
     r = ctx.gmres(A, dev(val), dev(b), x, mode="mixed", rlen=10, tol=1e-9)
     assert r["status"] == 1
+
+
+@pytest.mark.parametrize("spec,mode,prec", [("cd27:16", "mixed", "identity"), ("lap2d:48", "baseline", "jacobi"), ("cd27:12", "single", "jacobi")])
+def test_packed_and_csr_inner_operator_agree(ctx, g, orc, spec, mode, prec):
+    """the solver multiplies with the packed copy of the matrix by default; with packing off it uses the CSR kernel:
+    same iteration counts, histories within the fp32/fp64 rounding envelope"""
+    import torch
+    rm, ind, val, xt, b = problem(orc, spec)
+    A = g.CSR(ctx, dev(rm), dev(ind))
+    out = []
+    for packed in (1, 0):
+        ctx.set_tuning("spmv_packed", packed)
+        x = torch.zeros(len(b), dtype=torch.float64, device="cuda:0")
+        out.append((ctx.gmres(A, dev(val), dev(b), x, mode=mode, prec=prec, orth="cgsr", rlen=25, tol=1e-8, max_restarts=200), host(x)))
+    ctx.set_tuning("spmv_packed", 1)
+    (r1, x1), (r0, x0) = out
+    assert r1["status"] == r0["status"] == 1
+    assert r1["total_iters"] == r0["total_iters"] and r1["total_restarts"] == r0["total_restarts"]
+    h1, h0 = r1["hist_inner"], r0["hist_inner"]
+    live = h0 >= 1e-4 * h0[0]
+    assert np.max(np.abs(h1 - h0)[live] / h0[live]) <= (2e-3 if mode != "baseline" else 1e-8)
+    assert np.linalg.norm(x1 - x0) <= 1e-6 * np.linalg.norm(x0)

@@ -17,7 +17,9 @@ ap.add_argument("--spec", default="cd27:256")
 ap.add_argument("--ks", default="1,2,4,8,16,25,32,50,64,75,100")
 ap.add_argument("--variants", default="default,stages2,stages1,noserp,passA_rb,rb16k")
 ap.add_argument("--no-spmv", action="store_true")
+ap.add_argument("--fuse-min", type=int, default=1, help="library default of fuse_min_cols (restored between variants)")
 args = ap.parse_args()
+FUSE_MIN_DEFAULT = args.fuse_min
 
 ctx = g.Context(0)
 n, m = args.n, args.m
@@ -39,9 +41,16 @@ VARIANTS = {
     "unfused": {"cgs2_fused": 0},
     "rb4k": {"passA_rb": 1, "gemvt_rows_per_block": 4096},
     "rb16k": {"passA_rb": 1, "gemvt_rows_per_block": 16384},
+    "direct16": {"vdirect_max_cols_a": 16, "vdirect_max_cols_b": 16},
+    "vrow48": {"vrow_max_cols": 48, "vrow_max_cols_a": 48},
+    "vrow64": {"vrow_max_cols": 64, "vrow_max_cols_a": 64},
+    "vrow_all": {"vdirect_max_cols_a": 0, "vdirect_max_cols_b": 0, "vrow_max_cols": 32},   # TMA row-owner kernel for every k1 <= 32
+    "vpass_all": {"vdirect_max_cols_a": 0, "vdirect_max_cols_b": 0, "vrow_max_cols": 0},   # TMA column-owner kernel for every k1
+    "regs_lt16": {"vdirect_max_cols_a": 0, "vdirect_max_cols_b": 0, "fuse_min_cols": 16, "vrow_max_cols": 0},   # round-1a policy
 }
 DEFAULTS = {"vpass_stages": 0, "vpass_serpentine": 1, "passA_rb": 0, "cgs2_fused": 1,
-            "gemvt_rows_per_block": 8192}
+            "gemvt_rows_per_block": 8192, "fuse_min_cols": FUSE_MIN_DEFAULT, "vrow_max_cols": 56,
+            "vdirect_max_cols_a": 8, "vdirect_max_cols_b": 8, "vrow_max_cols_a": 32}
 
 
 def run(orth, k, reps=3):
@@ -76,9 +85,10 @@ for vname in args.variants.split(","):
         a = run("cgs", k1)
         b = run("cgsr", k1)
         bytes3 = (3.0 * k1 + 4.0) * n * 4
-        if vname in ("unfused",):
+        if vname in ("unfused",) or "vpass" not in b or "vpass" not in a and not (vname.startswith("passA_rb") or vname.startswith("rb")):
             ms = sum(x[0] for x in b.values() if x) - b.get("elementwise", (0, 0))[0]
             print(f"{k1:>4} {'':>8} {'':>8} {'':>8} {'':>8} {'':>8} {'':>8} {ms:8.3f} {bytes3 / ms / 1e6:10.1f}   gemvt {gbs(b.get('gemvt')):.0f} gemvn {gbs(b.get('gemvn')):.0f}")
+            tot_ms += ms; tot_b += bytes3
             continue
         if vname.startswith("passA_rb") or vname.startswith("rb"):
             A = a.get("gemvt"); Bv = b.get("vpass")
@@ -102,12 +112,20 @@ if not args.no_spmv:
     x32 = torch.randn(nn, dtype=torch.float32, device="cuda:0"); y32 = torch.empty_like(x32)
     x64 = x32.double(); y64 = torch.empty_like(x64); b64 = torch.randn_like(x64)
     v32 = val.float()
-    for name, fn in [("spmv_f32", lambda: ctx.spmv(A, v32, 1.0, x32, 0.0, y32)), ("spmv_f64", lambda: ctx.spmv(A, val, 1.0, x64, 0.0, y64)),
-                     ("residual_f64_cast", lambda: ctx.residual_cast(A, val, b64, x64, None, y32))]:
+    P32 = g.Packed(ctx, A, v32)
+    P64 = g.Packed(ctx, A, val)
+    cases = [("spmv_f32", lambda: ctx.spmv(A, v32, 1.0, x32, 0.0, y32)), ("spmv_f64", lambda: ctx.spmv(A, val, 1.0, x64, 0.0, y64)),
+             ("residual_f64_cast", lambda: ctx.residual_cast(A, val, b64, x64, None, y32))]
+    if P32:
+        cases.append(("spmv_f32_packed", lambda: ctx.spmv_packed(P32, 1.0, x32, 0.0, y32)))
+        cases.append(("pack_update_f32", lambda: P32.update(v32)))
+    if P64:
+        cases.append(("spmv_f64_packed", lambda: ctx.spmv_packed(P64, 1.0, x64, 0.0, y64)))
+    for name, fn in cases:
         fn()
         ctx.prof_enable(True); ctx.prof_reset()
         for _ in range(5):
             fn()
         p = ctx.prof_get(); ctx.prof_enable(False)
-        c = "spmv_f32" if name == "spmv_f32" else "spmv_f64"
+        c = "elementwise" if name.startswith("pack_update") else ("spmv_f32" if "f32" in name else "spmv_f64")
         print(f"{name}: {p[c]['ms'] / 5:.3f} ms  {p[c]['bytes'] / p[c]['ms'] / 1e6:.0f} GB/s (algorithmic)")
