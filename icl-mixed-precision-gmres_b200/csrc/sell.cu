@@ -51,7 +51,7 @@ __device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(
 
 // slice_len[s] = 32 * L_s (elements); L_s = longest row, rounded up to a whole group when that costs <= 10 % padding
 // (one more 16-byte group is cheaper than up to G-1 single-element loads: cd27 27 -> 28; lap2d stays at 5 = 4 + 1)
-__global__ void sell_len_kernel(int nrows, int nslices, const int* __restrict__ row_map, int G, int64_t* __restrict__ slice_len) {
+__global__ void sell_len_kernel(int nrows, int nslices, const int* __restrict__ row_map, int G, int64_t* __restrict__ slice_len, int* has_rem) {
     const int s = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
     if (s >= nslices) return;
     const int r = s * SLICE + lane;
@@ -60,7 +60,10 @@ __global__ void sell_len_kernel(int nrows, int nslices, const int* __restrict__ 
     for (int o = 16; o > 0; o >>= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, o));
     const int rem = len % G;
     if (rem > 0 && (G - rem) * 10 <= len) len += G - rem;
-    if (lane == 0) slice_len[s] = (int64_t)len * SLICE;
+    if (lane == 0) {
+        slice_len[s] = (int64_t)len * SLICE;
+        if (len % G) *has_rem = 1;   // benign race: every writer stores 1
+    }
 }
 
 // packed indices (structure) and, with T != void, packed values; warp = slice, lane = row
@@ -125,7 +128,7 @@ __global__ void sell_fill_vals_kernel(int nrows, int nslices, const int* __restr
 
 // y[r] = alpha * sum_p v[r,p] x[c[r,p]] + beta * y[r]; products and sums individually rounded, nonzero order
 // (the CSR kernel's arithmetic for a row that lies inside one tile).
-template <class T>
+template <class T, bool HAS_REM>
 __global__ void __launch_bounds__(256) spmv_sell_kernel(int nrows, int nslices, const int64_t* __restrict__ slice_off, const int* __restrict__ sinds,
                                                          const T* __restrict__ svals, const T* __restrict__ x, T alpha, T beta, const T* y_in,
                                                          T* y_out, float* out32, const T* __restrict__ rowscale, const int* __restrict__ slice_list) {
@@ -166,8 +169,8 @@ __global__ void __launch_bounds__(256) spmv_sell_kernel(int nrows, int nslices, 
 #pragma unroll
         for (int q = 0; q < G; ++q) sum = add_rn(sum, mul_rn(pv0[q], __ldg(x + pc0[q])));
     }
-    // the L % G trailing positions, one element per lane
-    {
+    // the L % G trailing positions, one element per lane (compiled out for plans whose slices are all whole groups)
+    if (HAS_REM) {
         const int* it = sinds + off + (int64_t)ng * SLICE * G + lane;
         const T* vt = svals + off + (int64_t)ng * SLICE * G + lane;
         for (int t = 0; t < L - ng * G; ++t) sum = add_rn(sum, mul_rn(ldg_stream(vt + t * SLICE), __ldg(x + ldg_stream(it + t * SLICE))));
@@ -194,6 +197,7 @@ struct mpg_sell_plan {
     int* sinds = nullptr;          // [total]
     int* slice_list = nullptr;     // partitioned matrices: slices without halo columns first
     int n_interior = 0;
+    int has_rem = 0;               // some slice length is not a multiple of G
     unsigned long long uid = 0;    // distinguishes plans that happen to be allocated at the same address
 };
 
@@ -228,11 +232,13 @@ int sell_plan_get(mpg_ctx* ctx, const mpg_csr* A, int G, const mpg_sell_plan** o
     p->G = G;
     p->nslices = (int)cdiv(A->nrows, SLICE);
     int64_t* len = nullptr;
-    MPG_CUDA(ctx, pool_alloc(ctx, &len, sizeof(int64_t) * (size_t)(p->nslices + 1)));
+    MPG_CUDA(ctx, pool_alloc(ctx, &len, sizeof(int64_t) * (size_t)(p->nslices + 2)));
     MPG_CUDA(ctx, pool_alloc(ctx, &p->slice_off, sizeof(int64_t) * (size_t)(p->nslices + 1)));
-    MPG_CUDA(ctx, cudaMemsetAsync(len, 0, sizeof(int64_t) * (size_t)(p->nslices + 1), ctx->stream));
+    MPG_CUDA(ctx, cudaMemsetAsync(len, 0, sizeof(int64_t) * (size_t)(p->nslices + 2), ctx->stream));
     const int wgrid = (int)cdiv((int64_t)p->nslices * 32, 256);
-    sell_len_kernel<<<wgrid, 256, 0, ctx->stream>>>(A->nrows, p->nslices, A->row_map, G, len);
+    // len[nslices] (the scan's total slot, zero) doubles as the has_rem flag until the scan has consumed it... keep it separate:
+    int* rem_flag = reinterpret_cast<int*>(len + p->nslices + 1);
+    sell_len_kernel<<<wgrid, 256, 0, ctx->stream>>>(A->nrows, p->nslices, A->row_map, G, len, rem_flag);
     MPG_CHECK_LAUNCH(ctx);
     size_t tmp_bytes = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, len, p->slice_off, p->nslices + 1, ctx->stream);
@@ -241,6 +247,7 @@ int sell_plan_get(mpg_ctx* ctx, const mpg_csr* A, int G, const mpg_sell_plan** o
     cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, len, p->slice_off, p->nslices + 1, ctx->stream);
     MPG_CHECK_LAUNCH(ctx);
     MPG_CUDA(ctx, cudaMemcpyAsync(&p->total, p->slice_off + p->nslices, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    MPG_CUDA(ctx, cudaMemcpyAsync(&p->has_rem, rem_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     MPG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     cudaFree(tmp);
     cudaFree(len);
@@ -328,9 +335,13 @@ int spmv_packed(mpg_ctx* ctx, const mpg_packed* P, T alpha, const T* x, T beta, 
     const double bytes = (double)A->nnz * (s_ + 4) + 4 * (n_ + 1) + n_ * s_ + (y_out ? n_ * s_ : 0) + (beta != T(0) ? n_ * s_ : 0) + (out32 ? 4 * n_ : 0) +
                          (rowscale ? n_ * s_ : 0);
     ProfScope prof(ctx, sizeof(T) == 4 ? MPG_PROF_SPMV_F32 : MPG_PROF_SPMV_F64, bytes * ((double)s_count / p->nslices));
-    spmv_sell_kernel<T><<<(int)cdiv((int64_t)s_count * 32, 256), 256, 0, ctx->stream>>>(A->nrows, s_count, p->slice_off, p->sinds,
-                                                                                       static_cast<const T*>(P->svals), x, alpha, beta, y_in, y_out, out32,
-                                                                                       rowscale, list);
+    const int grid = (int)cdiv((int64_t)s_count * 32, 256);
+    if (p->has_rem)
+        spmv_sell_kernel<T, true><<<grid, 256, 0, ctx->stream>>>(A->nrows, s_count, p->slice_off, p->sinds, static_cast<const T*>(P->svals), x, alpha, beta,
+                                                                 y_in, y_out, out32, rowscale, list);
+    else
+        spmv_sell_kernel<T, false><<<grid, 256, 0, ctx->stream>>>(A->nrows, s_count, p->slice_off, p->sinds, static_cast<const T*>(P->svals), x, alpha, beta,
+                                                                  y_in, y_out, out32, rowscale, list);
     MPG_CHECK_LAUNCH(ctx);
     return MPG_OK;
 }
