@@ -80,7 +80,8 @@
         assert(matrix.ncols() == x.n());                                                                                          \
         assert(matrix.nrows() == y.n());                                                                                          \
         if (matrix.is_transposed()) Kokkos::abort("transposed SpMV (condest.cpp only) is not provided by the B200 backend\n");    \
-        B200_CHECK(mpg_spmv_##SFX(CTX, matrix.plan(), matrix.vals_data(), alpha, x.data(), beta, y.data()));                      \
+        if (matrix.packed()) B200_CHECK(mpg_spmv_packed_##SFX(CTX, matrix.packed(), alpha, x.data(), beta, y.data()));            \
+        else B200_CHECK(mpg_spmv_##SFX(CTX, matrix.plan(), matrix.vals_data(), alpha, x.data(), beta, y.data()));                 \
     }                                                                                                                             \
     template <> void gdmv<T, B200>(T alpha, Vect<T, B200> diag, Vect<T, B200> x, T beta, Vect<T, B200> y) { /* kernels.hpp:131-146 */ \
         B200_CHECK(mpg_gdmv_##SFX(CTX, diag.n(), alpha, diag.data(), x.data(), beta, y.data()));                                  \

@@ -49,12 +49,24 @@ template <class Type>
 class SparseMatrix<Type, B200> {
 private:
     std::shared_ptr<mpg_csr> plan_;  // SpMV plan over (row_map_, inds_); shared with precision-cast copies
+    // packed (sliced-ELL) copy of this matrix, the analogue of the cusparse handles create_cuda_handles() builds per
+    // SparseMatrix (types_cuda.hpp:53-60); null when the structure does not pack well.  Declared after plan_: it refers
+    // to the plan and is destroyed first.  Values are taken at construction (the reference never mutates a matrix).
+    std::shared_ptr<mpg_packed> packed_;
     bool transposed_ = false;
+
+    static int pack_create(const mpg_csr* A, const float* v, mpg_packed** out) { return mpg_pack_create_f32(B200Backend::context(), A, v, out); }
+    static int pack_create(const mpg_csr* A, const double* v, mpg_packed** out) { return mpg_pack_create_f64(B200Backend::context(), A, v, out); }
 
     void create_plan() {
         mpg_csr* p = nullptr;
         B200_CHECK(mpg_csr_create(B200Backend::context(), m_, n_, nnz_, row_map_.data(), inds_.data(), &p));
         plan_ = std::shared_ptr<mpg_csr>(p, [](mpg_csr* q) { mpg_csr_destroy(q); });
+    }
+    void create_packed() {
+        mpg_packed* q = nullptr;
+        B200_CHECK(pack_create(plan_.get(), vals_.data(), &q));
+        if (q) packed_ = std::shared_ptr<mpg_packed>(q, [](mpg_packed* r) { mpg_pack_destroy(r); });
     }
 
     template <class, class>
@@ -71,6 +83,7 @@ public:
                  Kokkos::View<Type*, typename B200::memory_space> vals)
         : m_(m), n_(n), nnz_(inds.extent(0)), row_map_(row_map), inds_(inds), vals_(vals) {
         create_plan();
+        create_packed();
     }
 
     // precision cast: shares row_map / inds / plan, converts the values (types_cuda.hpp:82-101)
@@ -79,6 +92,7 @@ public:
         : plan_(old.plan_), transposed_(old.is_transposed()), m_(old.m_), n_(old.n_), nnz_(old.inds_.extent(0)), row_map_(old.row_map_),
           inds_(old.inds_), vals_("vals", old.vals_.extent(0)) {
         copy(Vect<OldType, B200>(old.vals_), Vect<Type, B200>(vals_));
+        create_packed();
     }
 
     // host -> device (types_cuda.hpp:103-114)
@@ -90,6 +104,7 @@ public:
         Kokkos::deep_copy(inds_, old.inds_);
         Kokkos::deep_copy(vals_, old.vals_);
         create_plan();
+        create_packed();
     }
 
     int nrows() const { return m_; }
@@ -100,6 +115,7 @@ public:
     Type* vals_data() { return vals_.data(); }
     Vect<Type, B200> vals_vect() { return Vect<Type, B200>(vals_); }
     const mpg_csr* plan() const { return plan_.get(); }
+    const mpg_packed* packed() const { return packed_.get(); }
     void set_transpose(bool new_trans) { this->transposed_ = new_trans; }  // only condest.cpp uses it (out of scope)
     bool is_transposed() { return this->transposed_; }
 };
