@@ -809,7 +809,7 @@ int launch_vdirect_inst(mpg_ctx* ctx, int64_t n, int k1, const T* V, int64_t ldv
     return dist_finish_reduction(ctx, epi, k1, (int)sizeof(T));
 }
 
-// widest basis the register-resident kernel is built for.  Measured (profiles/r02_tune_vdirect.txt): it wins up to 8
+// widest basis the register-resident kernel is built for.  Measured (profiles/r01b_tune_vdirect.txt): it wins up to 8
 // columns; from 9 on the k1 accumulators (+ k1 live 16-byte vectors in pass B) cost too much occupancy and the
 // shared-memory staged kernels are faster.
 constexpr int kVdirectCap = 16;
