@@ -50,6 +50,11 @@ for dt, name in [(torch.float32, "float"), (torch.float64, "double")]:
     ms = timed(("spmv_f32", "spmv_f64"), lambda: ctx.spmv(A, v, 1.0, x, 0.0, y), args.trials)
     by = nnz * (s + 4) + 4 * (n + 1) + 2 * n * s
     out["gpu"][f"spmv_{name}"] = {"ms": ms, "GBps": by / ms / 1e6}
+    P = g.Packed(ctx, A, v)   # the operator the solver (and SparseMatrix<T,B200>) actually multiplies with
+    if P:
+        ms = timed(("spmv_f32", "spmv_f64"), lambda: ctx.spmv_packed(P, 1.0, x, 0.0, y), args.trials)
+        out["gpu"][f"spmv_{name}_packed"] = {"ms": ms, "GBps": by / ms / 1e6}
+    del P
     ms = timed(("reduce",), lambda: ctx.dot(x, y), args.trials)
     out["gpu"][f"dot_{name}"] = {"ms": ms, "GBps": 2 * n * s / ms / 1e6}
     for k1 in [int(c) for c in args.vcols.split(",")]:
