@@ -208,6 +208,9 @@ class Context:
 
     PROF_CLASSES = ["spmv_f32", "spmv_f64", "vpass", "gemvn", "elementwise", "reduce", "small", "gemvt"]
 
+    def debug_timing(self, buf):
+        self._chk(self.L.mpg_debug_timing(self.h, _ptr(buf) if buf is not None else None))
+
     def prof_enable(self, on=True):
         self._chk(self.L.mpg_prof_enable(self.h, C.c_int(int(on))))
 

@@ -111,6 +111,12 @@ extern "C" int mpg_set_tuning(mpg_ctx* ctx, const char* key, int value) {
     return MPG_OK;
 }
 
+extern "C" int mpg_debug_timing(mpg_ctx* ctx, unsigned long long* device_buf) {
+    if (!ctx) return MPG_ERR_ARG;
+    ctx->dbg = device_buf;
+    return MPG_OK;
+}
+
 extern "C" int mpg_prof_enable(mpg_ctx* ctx, int on) {
     if (!ctx) return MPG_ERR_ARG;
     ctx->prof_on = on != 0;

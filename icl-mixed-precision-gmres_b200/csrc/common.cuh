@@ -78,6 +78,9 @@ struct mpg_ctx {
     struct mpg_dist* dist = nullptr;
     double* red_raw = nullptr;   // kMaxCols + 8 doubles
 
+    // optional per-CTA phase timestamps of the staged V-pass kernels (mpg_debug_timing, tools/vpass_timeline.py)
+    unsigned long long* dbg = nullptr;
+
     // cached solver workspace (see solver.cu)
     void* ws = nullptr;
     void (*ws_free)(void*) = nullptr;
@@ -196,6 +199,12 @@ __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
+}
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
 }
 
 // streaming (read-once) loads: bypass L1 allocation so L1 stays available for gathered vectors
@@ -341,14 +350,37 @@ __device__ __forceinline__ void finish_reduction(const Epi& e, int count, double
     for (int j = threadIdx.x; j < count; j += blockDim.x) apply_epi<T>(e, j, red_s[j]);
 }
 
-// last CTA: fixed-order sum of the per-CTA partials of `count` columns, then finish_reduction
+// last CTA: fixed-order sum of the per-CTA partials of `count` columns, then finish_reduction.
+// Two shapes, chosen from (count, blockDim) only, so the summation order is a function of the launch configuration:
+//   * few columns: one warp per column, the blocks strided over the lanes, xor tree;
+//   * many columns (more than two per warp) and a scratch buffer of >= blockDim doubles in shared memory: thread
+//     (r, j) sums column j over the blocks r, r+R, ... with coalesced loads kept 8 deep in flight, then the R partial
+//     sums are added in r order.  (The warp-per-column shape serialises count/nwarps dependent L2 round trips: 22 us
+//     at 100 columns, tools/vpass_timeline.py.)
 template <class T>
-__device__ __forceinline__ void last_block_finish(const Epi& e, const double* partials, int ldp, int nblocks, int count) {
+__device__ __forceinline__ void last_block_finish(const Epi& e, const double* partials, int ldp, int nblocks, int count, double* scratch = nullptr) {
     __shared__ double red_s[kMaxCols + 8];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    for (int j = wid; j < count; j += nw) {
-        const double sred = reduce_partials_column(partials, ldp, nblocks, j);
-        if (lane == 0) red_s[j] = sred;
+    const int R = scratch ? min((int)blockDim.x / max(count, 1), 16) : 0;
+    if (count > 2 * nw && R >= 2) {
+        const int r = threadIdx.x / count, j = threadIdx.x - r * count;
+        if (r < R) {
+            double acc = 0.0;
+#pragma unroll 8
+            for (int b = r; b < nblocks; b += R) acc += __ldcg(partials + (size_t)b * ldp + j);
+            scratch[r * count + j] = acc;
+        }
+        __syncthreads();
+        for (int jj = threadIdx.x; jj < count; jj += blockDim.x) {
+            double t = scratch[jj];
+            for (int q = 1; q < R; ++q) t += scratch[q * count + jj];
+            red_s[jj] = t;
+        }
+    } else {
+        for (int j = wid; j < count; j += nw) {
+            const double sred = reduce_partials_column(partials, ldp, nblocks, j);
+            if (lane == 0) red_s[j] = sred;
+        }
     }
     __syncthreads();
     finish_reduction<T>(e, count, red_s);

@@ -88,7 +88,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volat
 template <class T, int TR, int MAXJ>
 __global__ void __launch_bounds__(2 * TR + 32, 1)
 vpass_kernel(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapW, int64_t n, int k1, T* w, const T* h_in,
-             int stages, int reverse, double* partials, int ldp, unsigned int* ticket, Epi epi) {
+             int stages, int reverse, double* partials, int ldp, unsigned int* ticket, Epi epi, unsigned long long* dbg) {
     constexpr int CT = 2 * TR;         // compute threads
     constexpr int NW = CT / 32;        // compute warps
     constexpr int RPL = TR / 32;       // rows per lane in the dot phase
@@ -108,6 +108,7 @@ vpass_kernel(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ C
         return tix * TR;
     };
 
+    if (dbg && tid == 0) dbg[blockIdx.x * 8 + 0] = globaltimer_ns();
     if (h_in) for (int j = tid; j < k1; j += CT + 32) h_s[j] = h_in[j];
     if (tid == 0) {
         for (int s = 0; s < stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
@@ -146,6 +147,7 @@ vpass_kernel(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ C
             T* ws = st + (size_t)k1 * TR;
             T* ps = ws + TR;
             mbar_wait(full + s, (uint32_t)((it / stages) & 1));
+            if (dbg && tid == 0 && it == 0) dbg[blockIdx.x * 8 + 1] = globaltimer_ns();
             if (h_in) {
                 // ---- phase 1: w' = w - V h ----
                 const int jb = half ? jsplit : 0, je = half ? k1 : jsplit;
@@ -181,6 +183,7 @@ vpass_kernel(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ C
             named_bar_sync(1, CT);
             if (tid == 0) mbar_arrive(empty + s);
         }
+        if (dbg && tid == 0) dbg[blockIdx.x * 8 + 2] = globaltimer_ns();
         // ---- per-CTA partials (one owner warp per column) ----
 #pragma unroll
         for (int jj = 0; jj < MAXJ; ++jj) {
@@ -190,8 +193,15 @@ vpass_kernel(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ C
                 if (lane == 0) partials[(size_t)blockIdx.x * ldp + j] = sred;
             }
         }
+        if (dbg && tid == 0) dbg[blockIdx.x * 8 + 3] = globaltimer_ns();
     }
-    if (grid_last_block(ticket)) last_block_finish<T>(epi, partials, ldp, gridDim.x, k1);
+    const bool last = grid_last_block(ticket);
+    if (dbg && tid == 0) dbg[blockIdx.x * 8 + 4] = globaltimer_ns();
+    if (last) {
+        // every tile of this CTA has been consumed: the staging buffers are free to serve as scratch
+        last_block_finish<T>(epi, partials, ldp, gridDim.x, k1, reinterpret_cast<double*>(smem_raw));
+        if (dbg && tid == 0) dbg[blockIdx.x * 8 + 5] = globaltimer_ns();
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -335,7 +345,10 @@ __global__ void __launch_bounds__(256) gemvt_kernel(int64_t n, int ncols, const 
         }
         __syncthreads();
     }
-    if (grid_last_block(ticket)) last_block_finish<T>(epi, partials, ldp, gridDim.x, ncols);
+    if (grid_last_block(ticket)) {
+        __shared__ double fin_s[256];
+        last_block_finish<T>(epi, partials, ldp, gridDim.x, ncols, fin_s);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -399,7 +412,10 @@ __global__ void __launch_bounds__(256, 2) gemvt_rb_kernel(int64_t n, int ncols, 
             __syncthreads();
         }
     }
-    if (grid_last_block(ticket)) last_block_finish<T>(epi, partials, ldp, nblocks, ncols);
+    if (grid_last_block(ticket)) {
+        __shared__ double fin_s[256];
+        last_block_finish<T>(epi, partials, ldp, nblocks, ncols, fin_s);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -509,7 +525,7 @@ vrow_kernel(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CU
         for (int q = 0; q < NW; ++q) t += red[q][tid];
         partials[(size_t)blockIdx.x * ldp + tid] = t;
     }
-    if (grid_last_block(ticket)) last_block_finish<T>(epi, partials, ldp, gridDim.x, k1);
+    if (grid_last_block(ticket)) last_block_finish<T>(epi, partials, ldp, gridDim.x, k1, reinterpret_cast<double*>(smem_raw));
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -720,7 +736,7 @@ int launch_vpass_inst(mpg_ctx* ctx, int64_t n, int k1, const T* V, int64_t ldv, 
     // pass left in L2, and the following gemv-N pass (forward) starts on the part this one leaves there
     const int reverse = (ctx->tune.vpass_serpentine && h_in) ? 1 : 0;
     const Epi epi = make_epi(ctx, fin == FIN_COEF_ACCUM ? EPI_COEF_ACCUM : EPI_COEF, coef_out, hcol, 0.0, 0.0);
-    kern<<<grid, 2 * TR + 32, smem, ctx->stream>>>(mapV, mapW, n, k1, w, h_in, stages, reverse, ctx->partials, kMaxCols + 8, ctx->ticket, epi);
+    kern<<<grid, 2 * TR + 32, smem, ctx->stream>>>(mapV, mapW, n, k1, w, h_in, stages, reverse, ctx->partials, kMaxCols + 8, ctx->ticket, epi, ctx->dbg);
     MPG_CHECK_LAUNCH(ctx);
     return dist_finish_reduction(ctx, epi, k1, (int)sizeof(T));
 }

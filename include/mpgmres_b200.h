@@ -52,6 +52,10 @@ const char* mpg_last_error(mpg_ctx* ctx);
 int mpg_num_sms(mpg_ctx* ctx);
 int64_t mpg_launch_count(mpg_ctx* ctx);              /* kernels launched through this context so far */
 int mpg_set_tuning(mpg_ctx* ctx, const char* key, int value); /* kernel variant knobs, see DESIGN.md */
+/* Development aid: with a device buffer of >= 8 * 160 uint64 attached, every CTA of the staged V-pass kernels stores
+ * %globaltimer at its phase boundaries (start, first tile in, last tile done, partials written, finish done);
+ * NULL detaches (tools/vpass_timeline.py). */
+int mpg_debug_timing(mpg_ctx* ctx, unsigned long long* device_buf);
 
 /* ---- per-kernel-class device timers (CUDA events on the launching stream; the reference has none) -- */
 enum { MPG_PROF_SPMV_F32 = 0, MPG_PROF_SPMV_F64 = 1, MPG_PROF_VPASS = 2, MPG_PROF_GEMVN = 3, MPG_PROF_ELEMENTWISE = 4,
