@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--tune", action="append", default=[], metavar="KEY=INT", help="mpg_set_tuning knob (experiments), e.g. --tune use_pdl=0")
     return ap.parse_args()
 
 
@@ -175,6 +176,8 @@ def main():
 
     dev = f"cuda:{local_rank}"
     ctx = g.Context(local_rank)
+    for kv in args.tune:
+        ctx.set_tuning(kv.split("=")[0], int(kv.split("=")[1]))
     peak, peak_src = measured_peaks()
 
     # ---- problem (device-resident; construction is outside the timed region like gmres_perf_test.cpp:408-421) ----
@@ -205,7 +208,7 @@ def main():
 
     # ---- timed region: K solves, device time from CUDA events; per-kernel-class timers on (for launch-bound small
     # workloads the per-launch event records would perturb the step, so the breakdown is taken in one extra solve) ----
-    prof_in_region = not flush
+    prof_in_region = (not flush) and n >= 8_000_000   # below ~8 M rows a kernel lasts < 100 us: event records between launches would perturb the step
     ctx.prof_enable(prof_in_region)
     ctx.prof_reset()
     sampler = ClockSampler(local_rank)
@@ -301,7 +304,9 @@ def main():
                        "time_to_solution_s": total_ms * 1e-3 / args.steps, "status": int(status),
                        "resNorm": res_norm, "errNorm": err_norm, "rel_res": res_norm / b_norm,
                        "l2": (f"working set {ws_bytes / 1e9:.2f} GB: L2 flushed (512 MB overwrite) between timed steps" if flush else
-                              f"working set {ws_bytes / 1e9:.1f} GB (matrix + basis) >> 126 MB L2; no flush needed")},
+                              f"working set {ws_bytes / 1e9:.1f} GB (matrix + basis) >> 126 MB L2; no flush needed"),
+                       "kernel_timers": ("CUDA events around every launch inside the timed region" if prof_in_region else
+                                         "one extra solve after the timed region (kernels of < 100 us: event records between launches would perturb the step)")},
             "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
     print(json.dumps(line), flush=True)
 

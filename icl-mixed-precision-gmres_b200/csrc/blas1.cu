@@ -93,6 +93,7 @@ extern "C" int mpg_set_tuning(mpg_ctx* ctx, const char* key, int value) {
     else if (k == "dist_peer_halo") ctx->tune.dist_peer_halo = value;
     else if (k == "dist_overlap") ctx->tune.dist_overlap = value;
     else if (k == "spmv_packed") ctx->tune.spmv_packed = value;
+    else if (k == "use_pdl") ctx->tune.use_pdl = value;
     else if (k == "vpass_stages") ctx->tune.vpass_stages = value;
     else if (k == "fuse_min_cols") ctx->tune.fuse_min_cols = value;
     else if (k == "vdirect_max_cols_a") ctx->tune.vdirect_max_cols_a = value;
@@ -346,6 +347,8 @@ __device__ __forceinline__ void store4(T* p, const T v[4]) {
 template <class TX, class TY, int OP>
 __global__ void __launch_bounds__(256) ew_kernel(int64_t n, TY alpha, const TY* __restrict__ alpha_dev, TY beta,
                                                   const TX* x, const TY* diag, TY* y, int aligned) {
+    pdl_trigger();
+    pdl_wait();
     if (alpha_dev) alpha = __ldg(alpha_dev);
     const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t gstride = (int64_t)gridDim.x * blockDim.x;
@@ -381,7 +384,7 @@ int launch_ew(mpg_ctx* ctx, int64_t n, TY alpha, const TY* alpha_dev, TY beta, c
     const int aligned = (((uintptr_t)x | (uintptr_t)diag | (uintptr_t)y) & 15) == 0;
     const double ew_bytes = (double)n * ((OP != EW_FILL ? sizeof(TX) : 0) + sizeof(TY) * (1 + (OP == EW_AXPY || OP == EW_NAXPY || OP == EW_GDMV) + (OP == EW_GDMV)));
     ProfScope prof(ctx, MPG_PROF_ELEMENTWISE, ew_bytes);
-    ew_kernel<TX, TY, OP><<<grid, 256, 0, ctx->stream>>>(n, alpha, alpha_dev, beta, x, diag, y, aligned);
+    MPG_CUDA(ctx, launch_pdl(ctx, ew_kernel<TX, TY, OP>, grid, 256, 0, n, alpha, alpha_dev, beta, x, diag, y, aligned));
     MPG_CHECK_LAUNCH(ctx);
     return MPG_OK;
 }
@@ -503,6 +506,8 @@ __global__ void __launch_bounds__(32) givens_step_kernel(int64_t k, T* h, int64_
     T* sc = sh + (k + 2);                          // k
     T* ss = sc + k;                                // k
     T* hcol = h + k * ldh;
+    pdl_trigger();
+    pdl_wait();
     for (int64_t j = threadIdx.x; j < k + 2; j += 32) sh[j] = hcol[j];
     for (int64_t j = threadIdx.x; j < k; j += 32) { sc[j] = cs[j]; ss[j] = sn[j]; }
     __syncwarp();
@@ -603,7 +608,7 @@ template <class T>
 int givens_step(mpg_ctx* ctx, int64_t k, T* h, int64_t ldh, T* cs, T* sn, T* s, double* resid, double* resid_host) {
     const size_t smem = sizeof(T) * (size_t)(3 * k + 2);
     ProfScope prof(ctx, MPG_PROF_SMALL, 0.0);
-    givens_step_kernel<T><<<1, 32, smem, ctx->stream>>>(k, h, ldh, cs, sn, s, resid, resid_host);
+    MPG_CUDA(ctx, launch_pdl(ctx, givens_step_kernel<T>, 1, 32, smem, k, h, ldh, cs, sn, s, resid, resid_host));
     MPG_CHECK_LAUNCH(ctx);
     return MPG_OK;
 }

@@ -37,6 +37,7 @@ struct Tuning {
     int red_ctas_per_sm = 4;
     int use_graph = 0;
     int dist_peer_halo = 1;   // multi-GPU halo exchange by stores into the neighbours' memory (0: pack + ncclSend/ncclRecv)
+    int use_pdl = 1;          // programmatic dependent launch for the kernels of the Arnoldi loop (off while profiling: events sit between launches)
     int spmv_packed = 1;      // solver: run the inner SpMV on the packed (sliced-ELL) copy of the matrix when it packs well (sell.cu)
     int dist_overlap = 1;     // multi-GPU SpMV: rows without halo columns run between the halo push and the wait for the neighbours' data
     int dist_peer_reduce = 1; // multi-GPU reductions inside the kernels over peer memory (0: NCCL all-reduce + epilogue kernel)
@@ -143,6 +144,22 @@ inline int fail(mpg_ctx* ctx, int code, const std::string& msg) {
                                                     " @" + __FILE__ + ":" + std::to_string(__LINE__)); \
     } while (0)
 
+// kernel<<<grid, block, smem, ctx->stream>>>(args...) with the programmatic-stream-serialization attribute
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(mpg_ctx* ctx, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (ctx->tune.use_pdl && !ctx->prof_on) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+
 #define MPG_REQUIRE(ctx, cond, msg)                                   \
     do {                                                              \
         if (!(cond)) return mpg::fail(ctx, MPG_ERR_ARG, (msg));       \
@@ -200,6 +217,14 @@ __device__ __forceinline__ float warp_sum(float v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
+
+// Programmatic dependent launch (sm_90+): kernels of the Arnoldi loop are launched with the programmatic-stream-
+// serialization attribute (launch_pdl below).  pdl_trigger() lets the NEXT kernel's CTAs be scheduled as soon as SM
+// resources free up, so its launch latency and prologue overlap this kernel's tail; pdl_wait() blocks until the
+// PREVIOUS kernel has completed and its memory is visible - it must precede the first global-memory access.  Both are
+// no-ops for kernels launched the ordinary way.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
     unsigned long long t;

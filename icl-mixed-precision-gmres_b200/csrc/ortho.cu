@@ -108,6 +108,8 @@ vpass_kernel(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ C
         return tix * TR;
     };
 
+    pdl_trigger();
+    pdl_wait();
     if (dbg && tid == 0) dbg[blockIdx.x * 8 + 0] = globaltimer_ns();
     if (h_in) for (int j = tid; j < k1; j += CT + 32) h_s[j] = h_in[j];
     if (tid == 0) {
@@ -215,6 +217,8 @@ __global__ void __launch_bounds__(256) gemvn_kernel(int64_t n, int k1, const T* 
                                                      T* y, double* x64, double* partials, unsigned int* ticket, Epi epi) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     T* ax = reinterpret_cast<T*>(smem_raw);
+    pdl_trigger();
+    pdl_wait();
     for (int j = threadIdx.x; j < k1; j += blockDim.x) ax[j] = alpha * x[j];
     __syncthreads();
     using V4 = typename std::conditional<sizeof(T) == 4, float4, double2>::type;
@@ -455,6 +459,8 @@ vrow_kernel(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CU
         return tix * TRW;
     };
 
+    pdl_trigger();
+    pdl_wait();
     if (tid < MAXK) h_s[tid] = (h_in && tid < k1) ? h_in[tid] : T(0);
     if (tid == 0) {
         for (int s = 0; s < stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, NW); }
@@ -547,6 +553,8 @@ __global__ void __launch_bounds__(256) vdirect_kernel(int64_t n, int k1, const T
     __shared__ double red[8][MAXK];
     __shared__ T h_s[MAXK];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    pdl_trigger();
+    pdl_wait();
     if (HAS_H && tid < MAXK) h_s[tid] = (tid < k1) ? h_in[tid] : T(0);
     __syncthreads();
 
@@ -736,7 +744,7 @@ int launch_vpass_inst(mpg_ctx* ctx, int64_t n, int k1, const T* V, int64_t ldv, 
     // pass left in L2, and the following gemv-N pass (forward) starts on the part this one leaves there
     const int reverse = (ctx->tune.vpass_serpentine && h_in) ? 1 : 0;
     const Epi epi = make_epi(ctx, fin == FIN_COEF_ACCUM ? EPI_COEF_ACCUM : EPI_COEF, coef_out, hcol, 0.0, 0.0);
-    kern<<<grid, 2 * TR + 32, smem, ctx->stream>>>(mapV, mapW, n, k1, w, h_in, stages, reverse, ctx->partials, kMaxCols + 8, ctx->ticket, epi, ctx->dbg);
+    MPG_CUDA(ctx, launch_pdl(ctx, kern, grid, 2 * TR + 32, smem, mapV, mapW, n, k1, w, h_in, stages, reverse, ctx->partials, (int)(kMaxCols + 8), ctx->ticket, epi, ctx->dbg));
     MPG_CHECK_LAUNCH(ctx);
     return dist_finish_reduction(ctx, epi, k1, (int)sizeof(T));
 }
@@ -787,7 +795,7 @@ int launch_vrow_inst(mpg_ctx* ctx, int64_t n, int k1, const T* V, int64_t ldv, T
     ProfScope prof(ctx, MPG_PROF_VPASS, (double)k1 * n * sizeof(T) + (h_in ? 2.0 * n * sizeof(T) : 0.0));
     const int reverse = (ctx->tune.vpass_serpentine && h_in) ? 1 : 0;   // same rule as vpass: a function of the pass only
     const Epi epi = make_epi(ctx, fin == FIN_COEF_ACCUM ? EPI_COEF_ACCUM : EPI_COEF, coef_out, hcol, 0.0, 0.0);
-    kern<<<grid, CT + 32, smem, ctx->stream>>>(*mapV, *mapW, n, k1, w, h_in, stages, reverse, ctx->partials, kMaxCols + 8, ctx->ticket, epi);
+    MPG_CUDA(ctx, launch_pdl(ctx, kern, grid, CT + 32, smem, *mapV, *mapW, n, k1, w, h_in, stages, reverse, ctx->partials, (int)(kMaxCols + 8), ctx->ticket, epi));
     MPG_CHECK_LAUNCH(ctx);
     return dist_finish_reduction(ctx, epi, k1, (int)sizeof(T));
 }
@@ -820,7 +828,7 @@ int launch_vdirect_inst(mpg_ctx* ctx, int64_t n, int k1, const T* V, int64_t ldv
     ProfScope prof(ctx, MPG_PROF_VPASS, (double)k1 * n * sizeof(T) + (h_in ? 2.0 * n * sizeof(T) : 0.0));
     const int reverse = (ctx->tune.vpass_serpentine && h_in) ? 1 : 0;   // same rule as vpass: a function of the pass only
     const Epi epi = make_epi(ctx, fin == FIN_COEF_ACCUM ? EPI_COEF_ACCUM : EPI_COEF, coef_out, hcol, 0.0, 0.0);
-    kern<<<grid, 256, 0, ctx->stream>>>(n, k1, V, ldv, w, h_in, reverse, ctx->partials, kMaxCols + 8, ctx->ticket, epi);
+    MPG_CUDA(ctx, launch_pdl(ctx, kern, grid, 256, 0, n, k1, V, ldv, w, h_in, reverse, ctx->partials, (int)(kMaxCols + 8), ctx->ticket, epi));
     MPG_CHECK_LAUNCH(ctx);
     return dist_finish_reduction(ctx, epi, k1, (int)sizeof(T));
 }
@@ -909,7 +917,7 @@ int gemvn(mpg_ctx* ctx, int64_t n, int k1, const T* M, int64_t ld, T alpha, cons
     ProfScope prof(ctx, MPG_PROF_GEMVN, (double)k1 * n * sizeof(T) + (beta != T(0) ? 2.0 : 1.0) * n * sizeof(T) + (x64 ? 16.0 * n : 0.0));
     const Epi epi = want_norm ? make_epi(ctx, EPI_NORM_INV, norm_out, inv_out, 0.0, 0.0) : Epi{EPI_NORM_INV, norm_out, inv_out, 0.0, 0.0, nullptr, PeerComm()};
 #define MPG_GEMVN(VV, NN, XX)                                                                                                   \
-    gemvn_kernel<T, VV, NN, XX><<<grid, 256, smem, ctx->stream>>>(n, k1, M, ld, alpha, x, beta, y, x64, ctx->partials, ctx->ticket, epi)
+    MPG_CUDA(ctx, launch_pdl(ctx, gemvn_kernel<T, VV, NN, XX>, grid, 256, smem, n, k1, M, ld, alpha, x, beta, y, x64, ctx->partials, ctx->ticket, epi))
     if (vec_ok) {
         if (want_norm) MPG_GEMVN(VEC, true, false);
         else if (x64) MPG_GEMVN(VEC, false, true);

@@ -135,6 +135,8 @@ __global__ void __launch_bounds__(256) spmv_sell_kernel(int nrows, int nslices, 
     constexpr int G = Grp<T>::G;
     using IV = typename Grp<T>::IV;
     using VV = typename Grp<T>::VV;
+    pdl_trigger();
+    pdl_wait();
     const int ws = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
     if (ws >= nslices) return;
     const int s = slice_list ? __ldg(slice_list + ws) : ws;
@@ -336,12 +338,9 @@ int spmv_packed(mpg_ctx* ctx, const mpg_packed* P, T alpha, const T* x, T beta, 
                          (rowscale ? n_ * s_ : 0);
     ProfScope prof(ctx, sizeof(T) == 4 ? MPG_PROF_SPMV_F32 : MPG_PROF_SPMV_F64, bytes * ((double)s_count / p->nslices));
     const int grid = (int)cdiv((int64_t)s_count * 32, 256);
-    if (p->has_rem)
-        spmv_sell_kernel<T, true><<<grid, 256, 0, ctx->stream>>>(A->nrows, s_count, p->slice_off, p->sinds, static_cast<const T*>(P->svals), x, alpha, beta,
-                                                                 y_in, y_out, out32, rowscale, list);
-    else
-        spmv_sell_kernel<T, false><<<grid, 256, 0, ctx->stream>>>(A->nrows, s_count, p->slice_off, p->sinds, static_cast<const T*>(P->svals), x, alpha, beta,
-                                                                  y_in, y_out, out32, rowscale, list);
+    auto kern = p->has_rem ? spmv_sell_kernel<T, true> : spmv_sell_kernel<T, false>;
+    MPG_CUDA(ctx, launch_pdl(ctx, kern, grid, 256, 0, A->nrows, s_count, (const int64_t*)p->slice_off, (const int*)p->sinds, static_cast<const T*>(P->svals), x, alpha,
+                             beta, y_in, y_out, out32, rowscale, list));
     MPG_CHECK_LAUNCH(ctx);
     return MPG_OK;
 }
