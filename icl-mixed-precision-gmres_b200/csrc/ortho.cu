@@ -16,6 +16,10 @@
 // (cp.async.bulk.shared::cluster.global + mbarrier complete_tx), multi-stage, so the loads are in flight
 // while the previous tile is being consumed; each element is read from HBM once and from shared memory
 // twice.  (Since round 1b: one 2-D TMA tensor load per tile issued by a dedicated producer warp.)
+// Three kernels implement passes A/B, chosen by the basis width k1 only (tools/tune.py, profiles/r01b_tune_vdirect.txt):
+//   vdirect  k1 <= 8          no staging, 16-byte loads straight into registers, one accumulator per column per thread
+//   vrow     9 .. 32 (A) / 56 (B)   TMA-staged tiles, ROW-owner threads (no barrier inside a tile)
+//   vpass    wider            TMA-staged tiles, update by row then dot products by COLUMN-owner warps
 // Partial dot products stay in registers across all tiles of a CTA (warp w owns columns
 // w, w+NW, ...), are written once per CTA as doubles, and the last CTA to finish sums them in a fixed
 // order (deterministic, no float atomics) and runs the tiny epilogue (h += c, ...).

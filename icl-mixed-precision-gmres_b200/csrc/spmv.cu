@@ -12,6 +12,9 @@
 //     warp-per-row when it holds few long ones;
 //   * rows that straddle a tile boundary leave partial sums in carry_in / carry_out; a tiny fix-up kernel
 //     (one thread per tile) adds them in tile order, so results are deterministic (no float atomics).
+// This is the operator-surface SpMV on raw CSR arrays (any structure, values passed per call) and the fp64 residual
+// kernel; the solver's inner iterations and SparseMatrix<T,B200> multiply with the packed copy of sell.cu when the
+// structure packs (the x gathers of this kernel - one per nonzero - make it L1TEX-tag bound at ~75 % of the roofline).
 // The plan (tile -> first row) is built once per matrix structure on the device (mpg_csr_create), the
 // analogue of the reference's create_cuda_handles (types_cuda.hpp:53-60); fp32 and fp64 value arrays
 // share it exactly as SparseMatrix<float,Cuda> aliases row_map/inds (types_cuda.hpp:82-91).
