@@ -94,6 +94,7 @@ extern "C" int mpg_set_tuning(mpg_ctx* ctx, const char* key, int value) {
     else if (k == "dist_overlap") ctx->tune.dist_overlap = value;
     else if (k == "spmv_packed") ctx->tune.spmv_packed = value;
     else if (k == "use_pdl") ctx->tune.use_pdl = value;
+    else if (k == "fuse_tail") ctx->tune.fuse_tail = value;
     else if (k == "vpass_stages") ctx->tune.vpass_stages = value;
     else if (k == "fuse_min_cols") ctx->tune.fuse_min_cols = value;
     else if (k == "vdirect_max_cols_a") ctx->tune.vdirect_max_cols_a = value;
@@ -500,14 +501,12 @@ __global__ void rot_vec_kernel(int64_t k, T* a, const T* c, const T* s) {
 // gmres.cpp:219-226 in one launch.  One warp: lanes prefetch c/s/h into shared memory, lane 0 runs the
 // dependent rotation chain from shared memory.
 template <class T>
-__global__ void __launch_bounds__(32) givens_step_kernel(int64_t k, T* h, int64_t ldh, T* cs, T* sn, T* s, double* resid, double* resid_host) {
-    extern __shared__ unsigned char smem_raw[];
+__device__ __forceinline__ void givens_step_body(unsigned char* smem_raw, int64_t k, T* h, int64_t ldh, T* cs, T* sn, T* s, double* resid,
+                                                 double* resid_host) {
     T* sh = reinterpret_cast<T*>(smem_raw);        // k+2
     T* sc = sh + (k + 2);                          // k
     T* ss = sc + k;                                // k
     T* hcol = h + k * ldh;
-    pdl_trigger();
-    pdl_wait();
     for (int64_t j = threadIdx.x; j < k + 2; j += 32) sh[j] = hcol[j];
     for (int64_t j = threadIdx.x; j < k; j += 32) { sc[j] = cs[j]; ss[j] = sn[j]; }
     __syncwarp();
@@ -537,6 +536,44 @@ __global__ void __launch_bounds__(32) givens_step_kernel(int64_t k, T* h, int64_
     }
     __syncwarp();
     for (int64_t j = threadIdx.x; j < k + 2; j += 32) hcol[j] = sh[j];
+}
+
+template <class T>
+__global__ void __launch_bounds__(32) givens_step_kernel(int64_t k, T* h, int64_t ldh, T* cs, T* sn, T* s, double* resid, double* resid_host) {
+    extern __shared__ unsigned char smem_raw[];
+    pdl_trigger();
+    pdl_wait();
+    givens_step_body<T>(smem_raw, k, h, ldh, cs, sn, s, resid, resid_host);
+}
+
+// Tail of an Arnoldi step in ONE launch: V(:,k+1) = w * (1/h(k+1,k))  (Orthogonalization.hpp:58-59) in all blocks but the
+// last, the Givens update of column k (gmres.cpp:219-226) in warp 0 of the last block.  The two are independent: both
+// only consume what the orthogonalisation left behind (w, 1/h(k+1,k), h(:,k)).
+template <class T>
+__global__ void __launch_bounds__(256) arnoldi_tail_kernel(int64_t n, const T* __restrict__ inv_dev, const T* x, T* y, int aligned, int64_t k, T* h,
+                                                            int64_t ldh, T* cs, T* sn, T* s, double* resid, double* resid_host) {
+    extern __shared__ unsigned char smem_raw[];
+    pdl_trigger();
+    pdl_wait();
+    if (blockIdx.x == gridDim.x - 1) {
+        if (threadIdx.x < 32) givens_step_body<T>(smem_raw, k, h, ldh, cs, sn, s, resid, resid_host);
+        return;
+    }
+    const T alpha = __ldg(inv_dev);
+    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t gstride = (int64_t)(gridDim.x - 1) * blockDim.x;
+    for (int64_t i0 = gtid * 4; i0 < n; i0 += gstride * 4) {
+        const int cnt = (int)min((int64_t)4, n - i0);
+        if (aligned && cnt == 4) {
+            T v[4];
+            load4(x + i0, v);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) v[c] = alpha * v[c];
+            store4(y + i0, v);
+        } else {
+            for (int c = 0; c < cnt; ++c) y[i0 + c] = alpha * x[i0 + c];
+        }
+    }
 }
 
 // netlib ?trsv, Upper/NoTrans/NonUnit in column form (the oracle's order); Lower and Trans forms are the
@@ -612,6 +649,19 @@ int givens_step(mpg_ctx* ctx, int64_t k, T* h, int64_t ldh, T* cs, T* sn, T* s, 
     MPG_CHECK_LAUNCH(ctx);
     return MPG_OK;
 }
+template <class T>
+int arnoldi_tail(mpg_ctx* ctx, int64_t n, const T* inv_dev, const T* w, T* vnext, int64_t k, T* h, int64_t ldh, T* cs, T* sn, T* s, double* resid,
+                 double* resid_host) {
+    const size_t smem = sizeof(T) * (size_t)(3 * k + 2);
+    const int grid = (int)std::min<int64_t>(std::max<int64_t>(cdiv(n, 256 * 4), 1), (int64_t)ctx->num_sms * 16) + 1;
+    const int aligned = (((uintptr_t)w | (uintptr_t)vnext) & 15) == 0;
+    ProfScope prof(ctx, MPG_PROF_ELEMENTWISE, 2.0 * (double)n * sizeof(T));
+    MPG_CUDA(ctx, launch_pdl(ctx, arnoldi_tail_kernel<T>, grid, 256, smem, n, inv_dev, w, vnext, aligned, k, h, ldh, cs, sn, s, resid, resid_host));
+    MPG_CHECK_LAUNCH(ctx);
+    return MPG_OK;
+}
+template int arnoldi_tail<float>(mpg_ctx*, int64_t, const float*, const float*, float*, int64_t, float*, int64_t, float*, float*, float*, double*, double*);
+template int arnoldi_tail<double>(mpg_ctx*, int64_t, const double*, const double*, double*, int64_t, double*, int64_t, double*, double*, double*, double*, double*);
 template int givens_step<float>(mpg_ctx*, int64_t, float*, int64_t, float*, float*, float*, double*, double*);
 template int givens_step<double>(mpg_ctx*, int64_t, double*, int64_t, double*, double*, double*, double*, double*);
 template <class T>

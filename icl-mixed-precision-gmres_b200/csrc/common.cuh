@@ -37,6 +37,7 @@ struct Tuning {
     int red_ctas_per_sm = 4;
     int use_graph = 0;
     int dist_peer_halo = 1;   // multi-GPU halo exchange by stores into the neighbours' memory (0: pack + ncclSend/ncclRecv)
+    int fuse_tail = 1;        // solver: normalisation of the new basis vector and the Givens update of the column in one launch
     int use_pdl = 1;          // programmatic dependent launch for the kernels of the Arnoldi loop (off while profiling: events sit between launches)
     int spmv_packed = 1;      // solver: run the inner SpMV on the packed (sliced-ELL) copy of the matrix when it packs well (sell.cu)
     int dist_overlap = 1;     // multi-GPU SpMV: rows without halo columns run between the halo push and the wait for the neighbours' data

@@ -735,10 +735,10 @@ int launch_vpass_inst(mpg_ctx* ctx, int64_t n, int k1, const T* V, int64_t ldv, 
     const int64_t ntiles = cdiv(n, TR);
     const int grid = (int)std::min<int64_t>(std::min<int64_t>(ntiles, (int64_t)ctx->num_sms * ctas_per_sm), kMaxPartBlocks);
     auto kern = vpass_kernel<T, TR, MAXJ>;
-    static bool attr_set = false;   // per instantiation; one device per process
-    if (!attr_set) {
+    static bool attr_set[64] = {};   // per instantiation and device (the attribute is per device)
+    if (!attr_set[ctx->device & 63]) {
         MPG_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDynSmem));
-        attr_set = true;
+        attr_set[ctx->device & 63] = true;
     }
     // algorithmic bytes (fused CGS2 = 3 k1 n s + 4 n s): pass A reads V only (w was just written by the
     // SpMV and is counted there), pass B reads V, reads w, writes w'
@@ -791,10 +791,10 @@ int launch_vrow_inst(mpg_ctx* ctx, int64_t n, int k1, const T* V, int64_t ldv, T
     const int64_t ntiles = cdiv(n, TRW);
     const int grid = (int)std::min<int64_t>(std::min<int64_t>(ntiles, (int64_t)ctx->num_sms), kMaxPartBlocks);
     auto kern = vrow_kernel<T, CT, RPT, MAXK>;
-    static bool attr_set = false;   // per instantiation; one device per process
-    if (!attr_set) {
+    static bool attr_set[64] = {};   // per instantiation and device (the attribute is per device)
+    if (!attr_set[ctx->device & 63]) {
         MPG_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
-        attr_set = true;
+        attr_set[ctx->device & 63] = true;
     }
     ProfScope prof(ctx, MPG_PROF_VPASS, (double)k1 * n * sizeof(T) + (h_in ? 2.0 * n * sizeof(T) : 0.0));
     const int reverse = (ctx->tune.vpass_serpentine && h_in) ? 1 : 0;   // same rule as vpass: a function of the pass only
@@ -971,7 +971,7 @@ template int gemvt<double>(mpg_ctx*, int64_t, int, const double*, int64_t, doubl
 // GS::add_vector (Orthogonalization.hpp:51-60).  scratch: >= k1 + 2 elements of T in device memory
 // (CGSR's `weights`, Orthogonalization.hpp:113, plus the 1/norm scalar).
 template <class T>
-int add_vector(mpg_ctx* ctx, int orth, int64_t n, int64_t k, T* V, int64_t ldv, T* w, T* hcol, T* scratch, bool padded) {
+int add_vector(mpg_ctx* ctx, int orth, int64_t n, int64_t k, T* V, int64_t ldv, T* w, T* hcol, T* scratch, bool padded, bool skip_normalize) {
     const int k1 = (int)k + 1;
     T* weights = scratch;
     T* inv = scratch + k1;
@@ -1009,11 +1009,13 @@ int add_vector(mpg_ctx* ctx, int orth, int64_t n, int64_t k, T* V, int64_t ldv, 
             }
         }
     }
-    // V[:,k+1] = w * (1/h(k+1,k))   Orthogonalization.hpp:58-59 (one pass instead of copy + scal)
+    // V[:,k+1] = w * (1/h(k+1,k))   Orthogonalization.hpp:58-59 (one pass instead of copy + scal); the solver folds this
+    // pass into its arnoldi_tail launch (1/h(k+1,k) is left at scratch[k+1])
+    if (skip_normalize) return MPG_OK;
     return scal_devp(ctx, n, inv, w, vnext);
 }
-template int add_vector<float>(mpg_ctx*, int, int64_t, int64_t, float*, int64_t, float*, float*, float*, bool);
-template int add_vector<double>(mpg_ctx*, int, int64_t, int64_t, double*, int64_t, double*, double*, double*, bool);
+template int add_vector<float>(mpg_ctx*, int, int64_t, int64_t, float*, int64_t, float*, float*, float*, bool, bool);
+template int add_vector<double>(mpg_ctx*, int, int64_t, int64_t, double*, int64_t, double*, double*, double*, bool, bool);
 
 }  // namespace mpg
 
@@ -1030,7 +1032,7 @@ template int add_vector<double>(mpg_ctx*, int, int64_t, int64_t, double*, int64_
         MPG_REQUIRE(ctx, n >= 0 && k >= 0 && k + 2 <= kMaxCols && ldv >= n, "add_vector: bad dims");                              \
         MPG_REQUIRE(ctx, orth >= 0 && orth <= 2, "add_vector: bad orth");                                                         \
         T* scratch = reinterpret_cast<T*>(ctx->dscal + 64); /* k1 + 2 <= 264 elements */                                          \
-        return mpg::add_vector<T>(ctx, orth, n, k, V, ldv, w, hcol, scratch, false);                                              \
+        return mpg::add_vector<T>(ctx, orth, n, k, V, ldv, w, hcol, scratch, false, false);                                              \
     }
 MPG_DEF_GEMV(f32, float)
 MPG_DEF_GEMV(f64, double)

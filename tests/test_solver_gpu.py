@@ -210,3 +210,23 @@ def test_packed_and_csr_inner_operator_agree(ctx, g, orc, spec, mode, prec):
     live = h0 >= 1e-4 * h0[0]
     assert np.max(np.abs(h1 - h0)[live] / h0[live]) <= (2e-3 if mode != "baseline" else 1e-8)
     assert np.linalg.norm(x1 - x0) <= 1e-6 * np.linalg.norm(x0)
+
+
+@pytest.mark.parametrize("knob", ["fuse_tail", "use_pdl"])
+@pytest.mark.parametrize("spec,mode,orth", [("cd27:14", "mixed", "cgsr"), ("lap2d:40", "baseline", "mgs"), ("powerlaw:3000", "mixed", "cgs")])
+def test_launch_structure_knobs_do_not_change_bits(ctx, g, orc, knob, spec, mode, orth):
+    """fusing the normalisation with the Givens update, and programmatic dependent launch, only change how the same
+    kernels are launched: solution and residual history are bit-identical with the knob off"""
+    import torch
+    rm, ind, val, xt, b = problem(orc, spec)
+    A = g.CSR(ctx, dev(rm), dev(ind))
+    out = []
+    for v in (1, 0):
+        ctx.set_tuning(knob, v)
+        x = torch.zeros(len(b), dtype=torch.float64, device="cuda:0")
+        out.append((ctx.gmres(A, dev(val), dev(b), x, mode=mode, orth=orth, rlen=20, tol=1e-9, max_restarts=100), host(x)))
+    ctx.set_tuning(knob, 1)
+    (r1, x1), (r0, x0) = out
+    assert r1["total_iters"] == r0["total_iters"] and r1["status"] == r0["status"]
+    np.testing.assert_array_equal(r1["hist_inner"], r0["hist_inner"])
+    np.testing.assert_array_equal(x1, x0)
