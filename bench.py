@@ -226,7 +226,8 @@ def main():
         iters += r["total_iters"]; restarts += r["total_restarts"]; status = r["status"]
     torch.cuda.synchronize()
     clocks = sampler.stop()
-    total_ms = sum(a.elapsed_time(b) for a, b in evs)
+    step_ms = sorted(a.elapsed_time(b) for a, b in evs)
+    total_ms = sum(step_ms)
     launches = ctx.launches() - launches0
     prof_scale = 1.0
     if not prof_in_region:
@@ -237,6 +238,24 @@ def main():
     ctx.prof_enable(False)
     for p_ in prof.values():   # one profiled solve stands for each of the K identical timed solves
         p_["ms"] *= prof_scale; p_["bytes"] *= prof_scale; p_["launches"] = int(p_["launches"] * prof_scale)
+
+    # the reference's own timing window (gmres_perf_test.cpp:165-167) also covers allocating and zero-filling the
+    # workspace inside gmres_singleUpdate (gmres.cpp:147-157): one solve on a fresh context = workspace + plan + packed copy
+    # allocated inside the window
+    incl_alloc_ms = None
+    try:
+        ctx2 = g.Context(local_rank)
+        A2 = g.CSR(ctx2, rm, ind)
+        x2 = torch.zeros(n, dtype=torch.float64, device=dev)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ctx2.gmres(A2, val, b, x2, vals32=val32, hist_cap=1, **kw)
+        torch.cuda.synchronize()
+        incl_alloc_ms = (time.perf_counter() - t0) * 1e3
+        del A2, x2
+        ctx2.close()
+    except Exception as e:   # reported, never fatal for the bench line
+        incl_alloc_ms = f"failed: {e}"
 
     # post-solve check the reference prints (gmres_perf_test.cpp:169-178)
     res = b.clone(); ctx.spmv(A, val, -1.0, x, 1.0, res)
@@ -302,6 +321,8 @@ def main():
             "config": {"workload": args.workload, "mode": args.mode, "n_rows": n, "nnz": nnz, "restart_length": args.rlen, "tol": args.tol, "orth": args.orth,
                        "prec": "identity", "iters_per_solve": iters // max(args.steps, 1), "restarts_per_solve": restarts // max(args.steps, 1),
                        "time_to_solution_s": total_ms * 1e-3 / args.steps, "status": int(status),
+                       "step_ms_min_med_max": [round(step_ms[0], 3), round(step_ms[len(step_ms) // 2], 3), round(step_ms[-1], 3)],
+                       "first_solve_incl_workspace_alloc_ms": incl_alloc_ms if not isinstance(incl_alloc_ms, float) else round(incl_alloc_ms, 2),
                        "resNorm": res_norm, "errNorm": err_norm, "rel_res": res_norm / b_norm,
                        "l2": (f"working set {ws_bytes / 1e9:.2f} GB: L2 flushed (512 MB overwrite) between timed steps" if flush else
                               f"working set {ws_bytes / 1e9:.1f} GB (matrix + basis) >> 126 MB L2; no flush needed"),

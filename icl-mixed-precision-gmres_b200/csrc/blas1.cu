@@ -94,6 +94,7 @@ extern "C" int mpg_set_tuning(mpg_ctx* ctx, const char* key, int value) {
     else if (k == "dist_overlap") ctx->tune.dist_overlap = value;
     else if (k == "spmv_packed") ctx->tune.spmv_packed = value;
     else if (k == "use_pdl") ctx->tune.use_pdl = value;
+    else if (k == "pdl_max_rows") ctx->tune.pdl_max_rows = value;
     else if (k == "fuse_tail") ctx->tune.fuse_tail = value;
     else if (k == "vpass_stages") ctx->tune.vpass_stages = value;
     else if (k == "fuse_min_cols") ctx->tune.fuse_min_cols = value;
@@ -385,7 +386,7 @@ int launch_ew(mpg_ctx* ctx, int64_t n, TY alpha, const TY* alpha_dev, TY beta, c
     const int aligned = (((uintptr_t)x | (uintptr_t)diag | (uintptr_t)y) & 15) == 0;
     const double ew_bytes = (double)n * ((OP != EW_FILL ? sizeof(TX) : 0) + sizeof(TY) * (1 + (OP == EW_AXPY || OP == EW_NAXPY || OP == EW_GDMV) + (OP == EW_GDMV)));
     ProfScope prof(ctx, MPG_PROF_ELEMENTWISE, ew_bytes);
-    MPG_CUDA(ctx, launch_pdl(ctx, ew_kernel<TX, TY, OP>, grid, 256, 0, n, alpha, alpha_dev, beta, x, diag, y, aligned));
+    MPG_CUDA(ctx, launch_pdl(ctx, n, ew_kernel<TX, TY, OP>, grid, 256, 0, n, alpha, alpha_dev, beta, x, diag, y, aligned));
     MPG_CHECK_LAUNCH(ctx);
     return MPG_OK;
 }
@@ -645,7 +646,7 @@ template <class T>
 int givens_step(mpg_ctx* ctx, int64_t k, T* h, int64_t ldh, T* cs, T* sn, T* s, double* resid, double* resid_host) {
     const size_t smem = sizeof(T) * (size_t)(3 * k + 2);
     ProfScope prof(ctx, MPG_PROF_SMALL, 0.0);
-    MPG_CUDA(ctx, launch_pdl(ctx, givens_step_kernel<T>, 1, 32, smem, k, h, ldh, cs, sn, s, resid, resid_host));
+    MPG_CUDA(ctx, launch_pdl(ctx, (int64_t)0, givens_step_kernel<T>, 1, 32, smem, k, h, ldh, cs, sn, s, resid, resid_host));
     MPG_CHECK_LAUNCH(ctx);
     return MPG_OK;
 }
@@ -656,7 +657,7 @@ int arnoldi_tail(mpg_ctx* ctx, int64_t n, const T* inv_dev, const T* w, T* vnext
     const int grid = (int)std::min<int64_t>(std::max<int64_t>(cdiv(n, 256 * 4), 1), (int64_t)ctx->num_sms * 16) + 1;
     const int aligned = (((uintptr_t)w | (uintptr_t)vnext) & 15) == 0;
     ProfScope prof(ctx, MPG_PROF_ELEMENTWISE, 2.0 * (double)n * sizeof(T));
-    MPG_CUDA(ctx, launch_pdl(ctx, arnoldi_tail_kernel<T>, grid, 256, smem, n, inv_dev, w, vnext, aligned, k, h, ldh, cs, sn, s, resid, resid_host));
+    MPG_CUDA(ctx, launch_pdl(ctx, n, arnoldi_tail_kernel<T>, grid, 256, smem, n, inv_dev, w, vnext, aligned, k, h, ldh, cs, sn, s, resid, resid_host));
     MPG_CHECK_LAUNCH(ctx);
     return MPG_OK;
 }

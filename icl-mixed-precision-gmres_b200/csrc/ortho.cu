@@ -748,7 +748,7 @@ int launch_vpass_inst(mpg_ctx* ctx, int64_t n, int k1, const T* V, int64_t ldv, 
     // pass left in L2, and the following gemv-N pass (forward) starts on the part this one leaves there
     const int reverse = (ctx->tune.vpass_serpentine && h_in) ? 1 : 0;
     const Epi epi = make_epi(ctx, fin == FIN_COEF_ACCUM ? EPI_COEF_ACCUM : EPI_COEF, coef_out, hcol, 0.0, 0.0);
-    MPG_CUDA(ctx, launch_pdl(ctx, kern, grid, 2 * TR + 32, smem, mapV, mapW, n, k1, w, h_in, stages, reverse, ctx->partials, (int)(kMaxCols + 8), ctx->ticket, epi, ctx->dbg));
+    MPG_CUDA(ctx, launch_pdl(ctx, n, kern, grid, 2 * TR + 32, smem, mapV, mapW, n, k1, w, h_in, stages, reverse, ctx->partials, (int)(kMaxCols + 8), ctx->ticket, epi, ctx->dbg));
     MPG_CHECK_LAUNCH(ctx);
     return dist_finish_reduction(ctx, epi, k1, (int)sizeof(T));
 }
@@ -799,7 +799,7 @@ int launch_vrow_inst(mpg_ctx* ctx, int64_t n, int k1, const T* V, int64_t ldv, T
     ProfScope prof(ctx, MPG_PROF_VPASS, (double)k1 * n * sizeof(T) + (h_in ? 2.0 * n * sizeof(T) : 0.0));
     const int reverse = (ctx->tune.vpass_serpentine && h_in) ? 1 : 0;   // same rule as vpass: a function of the pass only
     const Epi epi = make_epi(ctx, fin == FIN_COEF_ACCUM ? EPI_COEF_ACCUM : EPI_COEF, coef_out, hcol, 0.0, 0.0);
-    MPG_CUDA(ctx, launch_pdl(ctx, kern, grid, CT + 32, smem, *mapV, *mapW, n, k1, w, h_in, stages, reverse, ctx->partials, (int)(kMaxCols + 8), ctx->ticket, epi));
+    MPG_CUDA(ctx, launch_pdl(ctx, n, kern, grid, CT + 32, smem, *mapV, *mapW, n, k1, w, h_in, stages, reverse, ctx->partials, (int)(kMaxCols + 8), ctx->ticket, epi));
     MPG_CHECK_LAUNCH(ctx);
     return dist_finish_reduction(ctx, epi, k1, (int)sizeof(T));
 }
@@ -832,7 +832,7 @@ int launch_vdirect_inst(mpg_ctx* ctx, int64_t n, int k1, const T* V, int64_t ldv
     ProfScope prof(ctx, MPG_PROF_VPASS, (double)k1 * n * sizeof(T) + (h_in ? 2.0 * n * sizeof(T) : 0.0));
     const int reverse = (ctx->tune.vpass_serpentine && h_in) ? 1 : 0;   // same rule as vpass: a function of the pass only
     const Epi epi = make_epi(ctx, fin == FIN_COEF_ACCUM ? EPI_COEF_ACCUM : EPI_COEF, coef_out, hcol, 0.0, 0.0);
-    MPG_CUDA(ctx, launch_pdl(ctx, kern, grid, 256, 0, n, k1, V, ldv, w, h_in, reverse, ctx->partials, (int)(kMaxCols + 8), ctx->ticket, epi));
+    MPG_CUDA(ctx, launch_pdl(ctx, n, kern, grid, 256, 0, n, k1, V, ldv, w, h_in, reverse, ctx->partials, (int)(kMaxCols + 8), ctx->ticket, epi));
     MPG_CHECK_LAUNCH(ctx);
     return dist_finish_reduction(ctx, epi, k1, (int)sizeof(T));
 }
@@ -921,7 +921,7 @@ int gemvn(mpg_ctx* ctx, int64_t n, int k1, const T* M, int64_t ld, T alpha, cons
     ProfScope prof(ctx, MPG_PROF_GEMVN, (double)k1 * n * sizeof(T) + (beta != T(0) ? 2.0 : 1.0) * n * sizeof(T) + (x64 ? 16.0 * n : 0.0));
     const Epi epi = want_norm ? make_epi(ctx, EPI_NORM_INV, norm_out, inv_out, 0.0, 0.0) : Epi{EPI_NORM_INV, norm_out, inv_out, 0.0, 0.0, nullptr, PeerComm()};
 #define MPG_GEMVN(VV, NN, XX)                                                                                                   \
-    MPG_CUDA(ctx, launch_pdl(ctx, gemvn_kernel<T, VV, NN, XX>, grid, 256, smem, n, k1, M, ld, alpha, x, beta, y, x64, ctx->partials, ctx->ticket, epi))
+    MPG_CUDA(ctx, launch_pdl(ctx, n, gemvn_kernel<T, VV, NN, XX>, grid, 256, smem, n, k1, M, ld, alpha, x, beta, y, x64, ctx->partials, ctx->ticket, epi))
     if (vec_ok) {
         if (want_norm) MPG_GEMVN(VEC, true, false);
         else if (x64) MPG_GEMVN(VEC, false, true);

@@ -357,7 +357,7 @@ int spmv_packed(mpg_ctx* ctx, const mpg_packed* P, T alpha, const T* x, T beta, 
     ProfScope prof(ctx, sizeof(T) == 4 ? MPG_PROF_SPMV_F32 : MPG_PROF_SPMV_F64, bytes * ((double)s_count / p->nslices));
     const int grid = (int)cdiv((int64_t)s_count * 32, 256);
     auto kern = p->has_rem ? spmv_sell_kernel<T, true> : spmv_sell_kernel<T, false>;
-    MPG_CUDA(ctx, launch_pdl(ctx, kern, grid, 256, 0, A->nrows, s_count, (const int64_t*)p->slice_off, (const int*)p->sinds, static_cast<const T*>(P->svals), x, alpha,
+    MPG_CUDA(ctx, launch_pdl(ctx, (int64_t)A->nrows, kern, grid, 256, 0, A->nrows, s_count, (const int64_t*)p->slice_off, (const int*)p->sinds, static_cast<const T*>(P->svals), x, alpha,
                              beta, y_in, y_out, out32, rowscale, list));
     MPG_CHECK_LAUNCH(ctx);
     return MPG_OK;
