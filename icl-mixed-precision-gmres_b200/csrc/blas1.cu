@@ -109,7 +109,6 @@ extern "C" int mpg_set_tuning(mpg_ctx* ctx, const char* key, int value) {
     else if (k == "vpass_serpentine") ctx->tune.vpass_serpentine = value;
     else if (k == "gemvn_ctas_per_sm") ctx->tune.gemvn_ctas_per_sm = value;
     else if (k == "red_ctas_per_sm") ctx->tune.red_ctas_per_sm = value;
-    else if (k == "use_graph") ctx->tune.use_graph = value;
     else return fail(ctx, MPG_ERR_ARG, "unknown tuning key " + k);
     return MPG_OK;
 }

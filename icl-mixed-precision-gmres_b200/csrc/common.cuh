@@ -35,7 +35,6 @@ struct Tuning {
     int cgs2_fused = 1;       // fused update + gemv-T second pass (3 passes) vs separate gemv-N, gemv-T (4 passes)
     int gemvn_ctas_per_sm = 4;
     int red_ctas_per_sm = 4;
-    int use_graph = 0;
     int dist_peer_halo = 1;   // multi-GPU halo exchange by stores into the neighbours' memory (0: pack + ncclSend/ncclRecv)
     int fuse_tail = 1;        // solver: normalisation of the new basis vector and the Givens update of the column in one launch
     int use_pdl = 1;          // programmatic dependent launch for the kernels of the Arnoldi loop: 0 off, 1 when the operand has at most
