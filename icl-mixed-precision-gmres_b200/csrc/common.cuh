@@ -38,8 +38,9 @@ struct Tuning {
     int dist_peer_halo = 1;   // multi-GPU halo exchange by stores into the neighbours' memory (0: pack + ncclSend/ncclRecv)
     int fuse_tail = 1;        // solver: normalisation of the new basis vector and the Givens update of the column in one launch
     int use_pdl = 1;          // programmatic dependent launch for the kernels of the Arnoldi loop: 0 off, 1 when the operand has at most
-                              // pdl_max_rows rows (measured: +11 % at 0.26 M rows, +1 % at 2 M, -8 % at 16.7 M), 2 always; off while profiling
-    int pdl_max_rows = 4000000;
+                              // pdl_max_rows rows (measured: +11 % at 0.26 M rows, +1 % at 2.1 M, -1 % at 4.1 M, -8 % at 16.7 M), 2 always;
+                              // off while profiling
+    int pdl_max_rows = 2500000;
     int spmv_packed = 1;      // solver: run the inner SpMV on the packed (sliced-ELL) copy of the matrix when it packs well (sell.cu)
     int dist_overlap = 1;     // multi-GPU SpMV: rows without halo columns run between the halo push and the wait for the neighbours' data
     int dist_peer_reduce = 1; // multi-GPU reductions inside the kernels over peer memory (0: NCCL all-reduce + epilogue kernel)
