@@ -154,6 +154,24 @@ class Packed:
     def update(self, vals):
         self.ctx._chk(getattr(self.ctx.L, "mpg_pack_update_" + self.sfx)(self.ctx.h, self.h, _ptr(vals)))
 
+    def arrays(self):
+        """(G, slice_off, inds, vals) copied to the host as numpy arrays (tests: bit-exact layout check against the oracle)"""
+        import numpy as np
+        G, ns, tot = C.c_int(), C.c_int(), C.c_int64()
+        po, pi, pv = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        rc = self.ctx.L.mpg_pack_describe(self.h, C.byref(G), C.byref(ns), C.byref(tot), C.byref(po), C.byref(pi), C.byref(pv))
+        if rc != 0:
+            raise MpgError("mpg_pack_describe failed")
+        self.ctx.sync()
+        dt = np.float32 if self.sfx == "f32" else np.float64
+        off = np.empty(ns.value + 1, np.int64)
+        ind = np.empty(tot.value, np.int32)
+        val = np.empty(tot.value, dt)
+        for dst, src in ((off, po), (ind, pi), (val, pv)):
+            if dst.nbytes:
+                self.ctx._chk(self.ctx.L.mpg_memcpy_d2h(self.ctx.h, dst.ctypes.data_as(C.c_void_p), src, C.c_size_t(dst.nbytes)))
+        return G.value, off, ind, val
+
     def __del__(self):
         try:
             if self.h:

@@ -384,6 +384,18 @@ template int spmv_packed<double>(mpg_ctx*, const mpg_packed*, double, const doub
 MPG_DEF_PACK(f32, float)
 MPG_DEF_PACK(f64, double)
 
+extern "C" int mpg_pack_describe(const mpg_packed* P, int* group, int* nslices, int64_t* total, const int64_t** slice_off, const int** inds,
+                                 const void** vals) {
+    if (!P || !P->plan) return MPG_ERR_ARG;
+    if (group) *group = P->plan->G;
+    if (nslices) *nslices = P->plan->nslices;
+    if (total) *total = P->plan->total;
+    if (slice_off) *slice_off = P->plan->slice_off;
+    if (inds) *inds = P->plan->sinds;
+    if (vals) *vals = P->svals;
+    return MPG_OK;
+}
+
 extern "C" int mpg_pack_destroy(mpg_packed* P) {
     if (!P) return MPG_OK;
     cudaSetDevice(P->device);

@@ -151,6 +151,10 @@ int mpg_pack_create_f64(mpg_ctx*, const mpg_csr* A, const double* vals, mpg_pack
 int mpg_pack_update_f32(mpg_ctx*, mpg_packed* P, const float* vals);
 int mpg_pack_update_f64(mpg_ctx*, mpg_packed* P, const double* vals);
 int mpg_pack_destroy(mpg_packed* P);
+/* Layout access for tests / diagnostics: group size G, slice count, padded element count and the DEVICE arrays
+ * slice_off[nslices + 1], inds[total], vals[total] (owned by the library; layout in csrc/sell.cu and DESIGN.md §2). */
+int mpg_pack_describe(const mpg_packed* P, int* group, int* nslices, int64_t* total, const int64_t** slice_off, const int** inds,
+                      const void** vals);
 int mpg_spmv_packed_f32(mpg_ctx*, const mpg_packed* P, float alpha, const float* x, float beta, float* y);
 int mpg_spmv_packed_f64(mpg_ctx*, const mpg_packed* P, double alpha, const double* x, double beta, double* y);
 /* Fused outer residual, replaces gmres.cpp:173-175 (copy + fp64 SpMV + cast kernel):

@@ -226,3 +226,39 @@ def partition_local(n, P, r, rm, ind):
     li = np.empty(nnz_l, np.int32)
     lib().orc_partition_local(_i64(n), C.c_int(P), C.c_int(r), _p(rm), _p(ind), _p(halo), _p(li))
     return halo, li
+
+
+def sell_pack(rm, ind, val, G):
+    """Restatement (numpy, test infrastructure) of the packed sliced-ELL layout of csrc/sell.cu, DESIGN.md §2: 32-row slices,
+    slice length L = longest row (rounded up to a multiple of G when that pads <= 10 %), the first floor(L/G)*G positions in
+    groups of G per lane, the L % G trailing positions one per lane; short rows padded with their first column and value 0.
+    Returns (slice_off[nslices + 1] int64, inds int32, vals)."""
+    n = len(rm) - 1
+    ns = (n + 31) // 32
+    lens = np.zeros(ns * 32, np.int64)
+    lens[:n] = np.diff(rm)
+    L = lens.reshape(ns, 32).max(axis=1) if ns else np.zeros(0, np.int64)
+    rem = L % G
+    up = (rem > 0) & ((G - rem) * 10 <= L)
+    L = np.where(up, L + G - rem, L)
+    off = np.zeros(ns + 1, np.int64)
+    off[1:] = np.cumsum(L * 32)
+    sind = np.zeros(int(off[-1]), np.int32)
+    sval = np.zeros(int(off[-1]), val.dtype)
+    for s in range(ns):
+        Ls = int(L[s]); ng = Ls // G; o = int(off[s])
+        p = np.arange(Ls)
+        pos_in_slice = np.where(p < ng * G, (p // G) * 32 * G + p % G, ng * 32 * G + (p - ng * G) * 32)   # + lane * (G or 1)
+        lane_mul = np.where(p < ng * G, G, 1)
+        for lane in range(32):
+            r = s * 32 + lane
+            ln = int(lens[r])
+            rs = int(rm[r]) if r < n else 0
+            c = np.full(Ls, ind[rs] if ln > 0 else 0, np.int32)
+            v = np.zeros(Ls, val.dtype)
+            c[:ln] = ind[rs:rs + ln]
+            v[:ln] = val[rs:rs + ln]
+            dst = o + pos_in_slice + lane * lane_mul
+            sind[dst] = c
+            sval[dst] = v
+    return off, sind, sval

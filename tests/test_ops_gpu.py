@@ -408,3 +408,20 @@ def test_pack_refuses_uneven_rows_and_handles_rows_without_entries(ctx, g, orc):
         yo = orc.spmv(rm2, ind2, v2, 1.0, x, 0.0, np.zeros(n, np.float32))
         np.testing.assert_allclose(host(yd), yo, rtol=0, atol=64 * np.finfo(np.float32).eps * max(1.0, np.abs(yo).max()))
         np.testing.assert_array_equal(host(yd)[lens == 0], 0)
+
+
+@pytest.mark.parametrize("spec", ["lap2d:37", "cd27:11", "cd27:16"])
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_packed_layout_bit_exact(ctx, g, orc, spec, dt):
+    """the packed (sliced-ELL) arrays the library builds == the oracle's restatement of the layout: index work, bit-exact"""
+    rm, ind, val = orc.gen(spec)
+    v = val.astype(dt)
+    A = g.CSR(ctx, dev(rm), dev(ind))
+    P = g.Packed(ctx, A, dev(v))
+    assert P
+    G, off, sind, sval = P.arrays()
+    assert G == (4 if dt == np.float32 else 2)
+    off_o, sind_o, sval_o = orc.sell_pack(rm, ind, v, G)
+    np.testing.assert_array_equal(off, off_o)
+    np.testing.assert_array_equal(sind, sind_o)
+    np.testing.assert_array_equal(sval, sval_o)

@@ -241,3 +241,33 @@ def test_partition_index_sets(orc, spec, P):
         rml = rm[lo:hi + 1] - rm[lo]
         yl = sp.csr_matrix((val[rm[lo]:rm[hi]], li, rml), shape=(hi - lo, len(xl))) @ xl
         np.testing.assert_allclose(yl, y[lo:hi], rtol=1e-13, atol=1e-13)
+
+
+@pytest.mark.parametrize("spec,G", [("cd27:5", 4), ("lap2d:9", 4), ("lap2d:9", 2), ("powerlaw:300", 2)])
+def test_packed_layout_restatement_is_a_permutation_of_the_csr_entries(orc, spec, G):
+    """oracle.sell_pack (the layout the GPU test compares the library's packed arrays with): every CSR entry appears exactly
+    once at the documented position, padding carries value 0 and a valid column, y = A x through the packed arrays is exact"""
+    rm, ind, val = orc.gen(spec)
+    n = len(rm) - 1
+    off, si, sv = orc.sell_pack(rm, ind, val, G)
+    assert off[0] == 0 and np.all(np.diff(off) % 32 == 0) and len(si) == off[-1] == len(sv)
+    assert np.count_nonzero(sv) == np.count_nonzero(val) and si.min() >= 0 and si.max() < n
+    x = np.arange(1, n + 1, dtype=np.float64)
+    y = np.zeros(n)
+    for s in range(len(off) - 1):
+        L = int(off[s + 1] - off[s]) // 32
+        ng = L // G
+        for lane in range(32):
+            r = s * 32 + lane
+            if r >= n:
+                continue
+            for p in range(L):
+                pos = off[s] + ((p // G) * 32 * G + lane * G + p % G if p < ng * G else ng * 32 * G + (p - ng * G) * 32 + lane)
+                y[r] += sv[pos] * x[si[pos]]
+    A = sp.csr_matrix((val, ind, rm), shape=(n, n))
+    np.testing.assert_allclose(y, A @ x, rtol=1e-13, atol=1e-9)
+    # slice lengths: longest row, rounded up to a multiple of G only when that pads <= 10 %
+    lens = np.zeros((len(off) - 1) * 32, np.int64); lens[:n] = np.diff(rm)
+    Lmax = lens.reshape(-1, 32).max(axis=1)
+    L = np.diff(off) // 32
+    assert np.all(L >= Lmax) and np.all(L - Lmax < G) and np.all((L == Lmax) | ((L - Lmax) * 10 <= Lmax))
