@@ -971,7 +971,7 @@ template int gemvt<double>(mpg_ctx*, int64_t, int, const double*, int64_t, doubl
 // GS::add_vector (Orthogonalization.hpp:51-60).  scratch: >= k1 + 2 elements of T in device memory
 // (CGSR's `weights`, Orthogonalization.hpp:113, plus the 1/norm scalar).
 template <class T>
-int add_vector(mpg_ctx* ctx, int orth, int64_t n, int64_t k, T* V, int64_t ldv, T* w, T* hcol, T* scratch, bool padded, bool skip_normalize) {
+int add_vector(mpg_ctx* ctx, int orth, int64_t n, int64_t k, T* V, int64_t ldv, T* w, T* hcol, T* scratch, bool skip_normalize) {
     const int k1 = (int)k + 1;
     T* weights = scratch;
     T* inv = scratch + k1;
@@ -1014,8 +1014,8 @@ int add_vector(mpg_ctx* ctx, int orth, int64_t n, int64_t k, T* V, int64_t ldv, 
     if (skip_normalize) return MPG_OK;
     return scal_devp(ctx, n, inv, w, vnext);
 }
-template int add_vector<float>(mpg_ctx*, int, int64_t, int64_t, float*, int64_t, float*, float*, float*, bool, bool);
-template int add_vector<double>(mpg_ctx*, int, int64_t, int64_t, double*, int64_t, double*, double*, double*, bool, bool);
+template int add_vector<float>(mpg_ctx*, int, int64_t, int64_t, float*, int64_t, float*, float*, float*, bool);
+template int add_vector<double>(mpg_ctx*, int, int64_t, int64_t, double*, int64_t, double*, double*, double*, bool);
 
 }  // namespace mpg
 
@@ -1032,7 +1032,7 @@ template int add_vector<double>(mpg_ctx*, int, int64_t, int64_t, double*, int64_
         MPG_REQUIRE(ctx, n >= 0 && k >= 0 && k + 2 <= kMaxCols && ldv >= n, "add_vector: bad dims");                              \
         MPG_REQUIRE(ctx, orth >= 0 && orth <= 2, "add_vector: bad orth");                                                         \
         T* scratch = reinterpret_cast<T*>(ctx->dscal + 64); /* k1 + 2 <= 264 elements */                                          \
-        return mpg::add_vector<T>(ctx, orth, n, k, V, ldv, w, hcol, scratch, false, false);                                              \
+        return mpg::add_vector<T>(ctx, orth, n, k, V, ldv, w, hcol, scratch, false);                                                     \
     }
 MPG_DEF_GEMV(f32, float)
 MPG_DEF_GEMV(f64, double)

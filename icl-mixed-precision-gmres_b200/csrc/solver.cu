@@ -42,7 +42,7 @@ template <class T> int trsv(mpg_ctx*, int, int, int64_t, const T*, int64_t, T*);
 template <class T> int spmv(mpg_ctx*, const mpg_csr*, const T*, T, const T*, T, const T*, T*, float*, const T* rowscale = nullptr, int part = SPMV_ALL);
 template <class T> int gemvn(mpg_ctx*, int64_t, int, const T*, int64_t, T, const T*, T, T*, bool, T*, T*, double*);
 template <class T> int gemvt(mpg_ctx*, int64_t, int, const T*, int64_t, T, const T*, T, T*);
-template <class T> int add_vector(mpg_ctx*, int, int64_t, int64_t, T*, int64_t, T*, T*, T*, bool, bool);
+template <class T> int add_vector(mpg_ctx*, int, int64_t, int64_t, T*, int64_t, T*, T*, T*, bool);
 template <class T> int arnoldi_tail(mpg_ctx*, int64_t, const T*, const T*, T*, int64_t, T*, int64_t, T*, T*, T*, double*, double*);
 template <class T> int pack_create(mpg_ctx*, const mpg_csr*, const T*, mpg_packed**);
 template <class T> int pack_update(mpg_ctx*, mpg_packed*, const T*);
@@ -292,10 +292,10 @@ int run_cycle(mpg_ctx* ctx, const mpg_gmres_params& p, Policy& pol, Workspace* w
         // orth.add_vector(k, w, h)     gmres.cpp:104,217
         if (ctx->tune.fuse_tail) {
             // orthogonalise, then ONE launch for V(:,k+1) = w / h(k+1,k) and the rotations (independent of each other)
-            MPG_TRY(add_vector<T>(ctx, p.orth, n, kk, V, ldv, w, h + (size_t)kk * ldh, scratch, true, true));
+            MPG_TRY(add_vector<T>(ctx, p.orth, n, kk, V, ldv, w, h + (size_t)kk * ldh, scratch, true));
             return arnoldi_tail<T>(ctx, n, scratch + (kk + 1), w, V + (size_t)(kk + 1) * ldv, kk, h, ldh, cs, sn, s, ws->hist + kk, resid_host);
         }
-        MPG_TRY(add_vector<T>(ctx, p.orth, n, kk, V, ldv, w, h + (size_t)kk * ldh, scratch, true, false));
+        MPG_TRY(add_vector<T>(ctx, p.orth, n, kk, V, ldv, w, h + (size_t)kk * ldh, scratch, false));
         // rot / rotg / rot             gmres.cpp:106-110,219-222 ; |s(k+1)| stays on the device
         return givens_step<T>(ctx, kk, h, ldh, cs, sn, s, ws->hist + kk, resid_host);
     };
