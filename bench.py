@@ -38,8 +38,8 @@ def parse():
     ap.add_argument("--orth", default="cgsr")
     ap.add_argument("--mode", default="mixed", choices=["mixed", "baseline", "single-prec", "single"])
     ap.add_argument("--max-restarts", type=int, default=1000)
-    ap.add_argument("--cpu-sample", default="auto", help="bounded sample of the workload for the CPU baseline (auto: cd27:128 with "
-                    "oracle/_ref's MKL build, cd27:96 with the slower oracle port)")
+    ap.add_argument("--cpu-sample", default="auto", help="CPU baseline workload of the b200 arm (auto: the bench workload itself, one complete solve; "
+                    "anything else is labelled as not being the bench workload and yields no parity block)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=2)
@@ -97,10 +97,39 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_reference_run(sample, rlen, tol, orth, max_restarts, full_rows, mode="mixed"):
-    """The reference's CPU implementation of the path on this box's host cores, on a bounded sample of the workload.
-    Uses oracle/_ref (the reference's own sources built against the MKL inside libtorch) when present, else the oracle
-    port.  Returns dict(value=<it/s scaled to the full workload>, ...)."""
+_HOST_THREADS = None
+
+
+def host_threads():
+    """host cores this process may use (affinity-aware).  Read ONCE, before the first OpenMP region: with OMP_PROC_BIND the
+    runtime later pins the calling thread to a single core and sched_getaffinity would then say 1."""
+    global _HOST_THREADS
+    if _HOST_THREADS is None:
+        try:
+            _HOST_THREADS = max(1, len(os.sched_getaffinity(0)))
+        except Exception:
+            _HOST_THREADS = max(1, os.cpu_count() or 1)
+    return _HOST_THREADS
+
+
+def force_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm must use every host core it can.  Call BEFORE the first
+    import of numpy / torch in this process (libgomp reads the environment once) - torch.set_num_threads covers the rest."""
+    nt = host_threads()
+    for k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[k] = str(nt)
+    os.environ.setdefault("OMP_PROC_BIND", "spread")    # automated.py:13-15
+    os.environ.setdefault("OMP_PLACES", "threads")
+    os.environ["MKL_DYNAMIC"] = "FALSE"
+    return nt
+
+
+def cpu_reference_run(workload, rlen, tol, orth, max_restarts, mode="mixed", want_hist=True):
+    """ONE solve of `workload` (the real thing, never a scaled stand-in) by the reference's own CPU implementation of the path on
+    this box's host cores: oracle/_ref (the reference's sources built against the MKL inside libtorch) when present, else the
+    oracle port.  Returns counts, seconds inside the reference's timing window (gmres_perf_test.cpp:165-167), the per-iteration
+    history and the post-solve fp64 resNorm / errNorm (gmres_perf_test.cpp:169-175)."""
+    nt = force_host_threads()
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import numpy as np
     import oracle as orc
@@ -109,46 +138,87 @@ def cpu_reference_run(sample, rlen, tol, orth, max_restarts, full_rows, mode="mi
         have_ref = oracle_ref.available()
     except Exception:
         have_ref = False
-    if sample == "auto":
-        sample = "cd27:128" if have_ref else "cd27:96"
-    rm, ind, val = orc.gen(sample)
+    import torch
+    torch.set_num_threads(nt)   # omp_set_num_threads + mkl_set_num_threads for this thread, whatever the environment said at start-up
+    t_setup = time.perf_counter()
+    rm, ind, val = orc.gen(workload)
     n = len(rm) - 1
     xt = orc.rand_vect(n, 42)
     b = np.zeros(n)
     orc.spmv(rm, ind, val, 1.0, xt, 0.0, b)
+    t_setup = time.perf_counter() - t_setup
     t0 = time.perf_counter()
     if have_ref:
-        r = oracle_ref.gmres(rm, ind, val, b, mode=mode, orth=orth, rlen=rlen, tol=tol, max_restarts=max_restarts)
-        kind, cores = "reference", oracle_ref.num_threads()
+        r = oracle_ref.gmres(rm, ind, val, b, true_x=xt, mode=mode, orth=orth, rlen=rlen, tol=tol, max_restarts=max_restarts)
+        kind, cores = "reference", int(oracle_ref.num_threads())
+        res_norm, err_norm = float(r["res_norm"]), float(r["err_norm"])
     else:
         r = orc.gmres(rm, ind, val, b, mode=mode, orth=orth, rlen=rlen, tol=tol, max_restarts=max_restarts)
-        kind, cores = "port", orc.num_threads()
-    dt = r.get("gmres_seconds", time.perf_counter() - t0)
-    its = int(r["total_iters"])
-    scale = n / float(full_rows)
-    return {"value": its / dt * scale, "unit": UNIT, "cores": int(cores), "kind": kind, "seconds": dt, "iters": its,
-            "sample": f"{sample} ({n} rows = {scale:.4f} of the workload's rows), one full GMRES-IR({rlen}) solve: {its} inner iterations in "
-                      f"{dt:.2f} s; it/s scaled by the row ratio to {full_rows} rows (every kernel on the path is bandwidth-bound, cost ~ rows)"}
+        kind, cores = "port", int(orc.num_threads())
+        res = b.copy(); orc.spmv(rm, ind, val, -1.0, r["x"], 1.0, res)
+        res_norm, err_norm = float(np.linalg.norm(res)), float(np.linalg.norm(r["x"] - xt))
+    dt = float(r.get("gmres_seconds", time.perf_counter() - t0))
+    out = {"workload": workload, "n_rows": int(n), "nnz": int(len(ind)), "kind": kind, "cores": cores, "seconds": dt, "setup_seconds": t_setup,
+           "iters": int(r["total_iters"]), "restarts": int(r["total_restarts"]), "status": int(r["status"]),
+           "resNorm": res_norm, "errNorm": err_norm, "b_norm": float(np.linalg.norm(b))}
+    if want_hist:
+        out["hist_inner"] = np.asarray(r["hist_inner"], dtype=np.float64)
+        out["hist_outer"] = np.asarray(r["hist_outer"], dtype=np.float64)
+    return out
+
+
+def parity_block(cpu, gpu_hist, gpu_iters, gpu_restarts, gpu_status, gpu_res, gpu_err):
+    """reference-vs-GPU comparison on the SAME inputs at the bench size (SURVEY.md §8d "parity acceptance"): counts, the
+    per-iteration |s(k+1)|/||M^-1 b|| history, post-solve fp64 norms."""
+    import numpy as np
+    hr = np.asarray(cpu["hist_inner"]); hg = np.asarray(gpu_hist)
+    m = int(min(len(hr), len(hg)))
+    dev = None
+    if m:
+        live = hr[:m] > 1e-4 * hr[0]    # entries below 1e-4 of the first are rounding noise in fp32
+        rel = np.abs(hg[:m] - hr[:m]) / np.maximum(np.abs(hr[:m]), 1e-300)
+        dev = float(rel[live].max()) if live.any() else 0.0
+    rd = lambda a, b: abs(a - b) / max(abs(b), 1e-300)
+    return {"against": f"{cpu['kind']} ({'oracle/_ref: the reference sources + MKL' if cpu['kind'] == 'reference' else 'oracle port'}), {cpu['cores']} host threads, "
+                       f"{cpu['workload']} full size, one solve in {cpu['seconds']:.2f} s",
+            "iters": [int(gpu_iters), cpu["iters"]], "restarts": [int(gpu_restarts), cpu["restarts"]], "status": [int(gpu_status), cpu["status"]],
+            "iters_equal": int(gpu_iters) == cpu["iters"], "restarts_equal": int(gpu_restarts) == cpu["restarts"],
+            "hist_len_compared": m, "hist_dev": dev,
+            "resNorm": [gpu_res, cpu["resNorm"]], "resNorm_rel_diff": rd(gpu_res, cpu["resNorm"]),
+            "errNorm": [gpu_err, cpu["errNorm"]], "errNorm_rel_diff": rd(gpu_err, cpu["errNorm"]),
+            "order": "[this backend, reference]"}
+
+
+CPU_MAX_STEPS = 2   # a cd27:256 solve is ~15-30 s on the host cores: the CPU arm times at most this many real solves, no warm-up repeats
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    kind, N = args.workload.split(":")[0], int(args.workload.split(":")[1])
-    full_rows = N ** 3 if kind == "cd27" else (N * N if kind == "lap2d" else N)
-    vals, total_it, total_t = [], 0, 0.0
+    if args.workload == "sweep":
+        import sweep
+        sweep.run_reference(args)
+        return
+    steps = max(1, min(args.steps, CPU_MAX_STEPS))
+    total_it, total_t = 0, 0.0
     last = None
-    for i in range(args.warmup + args.steps):
-        last = cpu_reference_run(args.cpu_sample, args.rlen, args.tol, args.orth, args.max_restarts, full_rows, args.mode)
-        if i >= args.warmup:
-            total_it += last["iters"]; total_t += last["seconds"]
-    scale = last["value"] / (last["iters"] / last["seconds"])
-    value = total_it / total_t * scale
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * total_t / max(args.steps, 1) / scale, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f32 inner / f64 outer (CPU)", "data": "synthetic",
-            "config": {"workload": args.workload, "restart_length": args.rlen, "tol": args.tol, "orth": args.orth, "prec": "identity"},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": last["cores"], "kind": last["kind"], "sample": last["sample"]},
+    for i in range(steps):
+        last = cpu_reference_run(args.workload, args.rlen, args.tol, args.orth, args.max_restarts, args.mode, want_hist=False)
+        total_it += last["iters"]; total_t += last["seconds"]
+    assert last["cores"] > 1 or host_threads() == 1, f"CPU arm is running on {last['cores']} thread(s) of {host_threads()}"
+    value = total_it / total_t
+    sample = (f"{args.workload} at full size ({last['n_rows']} rows, {last['nnz']} nonzeros), {steps} complete GMRES-IR({args.rlen}) solve(s), "
+              f"{last['iters']} inner iterations / {last['restarts']} restart checks each, timed inside the reference's own window "
+              f"(gmres_perf_test.cpp:165-167); no warm-up repeats, at most {CPU_MAX_STEPS} steps whatever --steps asks for")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": 0,
+            "steps_requested": args.steps, "warmup_requested": args.warmup,
+            "ms_per_step": 1e3 * total_t / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32 inner / f64 outer (CPU)" if args.mode == "mixed" else args.mode, "data": "synthetic",
+            "config": {"workload": args.workload, "mode": args.mode, "n_rows": last["n_rows"], "nnz": last["nnz"], "restart_length": args.rlen, "tol": args.tol,
+                       "orth": args.orth, "prec": "identity", "iters_per_solve": last["iters"], "restarts_per_solve": last["restarts"],
+                       "status": last["status"], "time_to_solution_s": total_t / steps, "resNorm": last["resNorm"], "errNorm": last["errNorm"],
+                       "rel_res": last["resNorm"] / last["b_norm"], "setup_seconds_untimed": round(last["setup_seconds"], 2)},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": last["cores"], "kind": last["kind"], "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
@@ -159,7 +229,12 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
+        force_host_threads()
         run_reference(args, rank, world)
+        return
+    if args.workload == "sweep":
+        import sweep
+        sweep.run_b200(args, rank, world, local_rank)
         return
 
     import numpy as np
@@ -308,11 +383,22 @@ def main():
                "d2h_ms": r2["d2h_ms"], "call": "mpg_gmres_solve_host (pinned host CSR + b in, x out)"}
         del h_rm, h_ind, h_val, h_b
 
-    # ---- CPU baseline on this box's host cores (bounded sample) ----
-    cpu = None
+    # ---- CPU baseline on this box's host cores: ONE complete solve of the same workload by the reference's own CPU path, and the
+    # parity block it yields at the bench size (same inputs: both sides generate the workload from the same frozen definition) ----
+    cpu = parity = None
     if not args.no_cpu_baseline:
-        c = cpu_reference_run(args.cpu_sample, args.rlen, args.tol, args.orth, args.max_restarts, n, args.mode)
-        cpu = {k: c[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        sample_wl = args.workload if args.cpu_sample == "auto" else args.cpu_sample
+        c = cpu_reference_run(sample_wl, args.rlen, args.tol, args.orth, args.max_restarts, args.mode)
+        cpu = {"value": c["iters"] / c["seconds"], "unit": UNIT, "cores": c["cores"], "kind": c["kind"],
+               "sample": (f"{sample_wl}{'' if sample_wl == args.workload else ' (NOT the bench workload ' + args.workload + '; unscaled)'}: one complete "
+                          f"GMRES-IR({args.rlen}) solve at full size, {c['iters']} inner iterations / {c['restarts']} restart checks in {c['seconds']:.2f} s "
+                          f"inside the reference's timing window (gmres_perf_test.cpp:165-167)"),
+               "seconds": c["seconds"], "iters": c["iters"], "restarts": c["restarts"], "resNorm": c["resNorm"], "errNorm": c["errNorm"]}
+        if sample_wl == args.workload:
+            x.zero_()
+            rp = ctx.gmres(A, val, b, x, vals32=val32, **kw)   # one more (untimed) solve with the full residual history
+            res = b.clone(); ctx.spmv(A, val, -1.0, x, 1.0, res)
+            parity = parity_block(c, rp["hist_inner"], rp["total_iters"], rp["total_restarts"], rp["status"], ctx.nrm2(res), ctx.nrm2(x - xt))
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -328,7 +414,7 @@ def main():
                               f"working set {ws_bytes / 1e9:.1f} GB (matrix + basis) >> 126 MB L2; no flush needed"),
                        "kernel_timers": ("CUDA events around every launch inside the timed region" if prof_in_region else
                                          "one extra solve after the timed region (kernels of < 100 us: event records between launches would perturb the step)")},
-            "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
+            "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "parity": parity, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
     print(json.dumps(line), flush=True)
 
 

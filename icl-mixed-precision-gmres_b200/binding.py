@@ -224,6 +224,11 @@ class Context:
     def set_tuning(self, key, value):
         self._chk(self.L.mpg_set_tuning(self.h, key.encode(), C.c_int(value)))
 
+    def get_tuning(self, key):
+        v = C.c_int()
+        self._chk(self.L.mpg_get_tuning(self.h, key.encode(), C.byref(v)))
+        return v.value
+
     PROF_CLASSES = ["spmv_f32", "spmv_f64", "vpass", "gemvn", "elementwise", "reduce", "small", "gemvt"]
 
     def debug_timing(self, buf):

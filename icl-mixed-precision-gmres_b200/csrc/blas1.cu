@@ -85,31 +85,33 @@ extern "C" const char* mpg_last_error(mpg_ctx* ctx) { return ctx ? ctx->last_err
 extern "C" int mpg_num_sms(mpg_ctx* ctx) { return ctx ? ctx->num_sms : 0; }
 extern "C" int64_t mpg_launch_count(mpg_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+// one table for set / get: the name of a knob and where it lives
+static int* tuning_slot(mpg_ctx* ctx, const std::string& k) {
+    mpg::Tuning& t = ctx->tune;
+#define MPG_KNOB(name) if (k == #name) return &t.name
+    MPG_KNOB(spmv_ctas_per_sm); MPG_KNOB(dist_peer_reduce); MPG_KNOB(dist_peer_halo); MPG_KNOB(dist_overlap); MPG_KNOB(spmv_packed);
+    MPG_KNOB(use_pdl); MPG_KNOB(pdl_max_rows); MPG_KNOB(fuse_tail); MPG_KNOB(vpass_stages); MPG_KNOB(fuse_min_cols);
+    MPG_KNOB(vdirect_max_cols_a); MPG_KNOB(vdirect_max_cols_b); MPG_KNOB(vrow_max_cols); MPG_KNOB(vrow_max_cols_a); MPG_KNOB(gemvt_rb);
+    MPG_KNOB(gemvt_rows_per_block); MPG_KNOB(passA_rb); MPG_KNOB(cgs2_fused); MPG_KNOB(vpass_serpentine); MPG_KNOB(gemvn_ctas_per_sm);
+    MPG_KNOB(red_ctas_per_sm); MPG_KNOB(residual_packed); MPG_KNOB(values_static); MPG_KNOB(spmv_sigma); MPG_KNOB(mgs_fused);
+    MPG_KNOB(dist_fuse_halo); MPG_KNOB(spin_limit_ms); MPG_KNOB(lookahead);
+#undef MPG_KNOB
+    return nullptr;
+}
 extern "C" int mpg_set_tuning(mpg_ctx* ctx, const char* key, int value) {
     if (!ctx || !key) return MPG_ERR_ARG;
     const std::string k(key);
-    if (k == "spmv_ctas_per_sm") ctx->tune.spmv_ctas_per_sm = value;
-    else if (k == "dist_peer_reduce") ctx->tune.dist_peer_reduce = value;
-    else if (k == "dist_peer_halo") ctx->tune.dist_peer_halo = value;
-    else if (k == "dist_overlap") ctx->tune.dist_overlap = value;
-    else if (k == "spmv_packed") ctx->tune.spmv_packed = value;
-    else if (k == "use_pdl") ctx->tune.use_pdl = value;
-    else if (k == "pdl_max_rows") ctx->tune.pdl_max_rows = value;
-    else if (k == "fuse_tail") ctx->tune.fuse_tail = value;
-    else if (k == "vpass_stages") ctx->tune.vpass_stages = value;
-    else if (k == "fuse_min_cols") ctx->tune.fuse_min_cols = value;
-    else if (k == "vdirect_max_cols_a") ctx->tune.vdirect_max_cols_a = value;
-    else if (k == "vdirect_max_cols_b") ctx->tune.vdirect_max_cols_b = value;
-    else if (k == "vrow_max_cols") ctx->tune.vrow_max_cols = std::max(0, std::min(value, 64));
-    else if (k == "vrow_max_cols_a") ctx->tune.vrow_max_cols_a = std::max(0, std::min(value, 64));
-    else if (k == "gemvt_rb") ctx->tune.gemvt_rb = value;
-    else if (k == "gemvt_rows_per_block") ctx->tune.gemvt_rows_per_block = value;
-    else if (k == "passA_rb") ctx->tune.passA_rb = value;
-    else if (k == "cgs2_fused") ctx->tune.cgs2_fused = value;
-    else if (k == "vpass_serpentine") ctx->tune.vpass_serpentine = value;
-    else if (k == "gemvn_ctas_per_sm") ctx->tune.gemvn_ctas_per_sm = value;
-    else if (k == "red_ctas_per_sm") ctx->tune.red_ctas_per_sm = value;
-    else return fail(ctx, MPG_ERR_ARG, "unknown tuning key " + k);
+    int* slot = tuning_slot(ctx, k);
+    if (!slot) return fail(ctx, MPG_ERR_ARG, "unknown tuning key " + k);
+    if (k == "vrow_max_cols" || k == "vrow_max_cols_a") value = std::max(0, std::min(value, 64));
+    *slot = value;
+    return MPG_OK;
+}
+extern "C" int mpg_get_tuning(mpg_ctx* ctx, const char* key, int* value) {
+    if (!ctx || !key || !value) return MPG_ERR_ARG;
+    int* slot = tuning_slot(ctx, key);
+    if (!slot) return fail(ctx, MPG_ERR_ARG, std::string("unknown tuning key ") + key);
+    *value = *slot;
     return MPG_OK;
 }
 
@@ -212,9 +214,14 @@ __global__ void __launch_bounds__(RED_THREADS) reduce_kernel(int64_t n, const T*
     const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t gstride = (int64_t)gridDim.x * blockDim.x;
     const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
-    T acc[VEC];
+    // dot: products accumulated in T (what BLAS ?dot does).  nrm2: squares accumulated in DOUBLE - for fp32 data that is exact
+    // scaling-free protection over the whole fp32 range (squares of 1e-45 .. 3e38 neither underflow nor overflow in fp64), the
+    // job BLAS ?nrm2 does with its scale / ssq recurrence (kernels_mkl.cpp:97-115); the kernel is HBM-bound either way.
+    // fp64 nrm2 is the plain sum of squares: safe for |x| in [1e-150, 1e150] (stated in the header).
+    using AT = typename std::conditional<IS_NRM2, double, T>::type;
+    AT acc[VEC];
 #pragma unroll
-    for (int c = 0; c < VEC; ++c) acc[c] = T(0);
+    for (int c = 0; c < VEC; ++c) acc[c] = AT(0);
     int64_t done = 0;
     if (aligned) {
         const int64_t nv = n / VEC;
@@ -226,14 +233,14 @@ __global__ void __launch_bounds__(RED_THREADS) reduce_kernel(int64_t n, const T*
             const T* pa = reinterpret_cast<const T*>(&a);
             const T* pb = reinterpret_cast<const T*>(&b);
 #pragma unroll
-            for (int c = 0; c < VEC; ++c) acc[c] = fma(pa[c], pb[c], acc[c]);
+            for (int c = 0; c < VEC; ++c) acc[c] = fma((AT)pa[c], (AT)pb[c], acc[c]);
         }
         done = nv * VEC;
     }
     for (int64_t i = done + gtid; i < n; i += gstride) {
         const T a = x[i];
         const T b = IS_NRM2 ? a : y[i];
-        acc[0] = fma(a, b, acc[0]);
+        acc[0] = fma((AT)a, (AT)b, acc[0]);
     }
     double s = 0.0;
 #pragma unroll

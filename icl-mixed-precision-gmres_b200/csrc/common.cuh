@@ -44,6 +44,14 @@ struct Tuning {
     int spmv_packed = 1;      // solver: run the inner SpMV on the packed (sliced-ELL) copy of the matrix when it packs well (sell.cu)
     int dist_overlap = 1;     // multi-GPU SpMV: rows without halo columns run between the halo push and the wait for the neighbours' data
     int dist_peer_reduce = 1; // multi-GPU reductions inside the kernels over peer memory (0: NCCL all-reduce + epilogue kernel)
+    int residual_packed = 1;  // solver: fp64 outer residual r = b - A x on a packed fp64 copy of the matrix (0: CSR kernel on the caller's arrays)
+    int values_static = 0;    // solver: 1 = the caller promises not to change matrix VALUES between solves on the same mpg_csr / value pointers,
+                              // so the packed copies are built once (the reference builds SparseMatrix<float>(A) once, outside its solve timer)
+    int spmv_sigma = 1;       // packed operator: sort rows by length inside windows (SELL-C-sigma) when the plain slices pad too much
+    int mgs_fused = 1;        // MGS: pairwise fused passes (w -= h_j v_j ; h_{j+1} = v_{j+1}.w in one kernel) instead of k+1 x {dot, naxpy}
+    int dist_fuse_halo = 1;   // multi-GPU: halo gather-and-push rides in the Arnoldi tail kernel, the wait in the boundary-slice SpMV
+    int spin_limit_ms = 20000; // multi-GPU: a device-side wait on a peer gives up after this long and raises the context's error word
+    int lookahead = 0;        // residual-driven restart policies: speculative Arnoldi steps in flight (0 = auto from a bandwidth estimate)
 };
 
 }  // namespace mpg

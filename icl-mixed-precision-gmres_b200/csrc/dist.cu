@@ -404,6 +404,8 @@ template int halo_exchange<double>(mpg_ctx*, double*);
 
 int64_t dist_halo(mpg_ctx* ctx) { return ctx->dist ? ctx->dist->n_halo : 0; }
 int64_t dist_nlocal(mpg_ctx* ctx) { return ctx->dist ? ctx->dist->n_local : -1; }
+int64_t dist_nglobal(mpg_ctx* ctx) { return ctx->dist ? ctx->dist->n_global : -1; }
+int dist_world(mpg_ctx* ctx) { return ctx->dist ? ctx->dist->world : 1; }
 
 }  // namespace mpg
 

@@ -53,6 +53,8 @@ template <class T> int halo_exchange(mpg_ctx*, T*);
 template <class T> int halo_begin(mpg_ctx*, T*);
 template <class T> int halo_finish(mpg_ctx*, T*);
 int64_t dist_halo(mpg_ctx*);
+int64_t dist_nglobal(mpg_ctx*);
+int dist_world(mpg_ctx*);
 }  // namespace mpg
 
 namespace {
@@ -69,6 +71,7 @@ struct Policy {
     int64_t second_len = 0;
     bool first_iteration = true;
     double loss_sq = 0;
+    double rows_per_rank = 0, nnz_per_rank = 0;   // rank-invariant size of one rank's share (look-ahead depth), set by size_estimate()
 
     Policy(const mpg_gmres_params& p)
         : kind(p.conv), tol(p.tol), rtol(p.restart_tol), rlen(p.restart_length), max_restarts(p.max_restarts), restart_tol(p.restart_tol) {}
@@ -214,6 +217,23 @@ int read_scalars(mpg_ctx* ctx, int count) {
 template <class T> T hs(mpg_ctx* ctx, int slot) { T v; memcpy(&v, ctx->hscal + slot, sizeof(T)); return v; }
 template <class T> T* ds(mpg_ctx* ctx, int slot) { return reinterpret_cast<T*>(ctx->dscal + slot); }
 
+// Rank-invariant estimate of one rank's share of the problem: local sizes on one GPU; with a communicator attached the global
+// row count / world and the all-reduced nonzero count / world (the slabs themselves differ between ranks).
+int size_estimate(mpg_ctx* ctx, const mpg_csr* A, Policy& pol) {
+    pol.rows_per_rank = (double)A->nrows;
+    pol.nnz_per_rank = (double)A->nnz;
+    if (!ctx->dist || !pol.needs_residual()) return MPG_OK;
+    const double h[2] = {(double)A->nnz, 1.0};
+    MPG_CUDA(ctx, cudaMemcpyAsync(ds<double>(ctx, 20), h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream));
+    MPG_TRY(dot_dev(ctx, 1, ds<double>(ctx, 20), ds<double>(ctx, 21), ds<double>(ctx, 22)));   // all-reduced over the ranks
+    MPG_CUDA(ctx, cudaMemcpyAsync(ctx->hscal + 22, ctx->dscal + 22, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    MPG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const double world = (double)dist_world(ctx);
+    pol.nnz_per_rank = ctx->hscal[22] / world;
+    pol.rows_per_rank = (double)dist_nglobal(ctx) / world;
+    return MPG_OK;
+}
+
 // Packed copy of the matrix the inner iterations multiply with (T = the inner precision).  The structure is cached in
 // the mpg_csr plan, the values are re-packed at every solve (one pass over the matrix; the caller may have changed them).
 // *out stays null when packing is switched off or the structure does not pack well: the CSR kernel is used then.
@@ -319,11 +339,13 @@ int run_cycle(mpg_ctx* ctx, const mpg_gmres_params& p, Policy& pol, Workspace* w
         // pinned memory and the host follows it while up to kLookahead further iterations are already enqueued.  A
         // restart decided at step k* leaves at most kLookahead-1 speculative steps behind; they only touch basis columns
         // > k*, Hessenberg columns >= k* and s[k*..], none of which solution_update(k*) reads.  The issue order is a
-        // function of the decisions alone, so all ranks of a multi-GPU run enqueue the same sequence.
+        // function of the decisions and of kLookahead alone.
         // Speculation wastes up to kLookahead-1 steps per restart; it pays when a step is short compared with the
         // ~30-50 us the GPU idles across a blocking read-back, so the depth follows a bandwidth estimate of the step time.
-        const double step_us = ((double)A->nnz * (sizeof(T) + 4) + 1.5 * (double)m * (double)n * sizeof(T)) / 6.0e6;
-        const int64_t kLookahead = step_us < 200.0 ? 3 : (step_us < 1000.0 ? 2 : 1);
+        // Multi-GPU: every step contains all-reduces, so all ranks MUST enqueue the same number of speculative steps - the depth
+        // is derived from rank-invariant quantities only (global rows and nonzeros / world size), never from the local slab.
+        const double step_us = (pol.nnz_per_rank * (sizeof(T) + 4) + 1.5 * (double)m * pol.rows_per_rank * sizeof(T)) / 6.0e6;
+        const int64_t kLookahead = ctx->tune.lookahead > 0 ? ctx->tune.lookahead : (step_us < 200.0 ? 3 : (step_us < 1000.0 ? 2 : 1));
         volatile double* hh = ws->hist_host;
         for (int64_t j = 0; j <= m; ++j) hh[j] = -1.0;   // |s| >= 0: negative = not written yet (stream is idle here)
         int64_t issued = 0, checked = 0;
@@ -394,6 +416,7 @@ int solve_mixed(mpg_ctx* ctx, const mpg_gmres_params& p, const mpg_csr* A, const
     const mpg_packed* packed = nullptr;
     MPG_TRY(get_packed<float>(ctx, ws, A, vals32, &packed));
     Policy pol(p);
+    MPG_TRY(size_estimate(ctx, A, pol));
     if (p.conv == MPG_CONV_ORTHLOSS) {
         MPG_TRY(fill_host(ctx, (m + 1) * (m + 1), 0.f, static_cast<float*>(ws->S)));  // IterUtil.hpp:191
         MPG_CUDA(ctx, cudaMemsetAsync(ws->V, 0, sizeof(float) * (size_t)ws->ldv * (size_t)(m + 1), ctx->stream));  // fresh View (see get_workspace)
@@ -462,6 +485,7 @@ int solve_uniform(mpg_ctx* ctx, const mpg_gmres_params& p, const mpg_csr* A, con
     const mpg_packed* packed = nullptr;
     MPG_TRY(get_packed<T>(ctx, ws, A, vals, &packed));
     Policy pol(p);
+    MPG_TRY(size_estimate(ctx, A, pol));
     if (p.conv == MPG_CONV_ORTHLOSS) {
         MPG_TRY(fill_host(ctx, (m + 1) * (m + 1), T(0), static_cast<T*>(ws->S)));
         MPG_CUDA(ctx, cudaMemsetAsync(ws->V, 0, sizeof(T) * (size_t)ws->ldv * (size_t)(m + 1), ctx->stream));

@@ -384,9 +384,10 @@ __global__ void jacobi_diag_kernel(int nrows, const int* __restrict__ row_map, c
     // the diagonal entry: LoadMatrix-canonical rows always hold it (LoadMatrix.hpp:62-66).  types.hpp:424-427 scans
     // for the first column >= i, which is the same entry on a sorted row; an equality scan also works on a
     // partitioned slab whose remote columns are renumbered past the local ones.
-    int j = row_map[i];
-    while (inds[j] != i) ++j;
-    const T v = vals[j];
+    // A row that stores no diagonal (raw CSR handed to mpg_csr_create is not checked) takes the small-pivot branch, i.e. v = 0.
+    T v = T(0);
+    for (int j = row_map[i], je = row_map[i + 1]; j < je; ++j)
+        if (inds[j] == i) { v = vals[j]; break; }
     if (v >= 0) diag[i] = T(1) / ((v < alpha) ? alpha : v);
     else diag[i] = T(1) / ((v > -alpha) ? -alpha : v);
 }

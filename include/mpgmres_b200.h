@@ -52,6 +52,7 @@ const char* mpg_last_error(mpg_ctx* ctx);
 int mpg_num_sms(mpg_ctx* ctx);
 int64_t mpg_launch_count(mpg_ctx* ctx);              /* kernels launched through this context so far */
 int mpg_set_tuning(mpg_ctx* ctx, const char* key, int value); /* kernel variant knobs, see DESIGN.md */
+int mpg_get_tuning(mpg_ctx* ctx, const char* key, int* value);
 /* Development aid: with a device buffer of >= 8 * 160 uint64 attached, every CTA of the staged V-pass kernels stores
  * %globaltimer at its phase boundaries (start, first tile in, last tile done, partials written, finish done);
  * NULL detaches (tools/vpass_timeline.py). */
@@ -78,6 +79,9 @@ int mpg_memset_zero(mpg_ctx* ctx, void* dst, size_t bytes);
  * axpy  kernels.hpp:47-51   (kernels_cuda.cpp:212-262)     naxpy kernels.hpp:59-60  (kernels_cuda.cpp:264-288)
  * scal  kernels.hpp:62-85   (kernels_cuda.cpp:291-392)     copy  kernels.hpp:11-30  fill kernels.hpp:88-101
  * gdmv  kernels.hpp:131-151
+ * nrm2 accumulates the squares in double: the fp32 form is safe over the whole fp32 range without scaling (the role of BLAS
+ * ?nrm2's scale/ssq recurrence, kernels_mkl.cpp:97-115); the fp64 form is the plain sum of squares, safe for |x| in
+ * [1e-150, 1e150].
  * `_dev` variants take/return the scalar in device memory (the Scalar<T,Device> overloads); the others
  * take host scalars / return to the host (and therefore synchronise), like the reference's two forms. */
 int mpg_dot_f32(mpg_ctx*, int64_t n, const float* x, const float* y, float* result_host);

@@ -15,7 +15,7 @@
 // Pinning: the reference has no tests or golden vectors.  The oracle is pinned
 // against oracle/_ref — the reference's own gmres.cpp / Orthogonalization.hpp / IterUtil.hpp /
 // kernels_mkl.cpp / gmres_perf_test.cpp compiled unmodified against a host Kokkos shim and the oneMKL
-// that ships inside libtorch_cpu.so (see oracle/Makefile, tests/test_oracle_vs_ref.py).
+// that ships inside libtorch_cpu.so (see oracle/Makefile, tests/test_oracle_pinned_cpu.py).
 //
 // Build: make -C oracle   (g++ -O2 -fopenmp -ffp-contract=off; FMA is used explicitly where BLAS
 // implementations use it, so results do not depend on compiler contraction).
@@ -60,8 +60,10 @@ T dot(size_t n, const T* x, const T* y) {
     return (T)s;
 }
 
-// kernels.hpp:40-44 / kernels_mkl.cpp:97-115 (cblas_?nrm2).  BLAS nrm2 is overflow-safe (scaled); the
-// values on this path are O(1)..O(1e5), so the unscaled blocked form is within rounding of it.
+// kernels.hpp:40-44 / kernels_mkl.cpp:97-115 (cblas_?nrm2).  BLAS nrm2 is overflow/underflow-safe through its scale / ssq
+// recurrence.  Restated here (and in the CUDA backend) as a sum of squares accumulated in DOUBLE: for fp32 data that is safe
+// over the whole fp32 range without any scaling (1e-45^2 .. 3e38^2 are normal doubles) and agrees with the scaled algorithm to
+// fp32 rounding; fp64 data is safe for |x| in [1e-150, 1e150].
 template <class T>
 T nrm2(size_t n, const T* x) {
     const size_t nb = (n + RBLK - 1) / RBLK;
@@ -69,9 +71,9 @@ T nrm2(size_t n, const T* x) {
 #pragma omp parallel for schedule(static)
     for (long b = 0; b < (long)nb; ++b) {
         const size_t lo = b * RBLK, hi = std::min(n, lo + RBLK);
-        T acc = 0;
-        for (size_t i = lo; i < hi; ++i) acc = fma_t(x[i], x[i], acc);
-        part[b] = (double)acc;
+        double acc = 0;
+        for (size_t i = lo; i < hi; ++i) acc = std::fma((double)x[i], (double)x[i], acc);
+        part[b] = acc;
     }
     double s = 0;
     for (size_t b = 0; b < nb; ++b) s += part[b];

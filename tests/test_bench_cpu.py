@@ -9,7 +9,7 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = os.path.join(ROOT, "oracle", "_ref", "gmres_perf_test")
-ARGS = ["--impl", "reference", "--steps", "1", "--warmup", "0", "--workload", "lap2d:48", "--rlen", "20", "--cpu-sample", "lap2d:48"]
+ARGS = ["--impl", "reference", "--steps", "1", "--warmup", "0", "--workload", "lap2d:48", "--rlen", "20"]
 
 
 def _json_lines(out):
@@ -28,7 +28,10 @@ def test_reference_arm_prints_one_contract_line():
     assert d["value"] > 0 and d["ms_per_step"] > 0
     assert d["config"]["workload"] == "lap2d:48"
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "reference" and cb["cores"] >= 1 and cb["value"] == d["value"] and "lap2d:48" in cb["sample"]
+    assert cb["kind"] == "reference" and cb["cores"] >= 1 and cb["value"] == d["value"] and "lap2d:48 at full size" in cb["sample"]
+    assert d["config"]["n_rows"] == 48 * 48 and d["config"]["iters_per_solve"] > 0 and d["config"]["resNorm"] > 0
+    # ms_per_step x steps is what was actually timed (no extrapolation)
+    assert abs(d["ms_per_step"] * d["steps"] * 1e-3 * d["value"] - d["config"]["iters_per_solve"] * d["steps"]) < 1e-6 * d["config"]["iters_per_solve"] + 1e-9
     assert d["e2e"] == {"value": d["value"], "unit": "it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["gpu_launches"] == 0
 
@@ -41,6 +44,20 @@ def test_reference_arm_under_torchrun_only_rank0_prints():
     assert out.returncode == 0, out.stderr[-2000:]
     lines = _json_lines(out.stdout)
     assert len(lines) == 1 and lines[0]["impl"] == "reference" and lines[0]["n_gpus"] == 2
+    # torchrun exports OMP_NUM_THREADS=1 to its workers: the CPU arm must not inherit that
+    ncpu = len(os.sched_getaffinity(0))
+    assert lines[0]["cpu_baseline"]["cores"] == ncpu or ncpu == 1
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="oracle/_ref not built")
+def test_reference_arm_caps_steps_and_reports_what_it_ran():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "20", "--warmup", "5", "--workload", "lap2d:48",
+                          "--rlen", "20"], capture_output=True, text=True, timeout=600, cwd=ROOT, env=dict(os.environ, OMP_NUM_THREADS="1"))
+    assert out.returncode == 0, out.stderr[-2000:]
+    d = _json_lines(out.stdout)[0]
+    assert d["steps"] == 2 and d["warmup"] == 0 and d["steps_requested"] == 20 and d["warmup_requested"] == 5
+    ncpu = len(os.sched_getaffinity(0))
+    assert d["cpu_baseline"]["cores"] == ncpu or ncpu == 1
 
 
 def test_product_arm_fails_loudly_without_a_gpu():

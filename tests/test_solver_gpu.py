@@ -5,11 +5,16 @@ solved on the GPU through the C ABI and compared with (a) the reference's record
 live on the same inputs:
   * status, outer index i and restart count: equal; inner iterations: equal (base policy) or within +-5 % (policies
     whose restart decision depends on a residual);
-  * residual history |s(k+1)|/||M^-1 b||: relative difference, while the residual is above 1e-4 of its start, at most
-        max(HIST_RTOL[mode], 4 x dev_oracle_vs_ref)
-    where dev_oracle_vs_ref is the recorded difference between the reference (MKL) and the oracle on that case - two
-    correct implementations of the same algorithm.  Well-conditioned cases sit at 1e-6..1e-4; the badly row-scaled
-    power-law matrix amplifies fp32 rounding to 5e-2..3e-1 for the reference as well, and the envelope follows it;
+  * residual history |s(k+1)|/||M^-1 b||, two checks:
+      (1) FIRST restart cycle while the residual is above 1e-2 of its start - no restart has fed rounding noise back yet -
+          within max(HIST_RTOL[mode], 4 x dev_first_cycle), never more than 5e-2;
+      (2) whole history while above 1e-4 of its start within min(max(HIST_RTOL[mode], 4 x dev_oracle_vs_ref), 5e-2), where
+          dev_* are the recorded differences between the reference (MKL) and the oracle on that case - two correct
+          implementations of the same algorithm.  Well-conditioned cases sit at 1e-6..1e-4.  On the badly row-scaled
+          power-law matrix every restart re-injects the fp32 rounding of the previous cycle into the new residual and
+          reference and oracle themselves differ by 5e-2..3e-1 in later cycles: there (recorded deviation > 1.25e-2, i.e.
+          where the 5e-2 cap would bind) check (2) is replaced by the restart-boundary residuals handed to check_initial
+          (same order of magnitude at every restart) + counts + final norms;
   * post-solve fp64 resNorm / errNorm (gmres_perf_test.cpp:169-178): same size as the reference's, or inside the
     stopping criterion."""
 import json
@@ -29,7 +34,7 @@ HIST_RTOL = {"mixed": 5e-3, "single": 5e-3, "single-prec": 1e-4, "baseline": 1e-
 
 
 def case_id(c):
-    extra = "".join(f"-{k}={c[k]}" for k in ("conv", "prec") if k in c)
+    extra = "".join(f"-{k}={c[k]}" for k in ("conv", "prec", "bscale") if k in c)
     return f"{c['spec']}-{c['mode']}-{c['orth']}{extra}"
 
 
@@ -37,11 +42,14 @@ def solver_kwargs(c):
     return {k: c[k] for k in ("mode", "orth", "rlen", "tol", "conv", "rtol", "prec") if k in c}
 
 
-def deviation(h, h0):
-    m = min(len(h), len(h0))
+def deviation(h, h0, floor=FLOOR, first=None):
+    m = min(len(h), len(h0)) if first is None else min(len(h), len(h0), first)
     a, b = np.asarray(h[:m]), np.asarray(h0[:m])
-    live = b >= FLOOR * b[0]
+    live = b >= floor * b[0]
     return float((np.abs(a - b) / np.maximum(b, 1e-300))[live].max()) if m and live.any() else 0.0
+
+
+HIST_CAP = 5e-2   # no history envelope is ever looser than this
 
 
 def gpu_solve(ctx, g, rm, ind, val, b, **kw):
@@ -56,7 +64,7 @@ def gpu_solve(ctx, g, rm, ind, val, b, **kw):
 @pytest.mark.parametrize("c", CASES, ids=case_id)
 def test_parity_with_reference_and_oracle(ctx, g, orc, c):
     import scipy.sparse as sp
-    rm, ind, val, xt, b = problem(orc, c["spec"])
+    rm, ind, val, xt, b = problem(orc, c["spec"], bscale=c.get("bscale", 1.0))
     kw = solver_kwargs(c)
     rg = gpu_solve(ctx, g, rm, ind, val, b, max_restarts=5000, **kw)
     ro = orc.gmres(rm, ind, val, b, max_restarts=5000, **kw)
@@ -70,11 +78,19 @@ def test_parity_with_reference_and_oracle(ctx, g, orc, c):
         assert (rg["total_iters"], rg["total_restarts"], rg["outer_i"]) == (ref["total_iters"], ref["total_restarts"], ref["outer_i"])
     for f in ("b_norm", "Minvb_norm", "A_norm"):
         assert abs(rg[f] - ro[f]) <= 1e-6 * abs(ro[f])
-    env = max(HIST_RTOL[c["mode"]], 4 * c["dev_oracle_vs_ref"])
+    # (1) first cycle, above 1e-2 of the start
+    env1 = min(max(HIST_RTOL[c["mode"]], 4 * c["dev_first_cycle"]), HIST_CAP)
+    for other, name in ((ro["hist_inner"], "oracle"), (ref["hist_inner"], "reference")):
+        d1 = deviation(rg["hist_inner"], other, floor=1e-2, first=c["rlen"])
+        assert d1 <= env1, f"first-cycle history vs {name} {d1:.3e} > envelope {env1:.3e}"
+    # (2) whole history, above 1e-4 of the start - unless the recorded reference-vs-oracle deviation shows that later cycles
+    # are restart-amplified rounding noise on this case
+    noisy = c["dev_oracle_vs_ref"] > HIST_CAP / 4
+    env = min(max(HIST_RTOL[c["mode"]], 4 * c["dev_oracle_vs_ref"]), HIST_CAP)
     d_or, d_ref = deviation(rg["hist_inner"], ro["hist_inner"]), deviation(rg["hist_inner"], ref["hist_inner"])
-    if not data_driven or rg["total_iters"] == ro["total_iters"]:
+    if not noisy and (not data_driven or rg["total_iters"] == ro["total_iters"]):
         assert d_or <= env, f"history vs oracle {d_or:.3e} > envelope {env:.3e}"
-    if not data_driven or rg["total_iters"] == ref["total_iters"]:
+    if not noisy and (not data_driven or rg["total_iters"] == ref["total_iters"]):
         assert d_ref <= env, f"history vs reference {d_ref:.3e} > envelope {env:.3e}"
     # what check_initial sees at each restart boundary
     hg, hr = rg["hist_outer"], np.asarray(ref["hist_outer"])
@@ -89,6 +105,9 @@ def test_parity_with_reference_and_oracle(ctx, g, orc, c):
     res, err = np.linalg.norm(b - A @ rg["x"]), np.linalg.norm(rg["x"] - xt)
     assert res <= max(8 * ref["res_norm"], c["tol"] * hr[0, 1])
     assert err <= max(8 * ref["err_norm"], 100 * c["tol"] * np.linalg.norm(xt))
+    if noisy and not data_driven:
+        # restart-boundary residuals of every cycle within a factor 2 of the reference's while they are above the noise floor
+        assert np.all(np.abs(np.log2(hg[:k, 0][above] / hr[:k, 0][above])) <= 1.0)
 
 
 def test_abort_and_x0(ctx, g, orc):
@@ -124,16 +143,20 @@ def test_kernel_variants_agree(ctx, g, orc):
     gemv-T.  Reduction grouping differs, so results agree to rounding, not bitwise."""
     rm, ind, val, xt, b = problem(orc, "cd27:20")
     base = gpu_solve(ctx, g, rm, ind, val, b, mode="mixed", rlen=40, tol=1e-9)
+    variants = [("cgs2_fused", 0), ("passA_rb", 1), ("fuse_min_cols", 16), ("vpass_serpentine", 0), ("gemvt_rb", 0), ("residual_packed", 0)]
+    defaults = {key: ctx.get_tuning(key) for key, _ in variants}   # restored from what the library reports, never from a literal
     try:
-        for key, value in [("cgs2_fused", 0), ("passA_rb", 1), ("fuse_min_cols", 1), ("vpass_serpentine", 0), ("gemvt_rb", 0)]:
+        for key, value in variants:
+            assert value != defaults[key], key
             ctx.set_tuning(key, value)
             r = gpu_solve(ctx, g, rm, ind, val, b, mode="mixed", rlen=40, tol=1e-9)
-            ctx.set_tuning(key, {"cgs2_fused": 1, "passA_rb": 0, "fuse_min_cols": 16, "vpass_serpentine": 1, "gemvt_rb": 1}[key])
+            ctx.set_tuning(key, defaults[key])
             assert r["total_iters"] == base["total_iters"] and r["total_restarts"] == base["total_restarts"]
             assert deviation(r["hist_inner"], base["hist_inner"]) <= 5e-3, key
     finally:
-        for key, value in [("cgs2_fused", 1), ("passA_rb", 0), ("fuse_min_cols", 16), ("vpass_serpentine", 1), ("gemvt_rb", 1)]:
+        for key, value in defaults.items():
             ctx.set_tuning(key, value)
+        assert ctx.get_tuning("fuse_min_cols") == 1
 
 
 @pytest.mark.parametrize("spec,rlen", [("lap2d:1024", 50), ("cd27:96", 100), ("powerlaw:400000", 50)])

@@ -26,11 +26,14 @@ def summation_bound(terms_abs_sum, nterms, dtype, c=8.0):
     return c * np.sqrt(max(nterms, 1)) * u * terms_abs_sum + 4 * u * terms_abs_sum
 
 
-def problem(orc, spec, seed=42):
-    """(row_map, inds, vals64, x_true, b) with b = A x_true in fp64 (gmres_perf_test.cpp:413-416)"""
+def problem(orc, spec, seed=42, bscale=1.0):
+    """(row_map, inds, vals64, x_true, b) with b = A x_true in fp64 (gmres_perf_test.cpp:413-416); bscale multiplies x_true
+    and b afterwards (scaled-magnitude cases of the golden file)"""
     rm, ind, val = orc.gen(spec)
     n = len(rm) - 1
     xt = orc.rand_vect(n, seed)
     b = np.zeros(n)
     orc.spmv(rm, ind, val, 1.0, xt, 0.0, b)
+    if bscale != 1.0:
+        xt, b = xt * bscale, b * bscale
     return rm, ind, val, xt, b
