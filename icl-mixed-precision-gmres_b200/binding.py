@@ -172,6 +172,27 @@ class Packed:
                 self.ctx._chk(self.ctx.L.mpg_memcpy_d2h(self.ctx.h, dst.ctypes.data_as(C.c_void_p), src, C.c_size_t(dst.nbytes)))
         return G.value, off, ind, val
 
+    def rows(self):
+        """(mode, lane_start, lane_len, lane_out, split_rows, chunk_base) of the plan as numpy arrays; mode 0 = plain slices of
+        consecutive rows (the lane arrays are None), 1 = SELL-C-sigma (tests: bit-exact check against the oracle)"""
+        import numpy as np
+        mode, chunk, sigma, nl, ns, nc = C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        ps, pl, po, pr, pb = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+        rc = self.ctx.L.mpg_pack_describe_rows(self.h, C.byref(mode), C.byref(chunk), C.byref(sigma), C.byref(nl), C.byref(ps), C.byref(pl), C.byref(po),
+                                               C.byref(ns), C.byref(nc), C.byref(pr), C.byref(pb))
+        if rc != 0:
+            raise MpgError("mpg_pack_describe_rows failed")
+        self.ctx.sync()
+        if mode.value == 0:
+            return 0, None, None, None, None, None
+
+        def fetch(ptr, count):
+            a = np.empty(count, np.int32)
+            if count:
+                self.ctx._chk(self.ctx.L.mpg_memcpy_d2h(self.ctx.h, a.ctypes.data_as(C.c_void_p), ptr, C.c_size_t(a.nbytes)))
+            return a
+        return mode.value, fetch(ps, nl.value), fetch(pl, nl.value), fetch(po, nl.value), fetch(pr, ns.value), fetch(pb, ns.value + 1)
+
     def __del__(self):
         try:
             if self.h:

@@ -6,6 +6,17 @@
 
 using namespace mpg;
 
+namespace mpg {
+// device-side waits on a peer GPU that timed out leave a code in the context's error word (common.cuh wait_flag)
+int check_dev_err(mpg_ctx* ctx) {
+    const unsigned int e = ctx->dev_err ? *reinterpret_cast<volatile unsigned int*>(ctx->dev_err) : 0u;
+    if (!e) return MPG_OK;
+    *reinterpret_cast<volatile unsigned int*>(ctx->dev_err) = 0u;
+    return fail(ctx, MPG_ERR_STATE, std::string("a device-side wait on a peer GPU timed out (") + ((e & DEV_ERR_REDUCE_TIMEOUT) ? "all-reduce " : "") +
+                                        ((e & DEV_ERR_HALO_TIMEOUT) ? "halo " : "") + "): a rank died, diverged or issued a different launch sequence");
+}
+}  // namespace mpg
+
 // =====================================================================================================
 // context
 // =====================================================================================================
@@ -36,6 +47,9 @@ extern "C" int mpg_ctx_create(int device, mpg_ctx** out) {
     MPG_CUDA(ctx, cudaMemset(ctx->dscal, 0, sizeof(double) * 1024));
     MPG_CUDA(ctx, cudaMallocHost(&ctx->hscal, sizeof(double) * 64));
     MPG_CUDA(ctx, cudaMalloc(&ctx->red_raw, sizeof(double) * (kMaxCols + 8)));
+    MPG_CUDA(ctx, cudaHostAlloc(&ctx->dev_err, sizeof(unsigned int) * 4, cudaHostAllocMapped));
+    ctx->dev_err[0] = 0;
+    MPG_CUDA(ctx, cudaHostGetDevicePointer(&ctx->dev_err_d, ctx->dev_err, 0));
     {   // keep freed pool memory cached (see pool_alloc)
         cudaMemPool_t pool = nullptr;
         if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess && pool) {
@@ -61,6 +75,7 @@ extern "C" int mpg_ctx_destroy(mpg_ctx* ctx) {
     cudaFree(ctx->ticket);
     cudaFree(ctx->dscal);
     cudaFreeHost(ctx->hscal);
+    cudaFreeHost(ctx->dev_err);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return MPG_OK;
@@ -79,7 +94,7 @@ extern "C" int mpg_ctx_use_own_stream(mpg_ctx* ctx) {
 extern "C" void* mpg_ctx_stream(mpg_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 extern "C" int mpg_sync(mpg_ctx* ctx) {
     MPG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return MPG_OK;
+    return mpg::check_dev_err(ctx);
 }
 extern "C" const char* mpg_last_error(mpg_ctx* ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
 extern "C" int mpg_num_sms(mpg_ctx* ctx) { return ctx ? ctx->num_sms : 0; }
@@ -94,7 +109,7 @@ static int* tuning_slot(mpg_ctx* ctx, const std::string& k) {
     MPG_KNOB(vdirect_max_cols_a); MPG_KNOB(vdirect_max_cols_b); MPG_KNOB(vrow_max_cols); MPG_KNOB(vrow_max_cols_a); MPG_KNOB(gemvt_rb);
     MPG_KNOB(gemvt_rows_per_block); MPG_KNOB(passA_rb); MPG_KNOB(cgs2_fused); MPG_KNOB(vpass_serpentine); MPG_KNOB(gemvn_ctas_per_sm);
     MPG_KNOB(red_ctas_per_sm); MPG_KNOB(residual_packed); MPG_KNOB(values_static); MPG_KNOB(spmv_sigma); MPG_KNOB(mgs_fused);
-    MPG_KNOB(dist_fuse_halo); MPG_KNOB(spin_limit_ms); MPG_KNOB(lookahead);
+    MPG_KNOB(dist_fuse_halo); MPG_KNOB(spin_limit_ms); MPG_KNOB(lookahead); MPG_KNOB(sell_variant); MPG_KNOB(sell_block);
 #undef MPG_KNOB
     return nullptr;
 }

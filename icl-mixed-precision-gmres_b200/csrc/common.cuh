@@ -51,6 +51,8 @@ struct Tuning {
     int mgs_fused = 1;        // MGS: pairwise fused passes (w -= h_j v_j ; h_{j+1} = v_{j+1}.w in one kernel) instead of k+1 x {dot, naxpy}
     int dist_fuse_halo = 1;   // multi-GPU: halo gather-and-push rides in the Arnoldi tail kernel, the wait in the boundary-slice SpMV
     int spin_limit_ms = 20000; // multi-GPU: a device-side wait on a peer gives up after this long and raises the context's error word
+    int sell_variant = -1;    // packed SpMV kernel variant: bit 0 = x gathers bypass L1, bit 1 = 4 groups per step; -1 = chosen from the plan
+    int sell_block = 0;       // packed SpMV threads per CTA (0 = 256)
     int lookahead = 0;        // residual-driven restart policies: speculative Arnoldi steps in flight (0 = auto from a bandwidth estimate)
 };
 
@@ -90,6 +92,11 @@ struct mpg_ctx {
     struct mpg_dist* dist = nullptr;
     double* red_raw = nullptr;   // kMaxCols + 8 doubles
 
+    // error word written by device-side waits that gave up (bounded spins on a peer GPU): mapped pinned host memory, so the
+    // host can read it without synchronising; 0 = fine
+    unsigned int* dev_err = nullptr;        // host pointer
+    unsigned int* dev_err_d = nullptr;      // device alias
+
     // optional per-CTA phase timestamps of the staged V-pass kernels (mpg_debug_timing, tools/vpass_timeline.py)
     unsigned long long* dbg = nullptr;
 
@@ -116,9 +123,9 @@ struct mpg_csr {
     // column first, then the others - lets the solver run the former while the halo is in flight
     int* tile_list = nullptr;      // [ntiles] or null
     int n_interior_tiles = 0;
-    // packed structure per group size (slot 0: 4 = fp32, slot 1: 2 = fp64), built on first use (sell.cu)
-    mpg_sell_plan* sell[2] = {nullptr, nullptr};
-    int sell_tried[2] = {0, 0};
+    // packed structure (shared by the fp32 and fp64 value arrays), built on first use (sell.cu)
+    mpg_sell_plan* sell = nullptr;
+    int sell_tried = 0;
 };
 
 namespace mpg {
@@ -184,6 +191,7 @@ inline cudaError_t launch_pdl(mpg_ctx* ctx, int64_t rows, void (*kern)(KArgs...)
     } while (0)
 
 inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+int check_dev_err(mpg_ctx* ctx);   // blas1.cu
 
 // dist.cu: all-reduce `count` raw sums over the ranks and apply the epilogue (no-op when no communicator is attached)
 int dist_finish_reduction(mpg_ctx* ctx, const struct Epi& e, int count, int tbytes);
@@ -314,7 +322,45 @@ struct PeerComm {
     unsigned long long seq = 0;
     double* mbox[kMaxPeers];
     unsigned long long* flag[kMaxPeers];
+    unsigned int* err = nullptr;            // device error word (mpg_ctx::dev_err_d)
+    unsigned long long spin_limit_ns = 0;   // 0: wait for ever
 };
+
+// Bounded wait on a flag another GPU publishes: spins on an acquire load until *flag >= seq; after spin_limit_ns it gives up,
+// raises the context's error word (the host reports MPG_ERR_STATE at its next synchronisation) and lets the kernel finish
+// with whatever data is there - a dead or diverged peer no longer hangs every GPU of the job.
+enum { DEV_ERR_REDUCE_TIMEOUT = 1, DEV_ERR_HALO_TIMEOUT = 2 };
+__device__ __forceinline__ void wait_flag(const unsigned long long* flag, unsigned long long seq, unsigned long long limit_ns, unsigned int* err, unsigned int code) {
+    unsigned long long v;
+    unsigned long long t0 = 0;
+    unsigned int spins = 0;
+    for (;;) {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
+        if (v >= seq) return;
+        if (limit_ns && (++spins & 1023u) == 0) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+            if (t0 == 0) t0 = t;
+            else if (t - t0 > limit_ns) {
+                if (err) atomicOr(err, code);
+                return;
+            }
+        }
+    }
+}
+
+// halo of an SpMV input that neighbour GPUs push into this GPU's memory (dist.cu): the flags to wait for
+struct HaloWait {
+    int npeers = 0;
+    const unsigned long long* flag[kMaxPeers];
+    unsigned long long seq = 0;
+    unsigned int* err = nullptr;
+    unsigned long long spin_limit_ns = 0;
+};
+__device__ __forceinline__ void halo_wait_block(const HaloWait& hw) {
+    if ((int)threadIdx.x < hw.npeers) wait_flag(hw.flag[threadIdx.x], hw.seq, hw.spin_limit_ns, hw.err, DEV_ERR_HALO_TIMEOUT);
+    __syncthreads();
+}
 
 enum EpiKind { EPI_DOT = 0, EPI_NRM2 = 1, EPI_COEF = 2, EPI_COEF_ACCUM = 3, EPI_NORM_INV = 4, EPI_GEMVT = 5, EPI_MAX = 6 };
 struct Epi {
@@ -367,10 +413,7 @@ __device__ __forceinline__ void finish_reduction(const Epi& e, int count, double
             unsigned long long* f = e.peer.flag[threadIdx.x] + slot * P + r;
             asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(e.peer.seq) : "memory");
             const unsigned long long* mine = e.peer.flag[r] + slot * P + threadIdx.x;
-            unsigned long long v;
-            do {
-                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
-            } while (v < e.peer.seq);
+            wait_flag(mine, e.peer.seq, e.peer.spin_limit_ns, e.peer.err, DEV_ERR_REDUCE_TIMEOUT);
         }
         __syncthreads();
         for (int j = threadIdx.x; j < count; j += blockDim.x) {

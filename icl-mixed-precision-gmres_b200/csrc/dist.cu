@@ -109,15 +109,12 @@ __global__ void __launch_bounds__(256) halo_push_kernel(PushArgs a, const T* __r
 struct WaitArgs {
     int npeers;
     const unsigned long long* flag[kMaxPeers];   // own flags for (slot, neighbour)
+    unsigned int* err;
+    unsigned long long spin_limit_ns;
 };
 template <class T>
 __global__ void __launch_bounds__(256) halo_wait_copy_kernel(WaitArgs a, unsigned long long seq, const T* inbox, T* tail, long long n_halo) {
-    if ((int)threadIdx.x < a.npeers) {
-        unsigned long long v;
-        do {
-            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(a.flag[threadIdx.x]) : "memory");
-        } while (v < seq);
-    }
+    if ((int)threadIdx.x < a.npeers) wait_flag(a.flag[threadIdx.x], seq, a.spin_limit_ns, a.err, DEV_ERR_HALO_TIMEOUT);
     __syncthreads();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_halo; i += (long long)gridDim.x * blockDim.x) tail[i] = __ldcv(inbox + i);
 }
@@ -304,6 +301,8 @@ Epi make_epi(mpg_ctx* ctx, int kind, void* p0, void* p1, double alpha, double be
         e.peer.world = d->world;
         e.peer.rank = d->rank;
         e.peer.seq = ++d->seq;   // every rank issues the same sequence of reductions
+        e.peer.err = ctx->dev_err_d;
+        e.peer.spin_limit_ns = (unsigned long long)std::max(ctx->tune.spin_limit_ms, 0) * 1000000ull;
         for (int q = 0; q < d->world; ++q) {
             e.peer.mbox[q] = static_cast<double*>(d->mbox_map[q]);
             e.peer.flag[q] = reinterpret_cast<unsigned long long*>(static_cast<char*>(d->mbox_map[q]) + d->mbox_data_bytes());
@@ -381,6 +380,8 @@ int halo_finish(mpg_ctx* ctx, T* x_ext) {
     const int slot = (int)(seq & 1);
     WaitArgs wa;
     wa.npeers = (int)d->peers.size();
+    wa.err = ctx->dev_err_d;
+    wa.spin_limit_ns = (unsigned long long)std::max(ctx->tune.spin_limit_ms, 0) * 1000000ull;
     for (size_t i = 0; i < d->peers.size(); ++i)
         wa.flag[i] = reinterpret_cast<const unsigned long long*>(static_cast<char*>(d->inbox_own) + d->inbox_data_bytes()) + slot * kMaxPeers + d->peers[i].rank;
     const T* inbox = reinterpret_cast<const T*>(static_cast<char*>(d->inbox_own) + (size_t)slot * (size_t)std::max<int64_t>(d->n_halo, 1) * 8);

@@ -1,25 +1,34 @@
-// sell.cu — packed SpMV operator: the CSR matrix re-laid as 32-row slices (sliced ELLPACK, SELL-32).
+// sell.cu — packed SpMV operator: the CSR matrix re-laid as 32-lane slices stored position-major (sliced ELLPACK).
 // Reference surface: the same y = alpha*A*x + beta*y of kernels.hpp:159-165; the packed form plays the role of the
 // reference's per-matrix library handles (create_cuda_handles, types_cuda.hpp:53-60: cusparse descriptors built once
 // per SparseMatrix and re-used by every spmv call).
 //
 // Why: the CSR kernel (spmv.cu) streams the matrix perfectly but gathers x with one thread per NONZERO, so one warp
 // gather touches ~10 different 128-byte lines of x (ncu: the kernel is L1TEX-tag bound at 73-77 % of the HBM
-// roofline, profiles/r01_ncu_summary.md).  In the packed layout one warp owns 32 consecutive rows and lane = row:
-//   * the p-th nonzeros of the 32 rows are adjacent in memory, G at a time per lane (G = 16 B / sizeof(T)), so
-//     indices and values are still read with fully coalesced 16-byte streaming loads;
-//   * a warp gather reads x[col_p(row)] for 32 consecutive rows - for stencil-like matrices 32 nearly consecutive
-//     entries of x: 1-2 lines instead of ~10;
-//   * every row is summed by its own lane in nonzero order: no shared memory, no cross-thread reduction, no
-//     rows cut by tile boundaries, no fix-up kernel.
-// Layout: slice s covers rows [32 s, 32 s + 32) and holds 32 * L_s elements, L_s = longest row of the slice.  The
-// first floor(L_s / G) * G positions are stored in groups of G per lane: element (row r, position p) lives at
-// slice_off[s] + (p / G) * 32 * G + (r % 32) * G + p % G; the remaining L_s % G positions are stored one per lane:
-// slice_off[s] + floor(L_s / G) * 32 * G + (p % G) * 32 + r % 32.  (L_s itself is rounded up to a multiple of G when
-// that costs at most 10 % padding.)  Shorter rows are padded by repeating their first column with value 0.  Matrices whose row lengths vary too much inside slices (padding > 25 %: the
-// power-law case) are not packed - callers keep the CSR kernel.
-// The packed INDICES depend only on the structure and are cached in the mpg_csr plan (one per G); the packed VALUES
-// belong to an mpg_packed object and are refreshed with mpg_pack_update.
+// roofline, profiles/r01_ncu_summary.md).  In the packed layout one warp owns 32 rows and lane = row:
+//   * the p-th nonzeros of the 32 rows are adjacent in memory, 4 at a time per lane, so indices and values are still
+//     read with fully coalesced 16-byte streaming loads;
+//   * a warp gather reads x[col_p(row)] for 32 rows - for stencil-like matrices 32 nearly consecutive entries of x:
+//     1-2 lines instead of ~10;
+//   * every row is summed by its own lane in nonzero order: no shared memory, no cross-thread reduction, no fix-up.
+//
+// Two structures, chosen per matrix (mpg_sell_plan::mode):
+//   PLAIN  slice s = rows [32 s, 32 s + 32).  Stencil-like matrices (padding <= 25 %).
+//   SIGMA  SELL-C-sigma for uneven row lengths (power-law): rows longer than CHUNK = 256 nonzeros are cut into
+//          "virtual rows" of at most CHUNK nonzeros; the virtual rows are sorted by length (descending, ties by index)
+//          inside windows of SIGMA = 4096 virtual rows; slice s = sorted positions [32 s, 32 s + 32).  A lane writes its
+//          sum to the row it stands for (vout[pos] >= 0) or, for a piece of a cut row, to partial[-1 - vout[pos]]; a
+//          small fix-up kernel adds the pieces of each cut row in nonzero order and applies the epilogue.  Per-row
+//          nonzero order is preserved inside every piece, results are bit-reproducible, y stays in caller order.
+// Layout of a slice (both modes): 32 * L_s elements, L_s = longest (virtual) row of the slice, rounded up to a whole
+// group of G = 4 when that pads <= 10 %.  The first floor(L_s / 4) * 4 positions are stored in groups of 4 per lane:
+// index of (lane l, position p) at slice_off[s] + (p / 4) * 128 + l * 4 + p % 4; the L_s % 4 trailing positions one per
+// lane: slice_off[s] + floor(L_s / 4) * 128 + (p % 4) * 32 + l.  fp32 values use the same addresses.  fp64 values share the
+// SAME index array (the reference's SparseMatrix<float> aliases row_map / inds of the fp64 matrix, types_cuda.hpp:82-91)
+// and store each group as two half-groups so that both 16-byte loads of a warp are fully coalesced:
+// (p / 4) * 128 + ((p % 4) / 2) * 64 + l * 2 + p % 2.  Shorter rows are padded by repeating their first column with
+// value 0.  The packed INDICES depend only on the structure and are cached in the mpg_csr plan; the packed VALUES belong
+// to an mpg_packed object and are refreshed with mpg_pack_update.
 #include <vector>
 
 #include "common.cuh"
@@ -29,50 +38,60 @@ using namespace mpg;
 namespace {
 
 constexpr int SLICE = 32;
-
-template <class T> struct Grp;
-template <> struct Grp<float> { static constexpr int G = 4; using IV = int4; using VV = float4; };
-template <> struct Grp<double> { static constexpr int G = 2; using IV = int2; using VV = double2; };
-
-__device__ __forceinline__ int2 ldg_stream2(const int2* p) {
-    int2 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v2.s32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
-    return r;
-}
-__device__ __forceinline__ int4 ldg_idx(const int4* p) { return ldg_stream(p); }
-__device__ __forceinline__ int2 ldg_idx(const int2* p) { return ldg_stream2(p); }
+constexpr int G = 4;
+constexpr int CHUNK = 256;     // longest virtual row (multiple of G)
+constexpr int SIGMA = 4096;    // sorting window in virtual rows (multiple of SLICE, power of two for the bitonic network)
+enum { MODE_PLAIN = 0, MODE_SIGMA = 1 };
 
 __device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
 __device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
 __device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
 __device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
 
-// slice_len[s] = 32 * L_s (elements); L_s = longest row, rounded up to a whole group when that costs <= 10 % padding
-// (one more 16-byte group is cheaper than up to G-1 single-element loads: cd27 27 -> 28; lap2d stays at 5 = 4 + 1)
-__global__ void sell_len_kernel(int nrows, int nslices, const int* __restrict__ row_map, int G, int64_t* __restrict__ slice_len, int* has_rem) {
+// where lane `pos` (a row in PLAIN mode, a sorted virtual row in SIGMA mode) finds its nonzeros in the CSR arrays
+struct LaneSrc {
+    int nrows;                 // PLAIN: rows; SIGMA: virtual rows
+    const int* row_map;        // PLAIN
+    const int* vstart;         // SIGMA: CSR offset of the first nonzero of the sorted virtual row
+    const int* vlen;           // SIGMA
+    __device__ __forceinline__ void get(int pos, int& start, int& len) const {
+        if (pos >= nrows) { start = 0; len = 0; return; }
+        if (vstart) { start = __ldg(vstart + pos); len = __ldg(vlen + pos); }
+        else { start = __ldg(row_map + pos); len = __ldg(row_map + pos + 1) - start; }
+    }
+};
+
+__device__ __forceinline__ int round_len(int len) {
+    const int rem = len % G;
+    if (rem > 0 && (G - rem) * 10 <= len) len += G - rem;   // one more 16-byte group is cheaper than up to 3 single-element loads: cd27 27 -> 28; lap2d stays 4 + 1
+    return len;
+}
+
+// slice_len[s] = 32 * L_s (elements)
+__global__ void sell_len_kernel(LaneSrc src, int nslices, int64_t* __restrict__ slice_len, int* has_rem) {
     const int s = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
     if (s >= nslices) return;
-    const int r = s * SLICE + lane;
-    int len = (r < nrows) ? __ldg(row_map + r + 1) - __ldg(row_map + r) : 0;
+    int start, len;
+    src.get(s * SLICE + lane, start, len);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, o));
-    const int rem = len % G;
-    if (rem > 0 && (G - rem) * 10 <= len) len += G - rem;
+    len = round_len(len);
     if (lane == 0) {
         slice_len[s] = (int64_t)len * SLICE;
         if (len % G) *has_rem = 1;   // benign race: every writer stores 1
     }
 }
 
-// exclusive prefix sum of n slice lengths, out[n] = total.  One 1024-thread block: per-thread chunk sums, Hillis-Steele
-// over the 1024 chunk sums, per-thread chunk write-out.  Plan-time only (4 MB at 16.7 M rows).
-__global__ void __launch_bounds__(1024) sell_scan_kernel(int n, const int64_t* __restrict__ in, int64_t* __restrict__ out) {
+// exclusive prefix sum of n values, out[n] = total.  One 1024-thread block: per-thread chunk sums, Hillis-Steele over the
+// 1024 chunk sums, per-thread chunk write-out.  Plan-time only.
+template <class TI, class TO>
+__global__ void __launch_bounds__(1024) scan_kernel(int64_t n, const TI* __restrict__ in, TO* __restrict__ out) {
     __shared__ int64_t part[1024];
     const int t = threadIdx.x;
-    const int chunk = (n + 1023) / 1024;
-    const int lo = min(t * chunk, n), hi = min(lo + chunk, n);
+    const int64_t chunk = (n + 1023) / 1024;
+    const int64_t lo = min((int64_t)t * chunk, n), hi = min(lo + chunk, n);
     int64_t s = 0;
-    for (int i = lo; i < hi; ++i) s += in[i];
+    for (int64_t i = lo; i < hi; ++i) s += (int64_t)in[i];
     part[t] = s;
     __syncthreads();
     for (int off = 1; off < 1024; off <<= 1) {
@@ -82,24 +101,86 @@ __global__ void __launch_bounds__(1024) sell_scan_kernel(int n, const int64_t* _
         __syncthreads();
     }
     int64_t run = t ? part[t - 1] : 0;
-    for (int i = lo; i < hi; ++i) {
-        out[i] = run;
-        run += in[i];
+    for (int64_t i = lo; i < hi; ++i) {
+        const int64_t v = (int64_t)in[i];
+        out[i] = (TO)run;
+        run += v;
     }
-    if (t == 1023) out[n] = part[1023];
+    if (t == 1023) out[n] = (TO)part[1023];
 }
 
-// packed indices (structure); warp = slice, lane = row.  halo_flag[s] = 1 if the slice references a column >= nrows
-template <int G>
-__global__ void sell_fill_inds_kernel(int nrows, int nslices, const int* __restrict__ row_map, const int* __restrict__ inds,
-                                      const int64_t* __restrict__ slice_off, int* __restrict__ sinds, int* __restrict__ halo_flag) {
+// ---- SIGMA structure -------------------------------------------------------------------------------------------------
+// per row: number of virtual rows, and that number again if the row is cut (0 otherwise)
+__global__ void vrow_count_kernel(int nrows, const int* __restrict__ row_map, int* __restrict__ nch, int* __restrict__ is_split, int* __restrict__ nch_split) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nrows) return;
+    const int len = row_map[r + 1] - row_map[r];
+    const int c = max(1, (len + CHUNK - 1) / CHUNK);
+    nch[r] = c;
+    is_split[r] = c > 1;
+    nch_split[r] = c > 1 ? c : 0;
+}
+// virtual rows in (row, piece) order: CSR offset, length, destination
+__global__ void vrow_fill_kernel(int nrows, const int* __restrict__ row_map, const int* __restrict__ vrow_off, const int* __restrict__ split_off,
+                                 const int* __restrict__ chunk_off, int* __restrict__ vstart, int* __restrict__ vlen, int* __restrict__ vout,
+                                 int* __restrict__ split_rows, int* __restrict__ chunk_base) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nrows) return;
+    const int rs = row_map[r], len = row_map[r + 1] - rs;
+    const int v0 = vrow_off[r], c = vrow_off[r + 1] - v0;
+    if (c == 1) { vstart[v0] = rs; vlen[v0] = len; vout[v0] = r; return; }
+    const int j = split_off[r], p0 = chunk_off[r];
+    split_rows[j] = r;
+    chunk_base[j] = p0;
+    for (int q = 0; q < c; ++q) {
+        vstart[v0 + q] = rs + q * CHUNK;
+        vlen[v0 + q] = min(CHUNK, len - q * CHUNK);
+        vout[v0 + q] = -1 - (p0 + q);
+    }
+}
+// one CTA per window of SIGMA virtual rows: bitonic sort of the unique keys ((CHUNK - len) << 12 | index in window), i.e.
+// by length descending, ties by index ascending; writes the three per-lane arrays in sorted order
+__global__ void __launch_bounds__(512) vrow_sort_kernel(int nv, const int* __restrict__ vstart, const int* __restrict__ vlen, const int* __restrict__ vout,
+                                                         int* __restrict__ sstart, int* __restrict__ slen, int* __restrict__ sout) {
+    __shared__ unsigned int key[SIGMA];
+    const int base = blockIdx.x * SIGMA;
+    for (int i = threadIdx.x; i < SIGMA; i += blockDim.x) {
+        const int v = base + i;
+        key[i] = v < nv ? (((unsigned)(CHUNK - vlen[v])) << 12) | (unsigned)i : 0xffffffffu;   // past the end: sorts last
+    }
+    __syncthreads();
+    for (int k = 2; k <= SIGMA; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < SIGMA; i += blockDim.x) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const unsigned a = key[i], b = key[ixj];
+                    const bool up = (i & k) == 0;
+                    if ((a > b) == up) { key[i] = b; key[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = threadIdx.x; i < SIGMA; i += blockDim.x) {
+        const int pos = base + i;
+        if (pos >= nv) continue;
+        const int v = base + (int)(key[i] & 0xfffu);
+        sstart[pos] = vstart[v];
+        slen[pos] = vlen[v];
+        sout[pos] = vout[v];
+    }
+}
+
+// packed indices (structure); warp = slice, lane = (virtual) row.  halo_flag[s] = 1 if the slice references a column >= halo_from
+__global__ void sell_fill_inds_kernel(LaneSrc src, int nslices, int halo_from, const int* __restrict__ inds, const int64_t* __restrict__ slice_off,
+                                      int* __restrict__ sinds, int* __restrict__ halo_flag) {
     const int s = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
     if (s >= nslices) return;
-    const int r = s * SLICE + lane;
     const int64_t off = slice_off[s];
     const int L = (int)((slice_off[s + 1] - off) / SLICE);
-    const int rs = (r < nrows) ? __ldg(row_map + r) : 0;
-    const int len = (r < nrows) ? __ldg(row_map + r + 1) - rs : 0;
+    int rs, len;
+    src.get(s * SLICE + lane, rs, len);
     const int pad = len > 0 ? __ldg(inds + rs) : 0;
     int any_halo = 0;
     const int ng = L / G;
@@ -109,15 +190,13 @@ __global__ void sell_fill_inds_kernel(int nrows, int nslices, const int* __restr
         for (int q = 0; q < G; ++q) {
             const int p = g * G + q;
             c[q] = p < len ? __ldg(inds + rs + p) : pad;
-            any_halo |= c[q] >= nrows;
+            any_halo |= c[q] >= halo_from;
         }
-        int* dst = sinds + off + (int64_t)g * SLICE * G + lane * G;
-#pragma unroll
-        for (int q = 0; q < G; ++q) dst[q] = c[q];
+        *reinterpret_cast<int4*>(sinds + off + (int64_t)g * SLICE * G + lane * G) = make_int4(c[0], c[1], c[2], c[3]);
     }
     for (int p = ng * G; p < L; ++p) {
         const int c = p < len ? __ldg(inds + rs + p) : pad;
-        any_halo |= c >= nrows;
+        any_halo |= c >= halo_from;
         sinds[off + (int64_t)ng * SLICE * G + (int64_t)(p - ng * G) * SLICE + lane] = c;
     }
     any_halo = __any_sync(0xffffffffu, any_halo);
@@ -125,97 +204,154 @@ __global__ void sell_fill_inds_kernel(int nrows, int nslices, const int* __restr
 }
 
 template <class T>
-__global__ void sell_fill_vals_kernel(int nrows, int nslices, const int* __restrict__ row_map, const T* __restrict__ vals,
-                                      const int64_t* __restrict__ slice_off, T* __restrict__ svals) {
-    constexpr int G = Grp<T>::G;
+__global__ void sell_fill_vals_kernel(LaneSrc src, int nslices, const T* __restrict__ vals, const int64_t* __restrict__ slice_off, T* __restrict__ svals) {
     const int s = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
     if (s >= nslices) return;
-    const int r = s * SLICE + lane;
     const int64_t off = slice_off[s];
     const int L = (int)((slice_off[s + 1] - off) / SLICE);
-    const int rs = (r < nrows) ? __ldg(row_map + r) : 0;
-    const int len = (r < nrows) ? __ldg(row_map + r + 1) - rs : 0;
+    int rs, len;
+    src.get(s * SLICE + lane, rs, len);
     const int ng = L / G;
     for (int g = 0; g < ng; ++g) {
-        typename Grp<T>::VV o;
-        T* po = reinterpret_cast<T*>(&o);
+        T v[G];
 #pragma unroll
         for (int q = 0; q < G; ++q) {
             const int p = g * G + q;
-            po[q] = p < len ? __ldg(vals + rs + p) : T(0);
+            v[q] = p < len ? __ldg(vals + rs + p) : T(0);
         }
-        *reinterpret_cast<typename Grp<T>::VV*>(svals + off + (int64_t)g * SLICE * G + lane * G) = o;
+        T* dst = svals + off + (int64_t)g * SLICE * G;
+        if (sizeof(T) == 4) {
+            *reinterpret_cast<float4*>(dst + lane * G) = make_float4((float)v[0], (float)v[1], (float)v[2], (float)v[3]);
+        } else {
+            *reinterpret_cast<double2*>(dst + lane * 2) = make_double2((double)v[0], (double)v[1]);
+            *reinterpret_cast<double2*>(dst + 64 + lane * 2) = make_double2((double)v[2], (double)v[3]);
+        }
     }
     for (int p = ng * G; p < L; ++p) svals[off + (int64_t)ng * SLICE * G + (int64_t)(p - ng * G) * SLICE + lane] = p < len ? __ldg(vals + rs + p) : T(0);
 }
 
+// one group of a lane: 4 values
+__device__ __forceinline__ void load_group(const float* gbase, int lane, float v[4]) {
+    const float4 t = ldg_stream(reinterpret_cast<const float4*>(gbase) + lane);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+__device__ __forceinline__ void load_group(const double* gbase, int lane, double v[4]) {
+    const double2 a = ldg_stream(reinterpret_cast<const double2*>(gbase) + lane);
+    const double2 b = ldg_stream(reinterpret_cast<const double2*>(gbase + 64) + lane);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+
+template <class T>
+__device__ __forceinline__ T sell_epilogue(int r, T sum, T alpha, T beta, const T* y_in, const T* __restrict__ rowscale) {
+    T v = (beta == T(0)) ? alpha * sum : fma(alpha, sum, beta * y_in[r]);
+    if (rowscale) {   // Jacobi: gdmv(1, d, v, 0, v), rounding sequence of the stand-alone kernel (kernels.hpp:143-145)
+        const T d = __ldg(rowscale + r);
+        v = add_rn(mul_rn(T(0), v), mul_rn(mul_rn(T(1), d), v));
+    }
+    return v;
+}
+
 // y[r] = alpha * sum_p v[r,p] x[c[r,p]] + beta * y[r]; products and sums individually rounded, nonzero order
 // (the CSR kernel's arithmetic for a row that lies inside one tile).
-template <class T, bool HAS_REM>
-__global__ void __launch_bounds__(256) spmv_sell_kernel(int nrows, int nslices, const int64_t* __restrict__ slice_off, const int* __restrict__ sinds,
+//   vout == null (PLAIN): lane `pos` is row `pos`.   vout != null (SIGMA): see the header comment.
+//   halo_wait != null: the slices of this launch read halo entries of x that a neighbour GPU is pushing (dist.cu); every CTA
+//   waits for the neighbours' exchange numbers before its first access to x.
+// gather of x: through L1 (stencil matrices: neighbouring lanes and rows share lines) or around it (NA: random columns never hit)
+template <bool NA> __device__ __forceinline__ float ldx(const float* p) { return NA ? ldg_stream(p) : __ldg(p); }
+template <bool NA> __device__ __forceinline__ double ldx(const double* p) { return NA ? ldg_stream(p) : __ldg(p); }
+
+template <class T, bool HAS_REM, bool NA, int UN>
+__global__ void __launch_bounds__(256, UN == 4 ? 5 : (sizeof(T) == 8 ? 6 : 8)) spmv_sell_kernel(int nlanes, int nslices, const int64_t* __restrict__ slice_off, const int* __restrict__ sinds,
                                                          const T* __restrict__ svals, const T* __restrict__ x, T alpha, T beta, const T* y_in,
-                                                         T* y_out, float* out32, const T* __restrict__ rowscale, const int* __restrict__ slice_list) {
-    constexpr int G = Grp<T>::G;
-    using IV = typename Grp<T>::IV;
-    using VV = typename Grp<T>::VV;
+                                                         T* y_out, float* out32, const T* __restrict__ rowscale, const int* __restrict__ slice_list,
+                                                         const int* __restrict__ vout, T* __restrict__ partial, const __grid_constant__ HaloWait hw) {
     pdl_trigger();
     pdl_wait();
+    if (hw.npeers > 0) halo_wait_block(hw);
     const int ws = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
     if (ws >= nslices) return;
     const int s = slice_list ? __ldg(slice_list + ws) : ws;
     const int64_t off = __ldg(slice_off + s);
     const int L = (int)((__ldg(slice_off + s + 1) - off) / SLICE);
     const int ng = L / G;
-    const IV* ip = reinterpret_cast<const IV*>(sinds + off) + lane;
-    const VV* vp = reinterpret_cast<const VV*>(svals + off) + lane;
+    const int4* ip = reinterpret_cast<const int4*>(sinds + off) + lane;
+    const T* vbase = svals + off;
     T sum = T(0);
     int g = 0;
-    // two groups per step: 4 streaming loads in flight, then 2 G gathers
-    for (; g + 2 <= ng; g += 2) {
-        const IV c0 = ldg_idx(ip + (size_t)g * SLICE), c1 = ldg_idx(ip + (size_t)(g + 1) * SLICE);
-        const VV v0 = ldg_stream(vp + (size_t)g * SLICE), v1 = ldg_stream(vp + (size_t)(g + 1) * SLICE);
-        const int* pc0 = reinterpret_cast<const int*>(&c0);
-        const int* pc1 = reinterpret_cast<const int*>(&c1);
-        const T* pv0 = reinterpret_cast<const T*>(&v0);
-        const T* pv1 = reinterpret_cast<const T*>(&v1);
-        T xv[2 * G];
+    // UN groups per step: the streaming loads of all of them in flight, then 4 UN gathers, then the row sum in nonzero order
+    for (; g + UN <= ng; g += UN) {
+        int4 c[UN];
+        T v[UN][4];
 #pragma unroll
-        for (int q = 0; q < G; ++q) { xv[q] = __ldg(x + pc0[q]); xv[G + q] = __ldg(x + pc1[q]); }
+        for (int u = 0; u < UN; ++u) c[u] = ldg_stream(ip + (size_t)(g + u) * SLICE);
 #pragma unroll
-        for (int q = 0; q < G; ++q) sum = add_rn(sum, mul_rn(pv0[q], xv[q]));
+        for (int u = 0; u < UN; ++u) load_group(vbase + (size_t)(g + u) * SLICE * G, lane, v[u]);
+        T xv[UN][4];
 #pragma unroll
-        for (int q = 0; q < G; ++q) sum = add_rn(sum, mul_rn(pv1[q], xv[G + q]));
+        for (int u = 0; u < UN; ++u) { xv[u][0] = ldx<NA>(x + c[u].x); xv[u][1] = ldx<NA>(x + c[u].y); xv[u][2] = ldx<NA>(x + c[u].z); xv[u][3] = ldx<NA>(x + c[u].w); }
+#pragma unroll
+        for (int u = 0; u < UN; ++u)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) sum = add_rn(sum, mul_rn(v[u][q], xv[u][q]));
     }
-    if (g < ng) {
-        const IV c0 = ldg_idx(ip + (size_t)g * SLICE);
-        const VV v0 = ldg_stream(vp + (size_t)g * SLICE);
-        const int* pc0 = reinterpret_cast<const int*>(&c0);
-        const T* pv0 = reinterpret_cast<const T*>(&v0);
-#pragma unroll
-        for (int q = 0; q < G; ++q) sum = add_rn(sum, mul_rn(pv0[q], __ldg(x + pc0[q])));
+    for (; g < ng; ++g) {
+        const int4 c0 = ldg_stream(ip + (size_t)g * SLICE);
+        T v0[4];
+        load_group(vbase + (size_t)g * SLICE * G, lane, v0);
+        const T x0 = ldx<NA>(x + c0.x), x1 = ldx<NA>(x + c0.y), x2 = ldx<NA>(x + c0.z), x3 = ldx<NA>(x + c0.w);
+        sum = add_rn(sum, mul_rn(v0[0], x0));
+        sum = add_rn(sum, mul_rn(v0[1], x1));
+        sum = add_rn(sum, mul_rn(v0[2], x2));
+        sum = add_rn(sum, mul_rn(v0[3], x3));
     }
-    // the L % G trailing positions, one element per lane (compiled out for plans whose slices are all whole groups)
+    // the L % 4 trailing positions, one element per lane (compiled out for plans whose slices are all whole groups)
     if (HAS_REM) {
         const int* it = sinds + off + (int64_t)ng * SLICE * G + lane;
         const T* vt = svals + off + (int64_t)ng * SLICE * G + lane;
-        for (int t = 0; t < L - ng * G; ++t) sum = add_rn(sum, mul_rn(ldg_stream(vt + t * SLICE), __ldg(x + ldg_stream(it + t * SLICE))));
+        const int nt = L - ng * G;
+        int ct[3];
+        T vv[3];
+#pragma unroll
+        for (int t = 0; t < 3; ++t) if (t < nt) { ct[t] = ldg_stream(it + t * SLICE); vv[t] = ldg_stream(vt + t * SLICE); }
+        T xt[3];
+#pragma unroll
+        for (int t = 0; t < 3; ++t) if (t < nt) xt[t] = ldx<NA>(x + ct[t]);
+#pragma unroll
+        for (int t = 0; t < 3; ++t) if (t < nt) sum = add_rn(sum, mul_rn(vv[t], xt[t]));
     }
-    const int r = s * SLICE + lane;
-    if (r < nrows) {
-        T v = (beta == T(0)) ? alpha * sum : fma(alpha, sum, beta * y_in[r]);
-        if (rowscale) {   // Jacobi: gdmv(1, d, v, 0, v), rounding sequence of the stand-alone kernel (kernels.hpp:143-145)
-            const T d = __ldg(rowscale + r);
-            v = add_rn(mul_rn(T(0), v), mul_rn(mul_rn(T(1), d), v));
-        }
-        if (y_out) y_out[r] = v;
-        if (out32) out32[r] = (float)v;
+    const int pos = s * SLICE + lane;
+    if (pos >= nlanes) return;
+    int r = pos;
+    if (vout) {
+        r = __ldg(vout + pos);
+        if (r < 0) { partial[-1 - r] = sum; return; }   // a piece of a cut row: sell_fixup_kernel finishes it
     }
+    const T v = sell_epilogue<T>(r, sum, alpha, beta, y_in, rowscale);
+    if (y_out) y_out[r] = v;
+    if (out32) out32[r] = (float)v;
+}
+
+// SIGMA mode: one thread per cut row adds its pieces in nonzero order and applies the epilogue
+template <class T>
+__global__ void sell_fixup_kernel(int nsplit, const int* __restrict__ split_rows, const int* __restrict__ chunk_base, const T* __restrict__ partial,
+                                  T alpha, T beta, const T* y_in, T* y_out, float* out32, const T* __restrict__ rowscale) {
+    pdl_trigger();
+    pdl_wait();
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nsplit) return;
+    const int r = split_rows[j];
+    T sum = T(0);
+    for (int p = chunk_base[j], pe = chunk_base[j + 1]; p < pe; ++p) sum = add_rn(sum, partial[p]);
+    const T v = sell_epilogue<T>(r, sum, alpha, beta, y_in, rowscale);
+    if (y_out) y_out[r] = v;
+    if (out32) out32[r] = (float)v;
 }
 
 }  // namespace
 
 struct mpg_sell_plan {
-    int G = 0;
+    int mode = MODE_PLAIN;
+    int nlanes = 0;                // PLAIN: rows; SIGMA: virtual rows
     int nslices = 0;
     int64_t total = 0;             // padded element count
     int64_t* slice_off = nullptr;  // [nslices + 1]
@@ -223,6 +359,15 @@ struct mpg_sell_plan {
     int* slice_list = nullptr;     // partitioned matrices: slices without halo columns first
     int n_interior = 0;
     int has_rem = 0;               // some slice length is not a multiple of G
+    // SIGMA
+    int* vstart = nullptr;         // [nlanes] sorted order
+    int* vlen = nullptr;
+    int* vout = nullptr;
+    int nsplit = 0;                // rows cut into pieces
+    int nchunks = 0;               // pieces of cut rows
+    int* split_rows = nullptr;     // [nsplit]
+    int* chunk_base = nullptr;     // [nsplit + 1]
+    void* partial = nullptr;       // [nchunks] doubles (either precision)
     unsigned long long uid = 0;    // distinguishes plans that happen to be allocated at the same address
 };
 
@@ -240,46 +385,100 @@ namespace mpg {
 void sell_plan_free(mpg_sell_plan* p) {
     if (!p) return;
     cudaFree(p->slice_off); cudaFree(p->sinds); cudaFree(p->slice_list);
+    cudaFree(p->vstart); cudaFree(p->vlen); cudaFree(p->vout); cudaFree(p->split_rows); cudaFree(p->chunk_base); cudaFree(p->partial);
     delete p;
 }
 
-// build (or fetch) the packed structure for group size G; *out = nullptr if the matrix does not pack well
-int sell_plan_get(mpg_ctx* ctx, const mpg_csr* A, int G, const mpg_sell_plan** out) {
-    *out = nullptr;
-    mpg_csr* Am = const_cast<mpg_csr*>(A);
-    const int slot = (G == 4) ? 0 : 1;
-    if (Am->sell_tried[slot]) { *out = Am->sell[slot]; return MPG_OK; }
-    Am->sell_tried[slot] = 1;
-    if (A->nrows == 0 || A->nnz == 0) return MPG_OK;
-    static unsigned long long next_uid = 0;
-    mpg_sell_plan* p = new mpg_sell_plan();
-    p->uid = ++next_uid;
-    p->G = G;
-    p->nslices = (int)cdiv(A->nrows, SLICE);
+static LaneSrc lane_src(const mpg_csr* A, const mpg_sell_plan* p) {
+    return p->mode == MODE_SIGMA ? LaneSrc{p->nlanes, nullptr, p->vstart, p->vlen} : LaneSrc{A->nrows, A->row_map, nullptr, nullptr};
+}
+
+// slice lengths -> slice_off, total, has_rem for the plan's current lane source
+static int plan_slices(mpg_ctx* ctx, const mpg_csr* A, mpg_sell_plan* p) {
+    p->nslices = (int)cdiv(p->nlanes, SLICE);
     int64_t* len = nullptr;
     MPG_CUDA(ctx, pool_alloc(ctx, &len, sizeof(int64_t) * (size_t)(p->nslices + 2)));
+    cudaFree(p->slice_off);
+    p->slice_off = nullptr;
     MPG_CUDA(ctx, pool_alloc(ctx, &p->slice_off, sizeof(int64_t) * (size_t)(p->nslices + 1)));
     MPG_CUDA(ctx, cudaMemsetAsync(len, 0, sizeof(int64_t) * (size_t)(p->nslices + 2), ctx->stream));
-    const int wgrid = (int)cdiv((int64_t)p->nslices * 32, 256);
-    // len[nslices] (the scan's total slot, zero) doubles as the has_rem flag until the scan has consumed it... keep it separate:
     int* rem_flag = reinterpret_cast<int*>(len + p->nslices + 1);
-    sell_len_kernel<<<wgrid, 256, 0, ctx->stream>>>(A->nrows, p->nslices, A->row_map, G, len, rem_flag);
+    sell_len_kernel<<<(int)cdiv((int64_t)p->nslices * 32, 256), 256, 0, ctx->stream>>>(lane_src(A, p), p->nslices, len, rem_flag);
     MPG_CHECK_LAUNCH(ctx);
-    sell_scan_kernel<<<1, 1024, 0, ctx->stream>>>(p->nslices, len, p->slice_off);
+    scan_kernel<int64_t, int64_t><<<1, 1024, 0, ctx->stream>>>((int64_t)p->nslices, len, p->slice_off);
     MPG_CHECK_LAUNCH(ctx);
     MPG_CUDA(ctx, cudaMemcpyAsync(&p->total, p->slice_off + p->nslices, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
     MPG_CUDA(ctx, cudaMemcpyAsync(&p->has_rem, rem_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     MPG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     cudaFree(len);
-    if ((double)p->total > 1.25 * (double)A->nnz + 4096.0 || p->total >= (int64_t)1 << 40) {   // too much padding: keep CSR
-        sell_plan_free(p);
-        return MPG_OK;
+    return MPG_OK;
+}
+
+// virtual rows, sorted inside windows (see the header comment)
+static int plan_sigma(mpg_ctx* ctx, const mpg_csr* A, mpg_sell_plan* p) {
+    const int n = A->nrows;
+    int *nch = nullptr, *is_split = nullptr, *nch_split = nullptr, *vrow_off = nullptr, *split_off = nullptr, *chunk_off = nullptr;
+    int *vstart = nullptr, *vlen = nullptr, *vout = nullptr;
+    auto drop = [&]() { cudaFree(nch); cudaFree(is_split); cudaFree(nch_split); cudaFree(vrow_off); cudaFree(split_off); cudaFree(chunk_off);
+                        cudaFree(vstart); cudaFree(vlen); cudaFree(vout); };
+#define MPG_CUDA_D(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { (void)cudaGetLastError(); drop(); return fail(ctx, MPG_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); } } while (0)
+    const size_t nb = sizeof(int) * (size_t)(n + 1);
+    MPG_CUDA_D(pool_alloc(ctx, &nch, nb)); MPG_CUDA_D(pool_alloc(ctx, &is_split, nb)); MPG_CUDA_D(pool_alloc(ctx, &nch_split, nb));
+    MPG_CUDA_D(pool_alloc(ctx, &vrow_off, nb)); MPG_CUDA_D(pool_alloc(ctx, &split_off, nb)); MPG_CUDA_D(pool_alloc(ctx, &chunk_off, nb));
+    vrow_count_kernel<<<(int)cdiv(n, 256), 256, 0, ctx->stream>>>(n, A->row_map, nch, is_split, nch_split);
+    scan_kernel<int, int><<<1, 1024, 0, ctx->stream>>>((int64_t)n, nch, vrow_off);
+    scan_kernel<int, int><<<1, 1024, 0, ctx->stream>>>((int64_t)n, is_split, split_off);
+    scan_kernel<int, int><<<1, 1024, 0, ctx->stream>>>((int64_t)n, nch_split, chunk_off);
+    ctx->launches += 4;
+    int tot[3] = {0, 0, 0};
+    MPG_CUDA_D(cudaMemcpyAsync(&tot[0], vrow_off + n, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    MPG_CUDA_D(cudaMemcpyAsync(&tot[1], split_off + n, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    MPG_CUDA_D(cudaMemcpyAsync(&tot[2], chunk_off + n, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    MPG_CUDA_D(cudaStreamSynchronize(ctx->stream));
+    p->nlanes = tot[0]; p->nsplit = tot[1]; p->nchunks = tot[2];
+    const size_t vb = sizeof(int) * (size_t)std::max(p->nlanes, 1);
+    MPG_CUDA_D(pool_alloc(ctx, &vstart, vb)); MPG_CUDA_D(pool_alloc(ctx, &vlen, vb)); MPG_CUDA_D(pool_alloc(ctx, &vout, vb));
+    MPG_CUDA_D(pool_alloc(ctx, &p->vstart, vb)); MPG_CUDA_D(pool_alloc(ctx, &p->vlen, vb)); MPG_CUDA_D(pool_alloc(ctx, &p->vout, vb));
+    MPG_CUDA_D(pool_alloc(ctx, &p->split_rows, sizeof(int) * (size_t)std::max(p->nsplit, 1)));
+    MPG_CUDA_D(pool_alloc(ctx, &p->chunk_base, sizeof(int) * (size_t)(p->nsplit + 1)));
+    MPG_CUDA_D(pool_alloc(ctx, &p->partial, sizeof(double) * (size_t)std::max(p->nchunks, 1)));
+    vrow_fill_kernel<<<(int)cdiv(n, 256), 256, 0, ctx->stream>>>(n, A->row_map, vrow_off, split_off, chunk_off, vstart, vlen, vout, p->split_rows, p->chunk_base);
+    MPG_CUDA_D(cudaMemcpyAsync(p->chunk_base + p->nsplit, &p->nchunks, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    vrow_sort_kernel<<<(int)cdiv(p->nlanes, SIGMA), 512, 0, ctx->stream>>>(p->nlanes, vstart, vlen, vout, p->vstart, p->vlen, p->vout);
+    ctx->launches += 2;
+    MPG_CUDA_D(cudaStreamSynchronize(ctx->stream));
+    MPG_CUDA_D(cudaGetLastError());
+#undef MPG_CUDA_D
+    drop();
+    p->mode = MODE_SIGMA;
+    return MPG_OK;
+}
+
+// build (or fetch) the packed structure; *out = nullptr if the matrix does not pack well
+int sell_plan_get(mpg_ctx* ctx, const mpg_csr* A, const mpg_sell_plan** out) {
+    *out = nullptr;
+    mpg_csr* Am = const_cast<mpg_csr*>(A);
+    if (Am->sell_tried) { *out = Am->sell; return MPG_OK; }
+    Am->sell_tried = 1;
+    if (A->nrows == 0 || A->nnz == 0) return MPG_OK;
+    static unsigned long long next_uid = 0;
+    mpg_sell_plan* p = new mpg_sell_plan();
+    struct Guard { mpg_sell_plan* p; ~Guard() { if (p) sell_plan_free(p); } } guard{p};   // error paths release what was built so far
+    p->uid = ++next_uid;
+    p->nlanes = A->nrows;
+    MPG_TRY(plan_slices(ctx, A, p));
+    const auto too_padded = [&]() { return (double)p->total > 1.25 * (double)A->nnz + 4096.0 || p->total >= (int64_t)1 << 40; };
+    if (too_padded()) {
+        if (!ctx->tune.spmv_sigma) return MPG_OK;
+        MPG_TRY(plan_sigma(ctx, A, p));
+        MPG_TRY(plan_slices(ctx, A, p));
+        if (too_padded()) return MPG_OK;   // keep CSR
     }
     MPG_CUDA(ctx, pool_alloc(ctx, &p->sinds, sizeof(int) * (size_t)std::max<int64_t>(p->total, 1)));
     const bool slab = A->ncols > A->nrows;
     if (slab) MPG_CUDA(ctx, pool_alloc(ctx, &p->slice_list, sizeof(int) * (size_t)p->nslices));
-    if (G == 4) sell_fill_inds_kernel<4><<<wgrid, 256, 0, ctx->stream>>>(A->nrows, p->nslices, A->row_map, A->inds, p->slice_off, p->sinds, p->slice_list);
-    else sell_fill_inds_kernel<2><<<wgrid, 256, 0, ctx->stream>>>(A->nrows, p->nslices, A->row_map, A->inds, p->slice_off, p->sinds, p->slice_list);
+    const int wgrid = (int)cdiv((int64_t)p->nslices * 32, 256);
+    sell_fill_inds_kernel<<<wgrid, 256, 0, ctx->stream>>>(lane_src(A, p), p->nslices, A->nrows, A->inds, p->slice_off, p->sinds, p->slice_list);
     MPG_CHECK_LAUNCH(ctx);
     if (slab) {
         // local slab of a partitioned matrix: order the slices [no halo column | some halo column]
@@ -293,7 +492,8 @@ int sell_plan_get(mpg_ctx* ctx, const mpg_csr* A, int G, const mpg_sell_plan** o
         MPG_CUDA(ctx, cudaMemcpyAsync(p->slice_list, list.data(), sizeof(int) * list.size(), cudaMemcpyHostToDevice, ctx->stream));
         MPG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
-    Am->sell[slot] = p;
+    guard.p = nullptr;
+    Am->sell = p;
     *out = p;
     return MPG_OK;
 }
@@ -303,7 +503,7 @@ int pack_update(mpg_ctx* ctx, mpg_packed* P, const T* vals) {
     const mpg_sell_plan* p = P->plan;
     const mpg_csr* A = P->A;
     ProfScope prof(ctx, MPG_PROF_ELEMENTWISE, (double)A->nnz * sizeof(T) + (double)p->total * sizeof(T));
-    sell_fill_vals_kernel<T><<<(int)cdiv((int64_t)p->nslices * 32, 256), 256, 0, ctx->stream>>>(A->nrows, p->nslices, A->row_map, vals, p->slice_off,
+    sell_fill_vals_kernel<T><<<(int)cdiv((int64_t)p->nslices * 32, 256), 256, 0, ctx->stream>>>(lane_src(A, p), p->nslices, vals, p->slice_off,
                                                                                              static_cast<T*>(P->svals));
     MPG_CHECK_LAUNCH(ctx);
     return MPG_OK;
@@ -316,11 +516,12 @@ template <class T>
 int pack_create(mpg_ctx* ctx, const mpg_csr* A, const T* vals, mpg_packed** out) {
     *out = nullptr;
     const mpg_sell_plan* plan = nullptr;
-    MPG_TRY(sell_plan_get(ctx, A, Grp<T>::G, &plan));
+    MPG_TRY(sell_plan_get(ctx, A, &plan));
     if (!plan) return MPG_OK;
     mpg_packed* P = new mpg_packed();
     P->A = A; P->plan = plan; P->plan_uid = plan->uid; P->tsize = (int)sizeof(T); P->device = ctx->device;
-    MPG_CUDA(ctx, pool_alloc(ctx, &P->svals, sizeof(T) * (size_t)std::max<int64_t>(plan->total, 1)));
+    cudaError_t e = pool_alloc(ctx, &P->svals, sizeof(T) * (size_t)std::max<int64_t>(plan->total, 1));
+    if (e != cudaSuccess) { (void)cudaGetLastError(); delete P; return fail(ctx, MPG_ERR_CUDA, std::string("pack_create: ") + cudaGetErrorString(e)); }
     *out = P;
     return pack_update<T>(ctx, P, vals);
 }
@@ -334,12 +535,13 @@ void pack_free(mpg_packed* P) {
 }
 
 bool pack_matches(const mpg_packed* P, const mpg_csr* A, int tsize) {
-    const mpg_sell_plan* cur = A->sell[tsize == 4 ? 0 : 1];
+    const mpg_sell_plan* cur = A->sell;
     return P && P->A == A && P->tsize == tsize && cur && cur == P->plan && cur->uid == P->plan_uid;
 }
 
 template <class T>
-int spmv_packed(mpg_ctx* ctx, const mpg_packed* P, T alpha, const T* x, T beta, const T* y_in, T* y_out, float* out32, const T* rowscale, int part) {
+int spmv_packed(mpg_ctx* ctx, const mpg_packed* P, T alpha, const T* x, T beta, const T* y_in, T* y_out, float* out32, const T* rowscale, int part,
+                const HaloWait* hw_in) {
     const mpg_sell_plan* p = P->plan;
     const mpg_csr* A = P->A;
     if (part != SPMV_ALL && !p->slice_list) {
@@ -348,22 +550,45 @@ int spmv_packed(mpg_ctx* ctx, const mpg_packed* P, T alpha, const T* x, T beta, 
     }
     const int s_first = part == SPMV_BOUNDARY ? p->n_interior : 0;
     const int s_count = part == SPMV_INTERIOR ? p->n_interior : p->nslices - s_first;
-    if (s_count == 0) return MPG_OK;
     const int* list = part == SPMV_ALL ? nullptr : p->slice_list + s_first;
-    // algorithmic bytes: the CSR figure of SURVEY.md §8d (the padding the packed layout reads on top is not counted)
+    // algorithmic bytes: the CSR figure of SURVEY.md §8d (padding and per-lane destinations the packed layout reads on top are not counted)
     const double n_ = A->nrows, s_ = sizeof(T);
     const double bytes = (double)A->nnz * (s_ + 4) + 4 * (n_ + 1) + n_ * s_ + (y_out ? n_ * s_ : 0) + (beta != T(0) ? n_ * s_ : 0) + (out32 ? 4 * n_ : 0) +
                          (rowscale ? n_ * s_ : 0);
     ProfScope prof(ctx, sizeof(T) == 4 ? MPG_PROF_SPMV_F32 : MPG_PROF_SPMV_F64, bytes * ((double)s_count / p->nslices));
-    const int grid = (int)cdiv((int64_t)s_count * 32, 256);
-    auto kern = p->has_rem ? spmv_sell_kernel<T, true> : spmv_sell_kernel<T, false>;
-    MPG_CUDA(ctx, launch_pdl(ctx, (int64_t)A->nrows, kern, grid, 256, 0, A->nrows, s_count, (const int64_t*)p->slice_off, (const int*)p->sinds, static_cast<const T*>(P->svals), x, alpha,
-                             beta, y_in, y_out, out32, rowscale, list));
-    MPG_CHECK_LAUNCH(ctx);
+    HaloWait hw;
+    hw.npeers = 0;
+    if (hw_in) hw = *hw_in;
+    if (s_count > 0) {
+        // SIGMA plans gather random columns: around L1, 4 groups per step (profiles/r02_tune_sell_sigma.txt); stencils: through L1, 2 groups
+        const int variant = ctx->tune.sell_variant >= 0 ? ctx->tune.sell_variant : (p->mode == MODE_SIGMA ? 3 : 0);
+        const int block = ctx->tune.sell_block > 0 ? std::min(ctx->tune.sell_block, 256) : 256;
+        const int grid = (int)cdiv((int64_t)s_count * 32, block);
+        void (*kern)(int, int, const int64_t*, const int*, const T*, const T*, T, T, const T*, T*, float*, const T*, const int*, const int*, T*, const HaloWait);
+        switch ((variant & 3) * 2 + (p->has_rem ? 1 : 0)) {
+            case 0: kern = spmv_sell_kernel<T, false, false, 2>; break;
+            case 1: kern = spmv_sell_kernel<T, true, false, 2>; break;
+            case 2: kern = spmv_sell_kernel<T, false, true, 2>; break;
+            case 3: kern = spmv_sell_kernel<T, true, true, 2>; break;
+            case 4: kern = spmv_sell_kernel<T, false, false, 4>; break;
+            case 5: kern = spmv_sell_kernel<T, true, false, 4>; break;
+            case 6: kern = spmv_sell_kernel<T, false, true, 4>; break;
+            default: kern = spmv_sell_kernel<T, true, true, 4>; break;
+        }
+        MPG_CUDA(ctx, launch_pdl(ctx, (int64_t)A->nrows, kern, grid, block, 0, p->nlanes, s_count, (const int64_t*)p->slice_off, (const int*)p->sinds,
+                                 static_cast<const T*>(P->svals), x, alpha, beta, y_in, y_out, out32, rowscale, list, (const int*)p->vout,
+                                 static_cast<T*>(p->partial), hw));
+        MPG_CHECK_LAUNCH(ctx);
+    }
+    if (p->nsplit > 0 && part != SPMV_INTERIOR) {
+        MPG_CUDA(ctx, launch_pdl(ctx, (int64_t)A->nrows, sell_fixup_kernel<T>, (int)cdiv(p->nsplit, 128), 128, 0, p->nsplit, (const int*)p->split_rows,
+                                 (const int*)p->chunk_base, static_cast<const T*>(p->partial), alpha, beta, y_in, y_out, out32, rowscale));
+        MPG_CHECK_LAUNCH(ctx);
+    }
     return MPG_OK;
 }
-template int spmv_packed<float>(mpg_ctx*, const mpg_packed*, float, const float*, float, const float*, float*, float*, const float*, int);
-template int spmv_packed<double>(mpg_ctx*, const mpg_packed*, double, const double*, double, const double*, double*, float*, const double*, int);
+template int spmv_packed<float>(mpg_ctx*, const mpg_packed*, float, const float*, float, const float*, float*, float*, const float*, int, const HaloWait*);
+template int spmv_packed<double>(mpg_ctx*, const mpg_packed*, double, const double*, double, const double*, double*, float*, const double*, int, const HaloWait*);
 
 }  // namespace mpg
 
@@ -379,7 +604,7 @@ template int spmv_packed<double>(mpg_ctx*, const mpg_packed*, double, const doub
     }                                                                                                                              \
     extern "C" int mpg_spmv_packed_##SFX(mpg_ctx* ctx, const mpg_packed* P, T alpha, const T* x, T beta, T* y) {                  \
         MPG_REQUIRE(ctx, P && x && y && P->tsize == (int)sizeof(T), "spmv_packed: null argument or wrong precision");             \
-        return mpg::spmv_packed<T>(ctx, P, alpha, x, beta, y, y, nullptr, nullptr, mpg::SPMV_ALL);                                \
+        return mpg::spmv_packed<T>(ctx, P, alpha, x, beta, y, y, nullptr, nullptr, mpg::SPMV_ALL, nullptr);                       \
     }
 MPG_DEF_PACK(f32, float)
 MPG_DEF_PACK(f64, double)
@@ -387,12 +612,30 @@ MPG_DEF_PACK(f64, double)
 extern "C" int mpg_pack_describe(const mpg_packed* P, int* group, int* nslices, int64_t* total, const int64_t** slice_off, const int** inds,
                                  const void** vals) {
     if (!P || !P->plan) return MPG_ERR_ARG;
-    if (group) *group = P->plan->G;
+    if (group) *group = G;
     if (nslices) *nslices = P->plan->nslices;
     if (total) *total = P->plan->total;
     if (slice_off) *slice_off = P->plan->slice_off;
     if (inds) *inds = P->plan->sinds;
     if (vals) *vals = P->svals;
+    return MPG_OK;
+}
+
+extern "C" int mpg_pack_describe_rows(const mpg_packed* P, int* mode, int* chunk, int* sigma, int* nlanes, const int** lane_start, const int** lane_len,
+                                      const int** lane_out, int* nsplit, int* nchunks, const int** split_rows, const int** chunk_base) {
+    if (!P || !P->plan) return MPG_ERR_ARG;
+    const mpg_sell_plan* p = P->plan;
+    if (mode) *mode = p->mode;
+    if (chunk) *chunk = CHUNK;
+    if (sigma) *sigma = SIGMA;
+    if (nlanes) *nlanes = p->nlanes;
+    if (lane_start) *lane_start = p->vstart;
+    if (lane_len) *lane_len = p->vlen;
+    if (lane_out) *lane_out = p->vout;
+    if (nsplit) *nsplit = p->nsplit;
+    if (nchunks) *nchunks = p->nchunks;
+    if (split_rows) *split_rows = p->split_rows;
+    if (chunk_base) *chunk_base = p->chunk_base;
     return MPG_OK;
 }
 

@@ -48,7 +48,7 @@ template <class T> int pack_create(mpg_ctx*, const mpg_csr*, const T*, mpg_packe
 template <class T> int pack_update(mpg_ctx*, mpg_packed*, const T*);
 void pack_free(mpg_packed*);
 bool pack_matches(const mpg_packed*, const mpg_csr*, int tsize);
-template <class T> int spmv_packed(mpg_ctx*, const mpg_packed*, T, const T*, T, const T*, T*, float*, const T*, int);
+template <class T> int spmv_packed(mpg_ctx*, const mpg_packed*, T, const T*, T, const T*, T*, float*, const T*, int, const HaloWait* = nullptr);
 template <class T> int halo_exchange(mpg_ctx*, T*);
 template <class T> int halo_begin(mpg_ctx*, T*);
 template <class T> int halo_finish(mpg_ctx*, T*);
@@ -135,7 +135,10 @@ struct Workspace {
     float* tmp32 = nullptr;   // n floats: single-prec preconditioner bridge (typesafe_apply, gmres.cpp:12-17)
     int64_t halo = 0;         // multi-GPU: halo slots appended to every SpMV input (tail of each basis column)
     void* xext = nullptr;     // multi-GPU: [x_local ; halo] copy of the iterate for the outer residual
-    mpg_packed* packed = nullptr;  // packed copy of the inner-precision matrix (sell.cu); values refreshed at every solve
+    // packed copies of the matrix (sell.cu): slot 0 = the operator of the inner iterations, slot 1 = the fp64 operator of the
+    // mixed-precision outer residual.  Values are refreshed at every solve unless the caller set values_static.
+    mpg_packed* packed[2] = {nullptr, nullptr};
+    const void* packed_src[2] = {nullptr, nullptr};   // value array the slot was last packed from
 };
 
 // replicated (not row-distributed) data: reductions over it must not be all-reduced
@@ -152,7 +155,8 @@ void ws_release(void* p) {
     cudaFree(ws->V); cudaFree(ws->w); cudaFree(ws->h); cudaFree(ws->cs); cudaFree(ws->sn); cudaFree(ws->s);
     cudaFree(ws->scratch); cudaFree(ws->hist); cudaFreeHost(ws->hist_host); cudaFree(ws->S); cudaFree(ws->u); cudaFree(ws->tmp32);
     cudaFree(ws->xext);
-    pack_free(ws->packed);
+    pack_free(ws->packed[0]);
+    pack_free(ws->packed[1]);
     delete ws;
 }
 
@@ -212,7 +216,7 @@ template <class T>
 int read_scalars(mpg_ctx* ctx, int count) {
     MPG_CUDA(ctx, cudaMemcpyAsync(ctx->hscal, ctx->dscal, sizeof(double) * (size_t)count, cudaMemcpyDeviceToHost, ctx->stream));
     MPG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return MPG_OK;
+    return check_dev_err(ctx);
 }
 template <class T> T hs(mpg_ctx* ctx, int slot) { T v; memcpy(&v, ctx->hscal + slot, sizeof(T)); return v; }
 template <class T> T* ds(mpg_ctx* ctx, int slot) { return reinterpret_cast<T*>(ctx->dscal + slot); }
@@ -238,17 +242,19 @@ int size_estimate(mpg_ctx* ctx, const mpg_csr* A, Policy& pol) {
 // the mpg_csr plan, the values are re-packed at every solve (one pass over the matrix; the caller may have changed them).
 // *out stays null when packing is switched off or the structure does not pack well: the CSR kernel is used then.
 template <class T>
-int get_packed(mpg_ctx* ctx, Workspace* ws, const mpg_csr* A, const T* vals, const mpg_packed** out) {
+int get_packed(mpg_ctx* ctx, Workspace* ws, int slot, const mpg_csr* A, const T* vals, const mpg_packed** out) {
     *out = nullptr;
     if (!ctx->tune.spmv_packed) return MPG_OK;
-    if (ws->packed && !pack_matches(ws->packed, A, (int)sizeof(T))) {
+    mpg_packed*& P = ws->packed[slot];
+    if (P && !pack_matches(P, A, (int)sizeof(T))) {
         MPG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        pack_free(ws->packed);
-        ws->packed = nullptr;
+        pack_free(P);
+        P = nullptr;
     }
-    if (!ws->packed) MPG_TRY(pack_create<T>(ctx, A, vals, &ws->packed));
-    else MPG_TRY(pack_update<T>(ctx, ws->packed, vals));
-    *out = ws->packed;
+    if (!P) MPG_TRY(pack_create<T>(ctx, A, vals, &P));
+    else if (!(ctx->tune.values_static && ws->packed_src[slot] == (const void*)vals)) MPG_TRY(pack_update<T>(ctx, P, vals));
+    ws->packed_src[slot] = vals;
+    *out = P;
     return MPG_OK;
 }
 
@@ -414,7 +420,11 @@ int solve_mixed(mpg_ctx* ctx, const mpg_gmres_params& p, const mpg_csr* A, const
     float* s = static_cast<float*>(ws->s);
     float* V = static_cast<float*>(ws->V);
     const mpg_packed* packed = nullptr;
-    MPG_TRY(get_packed<float>(ctx, ws, A, vals32, &packed));
+    MPG_TRY(get_packed<float>(ctx, ws, 0, A, vals32, &packed));
+    // fp64 operator of the outer residual on the same packed structure (one more pass over the values per solve; the CSR kernel
+    // gathers x once per nonzero and runs at ~0.55 of the roofline, the packed one at ~0.9)
+    const mpg_packed* packed64 = nullptr;
+    if (ctx->tune.residual_packed && packed) MPG_TRY(get_packed<double>(ctx, ws, 1, A, vals64, &packed64));
     Policy pol(p);
     MPG_TRY(size_estimate(ctx, A, pol));
     if (p.conv == MPG_CONV_ORTHLOSS) {
@@ -443,7 +453,8 @@ int solve_mixed(mpg_ctx* ctx, const mpg_gmres_params& p, const mpg_csr* A, const
             MPG_TRY(halo_exchange<double>(ctx, xe));
             xin = xe;
         }
-        MPG_TRY(spmv<double>(ctx, A, vals64, -1.0, xin, 1.0, b, nullptr, w));
+        if (packed64) MPG_TRY(spmv_packed<double>(ctx, packed64, -1.0, xin, 1.0, b, nullptr, w, nullptr, SPMV_ALL));
+        else MPG_TRY(spmv<double>(ctx, A, vals64, -1.0, xin, 1.0, b, nullptr, w));
         MPG_TRY(nrm2_dev(ctx, n, w, ds<float>(ctx, 0)));                       // r_norm   :176
         MPG_TRY(apply_prec<float>(ctx, n, w, jac32, nullptr, false, nullptr)); // M(w)     :177
         if (jac32) MPG_TRY(nrm2_dev(ctx, n, w, ds<float>(ctx, 1)));            // beta     :179 (same vector when M = I)
@@ -483,7 +494,7 @@ int solve_uniform(mpg_ctx* ctx, const mpg_gmres_params& p, const mpg_csr* A, con
     T* s = static_cast<T*>(ws->s);
     T* V = static_cast<T*>(ws->V);
     const mpg_packed* packed = nullptr;
-    MPG_TRY(get_packed<T>(ctx, ws, A, vals, &packed));
+    MPG_TRY(get_packed<T>(ctx, ws, 0, A, vals, &packed));
     Policy pol(p);
     MPG_TRY(size_estimate(ctx, A, pol));
     if (p.conv == MPG_CONV_ORTHLOSS) {
@@ -510,7 +521,8 @@ int solve_uniform(mpg_ctx* ctx, const mpg_gmres_params& p, const mpg_csr* A, con
             MPG_TRY(halo_exchange<T>(ctx, xe));
             xin = xe;
         }
-        MPG_TRY(spmv<T>(ctx, A, vals, T(-1), xin, T(1), b, w, nullptr));
+        if (packed && ctx->tune.residual_packed) MPG_TRY(spmv_packed<T>(ctx, packed, T(-1), xin, T(1), b, w, nullptr, nullptr, SPMV_ALL));
+        else MPG_TRY(spmv<T>(ctx, A, vals, T(-1), xin, T(1), b, w, nullptr));
         MPG_TRY(nrm2_dev(ctx, n, w, ds<T>(ctx, 0)));                           // r_norm :67
         MPG_TRY(apply_prec<T>(ctx, n, w, jac, jac32, bridge, ws->tmp32));      //        :68
         if (have_prec) MPG_TRY(nrm2_dev(ctx, n, w, ds<T>(ctx, 1)));            // beta   :70

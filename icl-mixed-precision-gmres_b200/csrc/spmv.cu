@@ -306,8 +306,7 @@ extern "C" int mpg_csr_destroy(mpg_csr* A) {
     cudaFree(A->tile_row);
     cudaFree(A->carry);
     cudaFree(A->tile_list);
-    mpg::sell_plan_free(A->sell[0]);
-    mpg::sell_plan_free(A->sell[1]);
+    mpg::sell_plan_free(A->sell);
     delete A;
     return MPG_OK;
 }

@@ -143,22 +143,30 @@ int mpg_spmv_f64(mpg_ctx*, const mpg_csr* A, const double* vals, double alpha, c
  * Jacobi::apply = gdmv(1, diag, y, 0, y) (types.hpp:444-446), bit-identical to the two separate calls. */
 int mpg_spmv_jacobi_f32(mpg_ctx*, const mpg_csr* A, const float* vals, const float* diag, const float* x, float* y);
 int mpg_spmv_jacobi_f64(mpg_ctx*, const mpg_csr* A, const double* vals, const double* diag, const double* x, double* y);
-/* Packed operator (sell.cu): the same matrix re-laid as 32-row slices stored position-major (sliced ELLPACK), the
+/* Packed operator (sell.cu): the same matrix re-laid as 32-lane slices stored position-major (sliced ELLPACK), the
  * analogue of the per-matrix library handles the reference builds once per SparseMatrix (create_cuda_handles,
- * types_cuda.hpp:53-60).  One lane per row: the gathers of x coalesce for stencil-like matrices.  mpg_pack_create
- * returns MPG_OK with *out == NULL when the structure does not pack well (row lengths too uneven: > 25 % padding);
- * keep using mpg_spmv_* then.  The packed object refers to A (destroy it before A); mpg_pack_update re-packs the
- * values after the caller changed them.  mpg_gmres_solve packs the inner-precision matrix itself. */
+ * types_cuda.hpp:53-60).  One lane per row: the gathers of x coalesce for stencil-like matrices.  Matrices with uneven
+ * row lengths (power-law) take the SELL-C-sigma form: rows longer than 256 nonzeros are cut into pieces, the pieces
+ * are sorted by length inside windows of 4096, a fix-up kernel adds the pieces of each cut row in order; y stays in
+ * caller order and results are bit-reproducible.  fp32 and fp64 value arrays share ONE packed index array.
+ * mpg_pack_create returns MPG_OK with *out == NULL when even that form pads > 25 %; keep using mpg_spmv_* then.
+ * The packed object refers to A (destroy it before A); mpg_pack_update re-packs the values after the caller changed
+ * them.  mpg_gmres_solve packs the matrices it multiplies with itself. */
 typedef struct mpg_packed mpg_packed;
 int mpg_pack_create_f32(mpg_ctx*, const mpg_csr* A, const float* vals, mpg_packed** out);
 int mpg_pack_create_f64(mpg_ctx*, const mpg_csr* A, const double* vals, mpg_packed** out);
 int mpg_pack_update_f32(mpg_ctx*, mpg_packed* P, const float* vals);
 int mpg_pack_update_f64(mpg_ctx*, mpg_packed* P, const double* vals);
 int mpg_pack_destroy(mpg_packed* P);
-/* Layout access for tests / diagnostics: group size G, slice count, padded element count and the DEVICE arrays
+/* Layout access for tests / diagnostics: group size (4), slice count, padded element count and the DEVICE arrays
  * slice_off[nslices + 1], inds[total], vals[total] (owned by the library; layout in csrc/sell.cu and DESIGN.md §2). */
 int mpg_pack_describe(const mpg_packed* P, int* group, int* nslices, int64_t* total, const int64_t** slice_off, const int** inds,
                       const void** vals);
+/* mode 0: lane = row (the lane arrays are NULL).  mode 1 (SELL-C-sigma): per lane, in sorted order, the CSR offset and
+ * length of its piece and its destination (row index, or -1 - piece number for a piece of a cut row); the cut rows and
+ * the first piece number of each (chunk_base[nsplit] = number of pieces).  DEVICE arrays owned by the library. */
+int mpg_pack_describe_rows(const mpg_packed* P, int* mode, int* chunk, int* sigma, int* nlanes, const int** lane_start, const int** lane_len,
+                           const int** lane_out, int* nsplit, int* nchunks, const int** split_rows, const int** chunk_base);
 int mpg_spmv_packed_f32(mpg_ctx*, const mpg_packed* P, float alpha, const float* x, float beta, float* y);
 int mpg_spmv_packed_f64(mpg_ctx*, const mpg_packed* P, double alpha, const double* x, double beta, double* y);
 /* Fused outer residual, replaces gmres.cpp:173-175 (copy + fp64 SpMV + cast kernel):

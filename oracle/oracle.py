@@ -228,16 +228,46 @@ def partition_local(n, P, r, rm, ind):
     return halo, li
 
 
-def sell_pack(rm, ind, val, G):
-    """Restatement (numpy, test infrastructure) of the packed sliced-ELL layout of csrc/sell.cu, DESIGN.md §2: 32-row slices,
-    slice length L = longest row (rounded up to a multiple of G when that pads <= 10 %), the first floor(L/G)*G positions in
-    groups of G per lane, the L % G trailing positions one per lane; short rows padded with their first column and value 0.
-    Returns (slice_off[nslices + 1] int64, inds int32, vals)."""
+SELL_G, SELL_CHUNK, SELL_SIGMA = 4, 256, 4096
+
+
+def sell_rows(rm, sigma_mode):
+    """lane table of the packed layout of csrc/sell.cu: (start, len, out) per lane.  PLAIN: lane = row.  SIGMA: rows longer
+    than SELL_CHUNK nonzeros are cut into pieces of at most SELL_CHUNK ("virtual rows", in (row, piece) order), the virtual rows
+    are sorted by length descending (ties: index ascending) inside windows of SELL_SIGMA; out = the row, or -1 - (piece number
+    among the pieces of all cut rows) for a piece of a cut row.  Also returns (split_rows, chunk_base)."""
     n = len(rm) - 1
-    ns = (n + 31) // 32
-    lens = np.zeros(ns * 32, np.int64)
-    lens[:n] = np.diff(rm)
-    L = lens.reshape(ns, 32).max(axis=1) if ns else np.zeros(0, np.int64)
+    lens = np.diff(rm).astype(np.int64)
+    if not sigma_mode:
+        return rm[:-1].astype(np.int32), lens.astype(np.int32), np.arange(n, dtype=np.int32), np.zeros(0, np.int32), np.zeros(1, np.int32)
+    nch = np.maximum(1, (lens + SELL_CHUNK - 1) // SELL_CHUNK)
+    vrow = np.repeat(np.arange(n), nch)                          # row of every virtual row
+    first = np.zeros(n + 1, np.int64); first[1:] = np.cumsum(nch)
+    piece = np.arange(len(vrow)) - first[vrow]
+    vstart = rm[vrow].astype(np.int64) + piece * SELL_CHUNK
+    vlen = np.minimum(SELL_CHUNK, lens[vrow] - piece * SELL_CHUNK)
+    split = nch > 1
+    split_rows = np.nonzero(split)[0].astype(np.int32)
+    cb = np.zeros(len(split_rows) + 1, np.int64); cb[1:] = np.cumsum(nch[split])
+    chunk_of_row = np.zeros(n, np.int64); chunk_of_row[split_rows] = cb[:-1]
+    vout = np.where(split[vrow], -1 - (chunk_of_row[vrow] + piece), vrow)
+    order = np.concatenate([w0 + np.lexsort((np.arange(min(SELL_SIGMA, len(vrow) - w0)), -vlen[w0:w0 + SELL_SIGMA]))
+                            for w0 in range(0, len(vrow), SELL_SIGMA)]) if len(vrow) else np.zeros(0, np.int64)
+    return vstart[order].astype(np.int32), vlen[order].astype(np.int32), vout[order].astype(np.int32), split_rows, cb.astype(np.int32)
+
+
+def sell_pack(rm, ind, val, sigma_mode=False):
+    """Restatement (numpy, test infrastructure) of the packed sliced-ELL layout of csrc/sell.cu, DESIGN.md §2: 32-lane slices,
+    slice length L = longest lane (rounded up to a multiple of 4 when that pads <= 10 %), the first floor(L/4)*4 positions in
+    groups of 4 per lane, the L % 4 trailing positions one per lane; short lanes padded with their first column and value 0.
+    fp64 values store each group as two half-groups ([lane][2] twice).  Returns (slice_off[nslices + 1] int64, inds int32, vals)."""
+    G = SELL_G
+    start, lens, _, _, _ = sell_rows(rm, sigma_mode)
+    nl = len(start)
+    ns = (nl + 31) // 32
+    lp = np.zeros(ns * 32, np.int64); lp[:nl] = lens
+    sp_ = np.zeros(ns * 32, np.int64); sp_[:nl] = start
+    L = lp.reshape(ns, 32).max(axis=1) if ns else np.zeros(0, np.int64)
     rem = L % G
     up = (rem > 0) & ((G - rem) * 10 <= L)
     L = np.where(up, L + G - rem, L)
@@ -245,20 +275,21 @@ def sell_pack(rm, ind, val, G):
     off[1:] = np.cumsum(L * 32)
     sind = np.zeros(int(off[-1]), np.int32)
     sval = np.zeros(int(off[-1]), val.dtype)
+    f64 = np.dtype(val.dtype) == np.float64
     for s in range(ns):
         Ls = int(L[s]); ng = Ls // G; o = int(off[s])
         p = np.arange(Ls)
-        pos_in_slice = np.where(p < ng * G, (p // G) * 32 * G + p % G, ng * 32 * G + (p - ng * G) * 32)   # + lane * (G or 1)
-        lane_mul = np.where(p < ng * G, G, 1)
+        in_grp = p < ng * G
         for lane in range(32):
-            r = s * 32 + lane
-            ln = int(lens[r])
-            rs = int(rm[r]) if r < n else 0
+            ln, rs = int(lp[s * 32 + lane]), int(sp_[s * 32 + lane])
             c = np.full(Ls, ind[rs] if ln > 0 else 0, np.int32)
             v = np.zeros(Ls, val.dtype)
             c[:ln] = ind[rs:rs + ln]
             v[:ln] = val[rs:rs + ln]
-            dst = o + pos_in_slice + lane * lane_mul
-            sind[dst] = c
-            sval[dst] = v
+            tail = ng * 32 * G + (p - ng * G) * 32 + lane
+            sind[o + np.where(in_grp, (p // G) * 32 * G + lane * G + p % G, tail)] = c
+            if f64:
+                sval[o + np.where(in_grp, (p // G) * 32 * G + ((p % G) // 2) * 64 + lane * 2 + p % 2, tail)] = v
+            else:
+                sval[o + np.where(in_grp, (p // G) * 32 * G + lane * G + p % G, tail)] = v
     return off, sind, sval

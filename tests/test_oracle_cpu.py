@@ -243,31 +243,55 @@ def test_partition_index_sets(orc, spec, P):
         np.testing.assert_allclose(yl, y[lo:hi], rtol=1e-13, atol=1e-13)
 
 
-@pytest.mark.parametrize("spec,G", [("cd27:5", 4), ("lap2d:9", 4), ("lap2d:9", 2), ("powerlaw:300", 2)])
-def test_packed_layout_restatement_is_a_permutation_of_the_csr_entries(orc, spec, G):
-    """oracle.sell_pack (the layout the GPU test compares the library's packed arrays with): every CSR entry appears exactly
-    once at the documented position, padding carries value 0 and a valid column, y = A x through the packed arrays is exact"""
+@pytest.mark.parametrize("spec,sigma,dt", [("cd27:5", False, np.float32), ("lap2d:9", False, np.float32), ("lap2d:9", False, np.float64),
+                                           ("powerlaw:300", False, np.float64), ("powerlaw:9000", True, np.float32), ("powerlaw:9000", True, np.float64)])
+def test_packed_layout_restatement_is_a_permutation_of_the_csr_entries(orc, spec, sigma, dt):
+    """oracle.sell_pack / sell_rows (the layout the GPU test compares the library's packed arrays with): every CSR entry appears
+    exactly once at the documented position, padding carries value 0 and a valid column, y = A x through the packed arrays
+    (lane sums scattered through the lane table, pieces of cut rows added) is exact"""
+    G = 4
     rm, ind, val = orc.gen(spec)
+    val = val.astype(dt)
     n = len(rm) - 1
-    off, si, sv = orc.sell_pack(rm, ind, val, G)
+    off, si, sv = orc.sell_pack(rm, ind, val, sigma_mode=sigma)
+    lstart, llen, lout, split_rows, chunk_base = orc.sell_rows(rm, sigma)
+    nl = len(lstart)
     assert off[0] == 0 and np.all(np.diff(off) % 32 == 0) and len(si) == off[-1] == len(sv)
     assert np.count_nonzero(sv) == np.count_nonzero(val) and si.min() >= 0 and si.max() < n
+    assert llen.sum() == len(ind) and (not sigma or llen.max() <= 256)
+    f64 = dt == np.float64
     x = np.arange(1, n + 1, dtype=np.float64)
     y = np.zeros(n)
+    partial = np.zeros(int(chunk_base[-1]))
     for s in range(len(off) - 1):
         L = int(off[s + 1] - off[s]) // 32
         ng = L // G
         for lane in range(32):
-            r = s * 32 + lane
-            if r >= n:
+            pos_lane = s * 32 + lane
+            if pos_lane >= nl:
                 continue
+            acc = 0.0
             for p in range(L):
-                pos = off[s] + ((p // G) * 32 * G + lane * G + p % G if p < ng * G else ng * 32 * G + (p - ng * G) * 32 + lane)
-                y[r] += sv[pos] * x[si[pos]]
-    A = sp.csr_matrix((val, ind, rm), shape=(n, n))
+                tail = ng * 32 * G + (p - ng * G) * 32 + lane
+                pi = off[s] + ((p // G) * 32 * G + lane * G + p % G if p < ng * G else tail)
+                pv = off[s] + (((p // G) * 32 * G + ((p % G) // 2) * 64 + lane * 2 + p % 2 if f64 else (p // G) * 32 * G + lane * G + p % G) if p < ng * G else tail)
+                acc += float(sv[pv]) * x[si[pi]]
+            o = int(lout[pos_lane])
+            if o >= 0:
+                y[o] = acc
+            else:
+                partial[-1 - o] = acc
+    for j, r in enumerate(split_rows):
+        y[r] = partial[chunk_base[j]:chunk_base[j + 1]].sum()
+    A = sp.csr_matrix((val.astype(np.float64), ind, rm), shape=(n, n))
     np.testing.assert_allclose(y, A @ x, rtol=1e-13, atol=1e-9)
-    # slice lengths: longest row, rounded up to a multiple of G only when that pads <= 10 %
-    lens = np.zeros((len(off) - 1) * 32, np.int64); lens[:n] = np.diff(rm)
+    if sigma:
+        # sorted by length (descending) inside every window of 4096 lanes; pieces of a cut row keep their order
+        for w0 in range(0, nl, 4096):
+            assert np.all(np.diff(llen[w0:w0 + 4096]) <= 0)
+        assert len(split_rows) == (np.diff(rm) > 256).sum() and off[-1] <= 1.25 * len(ind) + 4096
+    # slice lengths: longest lane, rounded up to a multiple of G only when that pads <= 10 %
+    lens = np.zeros((len(off) - 1) * 32, np.int64); lens[:nl] = llen
     Lmax = lens.reshape(-1, 32).max(axis=1)
     L = np.diff(off) // 32
     assert np.all(L >= Lmax) and np.all(L - Lmax < G) and np.all((L == Lmax) | ((L - Lmax) * 10 <= Lmax))
