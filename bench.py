@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--max-restarts", type=int, default=1000)
     ap.add_argument("--cpu-sample", default="auto", help="CPU baseline workload of the b200 arm (auto: the bench workload itself, one complete solve; "
                     "anything else is labelled as not being the bench workload and yields no parity block)")
+    ap.add_argument("--partition", default="rows", choices=["rows", "nnz"], help="N > 1: equal row blocks or nnz-balanced split points (SURVEY.md §8e)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=2)

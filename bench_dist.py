@@ -22,21 +22,33 @@ def main(args, rank, world, local_rank):
         ctx.set_tuning(kv.split("=")[0], int(kv.split("=")[1]))
     peak, peak_src = measured_peaks()
 
-    # ---- global problem -> this rank's slab (construction is outside the timed region) ----
-    rm, ind, val = ctx.gen(args.workload)
-    n = rm.numel() - 1
-    nnz_global = ind.numel()
-    part = g.dist.build_partition(rm, ind, val, n, rank, world)
-    del rm, ind, val
-    torch.cuda.empty_cache()
-    dctx = g.dist.DistContext(ctx, rank, world)
-    dctx.set_partition(part)
+    # ---- this rank's slab, generated ALONE (no rank ever holds the global matrix); construction is outside the timed region ----
+    _, _, _, _, _, n = ctx.gen_params(args.workload)
+    if getattr(args, "partition", "rows") == "nnz":
+        rm_global = ctx.gen_rowmap(args.workload).cpu().numpy()      # 4 (n + 1) bytes: the row map alone
+        bnd = g.dist.bounds_nnz(rm_global, world)
+        nnz_global = int(rm_global[-1])
+        del rm_global
+    else:
+        bnd = g.dist.bounds(n, world)
+        nnz_global = None
+    lo, hi = bnd[rank], bnd[rank + 1]
+    rm_l, ind_l, val_l = ctx.gen_slab(args.workload, lo, hi)
+    dctx = g.dist.DistContext(ctx, rank, world, native=True)
+    part = dctx.setup(n, bnd, rm_l, ind_l, val_l)                   # halo / send lists, mailboxes, inboxes: inside the library, over NCCL
     A = g.dist.local_csr(ctx, part)
-    xt_host = ctx.rand_vect(n, 42)
-    x_ext = torch.from_numpy(np.concatenate([xt_host[part.lo:part.hi], xt_host[part.halo_cols.cpu().numpy()]])).to(dev)
+    if nnz_global is None:
+        t_nnz = torch.tensor([float(ind_l.numel())], dtype=torch.float64, device=dev)
+        dist.all_reduce(t_nnz)
+        nnz_global = int(t_nnz.item())
+    xt_host = ctx.rand_vect(n, 42)                                  # a vector, not the matrix
+    dctx.attach()
+    x_ext = torch.cat([torch.from_numpy(xt_host[lo:hi]).to(dev), torch.zeros(part.n_halo, dtype=torch.float64, device=dev)])
+    dctx.halo_exchange(x_ext)                                       # the neighbours' entries of x_true
     xt = x_ext[:part.n_local].clone()
     b = torch.zeros(part.n_local, dtype=torch.float64, device=dev)
-    ctx.spmv(A, part.vals, 1.0, x_ext, 0.0, b)     # b = A x_true, rows of this rank (halo values taken from x_true directly)
+    dctx.detach()
+    ctx.spmv(A, part.vals, 1.0, x_ext, 0.0, b)                      # b = A x_true, rows of this rank
     val32 = torch.empty(part.vals.numel(), dtype=torch.float32, device=dev)
     ctx.copy(part.vals, val32)
     dctx.attach()
@@ -136,7 +148,8 @@ def main(args, rank, world, local_rank):
                 "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f32 inner / f64 outer", "data": "synthetic",
                 "config": {"workload": args.workload, "n_rows": n, "nnz": nnz_global, "restart_length": args.rlen, "tol": args.tol, "orth": args.orth,
-                           "prec": "identity", "partition": f"1-D row blocks, {world} ranks, rank 0: {part.n_local} rows + {part.n_halo} halo",
+                           "prec": "identity", "partition": f"1-D row blocks ({getattr(args, 'partition', 'rows')}-balanced split points), {world} ranks, "
+                                                            f"rank 0: {part.n_local} rows + {part.n_halo} halo; every rank generates and plans its slab alone",
                            "iters_per_solve": iters // max(args.steps, 1), "restarts_per_solve": restarts // max(args.steps, 1),
                            "time_to_solution_s": total_ms * 1e-3 / args.steps, "resNorm": res_norm, "errNorm": err_norm, "rel_res": res_norm / b_norm,
                            "l2": "per-rank working set >> 126 MB L2; no flush needed",

@@ -7,9 +7,13 @@ synthetic matrices (the reference only reads MatrixMarket files) and --json.
   python gmres_perf_test.py --gen cd27:256 --rlen 100 --orth cgsr --prec identity
 
 Flags as the reference: --Apath --bpath --rlen --rtol --repeat-iter --orthloss --tol --max-restarts --rand
---mode {mixed,baseline,single-prec,single} --orth {cgs,mgs,cgsr} --prec {identity,jacobi} --gpu (accepted, always on:
-there is no CPU path).  Defaults follow gmres_perf_test.cpp:313-325 except --prec (ilu is out of scope -> identity)."""
+--mode {mixed,baseline,single-prec,single} --orth {cgs,mgs,cgsr} --prec {identity,jacobi,ilu_jacobi} --jacobi-steps --gpu
+(accepted, always on: there is no CPU path).  Defaults follow gmres_perf_test.cpp:313-325 except --prec (the exact-ILU
+triangular solves are not provided -> identity).  --csv FILE appends the row automated.py:158-168 writes to
+history-<matrix>.csv (matrix, mode key, orth, rlen, rtol, rorth, tol, cuda, prec, i, total_iters, res, err, ilu s, gmres s)."""
+import csv
 import json
+import os
 import sys
 import time
 
@@ -18,7 +22,7 @@ import numpy as np
 
 def main(argv):
     a = dict(Apath=None, bpath=None, gen=None, rlen=0, rtol=0.0, orthloss=False, repeat=False, tol=1e-6, max_restarts=1000000, rand=42,
-             orth="mgs", mode="mixed", prec="identity", json=False)
+             orth="mgs", mode="mixed", prec="identity", json=False, jacobi_steps=1, csv=None)
     i = 1
     while i < len(argv):
         f = argv[i]
@@ -46,11 +50,12 @@ def main(argv):
                 print("Unknown Orthogonalization"); return 1
         elif f == "--prec":
             a["prec"] = val()
-            if a["prec"] in ("ilu", "ilu_jacobi"):
-                print("Preconditioner " + a["prec"] + " is not provided by the B200 backend (identity, jacobi)"); return 1
-            if a["prec"] not in ("identity", "jacobi"):
+            if a["prec"] == "ilu":
+                print("Preconditioner ilu (exact triangular solves) is not provided by the B200 backend (identity, jacobi, ilu_jacobi)"); return 1
+            if a["prec"] not in ("identity", "jacobi", "ilu_jacobi"):
                 print("Unknown Preconditioner"); return 1
-        elif f == "--jacobi-steps": val()
+        elif f == "--jacobi-steps": a["jacobi_steps"] = int(val())
+        elif f == "--csv": a["csv"] = val()
         elif f == "--gpu": pass
         elif f == "--json": a["json"] = True
         else:
@@ -77,7 +82,11 @@ def main(argv):
         b = torch.zeros(n, dtype=torch.float64, device=dev)
         ctx.spmv(A, val, 1.0, xt, 0.0, b)
     else:
-        raise SystemExit("--bpath (LoadVector) is not implemented yet")
+        xt = torch.zeros(n, dtype=torch.float64, device=dev)            # x_host = 0, b = LoadVector(bpath), :417-421
+        b_h = g.read_matrix_market_vector(a["bpath"])
+        if len(b_h) != n:
+            print(f"right-hand side has {len(b_h)} rows, the matrix {n}"); return 1
+        b = torch.from_numpy(b_h).to(dev)
     print(f"||x|| = {ctx.nrm2(xt):g}")                                   # :223-225
     print(f"||b|| = {ctx.nrm2(b):g}")
     print(f"||A|| = {ctx.nrm2(val):g}")
@@ -92,7 +101,7 @@ def main(argv):
     x = torch.zeros(n, dtype=torch.float64, device=dev)
     t0 = time.perf_counter()
     r = ctx.gmres(A, val, b, x, vals32=val32, mode=a["mode"], orth=a["orth"], conv=conv, prec=a["prec"], rlen=a["rlen"], tol=a["tol"],
-                  rtol=a["rtol"], max_restarts=a["max_restarts"], hist_cap=1)
+                  rtol=a["rtol"], max_restarts=a["max_restarts"], jacobi_steps=a["jacobi_steps"], hist_cap=1)
     ctx.sync()
     gmres_s = time.perf_counter() - t0                                   # wall clock around the solver call, :165-167
     if r["status"] == 1:
@@ -104,6 +113,14 @@ def main(argv):
     res_norm, err_norm = ctx.nrm2(res), ctx.nrm2(x - xt)
     print(f"  ilu took {prec_s:g}s; gmres took {gmres_s:g}s")            # :177-178
     print(f"  resNorm = {res_norm:g}; errNorm = {err_norm:g}")
+    if a["csv"]:
+        mat = a["gen"] or os.path.splitext(os.path.basename(a["Apath"]))[0]
+        key = {"baseline": "b", "mixed": "mp", "single-prec": "p", "single": "s"}[a["mode"]]
+        rt = ("R" if a["repeat"] else "") + (f"{a['rtol']:g}" if not a["orthloss"] else "0")
+        ro = f"{a['rtol']:g}" if a["orthloss"] else "0"
+        with open(a["csv"], "a", newline="") as fcsv:
+            csv.writer(fcsv, delimiter=",").writerow([mat, key, a["orth"].upper(), a["rlen"], rt, ro, f"{a['tol']:g}", "cuda", a["prec"], r["outer_i"],
+                                                      r["total_iters"], f"{res_norm:g}", f"{err_norm:g}", f"{prec_s:g}", f"{gmres_s:g}"])
     if a["json"]:
         print(json.dumps(dict(n=n, nnz=int(ind.numel()), status=r["status"], i=r["outer_i"], total_iterations=r["total_iters"],
                               restarts=r["total_restarts"], gmres_s=gmres_s, solve_ms=r["solve_ms"], resNorm=res_norm, errNorm=err_norm)))

@@ -5,10 +5,10 @@ the C++ drop-in headers under include/b200/.  This Python package is plumbing fo
 a ctypes binding that passes torch CUDA tensor pointers through the C ABI.  There is no CPU fallback:
 importing works anywhere, but every compute call needs the CUDA library and a CUDA device.
 """
-from .binding import (Context, CSR, Packed, GmresParams, GmresStats, MODES, ORTHS, CONVS, PRECS, load_library, library_path,
-                      exported_symbols, header_symbols, MpgError, read_matrix_market)
+from .binding import (Context, CSR, Packed, IluJacobi, GmresParams, GmresStats, MODES, ORTHS, CONVS, PRECS, load_library, library_path,
+                      exported_symbols, header_symbols, MpgError, read_matrix_market, read_matrix_market_vector)
 
 from . import dist  # noqa: E402,F401  (multi-GPU plumbing: partition builder + DistContext)
 
-__all__ = ["dist", "Context", "CSR", "Packed", "GmresParams", "GmresStats", "MODES", "ORTHS", "CONVS", "PRECS", "load_library",
-           "library_path", "exported_symbols", "header_symbols", "MpgError", "read_matrix_market"]
+__all__ = ["dist", "Context", "CSR", "Packed", "IluJacobi", "GmresParams", "GmresStats", "MODES", "ORTHS", "CONVS", "PRECS", "load_library",
+           "library_path", "exported_symbols", "header_symbols", "MpgError", "read_matrix_market", "read_matrix_market_vector"]

@@ -11,7 +11,7 @@ _LIB = None
 MODES = {"mixed": 0, "baseline": 1, "single-prec": 2, "single": 3}
 ORTHS = {"cgs": 0, "mgs": 1, "cgsr": 2}
 CONVS = {"base": 0, "relprecres": 1, "repeat": 2, "orthloss": 3}
-PRECS = {"identity": 0, "jacobi": 1}
+PRECS = {"identity": 0, "jacobi": 1, "ilu_jacobi": 2}
 
 
 class MpgError(RuntimeError):
@@ -21,7 +21,7 @@ class MpgError(RuntimeError):
 class GmresParams(C.Structure):
     _fields_ = [("mode", C.c_int32), ("orth", C.c_int32), ("conv", C.c_int32), ("prec", C.c_int32),
                 ("restart_length", C.c_int64), ("tol", C.c_double), ("restart_tol", C.c_double),
-                ("max_restarts", C.c_int64)]
+                ("max_restarts", C.c_int64), ("jacobi_steps", C.c_int64)]
 
 
 class GmresStats(C.Structure):
@@ -96,6 +96,23 @@ def read_matrix_market(path):
     finally:
         L.mpg_host_free(prm); L.mpg_host_free(pin); L.mpg_host_free(pv)
     return rm, ind, val
+
+
+def read_matrix_market_vector(path, col=0):
+    """column `col` of a MatrixMarket array / coordinate file as a float64 numpy array (mpg_mm_read_vector_host = the reference's
+    LoadVector, LoadMatrix.hpp:156-233).  Raises MpgError with the reference's exception text."""
+    import numpy as np
+    L = load_library()
+    n, pv = C.c_int64(), C.POINTER(C.c_double)()
+    err = C.create_string_buffer(256)
+    rc = L.mpg_mm_read_vector_host(str(path).encode(), C.c_int(col), C.byref(n), C.byref(pv), err, 256)
+    if rc != 0:
+        raise MpgError(err.value.decode() or f"mpg_mm_read_vector_host failed ({rc})")
+    try:
+        out = np.ctypeslib.as_array(pv, shape=(max(n.value, 1),))[:n.value].copy()
+    finally:
+        L.mpg_host_free(pv)
+    return out
 
 
 def _ptr(t):
@@ -202,6 +219,31 @@ class Packed:
             pass
 
 
+class IluJacobi:
+    """mpg_ilu_jacobi handle: ILU_Jacobi<Type>(ilu, steps) of types.hpp:251-372; sfx 'f32' | 'f64' is Type"""
+
+    def __init__(self, ctx, A, ilu_vals64, steps, sfx="f32"):
+        self.ctx, self.A, self.sfx = ctx, A, sfx
+        self.h = C.c_void_p()
+        ctx._chk(getattr(ctx.L, "mpg_ilu_jacobi_create_" + sfx)(ctx.h, A.h, _ptr(ilu_vals64), C.c_int(steps), C.byref(self.h)))
+
+    def apply(self, x):
+        self.ctx._chk(getattr(self.ctx.L, "mpg_ilu_jacobi_apply_" + self.sfx)(self.ctx.h, self.h, _ptr(x)))
+
+    def mv(self, lower, alpha, x, beta, y):
+        self.ctx._chk(getattr(self.ctx.L, "mpg_ilu_jacobi_mv_" + self.sfx)(self.ctx.h, self.h, C.c_int(int(lower)), _sc(x, alpha), _ptr(x), _sc(x, beta), _ptr(y)))
+
+    def __del__(self):
+        try:
+            if self.h:
+                if self.ctx.h:          # the context may already be closed at interpreter exit: never hand the library a null context
+                    self.ctx.sync()
+                self.ctx.L.mpg_ilu_jacobi_destroy(self.h)
+                self.h = C.c_void_p()
+        except Exception:
+            pass
+
+
 class Context:
     def __init__(self, device=0):
         import torch
@@ -237,6 +279,8 @@ class Context:
             raise MpgError(f"mpgmres_b200 error {rc}: {self.L.mpg_last_error(self.h).decode()}")
 
     def sync(self):
+        if not self.h:
+            raise MpgError("context is closed")
         self._chk(self.L.mpg_sync(self.h))
 
     def launches(self):
@@ -300,6 +344,43 @@ class Context:
             self._chk(self.L.mpg_gen_powerlaw_fill(self.h, C.c_int64(n), C.c_uint64(seed), C.c_int(lmin), C.c_int(gmax), _ptr(rm), _ptr(ind), _ptr(val)))
             return rm, ind, val
         raise ValueError(spec)
+
+    GEN_KINDS = {"lap2d": 0, "cd27": 1, "powerlaw": 2}
+
+    @classmethod
+    def gen_params(cls, spec):
+        """spec -> (kind, size, seed, lmin, gmax, n_rows)"""
+        kind, *a = spec.split(":")
+        a = [int(v) for v in a]
+        size = a[0]
+        seed = a[1] if len(a) > 1 else 7
+        lmin = a[2] if len(a) > 2 else 2
+        gmax = a[3] if len(a) > 3 else 15
+        n = size * size if kind == "lap2d" else (size ** 3 if kind == "cd27" else size)
+        return cls.GEN_KINDS[kind], size, seed, lmin, gmax, n
+
+    def gen_rowmap(self, spec):
+        """global row map of a synthetic matrix alone (int32 CUDA tensor, n + 1): what nnz-balanced split points need"""
+        import torch
+        k, size, seed, lmin, gmax, n = self.gen_params(spec)
+        rm = torch.empty(n + 1, dtype=torch.int32, device=f"cuda:{self.device}")
+        self._chk(self.L.mpg_gen_rowmap(self.h, C.c_int(k), C.c_int64(size), C.c_uint64(seed), C.c_int(lmin), C.c_int(gmax), _ptr(rm)))
+        return rm
+
+    def gen_slab(self, spec, lo, hi):
+        """rows [lo, hi) of a synthetic matrix: (row_map_local, inds with GLOBAL columns, vals64); no rank builds the global matrix"""
+        import torch
+        k, size, seed, lmin, gmax, n = self.gen_params(spec)
+        dev = f"cuda:{self.device}"
+        rm = torch.empty(hi - lo + 1, dtype=torch.int32, device=dev)
+        nnz = C.c_int64()
+        self._chk(self.L.mpg_gen_slab_rowmap(self.h, C.c_int(k), C.c_int64(size), C.c_uint64(seed), C.c_int(lmin), C.c_int(gmax), C.c_int64(lo), C.c_int64(hi),
+                                             _ptr(rm), C.byref(nnz)))
+        ind = torch.empty(nnz.value, dtype=torch.int32, device=dev)
+        val = torch.empty(nnz.value, dtype=torch.float64, device=dev)
+        self._chk(self.L.mpg_gen_slab_fill(self.h, C.c_int(k), C.c_int64(size), C.c_uint64(seed), C.c_int(lmin), C.c_int(gmax), C.c_int64(lo), C.c_int64(hi),
+                                           _ptr(rm), _ptr(ind), _ptr(val)))
+        return rm, ind, val
 
     def rand_vect(self, n, seed=42):
         import numpy as np
@@ -387,10 +468,23 @@ class Context:
     def jacobi_diag(self, A, vals, diag):
         self._chk(getattr(self.L, "mpg_jacobi_diag_" + _sfx(vals))(self.h, A.h, _ptr(vals), _ptr(diag)))
 
+    # ---- ILU(0) + Jacobi sweeps ----
+    def ilu0(self, A, vals64, eps_is_float=True):
+        """fp64 ILU(0) factors on A's structure (new torch tensor)"""
+        import torch
+        out = torch.empty_like(vals64)
+        self._chk(self.L.mpg_ilu0_f64(self.h, A.h, _ptr(vals64), C.c_int(int(eps_is_float)), _ptr(out)))
+        return out
+
+    def ilu0_levels(self, A):
+        v = C.c_int()
+        self._chk(self.L.mpg_ilu0_levels(self.h, A.h, C.byref(v)))
+        return v.value
+
     # ---- solver ----
     @staticmethod
-    def params(mode="mixed", orth="cgsr", conv="base", prec="identity", rlen=50, tol=1e-6, rtol=0.0, max_restarts=1000000):
-        return GmresParams(MODES[mode], ORTHS[orth], CONVS[conv], PRECS[prec], rlen, tol, rtol, max_restarts)
+    def params(mode="mixed", orth="cgsr", conv="base", prec="identity", rlen=50, tol=1e-6, rtol=0.0, max_restarts=1000000, jacobi_steps=1):
+        return GmresParams(MODES[mode], ORTHS[orth], CONVS[conv], PRECS[prec], rlen, tol, rtol, max_restarts, jacobi_steps)
 
     def gmres(self, A, vals64, b, x, vals32=None, hist_cap=None, **kw):
         """device-resident solve; x (torch float64 CUDA tensor) holds x0 on entry and the solution on exit"""

@@ -93,6 +93,7 @@ extern "C" int mpg_ctx_use_own_stream(mpg_ctx* ctx) {
 }
 extern "C" void* mpg_ctx_stream(mpg_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 extern "C" int mpg_sync(mpg_ctx* ctx) {
+    if (!ctx) return MPG_ERR_ARG;
     MPG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return mpg::check_dev_err(ctx);
 }
@@ -573,7 +574,8 @@ __global__ void __launch_bounds__(32) givens_step_kernel(int64_t k, T* h, int64_
 // only consume what the orthogonalisation left behind (w, 1/h(k+1,k), h(:,k)).
 template <class T>
 __global__ void __launch_bounds__(256) arnoldi_tail_kernel(int64_t n, const T* __restrict__ inv_dev, const T* x, T* y, int aligned, int64_t k, T* h,
-                                                            int64_t ldh, T* cs, T* sn, T* s, double* resid, double* resid_host) {
+                                                            int64_t ldh, T* cs, T* sn, T* s, double* resid, double* resid_host,
+                                                            const __grid_constant__ PushArgs push, int npush) {
     extern __shared__ unsigned char smem_raw[];
     pdl_trigger();
     pdl_wait();
@@ -581,9 +583,16 @@ __global__ void __launch_bounds__(256) arnoldi_tail_kernel(int64_t n, const T* _
         if (threadIdx.x < 32) givens_step_body<T>(smem_raw, k, h, ldh, cs, sn, s, resid, resid_host);
         return;
     }
+    const int new_blocks = (int)gridDim.x - 1 - npush;
+    if ((int)blockIdx.x >= new_blocks) {
+        // multi-GPU: the boundary rows of the NEW basis vector, w[idx] * (1/h), go straight into the halo tail of the neighbours'
+        // copy of that column (same product as the local store below: bit-identical values on both sides)
+        halo_push_block<T>(push, (int)blockIdx.x - new_blocks, x, inv_dev);
+        return;
+    }
     const T alpha = __ldg(inv_dev);
     const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t gstride = (int64_t)(gridDim.x - 1) * blockDim.x;
+    const int64_t gstride = (int64_t)new_blocks * blockDim.x;
     for (int64_t i0 = gtid * 4; i0 < n; i0 += gstride * 4) {
         const int cnt = (int)min((int64_t)4, n - i0);
         if (aligned && cnt == 4) {
@@ -673,17 +682,20 @@ int givens_step(mpg_ctx* ctx, int64_t k, T* h, int64_t ldh, T* cs, T* sn, T* s, 
 }
 template <class T>
 int arnoldi_tail(mpg_ctx* ctx, int64_t n, const T* inv_dev, const T* w, T* vnext, int64_t k, T* h, int64_t ldh, T* cs, T* sn, T* s, double* resid,
-                 double* resid_host) {
+                 double* resid_host, const PushArgs* push) {
     const size_t smem = sizeof(T) * (size_t)(3 * k + 2);
-    const int grid = (int)std::min<int64_t>(std::max<int64_t>(cdiv(n, 256 * 4), 1), (int64_t)ctx->num_sms * 16) + 1;
+    PushArgs pa;
+    if (push) pa = *push;
+    const int npush = pa.npeers * kPushBlocksPerPeer;
+    const int grid = (int)std::min<int64_t>(std::max<int64_t>(cdiv(n, 256 * 4), 1), (int64_t)ctx->num_sms * 16) + npush + 1;
     const int aligned = (((uintptr_t)w | (uintptr_t)vnext) & 15) == 0;
     ProfScope prof(ctx, MPG_PROF_ELEMENTWISE, 2.0 * (double)n * sizeof(T));
-    MPG_CUDA(ctx, launch_pdl(ctx, n, arnoldi_tail_kernel<T>, grid, 256, smem, n, inv_dev, w, vnext, aligned, k, h, ldh, cs, sn, s, resid, resid_host));
+    MPG_CUDA(ctx, launch_pdl(ctx, n, arnoldi_tail_kernel<T>, grid, 256, smem, n, inv_dev, w, vnext, aligned, k, h, ldh, cs, sn, s, resid, resid_host, pa, npush));
     MPG_CHECK_LAUNCH(ctx);
     return MPG_OK;
 }
-template int arnoldi_tail<float>(mpg_ctx*, int64_t, const float*, const float*, float*, int64_t, float*, int64_t, float*, float*, float*, double*, double*);
-template int arnoldi_tail<double>(mpg_ctx*, int64_t, const double*, const double*, double*, int64_t, double*, int64_t, double*, double*, double*, double*, double*);
+template int arnoldi_tail<float>(mpg_ctx*, int64_t, const float*, const float*, float*, int64_t, float*, int64_t, float*, float*, float*, double*, double*, const PushArgs*);
+template int arnoldi_tail<double>(mpg_ctx*, int64_t, const double*, const double*, double*, int64_t, double*, int64_t, double*, double*, double*, double*, double*, const PushArgs*);
 template int givens_step<float>(mpg_ctx*, int64_t, float*, int64_t, float*, float*, float*, double*, double*);
 template int givens_step<double>(mpg_ctx*, int64_t, double*, int64_t, double*, double*, double*, double*, double*);
 template <class T>

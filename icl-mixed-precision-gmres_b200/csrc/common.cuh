@@ -106,6 +106,7 @@ struct mpg_ctx {
 };
 
 struct mpg_sell_plan;   // sell.cu: packed (sliced-ELL) structure of a matrix
+struct mpg_ilu_plan;    // ilu.cu: diagonal positions + level schedule of the ILU(0) factorisation
 
 struct mpg_csr {
     int nrows = 0, ncols = 0;
@@ -126,11 +127,13 @@ struct mpg_csr {
     // packed structure (shared by the fp32 and fp64 value arrays), built on first use (sell.cu)
     mpg_sell_plan* sell = nullptr;
     int sell_tried = 0;
+    mpg_ilu_plan* ilu = nullptr;   // built on first factorisation (ilu.cu)
 };
 
 namespace mpg {
 
 void sell_plan_free(mpg_sell_plan* p);
+void ilu_plan_free(mpg_ilu_plan* p);
 
 // Plan / packed-matrix / per-solve temporaries come from the device's stream-ordered memory pool (release threshold
 // raised in mpg_ctx_create): building and dropping a multi-GB plan per call then re-uses the same physical memory
@@ -179,9 +182,10 @@ inline cudaError_t launch_pdl(mpg_ctx* ctx, int64_t rows, void (*kern)(KArgs...)
     return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
 }
 
-#define MPG_REQUIRE(ctx, cond, msg)                                   \
-    do {                                                              \
-        if (!(cond)) return mpg::fail(ctx, MPG_ERR_ARG, (msg));       \
+#define MPG_REQUIRE(ctx, cond, msg)                                                                                  \
+    do {                                                                                                             \
+        if ((ctx) == nullptr) return MPG_ERR_ARG; /* a null (closed) context is an argument error, never a crash */    \
+        if (!(cond)) return mpg::fail(ctx, MPG_ERR_ARG, (msg));                                                      \
     } while (0)
 
 #define MPG_TRY(expr)              \
@@ -345,6 +349,45 @@ __device__ __forceinline__ void wait_flag(const unsigned long long* flag, unsign
                 if (err) atomicOr(err, code);
                 return;
             }
+        }
+    }
+}
+
+// ---- halo exchange over NVLink peer memory (push model, dist.cu) --------------------------------------------------------
+// The sender gathers the rows a neighbour needs and stores them straight into that neighbour's memory - its inbox, or (fused
+// path) the halo tail of the neighbour's own copy of the Krylov basis column - then publishes the exchange number in the
+// neighbour's flag word; kPushBlocksPerPeer CTAs per neighbour (one SM cannot keep an NVLink busy with stores).
+constexpr int kPushBlocksPerPeer = 32;
+struct PushArgs {
+    int npeers = 0;
+    const int* send_idx[kMaxPeers];
+    long long count[kMaxPeers];
+    void* dst[kMaxPeers];                   // where our rows go in the neighbour's memory
+    unsigned long long* flag[kMaxPeers];    // the neighbour's flag for (slot, this rank)
+    unsigned long long seq = 0;
+    unsigned int* counters = nullptr;       // kMaxPeers arrival counters (device)
+};
+// block `pb` (0 <= pb < npeers * kPushBlocksPerPeer) of a push: dst[i] = scale * x[idx[i]] (scale == null: plain copy)
+template <class T>
+__device__ __forceinline__ void halo_push_block(const PushArgs& a, int pb, const T* __restrict__ x, const T* __restrict__ scale) {
+    const int q = pb / kPushBlocksPerPeer, part = pb % kPushBlocksPerPeer;
+    T* dst = static_cast<T*>(a.dst[q]);
+    const int* idx = a.send_idx[q];
+    const long long cnt = a.count[q];
+    if (scale) {
+        const T al = __ldg(scale);
+        for (long long i = (long long)part * blockDim.x + threadIdx.x; i < cnt; i += (long long)kPushBlocksPerPeer * blockDim.x) dst[i] = al * x[idx[i]];
+    } else {
+        for (long long i = (long long)part * blockDim.x + threadIdx.x; i < cnt; i += (long long)kPushBlocksPerPeer * blockDim.x) dst[i] = x[idx[i]];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        // the last block of this neighbour publishes the exchange number (its fence + the counter chain order all stores)
+        if (atomicAdd(a.counters + q, 1u) == kPushBlocksPerPeer - 1) {
+            a.counters[q] = 0u;
+            __threadfence_system();
+            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.flag[q]), "l"(a.seq) : "memory");
         }
     }
 }

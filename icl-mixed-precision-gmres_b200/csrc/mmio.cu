@@ -12,6 +12,7 @@
 #include <cctype>
 #include <cstdlib>
 #include <numeric>
+#include <string>
 #include <vector>
 
 #include "common.cuh"
@@ -103,6 +104,63 @@ extern "C" int mpg_mm_read_host(const char* path, int* nrows_out, int* ncols_out
     }
     *nrows_out = (int)M; *ncols_out = (int)N; *nnz_out = nnz;
     *row_map_out = row_map; *inds_out = inds; *vals_out = vals;
+    return MPG_OK;
+}
+
+// LoadVector<S>(file, col), LoadMatrix.hpp:156-233: column `col` of a MatrixMarket ARRAY file (dense, column-major) or of a
+// COORDINATE file (entries of other columns are skipped, missing entries are 0, the last duplicate wins).  Same exception
+// texts as the reference; the size line is read like mm_read_mtx_array_size / mm_read_mtx_crd_size (comment lines skipped).
+extern "C" int mpg_mm_read_vector_host(const char* path, int col, int64_t* n_out, double** vals_out, char* errbuf, int errlen) {
+    auto fail_msg = [&](const std::string& m) {
+        if (errbuf && errlen > 0) { std::snprintf(errbuf, (size_t)errlen, "%s", m.c_str()); }
+        return MPG_ERR_ARG;
+    };
+    if (!path || !n_out || !vals_out || col < 0) return fail_msg("null argument");
+    FILE* f = std::fopen(path, "rb");
+    if (!f) return fail_msg("Could not access file");                                  // :158-161
+    std::fseek(f, 0, SEEK_END);
+    const long sz = std::ftell(f);
+    std::fseek(f, 0, SEEK_SET);
+    std::vector<char> buf((size_t)sz + 1);
+    const size_t got = std::fread(buf.data(), 1, (size_t)sz, f);
+    std::fclose(f);
+    buf[got] = 0;
+    char* p = buf.data();
+    char* eol = std::strchr(p, '\n');
+    if (!eol) return fail_msg("Missing values in banner");                             // :165-177
+    std::string banner(p, eol);
+    for (auto& c : banner) c = (char)std::tolower((unsigned char)c);
+    char b0[64], b1[64], b2[64], b3[64], b4[64];
+    if (std::sscanf(banner.c_str(), "%63s %63s %63s %63s %63s", b0, b1, b2, b3, b4) != 5) return fail_msg("Missing values in banner");
+    if (std::string(b0) != "%%matrixmarket") return fail_msg("Banner is missing");
+    if (std::string(b1) != "matrix") return fail_msg("Unrecognized description");
+    const bool array = std::string(b2) == "array", coordinate = std::string(b2) == "coordinate";
+    if (!array && !coordinate) return fail_msg("Unrecognized description");
+    p = eol + 1;
+    while (*p == '%') { eol = std::strchr(p, '\n'); if (!eol) return fail_msg("Malformed matrix size information"); p = eol + 1; }
+    char* q;
+    const long M = std::strtol(p, &q, 10); if (q == p) return fail_msg("Malformed matrix size information"); p = q;   // :181-190
+    const long N = std::strtol(p, &q, 10); if (q == p) return fail_msg("Malformed matrix size information"); p = q;
+    long nz = 0;
+    if (coordinate) { nz = std::strtol(p, &q, 10); if (q == p) return fail_msg("Malformed matrix size information"); p = q; }
+    if (M < 0 || N < 0 || nz < 0) return fail_msg("Malformed matrix size information");
+    if (col >= N) return fail_msg("Column " + std::to_string(col) + " is too large for the " + std::to_string(N) + " vectors");   // :192-197
+    double* vals = (double*)std::calloc((size_t)std::max<long>(M, 1), sizeof(double));
+    if (!vals) return fail_msg("out of memory");
+    if (array) {                                                                       // :202-214
+        for (long i = 0; i < (long)col * M; ++i) { std::strtod(p, &q); if (q == p) { std::free(vals); return fail_msg("premature end of entries"); } p = q; }
+        for (long j = 0; j < M; ++j) { vals[j] = std::strtod(p, &q); if (q == p) { std::free(vals); return fail_msg("premature end of entries"); } p = q; }
+    } else {                                                                           // :215-227
+        for (long e = 0; e < nz; ++e) {
+            const long i = std::strtol(p, &q, 10); if (q == p) { std::free(vals); return fail_msg("premature end of entries"); } p = q;
+            const long j = std::strtol(p, &q, 10); if (q == p) { std::free(vals); return fail_msg("premature end of entries"); } p = q;
+            const double v = std::strtod(p, &q); if (q == p) { std::free(vals); return fail_msg("premature end of entries"); } p = q;
+            if (i < 1 || i > M) { std::free(vals); return fail_msg("entry index out of range"); }
+            if (j - 1 == col) vals[i - 1] = v;
+        }
+    }
+    *n_out = M;
+    *vals_out = vals;
     return MPG_OK;
 }
 

@@ -241,21 +241,22 @@ __device__ __forceinline__ void load_group(const double* gbase, int lane, double
     v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
 }
 
+// xadd != null: Jacobi sweep of the ILU factors (ilu.cu) - the SpMV result v = b - Op x is the correction, the stored value is
+//   x + v (axpy(1, temp, x), kernels.hpp:239) or, with rowscale = D^-1, 1*x + (1*d)*v (gdmv(1, diag, temp, 1, x), kernels.hpp:247)
 template <class T>
-__device__ __forceinline__ T sell_epilogue(int r, T sum, T alpha, T beta, const T* y_in, const T* __restrict__ rowscale) {
+__device__ __forceinline__ T sell_epilogue(int r, T sum, T alpha, T beta, const T* y_in, const T* __restrict__ rowscale, const T* xadd) {
     T v = (beta == T(0)) ? alpha * sum : fma(alpha, sum, beta * y_in[r]);
-    if (rowscale) {   // Jacobi: gdmv(1, d, v, 0, v), rounding sequence of the stand-alone kernel (kernels.hpp:143-145)
+    if (xadd) {
+        const T xo = xadd[r];
+        if (rowscale) v = add_rn(mul_rn(T(1), xo), mul_rn(mul_rn(T(1), __ldg(rowscale + r)), v));
+        else v = fma(T(1), v, xo);
+    } else if (rowscale) {   // Jacobi: gdmv(1, d, v, 0, v), rounding sequence of the stand-alone kernel (kernels.hpp:143-145)
         const T d = __ldg(rowscale + r);
         v = add_rn(mul_rn(T(0), v), mul_rn(mul_rn(T(1), d), v));
     }
     return v;
 }
 
-// y[r] = alpha * sum_p v[r,p] x[c[r,p]] + beta * y[r]; products and sums individually rounded, nonzero order
-// (the CSR kernel's arithmetic for a row that lies inside one tile).
-//   vout == null (PLAIN): lane `pos` is row `pos`.   vout != null (SIGMA): see the header comment.
-//   halo_wait != null: the slices of this launch read halo entries of x that a neighbour GPU is pushing (dist.cu); every CTA
-//   waits for the neighbours' exchange numbers before its first access to x.
 // gather of x: through L1 (stencil matrices: neighbouring lanes and rows share lines) or around it (NA: random columns never hit)
 template <bool NA> __device__ __forceinline__ float ldx(const float* p) { return NA ? ldg_stream(p) : __ldg(p); }
 template <bool NA> __device__ __forceinline__ double ldx(const double* p) { return NA ? ldg_stream(p) : __ldg(p); }
@@ -264,7 +265,7 @@ template <class T, bool HAS_REM, bool NA, int UN>
 __global__ void __launch_bounds__(256, UN == 4 ? 5 : (sizeof(T) == 8 ? 6 : 8)) spmv_sell_kernel(int nlanes, int nslices, const int64_t* __restrict__ slice_off, const int* __restrict__ sinds,
                                                          const T* __restrict__ svals, const T* __restrict__ x, T alpha, T beta, const T* y_in,
                                                          T* y_out, float* out32, const T* __restrict__ rowscale, const int* __restrict__ slice_list,
-                                                         const int* __restrict__ vout, T* __restrict__ partial, const __grid_constant__ HaloWait hw) {
+                                                         const int* __restrict__ vout, T* __restrict__ partial, const T* xadd, const __grid_constant__ HaloWait hw) {
     pdl_trigger();
     pdl_wait();
     if (hw.npeers > 0) halo_wait_block(hw);
@@ -326,7 +327,7 @@ __global__ void __launch_bounds__(256, UN == 4 ? 5 : (sizeof(T) == 8 ? 6 : 8)) s
         r = __ldg(vout + pos);
         if (r < 0) { partial[-1 - r] = sum; return; }   // a piece of a cut row: sell_fixup_kernel finishes it
     }
-    const T v = sell_epilogue<T>(r, sum, alpha, beta, y_in, rowscale);
+    const T v = sell_epilogue<T>(r, sum, alpha, beta, y_in, rowscale, xadd);
     if (y_out) y_out[r] = v;
     if (out32) out32[r] = (float)v;
 }
@@ -334,7 +335,7 @@ __global__ void __launch_bounds__(256, UN == 4 ? 5 : (sizeof(T) == 8 ? 6 : 8)) s
 // SIGMA mode: one thread per cut row adds its pieces in nonzero order and applies the epilogue
 template <class T>
 __global__ void sell_fixup_kernel(int nsplit, const int* __restrict__ split_rows, const int* __restrict__ chunk_base, const T* __restrict__ partial,
-                                  T alpha, T beta, const T* y_in, T* y_out, float* out32, const T* __restrict__ rowscale) {
+                                  T alpha, T beta, const T* y_in, T* y_out, float* out32, const T* __restrict__ rowscale, const T* xadd) {
     pdl_trigger();
     pdl_wait();
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -342,7 +343,7 @@ __global__ void sell_fixup_kernel(int nsplit, const int* __restrict__ split_rows
     const int r = split_rows[j];
     T sum = T(0);
     for (int p = chunk_base[j], pe = chunk_base[j + 1]; p < pe; ++p) sum = add_rn(sum, partial[p]);
-    const T v = sell_epilogue<T>(r, sum, alpha, beta, y_in, rowscale);
+    const T v = sell_epilogue<T>(r, sum, alpha, beta, y_in, rowscale, xadd);
     if (y_out) y_out[r] = v;
     if (out32) out32[r] = (float)v;
 }
@@ -541,7 +542,7 @@ bool pack_matches(const mpg_packed* P, const mpg_csr* A, int tsize) {
 
 template <class T>
 int spmv_packed(mpg_ctx* ctx, const mpg_packed* P, T alpha, const T* x, T beta, const T* y_in, T* y_out, float* out32, const T* rowscale, int part,
-                const HaloWait* hw_in) {
+                const HaloWait* hw_in, const T* xadd) {
     const mpg_sell_plan* p = P->plan;
     const mpg_csr* A = P->A;
     if (part != SPMV_ALL && !p->slice_list) {
@@ -560,11 +561,12 @@ int spmv_packed(mpg_ctx* ctx, const mpg_packed* P, T alpha, const T* x, T beta, 
     hw.npeers = 0;
     if (hw_in) hw = *hw_in;
     if (s_count > 0) {
-        // SIGMA plans gather random columns: around L1, 4 groups per step (profiles/r02_tune_sell_sigma.txt); stencils: through L1, 2 groups
-        const int variant = ctx->tune.sell_variant >= 0 ? ctx->tune.sell_variant : (p->mode == MODE_SIGMA ? 3 : 0);
-        const int block = ctx->tune.sell_block > 0 ? std::min(ctx->tune.sell_block, 256) : 256;
+        // measured (profiles/r02_tune_sell_sigma.txt): SIGMA plans (random columns) want 4 groups = 16 gathers in flight per lane, stencils 2;
+        // x always through L1 - the no-allocate hint on the gathers also demotes x in L2 and doubles the DRAM traffic
+        const int variant = ctx->tune.sell_variant >= 0 ? ctx->tune.sell_variant : (p->mode == MODE_SIGMA ? 2 : 0);
+        const int block = ctx->tune.sell_block > 0 ? std::min(ctx->tune.sell_block, 256) : 128;
         const int grid = (int)cdiv((int64_t)s_count * 32, block);
-        void (*kern)(int, int, const int64_t*, const int*, const T*, const T*, T, T, const T*, T*, float*, const T*, const int*, const int*, T*, const HaloWait);
+        void (*kern)(int, int, const int64_t*, const int*, const T*, const T*, T, T, const T*, T*, float*, const T*, const int*, const int*, T*, const T*, const HaloWait);
         switch ((variant & 3) * 2 + (p->has_rem ? 1 : 0)) {
             case 0: kern = spmv_sell_kernel<T, false, false, 2>; break;
             case 1: kern = spmv_sell_kernel<T, true, false, 2>; break;
@@ -577,18 +579,24 @@ int spmv_packed(mpg_ctx* ctx, const mpg_packed* P, T alpha, const T* x, T beta, 
         }
         MPG_CUDA(ctx, launch_pdl(ctx, (int64_t)A->nrows, kern, grid, block, 0, p->nlanes, s_count, (const int64_t*)p->slice_off, (const int*)p->sinds,
                                  static_cast<const T*>(P->svals), x, alpha, beta, y_in, y_out, out32, rowscale, list, (const int*)p->vout,
-                                 static_cast<T*>(p->partial), hw));
+                                 static_cast<T*>(p->partial), xadd, hw));
         MPG_CHECK_LAUNCH(ctx);
     }
     if (p->nsplit > 0 && part != SPMV_INTERIOR) {
         MPG_CUDA(ctx, launch_pdl(ctx, (int64_t)A->nrows, sell_fixup_kernel<T>, (int)cdiv(p->nsplit, 128), 128, 0, p->nsplit, (const int*)p->split_rows,
-                                 (const int*)p->chunk_base, static_cast<const T*>(p->partial), alpha, beta, y_in, y_out, out32, rowscale));
+                                 (const int*)p->chunk_base, static_cast<const T*>(p->partial), alpha, beta, y_in, y_out, out32, rowscale, xadd));
         MPG_CHECK_LAUNCH(ctx);
     }
     return MPG_OK;
 }
-template int spmv_packed<float>(mpg_ctx*, const mpg_packed*, float, const float*, float, const float*, float*, float*, const float*, int, const HaloWait*);
-template int spmv_packed<double>(mpg_ctx*, const mpg_packed*, double, const double*, double, const double*, double*, float*, const double*, int, const HaloWait*);
+template int spmv_packed<float>(mpg_ctx*, const mpg_packed*, float, const float*, float, const float*, float*, float*, const float*, int, const HaloWait*, const float*);
+template int spmv_packed<double>(mpg_ctx*, const mpg_packed*, double, const double*, double, const double*, double*, float*, const double*, int, const HaloWait*, const double*);
+
+int scan_i32(mpg_ctx* ctx, int64_t n, const int* in, int* out) {
+    scan_kernel<int, int><<<1, 1024, 0, ctx->stream>>>(n, in, out);
+    MPG_CHECK_LAUNCH(ctx);
+    return MPG_OK;
+}
 
 }  // namespace mpg
 
@@ -604,7 +612,7 @@ template int spmv_packed<double>(mpg_ctx*, const mpg_packed*, double, const doub
     }                                                                                                                              \
     extern "C" int mpg_spmv_packed_##SFX(mpg_ctx* ctx, const mpg_packed* P, T alpha, const T* x, T beta, T* y) {                  \
         MPG_REQUIRE(ctx, P && x && y && P->tsize == (int)sizeof(T), "spmv_packed: null argument or wrong precision");             \
-        return mpg::spmv_packed<T>(ctx, P, alpha, x, beta, y, y, nullptr, nullptr, mpg::SPMV_ALL, nullptr);                       \
+        return mpg::spmv_packed<T>(ctx, P, alpha, x, beta, y, y, nullptr, nullptr, mpg::SPMV_ALL, nullptr, nullptr);              \
     }
 MPG_DEF_PACK(f32, float)
 MPG_DEF_PACK(f64, double)

@@ -43,16 +43,23 @@ template <class T> int spmv(mpg_ctx*, const mpg_csr*, const T*, T, const T*, T, 
 template <class T> int gemvn(mpg_ctx*, int64_t, int, const T*, int64_t, T, const T*, T, T*, bool, T*, T*, double*);
 template <class T> int gemvt(mpg_ctx*, int64_t, int, const T*, int64_t, T, const T*, T, T*);
 template <class T> int add_vector(mpg_ctx*, int, int64_t, int64_t, T*, int64_t, T*, T*, T*, bool);
-template <class T> int arnoldi_tail(mpg_ctx*, int64_t, const T*, const T*, T*, int64_t, T*, int64_t, T*, T*, T*, double*, double*);
+template <class T> int arnoldi_tail(mpg_ctx*, int64_t, const T*, const T*, T*, int64_t, T*, int64_t, T*, T*, T*, double*, double*, const PushArgs* = nullptr);
 template <class T> int pack_create(mpg_ctx*, const mpg_csr*, const T*, mpg_packed**);
 template <class T> int pack_update(mpg_ctx*, mpg_packed*, const T*);
 void pack_free(mpg_packed*);
 bool pack_matches(const mpg_packed*, const mpg_csr*, int tsize);
-template <class T> int spmv_packed(mpg_ctx*, const mpg_packed*, T, const T*, T, const T*, T*, float*, const T*, int, const HaloWait* = nullptr);
+template <class T> int spmv_packed(mpg_ctx*, const mpg_packed*, T, const T*, T, const T*, T*, float*, const T*, int, const HaloWait* = nullptr, const T* xadd = nullptr);
+template <class T> int ilu_jacobi_apply_t(mpg_ctx*, mpg_ilu_jacobi*, T*);
 template <class T> int halo_exchange(mpg_ctx*, T*);
 template <class T> int halo_begin(mpg_ctx*, T*);
 template <class T> int halo_finish(mpg_ctx*, T*);
 int64_t dist_halo(mpg_ctx*);
+int dist_exchange_basis(mpg_ctx*, void* V, int64_t ldv, int tsize);
+bool dist_basis_ready(mpg_ctx*);
+template <class T> int halo_direct_args(mpg_ctx*, int64_t col, PushArgs*);
+template <class T> int halo_push_direct(mpg_ctx*, const T* x, int64_t col);
+int halo_wait_args(mpg_ctx*, HaloWait*);
+int halo_wait_only(mpg_ctx*);
 int64_t dist_nglobal(mpg_ctx*);
 int dist_world(mpg_ctx*);
 }  // namespace mpg
@@ -262,13 +269,15 @@ int get_packed(mpg_ctx* ctx, Workspace* ws, int slot, const mpg_csr* A, const T*
 //   jac != null: Jacobi, gdmv(1, diag, w, 0, w)  (types.hpp:444-446)
 //   bridge:      typesafe_apply with PrecType = float and Type = double (gmres.cpp:12-17): cast, apply, cast back
 template <class T>
-int apply_prec(mpg_ctx* ctx, int64_t n, T* w, const T* jac, const float* jac32, bool bridge, float* tmp32) {
+int apply_prec(mpg_ctx* ctx, int64_t n, T* w, const T* jac, const float* jac32, bool bridge, float* tmp32, mpg_ilu_jacobi* ilu = nullptr) {
     if (bridge) {
         MPG_TRY(cast_copy(ctx, n, reinterpret_cast<const double*>(w), tmp32));
-        if (jac32) MPG_TRY(gdmv_host(ctx, n, 1.f, jac32, tmp32, 0.f, tmp32));
+        if (ilu) MPG_TRY(ilu_jacobi_apply_t<float>(ctx, ilu, tmp32));
+        else if (jac32) MPG_TRY(gdmv_host(ctx, n, 1.f, jac32, tmp32, 0.f, tmp32));
         MPG_TRY(cast_copy(ctx, n, tmp32, reinterpret_cast<double*>(w)));
         return MPG_OK;
     }
+    if (ilu) return ilu_jacobi_apply_t<T>(ctx, ilu, w);   // ILU_Jacobi::apply = ilusv_jacobi (types.hpp:365-367)
     if (jac) MPG_TRY(gdmv_host(ctx, n, T(1), jac, w, T(0), w));
     return MPG_OK;
 }
@@ -277,7 +286,7 @@ int apply_prec(mpg_ctx* ctx, int64_t n, T* w, const T* jac, const float* jac32, 
 // number of inner iterations performed (the `k` handed to solution_update).
 template <class T>
 int run_cycle(mpg_ctx* ctx, const mpg_gmres_params& p, Policy& pol, Workspace* ws, const mpg_csr* A, const T* vals, const mpg_packed* P, const T* jac,
-              const float* jac32, bool bridge, T beta, double Minvb_norm, History& hist, int64_t* k_out, Action* act_out) {
+              const float* jac32, bool bridge, mpg_ilu_jacobi* ilu, T beta, double Minvb_norm, History& hist, int64_t* k_out, Action* act_out) {
     const int64_t n = ws->n, m = ws->m, ldv = ws->ldv, ldh = m + 1;
     T* V = static_cast<T*>(ws->V);
     T* w = static_cast<T*>(ws->w);
@@ -294,6 +303,7 @@ int run_cycle(mpg_ctx* ctx, const mpg_gmres_params& p, Policy& pol, Workspace* w
     MPG_TRY(fill_host(ctx, m + 1, T(0), s));
     MPG_TRY(fill_host(ctx, 1, beta, s));
 
+    int64_t pushed_col = -1;   // fused halo: basis column whose boundary rows are already on their way to the neighbours
     // one Arnoldi step, enqueued asynchronously
     auto enqueue_iteration = [&](int64_t kk, double* resid_host) -> int {
         // w = A v_k ; M(w)            gmres.cpp:98-102,210-215
@@ -304,7 +314,23 @@ int run_cycle(mpg_ctx* ctx, const mpg_gmres_params& p, Policy& pol, Workspace* w
             if (P) return spmv_packed<T>(ctx, P, T(1), vk, T(0), w, w, nullptr, rowscale, part);
             return spmv<T>(ctx, A, vals, T(1), vk, T(0), w, w, nullptr, rowscale, part);
         };
-        if (A->ncols > A->nrows && ctx->tune.dist_overlap) {
+        const bool slab = A->ncols > A->nrows;
+        const bool direct = slab && dist_basis_ready(ctx);   // fused halo: the neighbours write the halo tail of v_k themselves
+        if (direct) {
+            // v_k's boundary rows were pushed by the Arnoldi tail that produced v_k; the first vector of a cycle (and an unfused tail)
+            // is pushed here.  No wait-and-move launch: the SpMV on the slices that read halo columns waits for the flags itself.
+            if (pushed_col != kk) MPG_TRY(halo_push_direct<T>(ctx, vk, kk));
+            HaloWait hw;
+            MPG_TRY(halo_wait_args(ctx, &hw));
+            if (P) {
+                MPG_TRY(spmv_packed<T>(ctx, P, T(1), vk, T(0), w, w, nullptr, rowscale, SPMV_INTERIOR));
+                MPG_TRY(spmv_packed<T>(ctx, P, T(1), vk, T(0), w, w, nullptr, rowscale, SPMV_BOUNDARY, &hw));
+            } else {
+                MPG_TRY(mult(SPMV_INTERIOR));
+                MPG_TRY(halo_wait_only(ctx));
+                MPG_TRY(mult(SPMV_BOUNDARY));
+            }
+        } else if (slab && ctx->tune.dist_overlap) {
             // multi-GPU: send v_k's boundary rows, multiply the rows that need no halo while they travel, then the rest
             MPG_TRY(halo_begin<T>(ctx, vk));
             MPG_TRY(mult(SPMV_INTERIOR));
@@ -314,12 +340,15 @@ int run_cycle(mpg_ctx* ctx, const mpg_gmres_params& p, Policy& pol, Workspace* w
             MPG_TRY(halo_exchange<T>(ctx, vk));   // fill the halo tail of v_k (no-op on one GPU)
             MPG_TRY(mult(SPMV_ALL));
         }
-        if (!rowscale) MPG_TRY(apply_prec<T>(ctx, n, w, jac, jac32, bridge, ws->tmp32));
+        if (!rowscale) MPG_TRY(apply_prec<T>(ctx, n, w, jac, jac32, bridge, ws->tmp32, ilu));
         // orth.add_vector(k, w, h)     gmres.cpp:104,217
         if (ctx->tune.fuse_tail) {
             // orthogonalise, then ONE launch for V(:,k+1) = w / h(k+1,k) and the rotations (independent of each other)
             MPG_TRY(add_vector<T>(ctx, p.orth, n, kk, V, ldv, w, h + (size_t)kk * ldh, scratch, true));
-            return arnoldi_tail<T>(ctx, n, scratch + (kk + 1), w, V + (size_t)(kk + 1) * ldv, kk, h, ldh, cs, sn, s, ws->hist + kk, resid_host);
+            PushArgs pa;
+            if (direct) { MPG_TRY(halo_direct_args<T>(ctx, kk + 1, &pa)); pushed_col = kk + 1; }
+            return arnoldi_tail<T>(ctx, n, scratch + (kk + 1), w, V + (size_t)(kk + 1) * ldv, kk, h, ldh, cs, sn, s, ws->hist + kk, resid_host,
+                                   direct ? &pa : nullptr);
         }
         MPG_TRY(add_vector<T>(ctx, p.orth, n, kk, V, ldv, w, h + (size_t)kk * ldh, scratch, false));
         // rot / rotg / rot             gmres.cpp:106-110,219-222 ; |s(k+1)| stays on the device
@@ -411,10 +440,11 @@ int run_cycle(mpg_ctx* ctx, const mpg_gmres_params& p, Policy& pol, Workspace* w
 
 // ---- GMRES-IR: gmres_singleUpdate, gmres.cpp:135-245 ----------------------------------------------------------
 int solve_mixed(mpg_ctx* ctx, const mpg_gmres_params& p, const mpg_csr* A, const double* vals64, const float* vals32, const float* jac32,
-                const double* b, double* x, mpg_gmres_stats* st, History& hist) {
+                mpg_ilu_jacobi* ilu, const double* b, double* x, mpg_gmres_stats* st, History& hist) {
     const int64_t n = A->nrows, m = p.restart_length;
     Workspace* ws = nullptr;
     MPG_TRY(get_workspace(ctx, n, m, 4, p.conv == MPG_CONV_ORTHLOSS, false, &ws));
+    MPG_TRY(dist_exchange_basis(ctx, ws->V, ws->ldv, 4));
     float* w = static_cast<float*>(ws->w);
     float* h = static_cast<float*>(ws->h);
     float* s = static_cast<float*>(ws->s);
@@ -435,7 +465,7 @@ int solve_mixed(mpg_ctx* ctx, const mpg_gmres_params& p, const mpg_csr* A, const
     // setup norms, gmres.cpp:162-168 — three reductions, one readback
     MPG_TRY(nrm2_dev(ctx, n, b, ds<double>(ctx, 0)));
     MPG_TRY(cast_copy(ctx, n, b, w));
-    MPG_TRY(apply_prec<float>(ctx, n, w, jac32, nullptr, false, nullptr));
+    MPG_TRY(apply_prec<float>(ctx, n, w, jac32, nullptr, false, nullptr, ilu));
     MPG_TRY(nrm2_dev(ctx, n, w, ds<float>(ctx, 1)));
     MPG_TRY(nrm2_dev(ctx, A->nnz, vals32, ds<float>(ctx, 2)));
     MPG_TRY(read_scalars<double>(ctx, 3));
@@ -456,12 +486,12 @@ int solve_mixed(mpg_ctx* ctx, const mpg_gmres_params& p, const mpg_csr* A, const
         if (packed64) MPG_TRY(spmv_packed<double>(ctx, packed64, -1.0, xin, 1.0, b, nullptr, w, nullptr, SPMV_ALL));
         else MPG_TRY(spmv<double>(ctx, A, vals64, -1.0, xin, 1.0, b, nullptr, w));
         MPG_TRY(nrm2_dev(ctx, n, w, ds<float>(ctx, 0)));                       // r_norm   :176
-        MPG_TRY(apply_prec<float>(ctx, n, w, jac32, nullptr, false, nullptr)); // M(w)     :177
-        if (jac32) MPG_TRY(nrm2_dev(ctx, n, w, ds<float>(ctx, 1)));            // beta     :179 (same vector when M = I)
+        MPG_TRY(apply_prec<float>(ctx, n, w, jac32, nullptr, false, nullptr, ilu)); // M(w)     :177
+        if (jac32 || ilu) MPG_TRY(nrm2_dev(ctx, n, w, ds<float>(ctx, 1)));     // beta     :179 (same vector when M = I)
         MPG_TRY(nrm2_dev(ctx, n, x, ds<double>(ctx, 2)));                      // x_norm   :181
         MPG_TRY(read_scalars<double>(ctx, 3));
         const double r_norm = hs<float>(ctx, 0);
-        const float beta = jac32 ? hs<float>(ctx, 1) : hs<float>(ctx, 0);
+        const float beta = (jac32 || ilu) ? hs<float>(ctx, 1) : hs<float>(ctx, 0);
         const double x_norm = hs<double>(ctx, 2);
         hist.push_outer(r_norm, b_norm + A_norm * x_norm, beta, x_norm);
         const Action a0 = pol.check_initial(r_norm, b_norm + A_norm * x_norm, beta, Minvb_norm);   // :184
@@ -470,7 +500,7 @@ int solve_mixed(mpg_ctx* ctx, const mpg_gmres_params& p, const mpg_csr* A, const
 
         int64_t k = 0;
         Action act = NEXT;
-        MPG_TRY(run_cycle<float>(ctx, p, pol, ws, A, vals32, packed, jac32, nullptr, false, beta, Minvb_norm, hist, &k, &act));
+        MPG_TRY(run_cycle<float>(ctx, p, pol, ws, A, vals32, packed, jac32, nullptr, false, ilu, beta, Minvb_norm, hist, &k, &act));
         if (act == ABORTED) { st->status = 3; st->outer_i = i; break; }
 
         // solution_update, gmres.cpp:276-290: y = triu(H)^-1 s ; x += (double)(V_k y)  (Orthogonalization.hpp:67-73)
@@ -485,10 +515,11 @@ int solve_mixed(mpg_ctx* ctx, const mpg_gmres_params& p, const mpg_csr* A, const
 // ---- uniform precision: gmres_baseline<Orth,Device,Type,PrecType>, gmres.cpp:24-133 ---------------------------
 template <class T>
 int solve_uniform(mpg_ctx* ctx, const mpg_gmres_params& p, const mpg_csr* A, const T* vals, const T* jac, const float* jac32, bool bridge,
-                  const T* b, T* x, mpg_gmres_stats* st, History& hist) {
+                  mpg_ilu_jacobi* ilu, const T* b, T* x, mpg_gmres_stats* st, History& hist) {
     const int64_t n = A->nrows, m = p.restart_length;
     Workspace* ws = nullptr;
     MPG_TRY(get_workspace(ctx, n, m, (int)sizeof(T), p.conv == MPG_CONV_ORTHLOSS, bridge, &ws));
+    MPG_TRY(dist_exchange_basis(ctx, ws->V, ws->ldv, (int)sizeof(T)));
     T* w = static_cast<T*>(ws->w);
     T* h = static_cast<T*>(ws->h);
     T* s = static_cast<T*>(ws->s);
@@ -504,13 +535,13 @@ int solve_uniform(mpg_ctx* ctx, const mpg_gmres_params& p, const mpg_csr* A, con
 
     MPG_TRY(nrm2_dev(ctx, n, b, ds<T>(ctx, 0)));                               // b_norm      :54
     MPG_TRY(cast_copy(ctx, n, b, w));                                          // copy(b, w)  :56
-    MPG_TRY(apply_prec<T>(ctx, n, w, jac, jac32, bridge, ws->tmp32));          //             :57
+    MPG_TRY(apply_prec<T>(ctx, n, w, jac, jac32, bridge, ws->tmp32, ilu));     //             :57
     MPG_TRY(nrm2_dev(ctx, n, w, ds<T>(ctx, 1)));                               // Minvb_norm  :58
     MPG_TRY(nrm2_dev(ctx, A->nnz, vals, ds<T>(ctx, 2)));                       // A_norm      :60
     MPG_TRY(read_scalars<T>(ctx, 3));
     const T b_norm = hs<T>(ctx, 0), Minvb_norm = hs<T>(ctx, 1), A_norm = hs<T>(ctx, 2);
     st->b_norm = b_norm; st->Minvb_norm = Minvb_norm; st->A_norm = A_norm;
-    const bool have_prec = bridge || jac != nullptr;
+    const bool have_prec = bridge || jac != nullptr || ilu != nullptr;
 
     for (int64_t i = 0;; ++i) {
         // w = b - A x in Type: one kernel (gmres.cpp:62-63)
@@ -524,7 +555,7 @@ int solve_uniform(mpg_ctx* ctx, const mpg_gmres_params& p, const mpg_csr* A, con
         if (packed && ctx->tune.residual_packed) MPG_TRY(spmv_packed<T>(ctx, packed, T(-1), xin, T(1), b, w, nullptr, nullptr, SPMV_ALL));
         else MPG_TRY(spmv<T>(ctx, A, vals, T(-1), xin, T(1), b, w, nullptr));
         MPG_TRY(nrm2_dev(ctx, n, w, ds<T>(ctx, 0)));                           // r_norm :67
-        MPG_TRY(apply_prec<T>(ctx, n, w, jac, jac32, bridge, ws->tmp32));      //        :68
+        MPG_TRY(apply_prec<T>(ctx, n, w, jac, jac32, bridge, ws->tmp32, ilu)); //        :68
         if (have_prec) MPG_TRY(nrm2_dev(ctx, n, w, ds<T>(ctx, 1)));            // beta   :70
         MPG_TRY(nrm2_dev(ctx, n, x, ds<T>(ctx, 2)));                           // x_norm :72
         MPG_TRY(read_scalars<T>(ctx, 3));
@@ -539,7 +570,7 @@ int solve_uniform(mpg_ctx* ctx, const mpg_gmres_params& p, const mpg_csr* A, con
 
         int64_t k = 0;
         Action act = NEXT;
-        MPG_TRY(run_cycle<T>(ctx, p, pol, ws, A, vals, packed, jac, jac32, bridge, beta, (double)Minvb_norm, hist, &k, &act));
+        MPG_TRY(run_cycle<T>(ctx, p, pol, ws, A, vals, packed, jac, jac32, bridge, ilu, beta, (double)Minvb_norm, hist, &k, &act));
         if (act == ABORTED) { st->status = 3; st->outer_i = i; break; }
 
         // solution_update, gmres.cpp:291-303: y = triu(H)^-1 s ; x = 1*V_k y + 1*x (Orthogonalization.hpp:62-65)
@@ -559,8 +590,10 @@ extern "C" int mpg_gmres_solve(mpg_ctx* ctx, const mpg_gmres_params* pp, const m
     MPG_REQUIRE(ctx, pp && A && vals64 && b && x && st, "gmres_solve: null argument");
     const mpg_gmres_params p = *pp;
     MPG_REQUIRE(ctx, p.restart_length >= 1 && p.restart_length + 1 <= kMaxCols, "gmres_solve: restart length must be in [1, 255]");
-    MPG_REQUIRE(ctx, p.mode >= 0 && p.mode <= 3 && p.orth >= 0 && p.orth <= 2 && p.conv >= 0 && p.conv <= 3 && p.prec >= 0 && p.prec <= 1,
+    MPG_REQUIRE(ctx, p.mode >= 0 && p.mode <= 3 && p.orth >= 0 && p.orth <= 2 && p.conv >= 0 && p.conv <= 3 && p.prec >= 0 && p.prec <= 2,
                 "gmres_solve: bad enum");
+    MPG_REQUIRE(ctx, p.prec != MPG_PREC_ILU_JACOBI || (ctx->dist == nullptr && p.jacobi_steps >= 0 && p.jacobi_steps <= 1000),
+                "gmres_solve: ilu_jacobi needs the whole matrix on one GPU and 0 <= jacobi_steps <= 1000");
     MPG_REQUIRE(ctx, (int64_t)A->ncols == (int64_t)A->nrows + dist_halo(ctx), "gmres_solve: matrix must be square (local slab: nrows + halo columns)");
     memset(st, 0, sizeof(*st));
     History hist{hist_inner, cap_inner, hist_outer, cap_outer};
@@ -576,9 +609,13 @@ extern "C" int mpg_gmres_solve(mpg_ctx* ctx, const mpg_gmres_params* pp, const m
     double* vals_rt = nullptr;
     float *jac32 = nullptr, *b32 = nullptr, *x32 = nullptr;
     double* jac64 = nullptr;
+    double* ilu_vals = nullptr;
+    mpg_ilu_jacobi* ilu = nullptr;
     int rc = MPG_OK;
     auto cleanup = [&]() {
         cudaStreamSynchronize(ctx->stream);
+        mpg_ilu_jacobi_destroy(ilu);
+        cudaFree(ilu_vals);
         cudaFree(vals32_own); cudaFree(vals_rt); cudaFree(jac32); cudaFree(jac64); cudaFree(b32); cudaFree(x32);
         cudaEventDestroy(e0); cudaEventDestroy(e1);
     };
@@ -591,13 +628,21 @@ extern "C" int mpg_gmres_solve(mpg_ctx* ctx, const mpg_gmres_params* pp, const m
         MPG_TRY_C(cast_copy(ctx, nnz, vals64, vals32_own));
         vals32 = vals32_own;
     }
+    if (p.prec == MPG_PREC_ILU_JACOBI) {
+        // ILU_Jacobi<PrecType>(ilu0<PrecType>(A), jacobi_steps) on the fp64 matrix (gmres_perf_test.cpp:75-78,145-148): the "ilu took" window
+        const bool prec_f64 = (p.mode == MPG_MODE_BASELINE);   // PrecType = double only for <double,double>
+        MPG_CUDA_C(pool_alloc(ctx, &ilu_vals, sizeof(double) * (size_t)std::max<int64_t>(nnz, 1)));
+        MPG_TRY_C(mpg_ilu0_f64(ctx, A, vals64, prec_f64 ? 0 : 1, ilu_vals));
+        if (prec_f64) MPG_TRY_C(mpg_ilu_jacobi_create_f64(ctx, A, ilu_vals, (int)p.jacobi_steps, &ilu));
+        else MPG_TRY_C(mpg_ilu_jacobi_create_f32(ctx, A, ilu_vals, (int)p.jacobi_steps, &ilu));
+    }
     if (p.mode == MPG_MODE_MIXED) {
         if (p.prec == MPG_PREC_JACOBI) {  // Jacobi<float>(A) on the fp32-cast matrix, gmres_perf_test.cpp:149
             MPG_CUDA_C(pool_alloc(ctx, &jac32, sizeof(float) * (size_t)n));
             MPG_TRY_C(mpg_jacobi_diag_f32(ctx, A, vals32, jac32));
         }
         MPG_CUDA_C(cudaEventRecord(e0, ctx->stream));
-        MPG_TRY_C(solve_mixed(ctx, p, A, vals64, vals32, jac32, b, x, st, hist));
+        MPG_TRY_C(solve_mixed(ctx, p, A, vals64, vals32, jac32, ilu, b, x, st, hist));
     } else if (p.mode == MPG_MODE_BASELINE || p.mode == MPG_MODE_SINGLE_PREC) {
         // DoBaselineProblem hands the solver the fp32-rounded matrix converted back to double
         // (gmres_perf_test.cpp:66,101 + implicit conversion)
@@ -609,7 +654,7 @@ extern "C" int mpg_gmres_solve(mpg_ctx* ctx, const mpg_gmres_params* pp, const m
             else { MPG_CUDA_C(pool_alloc(ctx, &jac64, sizeof(double) * (size_t)n)); MPG_TRY_C(mpg_jacobi_diag_f64(ctx, A, vals64, jac64)); }
         }
         MPG_CUDA_C(cudaEventRecord(e0, ctx->stream));
-        MPG_TRY_C(solve_uniform<double>(ctx, p, A, vals_rt, jac64, jac32, bridge, b, x, st, hist));
+        MPG_TRY_C(solve_uniform<double>(ctx, p, A, vals_rt, jac64, jac32, bridge, ilu, b, x, st, hist));
     } else {
         if (p.prec == MPG_PREC_JACOBI) { MPG_CUDA_C(pool_alloc(ctx, &jac32, sizeof(float) * (size_t)n)); MPG_TRY_C(mpg_jacobi_diag_f32(ctx, A, vals32, jac32)); }
         MPG_CUDA_C(pool_alloc(ctx, &b32, sizeof(float) * (size_t)n));
@@ -617,7 +662,7 @@ extern "C" int mpg_gmres_solve(mpg_ctx* ctx, const mpg_gmres_params* pp, const m
         MPG_TRY_C(cast_copy(ctx, n, b, b32));   // copy(b, b_type)  gmres_perf_test.cpp:97-98
         MPG_TRY_C(cast_copy(ctx, n, x, x32));
         MPG_CUDA_C(cudaEventRecord(e0, ctx->stream));
-        MPG_TRY_C(solve_uniform<float>(ctx, p, A, vals32, jac32, nullptr, false, b32, x32, st, hist));
+        MPG_TRY_C(solve_uniform<float>(ctx, p, A, vals32, jac32, nullptr, false, ilu, b32, x32, st, hist));
         MPG_CUDA_C(cudaEventRecord(e1, ctx->stream));
         MPG_TRY_C(cast_copy(ctx, n, x32, x));   // copy(x_type, x)  gmres_perf_test.cpp:104-105
     }

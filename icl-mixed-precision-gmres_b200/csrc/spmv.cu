@@ -307,6 +307,7 @@ extern "C" int mpg_csr_destroy(mpg_csr* A) {
     cudaFree(A->carry);
     cudaFree(A->tile_list);
     mpg::sell_plan_free(A->sell);
+    mpg::ilu_plan_free(A->ilu);
     delete A;
     return MPG_OK;
 }

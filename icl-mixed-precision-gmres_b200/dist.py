@@ -11,26 +11,40 @@ from .binding import Context, CSR, _ptr
 
 
 def bounds(n, world):
+    """equal row blocks: rank r owns rows [floor(r n / P), floor((r + 1) n / P))"""
     return [(r * n) // world for r in range(world + 1)]
+
+
+def bounds_nnz(row_map_host, world):
+    """nnz-balanced split points: bounds[k] = smallest row i with row_map[i] >= floor(k nnz / P) (mpg_partition_bounds_nnz)"""
+    import numpy as np
+    from .binding import load_library
+    rm = np.ascontiguousarray(row_map_host, np.int32)
+    out = (C.c_int64 * (world + 1))()
+    rc = load_library().mpg_partition_bounds_nnz(C.c_int64(len(rm) - 1), C.c_int(world), rm.ctypes.data_as(C.c_void_p), out)
+    if rc != 0:
+        raise ValueError("mpg_partition_bounds_nnz failed")
+    return list(out)
 
 
 class Partition:
     """this rank's share of a 1-D row-partitioned CSR matrix"""
 
-    def __init__(self, n_global, rank, world, row_map, inds, vals, halo_cols, peers):
+    def __init__(self, n_global, rank, world, row_map, inds, vals, halo_cols, peers, b=None):
         self.n_global, self.rank, self.world = n_global, rank, world
         self.row_map, self.inds, self.vals = row_map, inds, vals      # local slab, columns renumbered [local | halo]
         self.halo_cols = halo_cols                                    # int64 global ids, ascending
         self.peers = peers                                            # list of dict(rank, send_idx, recv_offset, recv_count)
-        b = bounds(n_global, world)
+        b = bounds(n_global, world) if b is None else list(b)
+        self.bounds = b
         self.lo, self.hi = b[rank], b[rank + 1]
         self.n_local, self.n_halo = self.hi - self.lo, int(halo_cols.numel())
 
 
-def local_slab(row_map, inds, vals, n_global, rank, world):
+def local_slab(row_map, inds, vals, n_global, rank, world, b=None):
     """(row_map_local, local_inds, vals_local, halo_cols) for rank `rank`; pure tensor ops on the inputs' device"""
     import torch
-    b = bounds(n_global, world)
+    b = bounds(n_global, world) if b is None else list(b)
     lo, hi = b[rank], b[rank + 1]
     p0, p1 = int(row_map[lo]), int(row_map[hi])
     rm = (row_map[lo:hi + 1] - row_map[lo]).to(torch.int32)
@@ -41,12 +55,14 @@ def local_slab(row_map, inds, vals, n_global, rank, world):
     return rm.contiguous(), li.contiguous(), vals[p0:p1].clone(), halo_cols   # clone: a slice keeps the parent's (possibly odd) offset
 
 
-def build_partition(row_map, inds, vals, n_global, rank, world, group=None):
-    """slab + halo plan.  Collective: every rank calls it (the send lists come from the peers' halo lists)."""
+def build_partition(row_map, inds, vals, n_global, rank, world, group=None, b=None):
+    """slab + halo plan from the GLOBAL matrix with torch tensor ops (any device): the CPU-testable restatement of the plan
+    (tests/test_dist_cpu.py, gloo).  The product path is DistContext.setup (native, from the slab alone).
+    Collective: every rank calls it (the send lists come from the peers' halo lists)."""
     import torch
     import torch.distributed as dist
-    rm, li, v, halo_cols = local_slab(row_map, inds, vals, n_global, rank, world)
-    b = bounds(n_global, world)
+    b = bounds(n_global, world) if b is None else list(b)
+    rm, li, v, halo_cols = local_slab(row_map, inds, vals, n_global, rank, world, b)
     owner_lo = torch.tensor(b[:-1], dtype=torch.int64, device=halo_cols.device)
     owner = torch.searchsorted(owner_lo, halo_cols, right=True) - 1 if halo_cols.numel() else halo_cols
     need = {}
@@ -74,13 +90,13 @@ def build_partition(row_map, inds, vals, n_global, rank, world, group=None):
         peers.append(dict(rank=q, send_idx=send_idx, recv_offset=recv_off, recv_count=recv_cnt))
         recv_off += recv_cnt
     assert recv_off == halo_cols.numel()
-    return Partition(n_global, rank, world, rm, li, v, halo_cols, peers)
+    return Partition(n_global, rank, world, rm, li, v, halo_cols, peers, b)
 
 
 class DistContext:
     """NCCL communicator + halo plan attached to a Context (C ABI: mpg_dist_*)."""
 
-    def __init__(self, ctx: Context, rank, world, group=None, peer_reduce=True):
+    def __init__(self, ctx: Context, rank, world, group=None, peer_reduce=True, native=False):
         import torch
         import torch.distributed as dist
         self.ctx, self.rank, self.world = ctx, rank, world
@@ -97,7 +113,7 @@ class DistContext:
         self._keep = None
         # peer-memory mailboxes for the in-kernel all-reduce (CUDA IPC handles all-gathered in rank order)
         self.peer_reduce = False
-        if world > 1 and world <= 8 and peer_reduce:
+        if world > 1 and world <= 8 and peer_reduce and not native:   # (native: mpg_dist_setup exchanges the handles itself, over NCCL)
             hb = (C.c_ubyte * 64)()
             ctx._chk(ctx.L.mpg_dist_mailbox_handle(ctx.h, self.h, hb))
             handles = [None] * world
@@ -131,6 +147,33 @@ class DistContext:
             rnh = (C.c_int64 * max(n, 1))(*[allinfo[p["rank"]]["n_halo"] for p in part.peers])
             ctx._chk(ctx.L.mpg_dist_open_halo(ctx.h, self.h, allh, roff, rnh))
             dist.barrier(group=self._group)
+
+    def setup(self, n_global, b, row_map_local, inds_global, vals):
+        """NATIVE set-up from this rank's slab alone (mpg_dist_setup): inds_global (int32 CUDA tensor, global columns) is renumbered
+        in place to [local | halo]; halo / send lists, mailboxes and inboxes are built and exchanged inside the library over NCCL.
+        Returns a Partition (halo_cols fetched from the library for tests / diagnostics).  Collective."""
+        import numpy as np
+        import torch
+        ctx = self.ctx
+        barr = (C.c_int64 * (self.world + 1))(*[int(v) for v in b])
+        nh = C.c_int64()
+        ctx._chk(ctx.L.mpg_dist_setup(ctx.h, self.h, C.c_int64(n_global), barr, C.c_int64(inds_global.numel()), _ptr(inds_global), C.byref(nh)))
+        self.peer_reduce = self.world > 1
+        halo = np.empty(nh.value, np.int64)
+        ctx._chk(ctx.L.mpg_dist_halo_cols(ctx.h, self.h, halo.ctypes.data_as(C.c_void_p)))
+        peers = []
+        i = 0
+        while True:
+            pr, sc, ro, rc = C.c_int(), C.c_int64(), C.c_int64(), C.c_int64()
+            if ctx.L.mpg_dist_peer_info(ctx.h, self.h, C.c_int(i), C.byref(pr), C.byref(sc), C.byref(ro), C.byref(rc), None) != 0:
+                break
+            sidx = np.empty(sc.value, np.int32)
+            ctx._chk(ctx.L.mpg_dist_peer_info(ctx.h, self.h, C.c_int(i), None, None, None, None, sidx.ctypes.data_as(C.c_void_p)))
+            peers.append(dict(rank=pr.value, send_idx=torch.from_numpy(sidx), recv_offset=ro.value, recv_count=rc.value))
+            i += 1
+        part = Partition(n_global, self.rank, self.world, row_map_local, inds_global, vals, torch.from_numpy(halo).to(inds_global.device), peers, b)
+        self._keep = part
+        return part
 
     def attach(self):
         self.ctx._chk(self.ctx.L.mpg_ctx_attach_dist(self.ctx.h, self.h))

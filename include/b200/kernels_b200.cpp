@@ -86,12 +86,24 @@
     template <> void gdmv<T, B200>(T alpha, Vect<T, B200> diag, Vect<T, B200> x, T beta, Vect<T, B200> y) { /* kernels.hpp:131-146 */ \
         B200_CHECK(mpg_gdmv_##SFX(CTX, diag.n(), alpha, diag.data(), x.data(), beta, y.data()));                                  \
     }                                                                                                                             \
-    template <> void ilusv<T, B200>(ILU<T, B200>, Vect<T, B200>) { /* :617-695, out of scope */                                    \
-        Kokkos::abort("ilusv is not provided by the B200 backend\n");                                                             \
+    template <> void ilusv<T, B200>(ILU<T, B200>, Vect<T, B200>) { /* :617-695 csrsv2: not provided */                            \
+        Kokkos::abort("ilusv (exact triangular solves) is not provided by the B200 backend; use --prec ilu_jacobi\n");           \
     }                                                                                                                             \
-    template <> ILU<T, B200> ilu0<T, B200>(SparseMatrix<double, B200>) { /* :714-791, out of scope */                              \
-        Kokkos::abort("ilu0 is not provided by the B200 backend (use --prec identity or jacobi)\n");                              \
-        return ILU<T, B200>();                                                                                                    \
+    template <> ILU<T, B200> ilu0<T, B200>(SparseMatrix<double, B200> matrix) { /* :714-791 csrilu02 -> level-scheduled IKJ */    \
+        assert(matrix.nrows() == matrix.ncols());                                                                                 \
+        Kokkos::View<double*, typename B200::memory_space> vals("ilu::vals64", (size_t)matrix.nnz());                             \
+        B200_CHECK(mpg_ilu0_f64(CTX, matrix.plan(), matrix.vals_data(), sizeof(T) == 4, vals.data()));                            \
+        Kokkos::View<T*, typename B200::memory_space> vals_type("ilu::vals", (size_t)matrix.nnz());   /* type_convert, :697-712 */ \
+        copy(Vect<double, B200>(vals), Vect<T, B200>(vals_type));                                                                 \
+        B200_CHECK(mpg_sync(CTX));                                                                                                \
+        return ILU<T, B200>(matrix.nrows(), matrix.nnz(), matrix.row_map_, matrix.inds_, vals_type);                              \
+    }                                                                                                                             \
+    template <> void ilusv_jacobi<T, B200>(ILU_Jacobi<T, B200> ilu, Vect<T, B200> x) { /* kernels.hpp:227-248, one launch per sweep */ \
+        assert(ilu.n() == (int)x.n());                                                                                            \
+        B200_CHECK(mpg_ilu_jacobi_apply_##SFX(CTX, ilu.handles().h.get(), x.data()));                                             \
+    }                                                                                                                             \
+    template <> void ilu_jacobi_mv<T, B200>(bool lower, T alpha, ILU_Jacobi<T, B200> ilu, Vect<T, B200> x, T beta, Vect<T, B200> y) { /* kernels.hpp:172-216 */ \
+        B200_CHECK(mpg_ilu_jacobi_mv_##SFX(CTX, ilu.handles().h.get(), lower ? 1 : 0, alpha, x.data(), beta, y.data()));          \
     }
 
 B200_BLAS1(float, f32)

@@ -376,12 +376,14 @@ struct SolveOptions {                 // gmres_perf_test.cpp:313-339 (--rlen --t
     int conv = MPG_CONV_BASE;
     int prec = MPG_PREC_IDENTITY;
     int orth = MPG_ORTH_CGSR;
+    int64_t jacobi_steps = 1;         // --jacobi-steps, for prec = MPG_PREC_ILU_JACOBI
 };
 namespace detail {
 inline SolveResult solve(int mode, const SolveOptions& o, const SparseMatrix<double>& A, const float* vals32, Vect<double> b, Vect<double> x) {
     mpg_gmres_params p;
     p.mode = mode; p.orth = o.orth; p.conv = o.conv; p.prec = o.prec;
     p.restart_length = o.restart_length; p.tol = o.tol; p.restart_tol = o.restart_tol; p.max_restarts = o.max_restarts;
+    p.jacobi_steps = o.jacobi_steps;
     SolveResult r;
     const int64_t cap = std::min<int64_t>((o.max_restarts + 2) * o.restart_length, 4000000);
     r.hist_inner.assign((size_t)cap, 0.0);

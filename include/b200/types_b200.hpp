@@ -5,7 +5,7 @@
 //   * struct B200          replaces struct Cuda                 types_cuda.hpp:39-44
 //   * SparseMatrix<T,B200> replaces SparseMatrix<T,Cuda>        types_cuda.hpp:47-152 (+ the SpMV plan, shared between
 //                                                               the fp64 matrix and its fp32 copy like row_map/inds)
-//   * ILU<T,B200>, ILU_Jacobi_handles<B200>: declared so the harness compiles; out of scope
+//   * ILU<T,B200>, ILU_Jacobi_handles<B200>: ILU(0) factors + Jacobi-sweep application; exact triangular solves not provided
 // The operator surface itself is specialised in kernels_b200.cpp.
 #ifndef TYPES_B200_HPP
 #define TYPES_B200_HPP
@@ -120,26 +120,66 @@ public:
     bool is_transposed() { return this->transposed_; }
 };
 
-// ILU(0) and its triangular solves are out of scope for this backend (cusparse csrilu02 / csrsv2 in the reference,
-// kernels_cuda.cpp:13-107,617-791; csrsv2 no longer exists in CUDA 12).  The types exist so gmres_perf_test.cpp compiles;
-// selecting --prec ilu / ilu_jacobi with this device aborts with a message.
+// ILU(0): ilu0<Type,B200> factors on the device (level-scheduled IKJ, kernels_b200.cpp); ILU_Jacobi<Type,B200> - the class of
+// types.hpp:251-372, unchanged - applies the factors with Jacobi sweeps through ILU_Jacobi_handles<B200>, one fused launch per
+// sweep.  The EXACT triangular solves of ILU<>::apply (cusparse csrsv2 in the reference, kernels_cuda.cpp:617-695; the API is gone
+// from CUDA 12) are not provided: --prec ilu with this device aborts with a message, --prec ilu_jacobi works.
 template <class Type>
 class ILU<Type, B200> : public LinearOperator<Type, B200> {
-public:
+private:
     int n_ = 0, nnz_ = 0;
     Kokkos::View<int*, typename B200::memory_space> row_map_;
     Kokkos::View<int*, typename B200::memory_space> inds_;
     Kokkos::View<Type*, typename B200::memory_space> vals_;
+
+    template <class, class>
+    friend class ILU;
+    template <class, class>
+    friend class ILU_Jacobi;
+
+public:
+    ILU() {}
+    ILU(int n, int nnz, Kokkos::View<int*, typename B200::memory_space> row_map, Kokkos::View<int*, typename B200::memory_space> inds,
+        Kokkos::View<Type*, typename B200::memory_space> vals)
+        : n_(n), nnz_(nnz), row_map_(row_map), inds_(inds), vals_(vals) {}
     int n() const { return n_; }
     int nnz() const { return nnz_; }
-    void apply(Vect<Type, B200>) { Kokkos::abort("ILU preconditioning is not provided by the B200 backend (use --prec identity or jacobi)\n"); }
+    int* row_map_data() { return row_map_.data(); }
+    int* inds_data() { return inds_.data(); }
+    Type* vals_data() { return vals_.data(); }
+    void apply(Vect<Type, B200>) { Kokkos::abort("exact ILU triangular solves are not provided by the B200 backend (use --prec ilu_jacobi, jacobi or identity)\n"); }
 };
+// per-preconditioner library objects: structure plan + the split / packed L and U operators (mpg_ilu_jacobi)
 template <>
 class ILU_Jacobi_handles<B200> {
 public:
+    std::shared_ptr<mpg_csr> plan;
+    std::shared_ptr<mpg_ilu_jacobi> h;
     template <class Type>
-    ILU_Jacobi_handles(const ILU_Jacobi<Type, B200>&) {}
+    ILU_Jacobi_handles(const ILU_Jacobi<Type, B200>& ilu_const);
 };
+
+template <> void ilusv_jacobi<float, B200>(ILU_Jacobi<float, B200> ilu, Vect<float, B200> x);
+template <> void ilusv_jacobi<double, B200>(ILU_Jacobi<double, B200> ilu, Vect<double, B200> x);
+template <> void ilu_jacobi_mv<float, B200>(bool lower, float alpha, ILU_Jacobi<float, B200> ilu, Vect<float, B200> x, float beta, Vect<float, B200> y);
+template <> void ilu_jacobi_mv<double, B200>(bool lower, double alpha, ILU_Jacobi<double, B200> ilu, Vect<double, B200> x, double beta, Vect<double, B200> y);
+
+template <class Type>
+ILU_Jacobi_handles<B200>::ILU_Jacobi_handles(const ILU_Jacobi<Type, B200>& ilu_const) {
+    ILU_Jacobi<Type, B200>& ilu = const_cast<ILU_Jacobi<Type, B200>&>(ilu_const);   // the accessors of types.hpp:318-349 are not const
+    mpg_ctx* ctx = B200Backend::context();
+    mpg_csr* p = nullptr;
+    B200_CHECK(mpg_csr_create(ctx, ilu.n(), ilu.n(), ilu.nnz(), ilu.row_map_data(), ilu.inds_data(), &p));
+    plan = std::shared_ptr<mpg_csr>(p, [](mpg_csr* q) { mpg_csr_destroy(q); });
+    // the library takes the factors in fp64 (what ilu0 produced before type_convert); widening Type -> double is exact
+    Kokkos::View<double*, typename B200::memory_space> wide("ilu::vals64", (size_t)ilu.nnz());
+    copy(Vect<Type, B200>(ilu.vals_view()), Vect<double, B200>(wide));
+    mpg_ilu_jacobi* m = nullptr;
+    if (sizeof(Type) == 4) B200_CHECK(mpg_ilu_jacobi_create_f32(ctx, p, wide.data(), ilu.steps(), &m));
+    else B200_CHECK(mpg_ilu_jacobi_create_f64(ctx, p, wide.data(), ilu.steps(), &m));
+    B200_CHECK(mpg_sync(ctx));
+    h = std::shared_ptr<mpg_ilu_jacobi>(m, [](mpg_ilu_jacobi* q) { mpg_ilu_jacobi_destroy(q); });
+}
 
 // ---- specialisations of the header-inline generic operators (kernels.hpp:11-20,131-146) -------------------------------
 // declared here, before the driver uses them; defined in kernels_b200.cpp

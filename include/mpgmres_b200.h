@@ -174,6 +174,26 @@ int mpg_spmv_packed_f64(mpg_ctx*, const mpg_packed* P, double alpha, const doubl
 int mpg_residual_f64_cast_f32(mpg_ctx*, const mpg_csr* A, const double* vals, const double* b, const double* x,
                               double* r64, float* w32);
 
+/* ---- ILU(0) + Jacobi-sweep triangular solves: ilu0 kernels.hpp:163-164 (kernels_cuda.cpp:714-791), ILU_Jacobi
+ * types.hpp:251-372, ilu_jacobi_mv / ilusv_jacobi kernels.hpp:172-248.  (The exact triangular solves of ILU<>::apply -
+ * cusparse csrsv2, kernels_cuda.cpp:617-695, removed from CUDA 12 - are not provided.)
+ * mpg_ilu0_f64 factors the fp64 matrix on its own sparsity pattern (level-scheduled IKJ, bit-identical to the sequential
+ * loop of kernels_mkl.cpp:451-484 with the diagonal positions filled in); eps_is_float selects the pivot-boost threshold
+ * eps(Type) * max_i sum_j |a_ij| of ilu0<float> / ilu0<double>.  vals_out may not alias vals_in. */
+typedef struct mpg_ilu_jacobi mpg_ilu_jacobi;
+int mpg_ilu0_f64(mpg_ctx*, const mpg_csr* A, const double* vals_in, int eps_is_float, double* vals_out);
+int mpg_ilu0_levels(mpg_ctx*, const mpg_csr* A, int* nlevels);   /* depth of the dependency schedule (diagnostics) */
+/* ILU_Jacobi<Type>(ilu, steps): converts the factors to Type, extracts 1/diag (types.hpp:290-304) */
+int mpg_ilu_jacobi_create_f32(mpg_ctx*, const mpg_csr* A, const double* ilu_vals, int steps, mpg_ilu_jacobi** out);
+int mpg_ilu_jacobi_create_f64(mpg_ctx*, const mpg_csr* A, const double* ilu_vals, int steps, mpg_ilu_jacobi** out);
+int mpg_ilu_jacobi_destroy(mpg_ilu_jacobi* M);
+/* ilusv_jacobi: x <- approximately U^-1 L^-1 x with `steps` Jacobi sweeps per triangle, one fused launch per sweep */
+int mpg_ilu_jacobi_apply_f32(mpg_ctx*, mpg_ilu_jacobi* M, float* x);
+int mpg_ilu_jacobi_apply_f64(mpg_ctx*, mpg_ilu_jacobi* M, double* x);
+/* ilu_jacobi_mv: lower: y = beta*y + alpha*(x + L x); upper: y = y - U x (alpha, beta ignored as in kernels.hpp:205-216) */
+int mpg_ilu_jacobi_mv_f32(mpg_ctx*, const mpg_ilu_jacobi* M, int lower, float alpha, const float* x, float beta, float* y);
+int mpg_ilu_jacobi_mv_f64(mpg_ctx*, const mpg_ilu_jacobi* M, int lower, double alpha, const double* x, double beta, double* y);
+
 /* ---- Fused Arnoldi step: GS::add_vector, Orthogonalization.hpp:51-60 + the kernels at :76-136 ------------
  * orth: 0 CGS, 1 MGS, 2 CGSR<2> (CGS2).  V is n x (k+2) column-major with leading dimension ldv.
  * In:  w (A*v_k), V[:,0:k+1].  Out: hcol[0..k] coefficients, hcol[k+1] = ||w_orth||, V[:,k+1] = w_orth/hcol[k+1];
@@ -185,7 +205,7 @@ int mpg_add_vector_f64(mpg_ctx*, int orth, int64_t n, int64_t k, double* V, int6
 enum { MPG_MODE_MIXED = 0, MPG_MODE_BASELINE = 1, MPG_MODE_SINGLE_PREC = 2, MPG_MODE_SINGLE = 3 }; /* gmres_perf_test.cpp:31-36 */
 enum { MPG_ORTH_CGS = 0, MPG_ORTH_MGS = 1, MPG_ORTH_CGSR = 2 };                                    /* :17-22 */
 enum { MPG_CONV_BASE = 0, MPG_CONV_RELPRECRES = 1, MPG_CONV_REPEAT = 2, MPG_CONV_ORTHLOSS = 3 };   /* :185-196 */
-enum { MPG_PREC_IDENTITY = 0, MPG_PREC_JACOBI = 1 };                                               /* :24-29 */
+enum { MPG_PREC_IDENTITY = 0, MPG_PREC_JACOBI = 1, MPG_PREC_ILU_JACOBI = 2 };                      /* :24-29 (exact ilu: not provided) */
 
 typedef struct mpg_gmres_params {
     int32_t mode, orth, conv, prec;
@@ -193,6 +213,7 @@ typedef struct mpg_gmres_params {
     double tol;             /* --tol   */
     double restart_tol;     /* --rtol  */
     int64_t max_restarts;   /* --max-restarts */
+    int64_t jacobi_steps;   /* --jacobi-steps (MPG_PREC_ILU_JACOBI), gmres_perf_test.cpp:323,386-387 */
 } mpg_gmres_params;
 
 typedef struct mpg_gmres_stats {
@@ -230,6 +251,14 @@ int mpg_gen_lap2d(mpg_ctx*, int64_t N, int* row_map, int* inds, double* vals);
 int mpg_gen_cd27(mpg_ctx*, int64_t N, int* row_map, int* inds, double* vals);
 int mpg_gen_powerlaw_rowmap(mpg_ctx*, int64_t n, uint64_t seed, int lmin, int gmax, int* row_map, int64_t* nnz_host);
 int mpg_gen_powerlaw_fill(mpg_ctx*, int64_t n, uint64_t seed, int lmin, int gmax, const int* row_map, int* inds, double* vals);
+/* Row-range forms: rows [lo, hi) of the same matrices with GLOBAL column indices and a local row map, so that every rank of a
+ * multi-GPU run generates only its slab (mpg_dist_setup renumbers the columns).  kind: 0 lap2d (size = N), 1 cd27 (size = N),
+ * 2 powerlaw (size = n; seed, lmin, gmax as above).  mpg_gen_rowmap: the global row map alone (nnz-balanced split points). */
+int mpg_gen_slab_rowmap(mpg_ctx*, int kind, int64_t size, uint64_t seed, int lmin, int gmax, int64_t lo, int64_t hi, int* row_map_local,
+                        int64_t* nnz_local_host);
+int mpg_gen_slab_fill(mpg_ctx*, int kind, int64_t size, uint64_t seed, int lmin, int gmax, int64_t lo, int64_t hi, int* row_map_local,
+                      int* inds_global, double* vals);
+int mpg_gen_rowmap(mpg_ctx*, int kind, int64_t size, uint64_t seed, int lmin, int gmax, int* row_map);
 /* gmres_perf_test.cpp:39-51 rand_vect (host; libstdc++ mt19937 + uniform_real_distribution<float>) */
 int mpg_rand_vect_host(int64_t n, uint32_t seed, double* out_host);
 
@@ -257,6 +286,14 @@ int mpg_dist_open_mailboxes(mpg_ctx*, mpg_dist* d, const void* handles_world_x_6
 int mpg_dist_halo_handle(mpg_ctx*, mpg_dist* d, void* handle64_host);
 int mpg_dist_open_halo(mpg_ctx*, mpg_dist* d, const void* handles_world_x_64_host, const int64_t* remote_offsets_host,
                        const int64_t* remote_nhalo_host);
+/* Native set-up from this rank's slab ALONE (no rank ever holds the global matrix): bounds_host[world + 1] = first row of every
+ * rank (mpg_partition_bounds / mpg_partition_bounds_nnz), inds_dev = the slab's column indices, GLOBAL on entry, renumbered
+ * [local | halo] on return.  Builds halo and send lists on the device, exchanges them and the CUDA IPC handles of mailboxes
+ * and inboxes over the communicator; equivalent to mpg_dist_set_partition + mailbox / halo hand-shakes.  Collective. */
+int mpg_dist_setup(mpg_ctx*, mpg_dist* d, int64_t n_global, const int64_t* bounds_host, int64_t nnz_local, int* inds_dev, int64_t* n_halo);
+int mpg_dist_halo_cols(mpg_ctx*, const mpg_dist* d, int64_t* halo_cols_host /* n_halo */);
+int mpg_dist_peer_info(mpg_ctx*, const mpg_dist* d, int i, int* peer_rank, int64_t* send_count, int64_t* recv_offset, int64_t* recv_count,
+                       int* send_idx_host /* may be NULL */);
 int mpg_ctx_attach_dist(mpg_ctx*, mpg_dist* d); /* NULL detaches */
 int mpg_dist_info(const mpg_dist* d, int* rank, int* world, int64_t* n_global, int64_t* n_local, int64_t* n_halo);
 int mpg_halo_exchange_f32(mpg_ctx*, float* x_ext);  /* x_ext = [n_local owned | n_halo halo slots] */
@@ -267,10 +304,16 @@ int mpg_allreduce_sum_f64(mpg_ctx*, double* buf_dev, int64_t count);
  * the library and released with mpg_host_free.  errbuf receives the reference's exception text on failure. ------------ */
 int mpg_mm_read_host(const char* path, int* nrows, int* ncols, int64_t* nnz, int** row_map_host, int** inds_host, double** vals_host,
                      char* errbuf, int errlen);
+/* LoadVector<S>(file, col), LoadMatrix.hpp:156-233 (--bpath, gmres_perf_test.cpp:417-421): column `col` of an array or
+ * coordinate MatrixMarket file as n doubles (malloc'ed, release with mpg_host_free) */
+int mpg_mm_read_vector_host(const char* path, int col, int64_t* n, double** vals_host, char* errbuf, int errlen);
 void mpg_host_free(void* p);
 
 /* ---- 1-D row partition (new functionality, host-side, bit-exact vs the oracle) ------------- */
 int mpg_partition_bounds(int64_t n, int P, int64_t* bounds_host /* P+1 */);
+/* nnz-balanced split points: bounds[k] = the smallest row i with row_map[i] >= floor(k * nnz / P); bounds[0] = 0,
+ * bounds[P] = n.  row_map_host is the GLOBAL row map (4 (n + 1) bytes - small even when the matrix itself does not fit). */
+int mpg_partition_bounds_nnz(int64_t n, int P, const int* row_map_host, int64_t* bounds_host /* P+1 */);
 /* halo_cols_host/local_inds_host may be NULL to query sizes.  Returns the halo count through *n_halo. */
 int mpg_partition_local(int64_t n, int P, int r, const int* row_map_host, const int* inds_host, int64_t* n_halo,
                         int64_t* halo_cols_host, int* local_inds_host);

@@ -25,6 +25,8 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <limits>
+#include <memory>
 #include <random>
 #include <vector>
 
@@ -342,17 +344,119 @@ double givens_step(size_t k, T* h, size_t ldh, T* cs, T* sn, T* s) {
     return std::fabs((double)s[k + 1]);
 }
 
+// ------------------------------------------------------------------------------------------------
+// ILU(0) + Jacobi-sweep triangular solves.
+//   ilu0      restates ilu0_impl of kernels_mkl.cpp:420-487 - sequential IKJ elimination on the sparsity pattern of A in
+//             fp64, merge of row i with row k right of the pivot, pivots with magnitude below alpha = eps(Type) *
+//             max_i sum_j |a_ij| replaced by +-alpha (the same boost the CUDA path asks cusparse for, kernels_cuda.cpp:
+//             747-761) - with ONE correction: the reference allocates diag_inds zero-filled (:448) and never fills it, so
+//             its MKL path reads vals(0) as every pivot (:457) and clamps vals(0) (:477-483).  Here diag_inds(k) is what the
+//             code plainly intends, the position of the diagonal entry of row k (as ILU_Jacobi::create_handles computes it,
+//             types.hpp:296-303).  There is therefore NO reference output to pin this against ("parity unpinned" for
+//             this row); the restatement is the definition, the CUDA factorisation reproduces it bit for bit.
+//   IluJacobi restates ILU_Jacobi (types.hpp:251-372), ilu_jacobi_mv and ilusv_jacobi (kernels.hpp:172-248) literally,
+//             including that the upper-triangle form ignores its alpha / beta arguments (:205-216).
+// ------------------------------------------------------------------------------------------------
+void ilu0(int n, const int* rm, const int* in, const double* vals_in, double eps_type, double* vals) {
+    const size_t nnz = rm[n];
+    std::copy(vals_in, vals_in + nnz, vals);
+    double alpha = 0;
+    for (int i = 0; i < n; ++i) {
+        double sum = 0;
+        for (int k = rm[i]; k < rm[i + 1]; ++k) sum += std::fabs(vals[k]);
+        if (alpha < sum) alpha = sum;
+    }
+    alpha *= eps_type;
+    std::vector<int> diag(n);
+    for (int i = 0; i < n; ++i) {
+        int j = rm[i];
+        while (in[j] < i) ++j;
+        diag[i] = j;
+    }
+    for (int i = 1; i < n; ++i) {
+        const int rowEnd = rm[i + 1];
+        for (int k_ind = rm[i]; in[k_ind] < i; ++k_ind) {
+            const int k = in[k_ind];
+            int prev = diag[k];
+            const int prev_end = rm[k + 1];
+            const double factor = vals[k_ind] / vals[prev];
+            vals[k_ind] = factor;
+            prev += 1;
+            for (int j_ind = k_ind + 1; j_ind < rowEnd && prev < prev_end;) {
+                if (in[prev] < in[j_ind]) ++prev;
+                else if (in[prev] > in[j_ind]) ++j_ind;
+                else { vals[j_ind] = std::fma(-factor, vals[prev], vals[j_ind]); ++prev; ++j_ind; }
+            }
+        }
+        double& d = vals[diag[i]];
+        if (d >= 0) { if (d < alpha) d = alpha; }
+        else if (d > -alpha) d = -alpha;
+    }
+}
+
+template <class T>
+struct IluJacobi {
+    int n, steps;
+    const int* rm;
+    const int* in;
+    std::vector<T> vals, diag, temp1, temp2;
+    std::vector<int> diag_inds;
+    IluJacobi(int n_, const int* rm_, const int* in_, const double* ilu_vals, int steps_)
+        : n(n_), steps(steps_), rm(rm_), in(in_), vals(rm_[n_]), diag(n_), temp1(n_), temp2(n_), diag_inds(n_) {
+        for (size_t p = 0; p < vals.size(); ++p) vals[p] = (T)ilu_vals[p];        // type_convert, kernels_cuda.cpp:697-712
+        for (int i = 0; i < n; ++i) {                                              // create_handles, types.hpp:290-304
+            int j = rm[i];
+            while (in[j] < i) ++j;
+            diag[i] = T(1) / vals[j];
+            diag_inds[i] = j;
+        }
+    }
+    void mv(bool lower, T alpha, const T* x, T beta, T* y) const {                 // ilu_jacobi_mv, kernels.hpp:172-216
+#pragma omp parallel for schedule(static)
+        for (int i = 0; i < n; ++i) {
+            if (lower) {
+                T sum = x[i];
+                for (int j = rm[i]; j < diag_inds[i]; ++j) sum = fma_t(vals[j], x[in[j]], sum);
+                y[i] = beta * y[i] + alpha * sum;
+            } else {
+                T sum = 0;
+                for (int j = diag_inds[i]; j < rm[i + 1]; ++j) sum = fma_t(vals[j], x[in[j]], sum);
+                y[i] = T(1) * y[i] + T(-1) * sum;
+            }
+        }
+    }
+    void apply(T* x) {                                                             // ilusv_jacobi, kernels.hpp:227-248
+        T* b = temp1.data();
+        T* temp = temp2.data();
+        std::copy(x, x + n, b);
+        for (int s = 0; s < steps; ++s) {                                          // approximate inverse of L
+            std::copy(b, b + n, temp);
+            mv(true, T(-1), x, T(1), temp);
+            for (int i = 0; i < n; ++i) x[i] = fma_t(T(1), temp[i], x[i]);         // axpy(1.0, temp, x)
+        }
+        std::copy(x, x + n, b);
+        for (int s = 0; s < steps; ++s) {                                          // approximate inverse of U
+            std::copy(b, b + n, temp);
+            mv(false, T(-1), x, T(0), temp);
+            for (int i = 0; i < n; ++i) x[i] = T(1) * x[i] + (T(1) * diag[i]) * temp[i];   // gdmv(1.0, diag, temp, 1.0, x), kernels.hpp:143-145
+        }
+    }
+};
+
 // gmres.cpp:135-245 gmres_singleUpdate.  jac32: optional Jacobi diagonal (types.hpp:381-448; apply = gdmv
 // kernels.hpp:131-151: y = 0*y + 1*diag*x -> with beta==0 still computes beta*y; y finite here).
 void gmres_mixed(Conv<float>& conv, int orth, int n, const int* row_map, const int* inds, const double* vals64,
-                 const float* vals32, const float* jac32, const double* b, double* x, Stats& st, Hist& hist) {
+                 const float* vals32, const float* jac32, const double* b, double* x, Stats& st, Hist& hist, IluJacobi<float>* iluj = nullptr) {
     const size_t m = conv.rlen;
     const size_t nnz = row_map[n];
     GS<float> gs(n, m, orth);
     std::vector<float> cs(m + 1, 0.f), sn(m + 1, 0.f), s(m + 1, 0.f), w(n, 0.f), h((m + 1) * m, 0.f);
     std::vector<double> r_accum(n, 0.0);
     const size_t ldh = m + 1;
-    auto applyM = [&](float* v) { if (jac32) for (int i = 0; i < n; ++i) v[i] = 0.f * v[i] + 1.f * jac32[i] * v[i]; };
+    auto applyM = [&](float* v) {
+        if (iluj) iluj->apply(v);                                                       // ILU_Jacobi::apply, types.hpp:365-367
+        else if (jac32) for (int i = 0; i < n; ++i) v[i] = 0.f * v[i] + 1.f * jac32[i] * v[i];
+    };
 
     conv.setup(gs);
     const double b_norm = nrm2<double>(n, b);                       // gmres.cpp:162
@@ -403,19 +507,25 @@ void gmres_mixed(Conv<float>& conv, int orth, int n, const int* row_map, const i
 // (gmres.cpp:12-22): when PrecType != Type the vector is cast to PrecType, preconditioned, cast back.
 template <class T>
 void gmres_uniform(Conv<T>& conv, int orth, bool prec_is_float, int n, const int* row_map, const int* inds,
-                   const T* vals, const T* jac, const T* b, T* x, Stats& st, Hist& hist) {
+                   const T* vals, const T* jac, const T* b, T* x, Stats& st, Hist& hist, IluJacobi<T>* iluj = nullptr, IluJacobi<float>* iluj32 = nullptr) {
     const size_t m = conv.rlen;
     const size_t nnz = row_map[n];
     GS<T> gs(n, m, orth);
     std::vector<T> cs(m + 1, T(0)), sn(m + 1, T(0)), s(m + 1, T(0)), w(n, T(0)), h((m + 1) * m, T(0));
     const size_t ldh = m + 1;
     const bool roundtrip = prec_is_float && sizeof(T) == 8;
+    std::vector<float> rt32(roundtrip && iluj32 ? n : 0);
     auto applyM = [&](T* v) {
-        if (roundtrip) for (int i = 0; i < n; ++i) {
+        if (roundtrip && iluj32) {   // typesafe_apply with an ILU_Jacobi<float>: cast the whole vector, apply, cast back
+            for (int i = 0; i < n; ++i) rt32[i] = (float)v[i];
+            iluj32->apply(rt32.data());
+            for (int i = 0; i < n; ++i) v[i] = (T)rt32[i];
+        } else if (roundtrip) for (int i = 0; i < n; ++i) {
             float t = (float)v[i];
             if (jac) t = 0.f * t + 1.f * (float)jac[i] * t;
             v[i] = (T)t;
-        } else if (jac) for (int i = 0; i < n; ++i) v[i] = T(0) * v[i] + T(1) * jac[i] * v[i];
+        } else if (iluj) iluj->apply(v);
+        else if (jac) for (int i = 0; i < n; ++i) v[i] = T(0) * v[i] + T(1) * jac[i] * v[i];
     };
 
     conv.setup(gs);
@@ -685,19 +795,24 @@ void orc_jacobi_diag_f32(int n, const int* rm, const int* in, const float* v, fl
 // vals64 is the fp64 matrix.  Modes 1-3 follow DoBaselineProblem (gmres_perf_test.cpp:53-118): the solver
 // matrix is the fp32-rounded one (quirk, :66 + implicit conversion) and b is cast to Type (:97-98).
 // stats_out: Stats; hist_inner[cap_inner], hist_outer[4*cap_outer] may be null.
-int orc_gmres(int mode, int orth, int conv_kind, int prec, int64_t rlen, double tol, double rtol, int64_t max_restarts,
-              int n, const int* row_map, const int* inds, const double* vals64, const double* b, double* x,
-              Stats* st, double* hist_inner, int64_t cap_inner, double* hist_outer, int64_t cap_outer) {
+int orc_gmres2(int mode, int orth, int conv_kind, int prec, int jacobi_steps, int64_t rlen, double tol, double rtol, int64_t max_restarts,
+               int n, const int* row_map, const int* inds, const double* vals64, const double* b, double* x,
+               Stats* st, double* hist_inner, int64_t cap_inner, double* hist_outer, int64_t cap_outer) {
     std::memset(st, 0, sizeof(Stats));
     Hist hist{hist_inner, cap_inner, hist_outer, cap_outer};
     const size_t nnz = row_map[n];
     std::vector<float> vals32(nnz);
     copy_cast<double, float>(nnz, vals64, vals32.data());  // types_cuda.hpp:82-101 precision-cast ctor
+    // prec == 2: ILU_Jacobi<PrecType>(ilu0<PrecType>(A), jacobi_steps), gmres_perf_test.cpp:75-78,145-148 - factored from the fp64 matrix
+    std::vector<double> ilu_vals;
+    auto factor = [&](double eps_type) { ilu_vals.resize(nnz); ilu0(n, row_map, inds, vals64, eps_type, ilu_vals.data()); };
     if (mode == 0) {
         Conv<float> conv(conv_kind, tol, rtol, rlen, max_restarts);
         std::vector<float> jac;
         if (prec == 1) { jac.resize(n); orc_jacobi_diag_f32(n, row_map, inds, vals32.data(), jac.data()); }  // Jacobi<float>(A) gmres_perf_test.cpp:149
-        gmres_mixed(conv, orth, n, row_map, inds, vals64, vals32.data(), prec == 1 ? jac.data() : nullptr, b, x, *st, hist);
+        std::unique_ptr<IluJacobi<float>> M;
+        if (prec == 2) { factor(std::numeric_limits<float>::epsilon()); M.reset(new IluJacobi<float>(n, row_map, inds, ilu_vals.data(), jacobi_steps)); }
+        gmres_mixed(conv, orth, n, row_map, inds, vals64, vals32.data(), prec == 1 ? jac.data() : nullptr, b, x, *st, hist, M.get());
         st->total_iters = conv.total_iters; st->total_restarts = conv.total_restarts;
     } else if (mode == 1 || mode == 2) {
         std::vector<double> vals_rt(nnz);
@@ -709,20 +824,45 @@ int orc_gmres(int mode, int orth, int conv_kind, int prec, int64_t rlen, double 
             if (mode == 1) orc_jacobi_diag_f64(n, row_map, inds, vals64, jac.data());       // Jacobi<double>(A)
             else { std::vector<float> j32(n); orc_jacobi_diag_f32(n, row_map, inds, vals32.data(), j32.data()); copy_cast<float, double>(n, j32.data(), jac.data()); }
         }
-        gmres_uniform<double>(conv, orth, mode == 2, n, row_map, inds, vals_rt.data(), prec == 1 ? jac.data() : nullptr, b, x, *st, hist);
+        std::unique_ptr<IluJacobi<double>> M64;
+        std::unique_ptr<IluJacobi<float>> M32;
+        if (prec == 2 && mode == 1) { factor(std::numeric_limits<double>::epsilon()); M64.reset(new IluJacobi<double>(n, row_map, inds, ilu_vals.data(), jacobi_steps)); }
+        if (prec == 2 && mode == 2) { factor(std::numeric_limits<float>::epsilon()); M32.reset(new IluJacobi<float>(n, row_map, inds, ilu_vals.data(), jacobi_steps)); }
+        gmres_uniform<double>(conv, orth, mode == 2, n, row_map, inds, vals_rt.data(), prec == 1 ? jac.data() : nullptr, b, x, *st, hist, M64.get(), M32.get());
         st->total_iters = conv.total_iters; st->total_restarts = conv.total_restarts;
     } else {
         Conv<float> conv(conv_kind, tol, rtol, rlen, max_restarts);
         std::vector<float> jac, b32(n), x32(n);
         if (prec == 1) { jac.resize(n); orc_jacobi_diag_f32(n, row_map, inds, vals32.data(), jac.data()); }
+        std::unique_ptr<IluJacobi<float>> M;
+        if (prec == 2) { factor(std::numeric_limits<float>::epsilon()); M.reset(new IluJacobi<float>(n, row_map, inds, ilu_vals.data(), jacobi_steps)); }
         copy_cast<double, float>(n, b, b32.data());
         copy_cast<double, float>(n, x, x32.data());
-        gmres_uniform<float>(conv, orth, false, n, row_map, inds, vals32.data(), prec == 1 ? jac.data() : nullptr, b32.data(), x32.data(), *st, hist);
+        gmres_uniform<float>(conv, orth, false, n, row_map, inds, vals32.data(), prec == 1 ? jac.data() : nullptr, b32.data(), x32.data(), *st, hist, M.get());
         copy_cast<float, double>(n, x32.data(), x);
         st->total_iters = conv.total_iters; st->total_restarts = conv.total_restarts;
     }
     st->n_hist_inner = hist.ni; st->n_hist_outer = hist.no;
     return 0;
+}
+int orc_gmres(int mode, int orth, int conv_kind, int prec, int64_t rlen, double tol, double rtol, int64_t max_restarts,
+              int n, const int* row_map, const int* inds, const double* vals64, const double* b, double* x,
+              Stats* st, double* hist_inner, int64_t cap_inner, double* hist_outer, int64_t cap_outer) {
+    return orc_gmres2(mode, orth, conv_kind, prec, 1, rlen, tol, rtol, max_restarts, n, row_map, inds, vals64, b, x, st, hist_inner, cap_inner, hist_outer, cap_outer);
+}
+
+// ILU(0) of the fp64 matrix (eps_is_float: the boost threshold uses numeric_limits<float>::epsilon(), i.e. ilu0<float>) and the
+// Jacobi-sweep application of the factors in either precision
+void orc_ilu0(int n, const int* rm, const int* in, const double* vals, int eps_is_float, double* out) {
+    ilu0(n, rm, in, vals, eps_is_float ? (double)std::numeric_limits<float>::epsilon() : std::numeric_limits<double>::epsilon(), out);
+}
+void orc_ilu_jacobi_apply_f32(int n, const int* rm, const int* in, const double* ilu_vals, int steps, float* x) { IluJacobi<float>(n, rm, in, ilu_vals, steps).apply(x); }
+void orc_ilu_jacobi_apply_f64(int n, const int* rm, const int* in, const double* ilu_vals, int steps, double* x) { IluJacobi<double>(n, rm, in, ilu_vals, steps).apply(x); }
+void orc_ilu_jacobi_mv_f32(int n, const int* rm, const int* in, const double* ilu_vals, int lower, float alpha, const float* x, float beta, float* y) {
+    IluJacobi<float>(n, rm, in, ilu_vals, 1).mv(lower != 0, alpha, x, beta, y);
+}
+void orc_ilu_jacobi_mv_f64(int n, const int* rm, const int* in, const double* ilu_vals, int lower, double alpha, const double* x, double beta, double* y) {
+    IluJacobi<double>(n, rm, in, ilu_vals, 1).mv(lower != 0, alpha, x, beta, y);
 }
 
 // A bounded sample of the hot loop for the CPU baseline: `iters` GMRES-IR inner iterations (SpMV fp32 +
@@ -734,6 +874,38 @@ int orc_gmres(int mode, int orth, int conv_kind, int prec, int64_t rlen, double 
 // remote columns -> n_local + rank in the ascending sorted-unique list of remote globals (halo_cols).
 void orc_partition_bounds(int64_t n, int P, int64_t* bounds) {
     for (int r = 0; r <= P; ++r) bounds[r] = (int64_t)(((__int128)r * n) / P);
+}
+// nnz-balanced split points (SURVEY.md §8e "row_map[lo_r] ~ r nnz / P"): bounds[k] = the smallest row i with
+// row_map[i] >= floor(k nnz / P); bounds[0] = 0, bounds[P] = n.  Plain linear scan - the definition, not an algorithm.
+void orc_partition_bounds_nnz(int64_t n, int P, const int* row_map, int64_t* bounds) {
+    const int64_t nnz = row_map[n];
+    for (int k = 0; k <= P; ++k) {
+        const int64_t target = (int64_t)(((__int128)k * nnz) / P);
+        int64_t i = 0;
+        while (i < n && (int64_t)row_map[i] < target) ++i;
+        bounds[k] = i;
+    }
+    bounds[0] = 0;
+    bounds[P] = n;
+}
+// halo / local numbering for an arbitrary row range [lo, hi) (same definition as orc_partition_local)
+int64_t orc_partition_local_range(int64_t lo, int64_t hi, const int* row_map, const int* inds, int64_t* halo_cols, int* local_inds) {
+    std::vector<int64_t> remote;
+    for (int64_t p = row_map[lo]; p < row_map[hi]; ++p) {
+        const int64_t c = inds[p];
+        if (c < lo || c >= hi) remote.push_back(c);
+    }
+    std::sort(remote.begin(), remote.end());
+    remote.erase(std::unique(remote.begin(), remote.end()), remote.end());
+    if (halo_cols) std::copy(remote.begin(), remote.end(), halo_cols);
+    if (local_inds) {
+        const int64_t nl = hi - lo;
+        for (int64_t p = row_map[lo]; p < row_map[hi]; ++p) {
+            const int64_t c = inds[p];
+            local_inds[p - row_map[lo]] = (int)((c >= lo && c < hi) ? c - lo : nl + (std::lower_bound(remote.begin(), remote.end(), c) - remote.begin()));
+        }
+    }
+    return (int64_t)remote.size();
 }
 // returns number of halo columns; if halo_cols != null fills it (size >= return value) and local_inds
 // (size nnz_local).  Call once with nulls to size.

@@ -15,7 +15,7 @@ _LIB = None
 MODES = {"mixed": 0, "baseline": 1, "single-prec": 2, "single": 3}
 ORTHS = {"cgs": 0, "mgs": 1, "cgsr": 2}
 CONVS = {"base": 0, "relprecres": 1, "repeat": 2, "orthloss": 3}
-PRECS = {"identity": 0, "jacobi": 1}
+PRECS = {"identity": 0, "jacobi": 1, "ilu_jacobi": 2}
 
 
 class Stats(C.Structure):
@@ -192,7 +192,7 @@ def cast(x, dtype):
 
 # ---- solver ----------------------------------------------------------------------------------------
 def gmres(rm, ind, val64, b, x0=None, mode="mixed", orth="cgsr", conv="base", prec="identity", rlen=50, tol=1e-6,
-          rtol=0.0, max_restarts=1000000, hist_cap=None):
+          rtol=0.0, max_restarts=1000000, hist_cap=None, jacobi_steps=1):
     n = len(rm) - 1
     x = np.zeros(n, np.float64) if x0 is None else np.array(x0, np.float64)
     st = Stats()
@@ -200,7 +200,7 @@ def gmres(rm, ind, val64, b, x0=None, mode="mixed", orth="cgsr", conv="base", pr
     cap_inner = hist_cap if hist_cap is not None else min(cap_outer * int(rlen), 4000000)
     hi = np.zeros(max(cap_inner, 1), np.float64)
     ho = np.zeros(4 * cap_outer, np.float64)
-    lib().orc_gmres(C.c_int(MODES[mode]), C.c_int(ORTHS[orth]), C.c_int(CONVS[conv]), C.c_int(PRECS[prec]), _i64(rlen),
+    lib().orc_gmres2(C.c_int(MODES[mode]), C.c_int(ORTHS[orth]), C.c_int(CONVS[conv]), C.c_int(PRECS[prec]), C.c_int(jacobi_steps), _i64(rlen),
                     _d(tol), _d(rtol), _i64(max_restarts), C.c_int(n), _p(rm), _p(ind), _p(val64), _p(b), _p(x),
                     C.byref(st), _p(hi), _i64(cap_inner), _p(ho), _i64(cap_outer))
     res = {f: getattr(st, f) for f, _ in Stats._fields_}
@@ -210,11 +210,46 @@ def gmres(rm, ind, val64, b, x0=None, mode="mixed", orth="cgsr", conv="base", pr
     return res
 
 
+# ---- ILU(0) + Jacobi sweeps (restated; see oracle.cpp) ----
+def ilu0(rm, ind, val64, eps_is_float=True):
+    out = np.empty(len(val64), np.float64)
+    lib().orc_ilu0(C.c_int(len(rm) - 1), _p(rm), _p(ind), _p(val64), C.c_int(int(eps_is_float)), _p(out))
+    return out
+
+
+def ilu_jacobi_apply(rm, ind, ilu_vals, steps, x):
+    """ilusv_jacobi (kernels.hpp:227-248) in x's precision, in place"""
+    getattr(lib(), "orc_ilu_jacobi_apply_" + _sfx(x.dtype))(C.c_int(len(rm) - 1), _p(rm), _p(ind), _p(ilu_vals), C.c_int(steps), _p(x))
+    return x
+
+
+def ilu_jacobi_mv(rm, ind, ilu_vals, lower, alpha, x, beta, y):
+    getattr(lib(), "orc_ilu_jacobi_mv_" + _sfx(x.dtype))(C.c_int(len(rm) - 1), _p(rm), _p(ind), _p(ilu_vals), C.c_int(int(lower)), _sc(x.dtype, alpha), _p(x),
+                                                          _sc(x.dtype, beta), _p(y))
+    return y
+
+
 # ---- partition -------------------------------------------------------------------------------------
 def partition_bounds(n, P):
     b = np.empty(P + 1, np.int64)
     lib().orc_partition_bounds(_i64(n), C.c_int(P), _p(b))
     return b
+
+
+def partition_bounds_nnz(rm, P):
+    b = np.empty(P + 1, np.int64)
+    lib().orc_partition_bounds_nnz(_i64(len(rm) - 1), C.c_int(P), _p(rm), _p(b))
+    return b
+
+
+def partition_local_range(lo, hi, rm, ind):
+    """(halo_cols, local_inds) of the slab of rows [lo, hi) (any split points)"""
+    lib().orc_partition_local_range.restype = C.c_int64
+    nh = lib().orc_partition_local_range(_i64(lo), _i64(hi), _p(rm), _p(ind), None, None)
+    halo = np.empty(nh, np.int64)
+    li = np.empty(int(rm[hi] - rm[lo]), np.int32)
+    lib().orc_partition_local_range(_i64(lo), _i64(hi), _p(rm), _p(ind), _p(halo), _p(li))
+    return halo, li
 
 
 def partition_local(n, P, r, rm, ind):

@@ -74,3 +74,14 @@ def load_matrix(path):
     rm, ind, val = np.empty(n.value + 1, np.int32), np.empty(nnz.value, np.int32), np.empty(nnz.value, np.float64)
     lib().ref_load_matrix(str(path).encode(), C.byref(n), C.byref(nnz), _p(rm), _p(ind), _p(val), err, 256)
     return rm, ind, val
+
+
+def load_vector(path, col=0):
+    """the reference's own LoadVector<double>(file, col) -> float64 array; raises ValueError with its exception text"""
+    n = C.c_long()
+    err = C.create_string_buffer(256)
+    if lib().ref_load_vector(str(path).encode(), C.c_int(col), C.byref(n), None, err, 256) != 0:
+        raise ValueError(err.value.decode())
+    out = np.empty(n.value, np.float64)
+    lib().ref_load_vector(str(path).encode(), C.c_int(col), C.byref(n), _p(out), err, 256)
+    return out

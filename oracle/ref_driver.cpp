@@ -184,6 +184,19 @@ int ref_load_matrix(const char* path, int* n, long* nnz, int* row_map, int* inds
     }
 }
 
+// the reference's own LoadVector<double>(file, col) (LoadMatrix.hpp:156-233); call with out == null for the length
+int ref_load_vector(const char* path, int col, long* n, double* out, char* err, int errlen) {
+    try {
+        Vect<double, MKL> v = LoadVector<double>(const_cast<char*>(path), col);
+        *n = (long)v.n();
+        if (out) for (long i = 0; i < *n; ++i) out[i] = v.data()[i];
+        return 0;
+    } catch (const std::exception& e) {
+        if (err && errlen > 0) std::snprintf(err, (size_t)errlen, "%s", e.what());
+        return 1;
+    }
+}
+
 int ref_num_threads() { return MKL_Get_Max_Threads(); }
 
 // same argument meaning as orc_gmres (oracle/oracle.cpp); true_x may be null (then err_norm = ||x||)

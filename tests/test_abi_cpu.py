@@ -75,3 +75,27 @@ def test_size_queries(g, orc):
         assert L.mpg_lap2d_nnz(N) == 5 * N * N - 4 * N
         assert L.mpg_cd27_nnz(N) == (3 * N - 2) ** 3
     assert L.mpg_cd27_nnz(256) == 449455096  # config 3
+
+
+def test_nnz_balanced_split_points_match_oracle(g, orc):
+    """mpg_partition_bounds_nnz vs the oracle's linear-scan definition, bit-exact; each slab's nonzero count is
+    within one row of nnz / P"""
+    for spec in ["lap2d:9", "cd27:6", "powerlaw:400", "powerlaw:20000"]:
+        rm, ind, val = orc.gen(spec)
+        n, nnz = len(rm) - 1, int(rm[-1])
+        for P in (1, 2, 3, 4, 8):
+            b = np.array(g.dist.bounds_nnz(rm, P), np.int64)
+            np.testing.assert_array_equal(b, orc.partition_bounds_nnz(rm, P))
+            assert b[0] == 0 and b[-1] == n and np.all(np.diff(b) >= 0)
+            share = np.diff(rm[b].astype(np.int64))
+            assert np.all(np.abs(share - nnz / P) <= np.diff(rm).max() + 1)
+    # the torch restatement of the plan honours explicit split points (bit-exact vs the oracle's range form)
+    import torch
+    rm, ind, val = orc.gen("powerlaw:3000")
+    n = len(rm) - 1
+    b = g.dist.bounds_nnz(rm, 3)
+    for r in range(3):
+        rml, li, v, halo = g.dist.local_slab(torch.from_numpy(rm), torch.from_numpy(ind), torch.from_numpy(val), n, r, 3, b)
+        halo_o, li_o = orc.partition_local_range(b[r], b[r + 1], rm, ind)
+        np.testing.assert_array_equal(halo.numpy(), halo_o)
+        np.testing.assert_array_equal(li.numpy(), li_o)

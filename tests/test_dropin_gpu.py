@@ -97,3 +97,33 @@ def test_python_harness_prints_the_reference_stdout_contract(orc, tmp_path):
     assert out.stdout.startswith("||x|| = ")
     bad = subprocess.run([sys.executable, os.path.join(ROOT, "gmres_perf_test.py"), "--bogus"], capture_output=True, text=True)
     assert bad.returncode == 1 and "Unknown flag" in bad.stdout      # gmres_perf_test.cpp:390-393
+
+
+def test_python_harness_bpath_and_csv_row(orc, tmp_path):
+    """--bpath (LoadVector, gmres_perf_test.cpp:417-421: x_true = 0, errNorm degenerates to ||x||) and the history CSV row of
+    automated.py:158-168, against the reference CLI's MKL path on the same matrix and right-hand-side files"""
+    import csv
+    import sys
+    if not os.path.exists(EXE):
+        pytest.skip("oracle/_ref/gmres_perf_test_b200 not built")
+    rm, ind, val, xt, b = problem(orc, "lap2d:30")
+    mtx, rhs = tmp_path / "a.mtx", tmp_path / "b.mtx"
+    write_mtx(mtx, rm, ind, val)
+    with open(rhs, "w") as f:
+        f.write(f"%%MatrixMarket matrix array real general\n{len(b)} 1\n")
+        for v in b:
+            f.write(f"{v:.17g}\n")
+    host = run_cli(mtx, False, "mixed", "cgsr", "identity", 30, 1e-9, ("--bpath", str(rhs)))
+    hist = tmp_path / "history-a.csv"
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "gmres_perf_test.py"), "--Apath", str(mtx), "--bpath", str(rhs), "--mode", "mixed", "--orth", "cgsr",
+                          "--prec", "identity", "--rlen", "30", "--tol", "1e-9", "--csv", str(hist), "--gpu"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.startswith("||x|| = 0\n")
+    m = re.search(r"Found solution with rel prec res norm = (\S+) when k = (\d+) and i = (\d+)\s+total iterations = (\d+)", out.stdout)
+    assert m and (int(m.group(3)), int(m.group(4))) == (host["i"], host["iters"]), out.stdout
+    r = re.search(r"resNorm = (\S+); errNorm = (\S+)", out.stdout)
+    assert abs(float(r.group(2)) - np.linalg.norm(xt)) <= 1e-5 * np.linalg.norm(xt)        # errNorm = ||x - 0||
+    assert abs(float(r.group(2)) - host["err"]) <= 1e-5 * host["err"]
+    row = next(csv.reader(open(hist)))
+    assert row[:9] == ["a", "mp", "CGSR", "30", "0", "0", "1e-09", "cuda", "identity"] and int(row[9]) == host["i"] and int(row[10]) == host["iters"]
+    assert len(row) == 15 and float(row[13]) >= 0 and float(row[14]) > 0

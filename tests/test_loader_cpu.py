@@ -57,3 +57,41 @@ def test_live_reference_loader_agrees(g):
         b = oracle_ref.load_matrix(os.path.join(HERE, "golden", "mm", name))
         for x, y in zip(a, b):
             np.testing.assert_array_equal(x, y)
+
+
+VEXP = json.load(open(os.path.join(HERE, "golden", "mmvec_expected.json")))
+
+
+@pytest.mark.parametrize("key", sorted(VEXP))
+def test_vector_loader_matches_reference_loadvector(g, key):
+    """mpg_mm_read_vector_host vs what the reference's own LoadVector<double>() (LoadMatrix.hpp:156-233, through oracle/_ref) returned
+    for the same file and column: array and coordinate forms, bit for bit"""
+    name, col = key.split(":")
+    v = g.read_matrix_market_vector(os.path.join(HERE, "golden", "mmvec", name), int(col))
+    np.testing.assert_array_equal(v, np.array([float.fromhex(x) for x in VEXP[key]]))
+
+
+def test_vector_loader_errors_like_the_reference(g, tmp_path):
+    with pytest.raises(g.MpgError, match="Could not access file"):
+        g.read_matrix_market_vector(tmp_path / "missing.mtx")
+    with pytest.raises(g.MpgError, match="Column 3 is too large for the 3 vectors"):                    # LoadMatrix.hpp:192-197
+        g.read_matrix_market_vector(os.path.join(HERE, "golden", "mmvec", "array_3cols.mtx"), 3)
+    p = tmp_path / "bad.mtx"
+    p.write_text("%MatrixMarket matrix array real general\n2 1\n1\n2\n")
+    with pytest.raises(g.MpgError, match="Banner is missing"):
+        g.read_matrix_market_vector(p)
+    p.write_text("%%MatrixMarket matrix array real general\n")
+    with pytest.raises(g.MpgError, match="Malformed matrix size information"):
+        g.read_matrix_market_vector(p)
+
+
+def test_live_reference_vector_loader_agrees(g):
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(HERE), "oracle"))
+    import oracle_ref
+    if not oracle_ref.available():
+        pytest.skip("oracle/_ref not built")
+    for key in sorted(VEXP):
+        name, col = key.split(":")
+        path = os.path.join(HERE, "golden", "mmvec", name)
+        np.testing.assert_array_equal(g.read_matrix_market_vector(path, int(col)), oracle_ref.load_vector(path, int(col)))

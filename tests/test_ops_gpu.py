@@ -471,3 +471,19 @@ def test_spmv_packed_sigma(ctx, g, orc, spec, dt):
     # Jacobi-scaled operator through the solver's own path is covered by tests/test_solver_gpu.py (powerlaw + prec=jacobi goldens)
     lens = np.diff(rm)
     assert (lens <= 256).sum() > 0.9 * n and (lens > 256).sum() > 0   # the case really has both kinds of rows
+
+@pytest.mark.parametrize("spec", ["lap2d:1", "lap2d:23", "cd27:1", "cd27:9", "powerlaw:5000", "powerlaw:5000:11:2:8"])
+def test_row_range_generators_equal_rows_of_the_global_matrix(ctx, g, orc, spec):
+    """mpg_gen_slab_*: rows [lo, hi) generated alone == the same rows cut out of the oracle's global matrix, bit for bit (global
+    column indices, local row map) - every rank of a multi-GPU run builds only its slab; mpg_gen_rowmap == the global row map"""
+    rm, ind, val = orc.gen(spec)
+    n = len(rm) - 1
+    np.testing.assert_array_equal(host(ctx.gen_rowmap(spec)), rm)
+    cuts = sorted({0, n, n // 3, (2 * n) // 3, min(n, 1), max(n - 1, 0)})
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
+        r, i, v = ctx.gen_slab(spec, lo, hi)
+        np.testing.assert_array_equal(host(r), rm[lo:hi + 1] - rm[lo])
+        np.testing.assert_array_equal(host(i), ind[rm[lo]:rm[hi]])
+        np.testing.assert_array_equal(host(v), val[rm[lo]:rm[hi]])
+    r, i, v = ctx.gen_slab(spec, 0, 0)
+    assert host(r).tolist() == [0] and i.numel() == 0

@@ -295,3 +295,49 @@ def test_packed_layout_restatement_is_a_permutation_of_the_csr_entries(orc, spec
     Lmax = lens.reshape(-1, 32).max(axis=1)
     L = np.diff(off) // 32
     assert np.all(L >= Lmax) and np.all(L - Lmax < G) and np.all((L == Lmax) | ((L - Lmax) * 10 <= Lmax))
+
+
+@pytest.mark.parametrize("spec", ["lap2d:12", "cd27:6", "powerlaw:800"])
+def test_ilu0_restatement_properties(orc, spec):
+    """oracle.ilu0 (sequential IKJ, kernels_mkl.cpp:451-484 with diag_inds filled in): L U reproduces A exactly on the pattern of A
+    (the defining property of ILU(0)), L is unit lower, pivots keep their sign; IluJacobi with many sweeps converges to the exact
+    triangular solves and its first sweep is the first-order Neumann term"""
+    rm, ind, val = orc.gen(spec)
+    n = len(rm) - 1
+    f = orc.ilu0(rm, ind, val, True)
+    A, F = csr(rm, ind, val), csr(rm, ind, f)
+    L, U = (sp.tril(F, -1) + sp.eye(n)).tocsr(), sp.triu(F).tocsr()
+    R = (L @ U - A).tocsr()
+    P = A.copy(); P.data[:] = 1
+    assert abs(R.multiply(P)).max() <= 64 * EPS[np.dtype(np.float64)] * abs(A).max() * np.diff(rm).max()
+    assert np.all(U.diagonal() > 0)
+    x0 = np.random.default_rng(1).standard_normal(n)
+    exact = spla.spsolve_triangular(U, spla.spsolve_triangular(L, x0, lower=True), lower=False)
+    if spec != "powerlaw:800":
+        x = orc.ilu_jacobi_apply(rm, ind, f, 80, x0.copy())
+        np.testing.assert_allclose(x, exact, rtol=0, atol=1e-9 * np.abs(exact).max())
+    # one sweep per triangle = (I - D^-1 S) D^-1 (I - N) x0 with L = I + N, U = D + S
+    N, D, S = sp.tril(F, -1), F.diagonal(), sp.triu(F, 1)
+    t = x0 - N @ x0
+    first = t / D - (S @ (t / D)) / D
+    # (kernels.hpp:236-248 with steps = 1: x <- x + (b - L x), then x <- x + D^-1 (b - U x) from x = b: = b + D^-1 b - D^-1 U b)
+    t2 = t + (t - U @ t) / D
+    x1 = orc.ilu_jacobi_apply(rm, ind, f, 1, x0.copy())
+    np.testing.assert_allclose(x1, t2, rtol=0, atol=1e-12 * max(1.0, np.abs(t2).max()))
+    del first
+    # mv forms
+    y0 = np.random.default_rng(2).standard_normal(n)
+    np.testing.assert_allclose(orc.ilu_jacobi_mv(rm, ind, f, True, 0.5, x0, -2.0, y0.copy()), -2.0 * y0 + 0.5 * (L @ x0), rtol=0, atol=1e-11 * np.abs(y0).max() * n ** 0.5)
+    np.testing.assert_allclose(orc.ilu_jacobi_mv(rm, ind, f, False, 3.0, x0, 7.0, y0.copy()), y0 - U @ x0, rtol=0, atol=1e-11 * (abs(U) @ np.abs(x0) + np.abs(y0)).max())
+
+
+def test_oracle_gmres_with_ilu_jacobi_converges(orc):
+    rm, ind, val, xt, b = problem(orc, "cd27:8")
+    r0 = orc.gmres(rm, ind, val, b, mode="mixed", rlen=30, tol=1e-9, max_restarts=50)
+    r2 = orc.gmres(rm, ind, val, b, mode="mixed", rlen=30, tol=1e-9, prec="ilu_jacobi", jacobi_steps=2, max_restarts=50)
+    r4 = orc.gmres(rm, ind, val, b, mode="baseline", rlen=30, tol=1e-10, prec="ilu_jacobi", jacobi_steps=4, max_restarts=50)
+    assert r0["status"] == r2["status"] == r4["status"] == 1
+    assert np.linalg.norm(r2["x"] - xt) <= 1e-6 * np.linalg.norm(xt) and np.linalg.norm(r4["x"] - xt) <= 1e-6 * np.linalg.norm(xt)
+    # more sweeps = better triangular solves = a faster-falling preconditioned Arnoldi residual (two sweeps alone are a weak
+    # preconditioner on this stencil: the Neumann series of L^-1 and U^-1 converges slowly when the off-diagonal row sums are ~0.5)
+    assert r4["hist_inner"][10] < r2["hist_inner"][10]

@@ -17,8 +17,17 @@ dev = f"cuda:{local}"
 dist.init_process_group("nccl", device_id=torch.device(dev))
 ctx = g.Context(local)
 report = {"ok": True, "cases": []}
-for spec, rlen, orth, peer in [("cd27:32", 60, "cgsr", True), ("cd27:32", 60, "cgsr", False), ("lap2d:200", 50, "cgsr", True), ("powerlaw:20000", 30, "cgsr", True),
-                               ("cd27:24", 40, "mgs", True), ("cd27:24", 40, "cgs", True), ("cd27:24", 40, "cgs", False), ("lap2d:120", 40, "relprecres", True), ("cd27:24", 40, "jacobi", True)]:
+# (spec, restart length, variant, in-kernel all-reduce?, split points)
+CASES = [("cd27:32", 60, "cgsr", True, "rows"), ("cd27:32", 60, "cgsr", False, "rows"), ("lap2d:200", 50, "cgsr", True, "rows"), ("powerlaw:20000", 30, "cgsr", True, "rows"),
+         ("cd27:24", 40, "mgs", True, "rows"), ("cd27:24", 40, "cgs", True, "rows"), ("cd27:24", 40, "cgs", False, "rows"), ("lap2d:120", 40, "relprecres", True, "rows"),
+         ("cd27:24", 40, "jacobi", True, "rows"),
+         # nnz-balanced split points: unequal slabs; with a residual-driven restart policy every rank must still enqueue the same
+         # number of speculative steps (the look-ahead depth is derived from rank-invariant sizes)
+         ("powerlaw:30000", 30, "cgsr", True, "nnz"), ("powerlaw:30000", 30, "relprecres", True, "nnz"), ("powerlaw:30000", 30, "relprecres", False, "nnz"),
+         ("lap2d:150", 40, "relprecres", True, "nnz")]
+if os.environ.get("DIST_CHECK_CASES"):
+    CASES = [CASES[int(i)] for i in os.environ["DIST_CHECK_CASES"].split(",")]
+for spec, rlen, orth, peer, split in CASES:
     rm, ind, val = ctx.gen(spec)
     n = rm.numel() - 1
     xt_host = ctx.rand_vect(n, 42)
@@ -34,10 +43,19 @@ for spec, rlen, orth, peer in [("cd27:32", 60, "cgsr", True), ("cd27:32", 60, "c
     if orth == "jacobi":       # diagonal preconditioner folded into the partitioned SpMV
         kw = dict(mode="mixed", orth="cgsr", prec="jacobi", rlen=rlen, tol=1e-9, max_restarts=300)
     r1 = ctx.gmres(A, val, b, x1, **kw)
-    # partitioned
-    part = g.dist.build_partition(rm, ind, val, n, rank, world)
-    dctx = g.dist.DistContext(ctx, rank, world, peer_reduce=peer)
-    dctx.set_partition(part)
+    # partitioned: the plan built natively from this rank's slab ALONE (mpg_gen_slab_* + mpg_dist_setup) must equal, bit for bit, the
+    # torch restatement built from the global matrix (the one tests/test_dist_cpu.py pins against the oracle)
+    bnd = g.dist.bounds_nnz(rm.cpu().numpy(), world) if split == "nnz" else g.dist.bounds(n, world)
+    ref_part = g.dist.build_partition(rm, ind, val, n, rank, world, b=bnd)
+    rm_l, ind_l, val_l = ctx.gen_slab(spec, bnd[rank], bnd[rank + 1])
+    dctx = g.dist.DistContext(ctx, rank, world, native=True)
+    part = dctx.setup(n, bnd, rm_l, ind_l, val_l)
+    plan_ok = (bool(torch.equal(part.row_map, ref_part.row_map)) and bool(torch.equal(part.inds, ref_part.inds)) and bool(torch.equal(part.vals, ref_part.vals))
+               and bool(torch.equal(part.halo_cols, ref_part.halo_cols)) and len(part.peers) == len(ref_part.peers)
+               and all(a["rank"] == b_["rank"] and a["recv_offset"] == b_["recv_offset"] and a["recv_count"] == b_["recv_count"]
+                       and np.array_equal(a["send_idx"].cpu().numpy(), b_["send_idx"].cpu().numpy()) for a, b_ in zip(part.peers, ref_part.peers)))
+    if not peer:
+        ctx.set_tuning("dist_peer_reduce", 0)
     Al = g.dist.local_csr(ctx, part)
     dctx.attach()
     # halo exchange delivers exactly the remote entries
@@ -59,9 +77,16 @@ for spec, rlen, orth, peer in [("cd27:32", 60, "cgsr", True), ("cd27:32", 60, "c
     r20 = ctx.gmres(Al, part.vals, bl, xl0, **kw)
     ctx.set_tuning("dist_overlap", 1)
     overlap_ok = bool(torch.equal(xl, xl0)) and np.array_equal(r2["hist_inner"], r20["hist_inner"])
+    # fused halo (push rides in the Arnoldi tail, wait in the boundary SpMV) vs the stand-alone push / wait-and-move kernels: same bits
+    ctx.set_tuning("dist_fuse_halo", 0)
+    xl1 = torch.zeros(part.n_local, dtype=torch.float64, device=dev)
+    r21 = ctx.gmres(Al, part.vals, bl, xl1, **kw)
+    ctx.set_tuning("dist_fuse_halo", 1)
+    overlap_ok = overlap_ok and bool(torch.equal(xl, xl1)) and np.array_equal(r2["hist_inner"], r21["hist_inner"])
+    ctx.set_tuning("dist_peer_reduce", 1)
     dctx.detach()
     # gather x and compare
-    xs = [torch.zeros(int(c), dtype=torch.float64, device=dev) for c in np.diff(g.dist.bounds(n, world))]
+    xs = [torch.zeros(int(c), dtype=torch.float64, device=dev) for c in np.diff(bnd)]
     dist.all_gather(xs, xl)
     xg = torch.cat(xs)
     err1, err2 = float((x1 - xt).norm()), float((xg - xt).norm())
@@ -82,9 +107,9 @@ for spec, rlen, orth, peer in [("cd27:32", 60, "cgsr", True), ("cd27:32", 60, "c
     else:
         counts_ok = r1["total_iters"] == r2["total_iters"] and r1["total_restarts"] == r2["total_restarts"]
         hist_ok = dev_hist <= env
-    ok = (halo_ok and overlap_ok and replicated and r1["status"] == r2["status"] == 1 and counts_ok and hist_ok and abs(nb - nb1) <= 1e-12 * nb1
+    ok = (plan_ok and halo_ok and overlap_ok and replicated and r1["status"] == r2["status"] == 1 and counts_ok and hist_ok and abs(nb - nb1) <= 1e-12 * nb1
           and err2 <= 4 * err1 + 1e-10)
-    report["cases"].append(dict(spec=spec, orth=orth, peer_reduce=dctx.peer_reduce, ok=ok, halo_ok=halo_ok, overlap_ok=overlap_ok, replicated=replicated, iters=(r1["total_iters"], r2["total_iters"]),
+    report["cases"].append(dict(spec=spec, orth=orth, peer_reduce=peer, split=split, rows=[int(v) for v in np.diff(bnd)], ok=ok, plan_ok=plan_ok, halo_ok=halo_ok, overlap_ok=overlap_ok, replicated=replicated, iters=(r1["total_iters"], r2["total_iters"]),
                                 dev_hist=dev_hist, err=(err1, err2), n_halo=part.n_halo, peers=len(part.peers)))
     report["ok"] = report["ok"] and ok
     dctx.close()
