@@ -1,12 +1,81 @@
 // blas1.cu — context, device memory, BLAS-1, casts, Givens / least-squares kernels.
 // Reference surface: kernels.hpp:11-114,128-151; reference CUDA backend: kernels_cuda.cpp:111-494,538-572.
+#include <mutex>
 #include <random>
+#include <unordered_map>
 
 #include "common.cuh"
 
 using namespace mpg;
 
 namespace mpg {
+// ---- block cache on top of the stream-ordered pool (see common.cuh) --------------------------------------------------------
+namespace blockcache {
+struct CachedBlock { void* p; size_t bytes; };
+struct BlockCache {
+    std::mutex mu;
+    std::unordered_map<void*, std::pair<size_t, int>> live;      // handed out: ptr -> (bytes, device)
+    std::vector<CachedBlock> parked[64];                         // per device
+    size_t parked_bytes[64] = {0};
+};
+BlockCache& block_cache() { static BlockCache c; return c; }
+constexpr size_t kCacheMinBytes = (size_t)1 << 20;
+constexpr size_t kCacheMaxParked = (size_t)24 << 30;             // per device
+}  // namespace blockcache
+using namespace blockcache;
+
+cudaError_t pool_alloc(mpg_ctx* ctx, void** p, size_t bytes) {
+    BlockCache& c = block_cache();
+    const int dev = ctx->device & 63;
+    if (bytes >= kCacheMinBytes) {
+        std::lock_guard<std::mutex> lock(c.mu);
+        auto& v = c.parked[dev];
+        int best = -1;
+        for (int i = 0; i < (int)v.size(); ++i)
+            if (v[(size_t)i].bytes >= bytes && v[(size_t)i].bytes <= bytes + bytes / 4 + kCacheMinBytes && (best < 0 || v[(size_t)i].bytes < v[(size_t)best].bytes)) best = i;
+        if (best >= 0) {
+            *p = v[(size_t)best].p;
+            c.live[*p] = {v[(size_t)best].bytes, dev};
+            c.parked_bytes[dev] -= v[(size_t)best].bytes;
+            v.erase(v.begin() + best);
+            return cudaSuccess;
+        }
+    }
+    const cudaError_t e = cudaMallocAsync(p, bytes, ctx->stream);
+    if (e == cudaSuccess && bytes >= kCacheMinBytes) {
+        std::lock_guard<std::mutex> lock(c.mu);
+        c.live[*p] = {bytes, dev};
+    }
+    return e;
+}
+void pool_free(void* p) {
+    if (!p) return;
+    BlockCache& c = block_cache();
+    size_t bytes = 0;
+    int dev = 0;
+    {
+        std::lock_guard<std::mutex> lock(c.mu);
+        auto it = c.live.find(p);
+        if (it != c.live.end()) { bytes = it->second.first; dev = it->second.second; c.live.erase(it); }
+    }
+    if (bytes == 0) { cudaFree(p); return; }
+    cudaDeviceSynchronize();                                     // what cudaFree guarantees: nobody is using the block any more
+    std::lock_guard<std::mutex> lock(c.mu);
+    if (c.parked_bytes[dev] + bytes > kCacheMaxParked || c.parked[dev].size() >= 256) { cudaFree(p); return; }
+    c.parked[dev].push_back({p, bytes});
+    c.parked_bytes[dev] += bytes;
+}
+void pool_trim(int device) {
+    BlockCache& c = block_cache();
+    std::vector<CachedBlock> drop;
+    {
+        std::lock_guard<std::mutex> lock(c.mu);
+        drop.swap(c.parked[device & 63]);
+        c.parked_bytes[device & 63] = 0;
+    }
+    for (auto& b : drop) cudaFree(b.p);
+}
+
 // device-side waits on a peer GPU that timed out leave a code in the context's error word (common.cuh wait_flag)
 int check_dev_err(mpg_ctx* ctx) {
     const unsigned int e = ctx->dev_err ? *reinterpret_cast<volatile unsigned int*>(ctx->dev_err) : 0u;
@@ -67,9 +136,11 @@ extern "C" int mpg_ctx_destroy(mpg_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->ws && ctx->ws_free) ctx->ws_free(ctx->ws);
+    if (ctx->ortho_cache && ctx->ortho_cache_free) ctx->ortho_cache_free(ctx->ortho_cache);
     for (auto& r : ctx->prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto e : ctx->prof_pool) cudaEventDestroy(e);
     cudaFree(ctx->arena);
+    pool_trim(ctx->device);
     cudaFree(ctx->red_raw);
     cudaFree(ctx->partials);
     cudaFree(ctx->ticket);
@@ -110,7 +181,7 @@ static int* tuning_slot(mpg_ctx* ctx, const std::string& k) {
     MPG_KNOB(vdirect_max_cols_a); MPG_KNOB(vdirect_max_cols_b); MPG_KNOB(vrow_max_cols); MPG_KNOB(vrow_max_cols_a); MPG_KNOB(gemvt_rb);
     MPG_KNOB(gemvt_rows_per_block); MPG_KNOB(passA_rb); MPG_KNOB(cgs2_fused); MPG_KNOB(vpass_serpentine); MPG_KNOB(gemvn_ctas_per_sm);
     MPG_KNOB(red_ctas_per_sm); MPG_KNOB(residual_packed); MPG_KNOB(values_static); MPG_KNOB(spmv_sigma); MPG_KNOB(mgs_fused);
-    MPG_KNOB(dist_fuse_halo); MPG_KNOB(spin_limit_ms); MPG_KNOB(lookahead); MPG_KNOB(sell_variant); MPG_KNOB(sell_block);
+    MPG_KNOB(dist_fuse_halo); MPG_KNOB(spin_limit_ms); MPG_KNOB(lookahead); MPG_KNOB(sell_variant); MPG_KNOB(sell_block); MPG_KNOB(trace);
 #undef MPG_KNOB
     return nullptr;
 }
@@ -273,6 +344,58 @@ __global__ void __launch_bounds__(RED_THREADS) reduce_kernel(int64_t n, const T*
     if (grid_last_block(ticket)) last_block_finish<T>(epi, partials, 1, gridDim.x, 1);
 }
 
+// One modified Gram-Schmidt step fused pairwise (MGS_Kernel::orthogonalize, Orthogonalization.hpp:98-106): w <- w - h_j v_j (the
+// naxpy of column j) and the partial sums of h_{j+1} = v_{j+1} . w (the dot of column j + 1) in ONE pass over w: 4 n s bytes per
+// column instead of 5 n s, half the launches.  Same element-to-thread mapping, the same fma per element and the same reduction
+// tree as the stand-alone reduce_kernel / ew_kernel pair: results are bit-identical to the unfused sequence.
+template <class T>
+__global__ void __launch_bounds__(RED_THREADS) mgs_step_kernel(int64_t n, const T* __restrict__ vj, const T* __restrict__ vj1, T* w,
+                                                                const T* __restrict__ hj_dev, double* partials, unsigned int* ticket, Epi epi) {
+    constexpr int VEC = 16 / sizeof(T);
+    using V = typename std::conditional<sizeof(T) == 4, float4, double2>::type;
+    pdl_trigger();
+    pdl_wait();
+    const T hj = __ldg(hj_dev);
+    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t gstride = (int64_t)gridDim.x * blockDim.x;
+    T acc[VEC];
+#pragma unroll
+    for (int c = 0; c < VEC; ++c) acc[c] = T(0);
+    const int64_t nv = n / VEC;
+    for (int64_t i = gtid; i < nv; i += gstride) {
+        const V a = ldg_stream(reinterpret_cast<const V*>(vj) + i);
+        const V b = ldg_stream(reinterpret_cast<const V*>(vj1) + i);
+        V c = reinterpret_cast<V*>(w)[i];
+        const T* pa = reinterpret_cast<const T*>(&a);
+        const T* pb = reinterpret_cast<const T*>(&b);
+        T* pc = reinterpret_cast<T*>(&c);
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) {
+            pc[q] = fma(-hj, pa[q], pc[q]);          // naxpy(h(j,k), v_col, w)
+            acc[q] = fma(pc[q], pb[q], acc[q]);      // dot(w, v_col + 1)
+        }
+        reinterpret_cast<V*>(w)[i] = c;
+    }
+    for (int64_t i = nv * VEC + gtid; i < n; i += gstride) {
+        const T wn = fma(-hj, vj[i], w[i]);
+        w[i] = wn;
+        acc[0] = fma(wn, vj1[i], acc[0]);
+    }
+    double sred = 0.0;
+#pragma unroll
+    for (int c = 0; c < VEC; ++c) sred += (double)acc[c];
+    sred = warp_sum(sred);
+    __shared__ double wsum[RED_THREADS / 32];
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = sred;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int q = 0; q < RED_THREADS / 32; ++q) t += wsum[q];
+        partials[blockIdx.x] = t;
+    }
+    if (grid_last_block(ticket)) last_block_finish<T>(epi, partials, 1, gridDim.x, 1);
+}
+
 template <class T, bool IS_NRM2>
 int launch_reduce(mpg_ctx* ctx, int64_t n, const T* x, const T* y, T* out_dev) {
     const int64_t per_block = RED_THREADS * (16 / sizeof(T)) * 4;
@@ -301,6 +424,20 @@ int dot_dev(mpg_ctx* ctx, int64_t n, const float* x, const float* y, float* out)
 int dot_dev(mpg_ctx* ctx, int64_t n, const double* x, const double* y, double* out) { return launch_reduce<double, false>(ctx, n, x, y, out); }
 int nrm2_dev(mpg_ctx* ctx, int64_t n, const float* x, float* out) { return launch_reduce<float, true>(ctx, n, x, x, out); }
 int nrm2_dev(mpg_ctx* ctx, int64_t n, const double* x, double* out) { return launch_reduce<double, true>(ctx, n, x, x, out); }
+// w -= h_j v_j ; h_{j+1} = v_{j+1} . w   (all four pointers 16-byte aligned; same grid as the stand-alone dot)
+template <class T>
+int mgs_step(mpg_ctx* ctx, int64_t n, const T* vj, const T* vj1, T* w, const T* hj_dev, T* hj1_dev) {
+    const int64_t per_block = RED_THREADS * (16 / sizeof(T)) * 4;
+    int grid = (int)std::min<int64_t>(std::max<int64_t>(1, cdiv(n, per_block)), (int64_t)ctx->num_sms * ctx->tune.red_ctas_per_sm);
+    grid = std::min(grid, kMaxPartBlocks);
+    ProfScope prof(ctx, MPG_PROF_REDUCE, 4.0 * (double)n * sizeof(T));
+    const Epi epi = make_epi(ctx, EPI_DOT, hj1_dev, nullptr, 0.0, 0.0);
+    MPG_CUDA(ctx, launch_pdl(ctx, n, mgs_step_kernel<T>, grid, RED_THREADS, 0, n, vj, vj1, w, hj_dev, ctx->partials, ctx->ticket, epi));
+    MPG_CHECK_LAUNCH(ctx);
+    return dist_finish_reduction(ctx, epi, 1, (int)sizeof(T));
+}
+template int mgs_step<float>(mpg_ctx*, int64_t, const float*, const float*, float*, const float*, float*);
+template int mgs_step<double>(mpg_ctx*, int64_t, const double*, const double*, double*, const double*, double*);
 }  // namespace mpg
 
 #define MPG_DEF_RED(SFX, T)                                                                                          \
@@ -686,7 +823,7 @@ int arnoldi_tail(mpg_ctx* ctx, int64_t n, const T* inv_dev, const T* w, T* vnext
     const size_t smem = sizeof(T) * (size_t)(3 * k + 2);
     PushArgs pa;
     if (push) pa = *push;
-    const int npush = pa.npeers * kPushBlocksPerPeer;
+    const int npush = pa.npeers * pa.bpp;
     const int grid = (int)std::min<int64_t>(std::max<int64_t>(cdiv(n, 256 * 4), 1), (int64_t)ctx->num_sms * 16) + npush + 1;
     const int aligned = (((uintptr_t)w | (uintptr_t)vnext) & 15) == 0;
     ProfScope prof(ctx, MPG_PROF_ELEMENTWISE, 2.0 * (double)n * sizeof(T));

@@ -7,6 +7,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <ctime>
 #include <string>
 #include <vector>
 
@@ -53,6 +54,7 @@ struct Tuning {
     int spin_limit_ms = 20000; // multi-GPU: a device-side wait on a peer gives up after this long and raises the context's error word
     int sell_variant = -1;    // packed SpMV kernel variant: bit 0 = x gathers bypass L1, bit 1 = 4 groups per step; -1 = chosen from the plan
     int sell_block = 0;       // packed SpMV threads per CTA (0 = 256)
+    int trace = 0;            // 1: host wall-clock of the set-up phases of every solve on stderr (diagnostics)
     int lookahead = 0;        // residual-driven restart policies: speculative Arnoldi steps in flight (0 = auto from a bandwidth estimate)
 };
 
@@ -100,6 +102,10 @@ struct mpg_ctx {
     // optional per-CTA phase timestamps of the staged V-pass kernels (mpg_debug_timing, tools/vpass_timeline.py)
     unsigned long long* dbg = nullptr;
 
+    // TMA tensor-map cache of the staged V-pass kernels (ortho.cu): per context, never shared between contexts
+    void* ortho_cache = nullptr;
+    void (*ortho_cache_free)(void*) = nullptr;
+
     // cached solver workspace (see solver.cu)
     void* ws = nullptr;
     void (*ws_free)(void*) = nullptr;
@@ -135,10 +141,14 @@ namespace mpg {
 void sell_plan_free(mpg_sell_plan* p);
 void ilu_plan_free(mpg_ilu_plan* p);
 
-// Plan / packed-matrix / per-solve temporaries come from the device's stream-ordered memory pool (release threshold
-// raised in mpg_ctx_create): building and dropping a multi-GB plan per call then re-uses the same physical memory
-// instead of mapping and unmapping it.  Freed with plain cudaFree (synchronising, returns the block to the pool).
-inline cudaError_t pool_alloc(mpg_ctx* ctx, void** p, size_t bytes) { return cudaMallocAsync(p, bytes, ctx->stream); }
+// Plan / packed-matrix / per-solve temporaries come from the device's stream-ordered memory pool (release threshold raised in
+// mpg_ctx_create) through a small per-device block cache (blas1.cu): pool_free() parks blocks of >= 1 MiB and pool_alloc() hands a
+// parked block of fitting size back, so that a caller who rebuilds plans and packed copies for every solve (the host-buffer entry
+// point, a new mpg_csr per call) reaches a steady state with NO driver allocation at all.  (Measured with peer access enabled on a
+// 2-GPU run: free + re-allocation of ~4 GB of plan arrays through the driver stalled 0.2-0.9 s every few solves.)
+cudaError_t pool_alloc(mpg_ctx* ctx, void** p, size_t bytes);
+void pool_free(void* p);          // synchronises the device like cudaFree; accepts null and blocks that did not come from pool_alloc
+void pool_trim(int device);       // releases every parked block of the device
 template <class P> inline cudaError_t pool_alloc(mpg_ctx* ctx, P** p, size_t bytes) { return pool_alloc(ctx, reinterpret_cast<void**>(p), bytes); }
 
 inline int fail(mpg_ctx* ctx, int code, const std::string& msg) {
@@ -195,6 +205,20 @@ inline cudaError_t launch_pdl(mpg_ctx* ctx, int64_t rows, void (*kern)(KArgs...)
     } while (0)
 
 inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+// diagnostics (knob `trace`): synchronise and print the host wall-clock since the previous mark
+struct Trace {
+    mpg_ctx* ctx;
+    double t0;
+    static double now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
+    explicit Trace(mpg_ctx* c) : ctx(c), t0(c->tune.trace ? now() : 0.0) {}
+    void mark(const char* what) {
+        if (!ctx->tune.trace) return;
+        cudaStreamSynchronize(ctx->stream);
+        const double t = now();
+        fprintf(stderr, "[mpg trace] %-28s %9.3f ms\n", what, t - t0);
+        t0 = t;
+    }
+};
 int check_dev_err(mpg_ctx* ctx);   // blas1.cu
 
 // dist.cu: all-reduce `count` raw sums over the ranks and apply the epilogue (no-op when no communicator is attached)
@@ -357,9 +381,10 @@ __device__ __forceinline__ void wait_flag(const unsigned long long* flag, unsign
 // The sender gathers the rows a neighbour needs and stores them straight into that neighbour's memory - its inbox, or (fused
 // path) the halo tail of the neighbour's own copy of the Krylov basis column - then publishes the exchange number in the
 // neighbour's flag word; kPushBlocksPerPeer CTAs per neighbour (one SM cannot keep an NVLink busy with stores).
-constexpr int kPushBlocksPerPeer = 32;
+constexpr int kPushBlocksMin = 32, kPushBlocksMax = 512;   // CTAs per neighbour: one SM cannot keep an NVLink busy with stores
 struct PushArgs {
     int npeers = 0;
+    int bpp = kPushBlocksMin;               // CTAs per neighbour of this launch (push_blocks())
     const int* send_idx[kMaxPeers];
     long long count[kMaxPeers];
     void* dst[kMaxPeers];                   // where our rows go in the neighbour's memory
@@ -367,24 +392,34 @@ struct PushArgs {
     unsigned long long seq = 0;
     unsigned int* counters = nullptr;       // kMaxPeers arrival counters (device)
 };
-// block `pb` (0 <= pb < npeers * kPushBlocksPerPeer) of a push: dst[i] = scale * x[idx[i]] (scale == null: plain copy)
+// 32 CTAs move a stencil halo (one 256^2 plane = 65 536 entries) in a few microseconds; an all-to-all halo of millions of
+// entries (power-law columns) needs the whole machine: ~4096 entries per CTA, capped
+inline int push_blocks(long long max_count) {
+    const long long b = (max_count + 4095) / 4096;
+    return (int)(b < kPushBlocksMin ? kPushBlocksMin : (b > kPushBlocksMax ? kPushBlocksMax : b));
+}
+// block `pb` (0 <= pb < npeers * bpp) of a push: dst[i] = scale * x[idx[i]] (scale == null: plain copy); 4 gathers in flight per thread
 template <class T>
 __device__ __forceinline__ void halo_push_block(const PushArgs& a, int pb, const T* __restrict__ x, const T* __restrict__ scale) {
-    const int q = pb / kPushBlocksPerPeer, part = pb % kPushBlocksPerPeer;
+    const int q = pb / a.bpp, part = pb % a.bpp;
     T* dst = static_cast<T*>(a.dst[q]);
     const int* idx = a.send_idx[q];
     const long long cnt = a.count[q];
-    if (scale) {
-        const T al = __ldg(scale);
-        for (long long i = (long long)part * blockDim.x + threadIdx.x; i < cnt; i += (long long)kPushBlocksPerPeer * blockDim.x) dst[i] = al * x[idx[i]];
-    } else {
-        for (long long i = (long long)part * blockDim.x + threadIdx.x; i < cnt; i += (long long)kPushBlocksPerPeer * blockDim.x) dst[i] = x[idx[i]];
+    const T al = scale ? __ldg(scale) : T(1);
+    const long long stride = (long long)a.bpp * blockDim.x;
+    long long i = (long long)part * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < cnt; i += 4 * stride) {
+        const int j0 = ldg_stream(idx + i), j1 = ldg_stream(idx + i + stride), j2 = ldg_stream(idx + i + 2 * stride), j3 = ldg_stream(idx + i + 3 * stride);
+        const T v0 = x[j0], v1 = x[j1], v2 = x[j2], v3 = x[j3];
+        if (scale) { dst[i] = al * v0; dst[i + stride] = al * v1; dst[i + 2 * stride] = al * v2; dst[i + 3 * stride] = al * v3; }
+        else { dst[i] = v0; dst[i + stride] = v1; dst[i + 2 * stride] = v2; dst[i + 3 * stride] = v3; }
     }
+    for (; i < cnt; i += stride) dst[i] = scale ? al * x[idx[i]] : x[idx[i]];
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
         // the last block of this neighbour publishes the exchange number (its fence + the counter chain order all stores)
-        if (atomicAdd(a.counters + q, 1u) == kPushBlocksPerPeer - 1) {
+        if (atomicAdd(a.counters + q, 1u) == (unsigned)a.bpp - 1u) {
             a.counters[q] = 0u;
             __threadfence_system();
             asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.flag[q]), "l"(a.seq) : "memory");

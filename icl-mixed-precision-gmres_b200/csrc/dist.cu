@@ -118,6 +118,7 @@ struct mpg_dist {
     };
     std::vector<Peer> peers;
     int64_t send_total = 0;
+    int64_t max_send_count = 0;            // longest send list (sizes the push grid)
     void* send_buf = nullptr;              // send_total doubles
     // peer-memory mailboxes for the in-kernel all-reduce (common.cuh PeerComm)
     void* mbox_own = nullptr;              // [kMboxSlots][world][kMboxStride] doubles, then [kMboxSlots][world] u64 flags
@@ -192,13 +193,17 @@ extern "C" int mpg_dist_set_partition(mpg_ctx* ctx, mpg_dist* d, int64_t n_globa
                                       const int* peer_ranks, const int64_t* send_counts, const int* const* send_idx_dev,
                                       const int64_t* recv_offsets, const int64_t* recv_counts) {
     MPG_REQUIRE(ctx, d && n_global >= 0 && n_local >= 0 && n_halo >= 0 && npeers >= 0, "dist_set_partition: bad argument");
+    // a rank without rows would return early from every reducing entry point and never join the cross-rank reductions: refuse it
+    MPG_REQUIRE(ctx, d->world == 1 || n_local >= 1, "dist_set_partition: every rank must own at least one row");
     d->n_global = n_global; d->n_local = n_local; d->n_halo = n_halo;
     d->peers.clear();
+    d->max_send_count = 0;
     int64_t off = 0;
     for (int i = 0; i < npeers; ++i) {
         MPG_REQUIRE(ctx, peer_ranks[i] >= 0 && peer_ranks[i] < d->world && peer_ranks[i] != d->rank, "dist_set_partition: bad peer rank");
         MPG_REQUIRE(ctx, recv_offsets[i] >= 0 && recv_offsets[i] + recv_counts[i] <= n_halo, "dist_set_partition: halo range out of bounds");
         d->peers.push_back({peer_ranks[i], send_counts[i], off, recv_counts[i], recv_offsets[i], send_idx_dev[i]});
+        d->max_send_count = std::max<int64_t>(d->max_send_count, send_counts[i]);
         off += send_counts[i];
     }
     d->send_total = off;
@@ -528,7 +533,8 @@ int halo_begin(mpg_ctx* ctx, T* x_ext) {
             pa.dst[i] = inbox + (size_t)slot * (size_t)std::max<int64_t>(d->remote_nhalo[i], 1) * 8 + (size_t)d->remote_off[i] * sizeof(T);
             pa.flag[i] = reinterpret_cast<unsigned long long*>(inbox + their_data) + slot * kMaxPeers + d->rank;
         }
-        halo_push_kernel<T><<<pa.npeers * kPushBlocksPerPeer, 256, 0, ctx->stream>>>(pa, x_ext);
+        pa.bpp = push_blocks(d->max_send_count);
+        halo_push_kernel<T><<<pa.npeers * pa.bpp, 256, 0, ctx->stream>>>(pa, x_ext);
         MPG_CHECK_LAUNCH(ctx);
         return MPG_OK;
     }
@@ -630,6 +636,7 @@ int halo_direct_args(mpg_ctx* ctx, int64_t col, PushArgs* pa) {
         pa->dst[i] = static_cast<T*>(vp.base) + (size_t)col * (size_t)vp.ldv + (size_t)vp.n_local + (size_t)d->remote_off[i];
         pa->flag[i] = reinterpret_cast<unsigned long long*>(inbox + their_data) + slot * kMaxPeers + d->rank;
     }
+    pa->bpp = push_blocks(d->max_send_count);
     return MPG_OK;
 }
 template int halo_direct_args<float>(mpg_ctx*, int64_t, PushArgs*);
@@ -643,7 +650,7 @@ int halo_push_direct(mpg_ctx* ctx, const T* x, int64_t col) {
     ProfScope prof(ctx, MPG_PROF_SMALL, 0.0);
     PushArgs pa;
     MPG_TRY(halo_direct_args<T>(ctx, col, &pa));
-    halo_push_kernel<T><<<pa.npeers * kPushBlocksPerPeer, 256, 0, ctx->stream>>>(pa, x);
+    halo_push_kernel<T><<<pa.npeers * pa.bpp, 256, 0, ctx->stream>>>(pa, x);
     MPG_CHECK_LAUNCH(ctx);
     return MPG_OK;
 }

@@ -199,10 +199,11 @@ extern "C" int mpg_gen_slab_rowmap(mpg_ctx* ctx, int kind, int64_t size, uint64_
 }
 extern "C" int mpg_gen_slab_fill(mpg_ctx* ctx, int kind, int64_t size, uint64_t seed, int lmin, int gmax, int64_t lo, int64_t hi, int* row_map_local,
                                  int* inds_global, double* vals) {
-    MPG_REQUIRE(ctx, kind >= 0 && kind <= 2 && size >= 1 && row_map_local && inds_global && vals, "gen_slab: bad argument");
+    MPG_REQUIRE(ctx, kind >= 0 && kind <= 2 && size >= 1 && row_map_local, "gen_slab: bad argument");
     const int64_t n = kind == 0 ? size * size : (kind == 1 ? size * size * size : size);
     MPG_REQUIRE(ctx, 0 <= lo && lo <= hi && hi <= n, "gen_slab: row range out of bounds");
-    if (hi == lo) return MPG_OK;
+    if (hi == lo) return MPG_OK;   // an empty slab has no entries (null arrays are fine)
+    MPG_REQUIRE(ctx, inds_global && vals, "gen_slab: null arrays");
     if (kind == 0) lap2d_kernel<<<(int)cdiv(hi - lo + 1, 256), 256, 0, ctx->stream>>>(size, lo, hi, row_map_local, inds_global, vals);
     else if (kind == 1) cd27_kernel<<<(int)cdiv(hi - lo + 1, 256), 256, 0, ctx->stream>>>(size, lo, hi, row_map_local, inds_global, vals);
     else powerlaw_fill_kernel<<<(int)cdiv((hi - lo) * 32, 256), 256, 0, ctx->stream>>>(n, lo, hi, seed, lmin, gmax, row_map_local, inds_global, vals);

@@ -160,8 +160,8 @@ __global__ void split_fill_kernel(int n, const int* __restrict__ row_map, const 
 namespace mpg {
 void ilu_plan_free(mpg_ilu_plan* p) {
     if (!p) return;
-    cudaFree(p->diag_pos);
-    cudaFree(p->level_rows);
+    pool_free(p->diag_pos);
+    pool_free(p->level_rows);
     delete p;
 }
 
@@ -177,7 +177,7 @@ int ilu_plan_get(mpg_ctx* ctx, const mpg_csr* A, const mpg_ilu_plan** out) {
     MPG_CUDA(ctx, pool_alloc(ctx, &p->level_rows, sizeof(int) * (size_t)std::max(n, 1)));
     MPG_CUDA(ctx, pool_alloc(ctx, &level, sizeof(int) * (size_t)std::max(n, 1)));
     MPG_CUDA(ctx, pool_alloc(ctx, &flags, sizeof(int) * 4));
-    struct Tmp { int* a; int* b; int** c; ~Tmp() { cudaFree(a); cudaFree(b); if (*c) cudaFree(*c); } } tmp{level, flags, &hist};
+    struct Tmp { int* a; int* b; int** c; ~Tmp() { pool_free(a); pool_free(b); if (*c) pool_free(*c); } } tmp{level, flags, &hist};
     MPG_CUDA(ctx, cudaMemsetAsync(level, 0, sizeof(int) * (size_t)std::max(n, 1), ctx->stream));
     MPG_CUDA(ctx, cudaMemsetAsync(flags, 0, sizeof(int) * 4, ctx->stream));
     const int grid = (int)cdiv(std::max(n, 1), 256);
@@ -269,8 +269,8 @@ extern "C" int mpg_ilu_jacobi_destroy(mpg_ilu_jacobi* M) {
     cudaSetDevice(M->device);
     mpg::pack_free(M->PL); mpg::pack_free(M->PU);
     mpg_csr_destroy(M->L); mpg_csr_destroy(M->U);
-    cudaFree(M->rmL); cudaFree(M->indL); cudaFree(M->rmU); cudaFree(M->indU);
-    cudaFree(M->valL); cudaFree(M->valU); cudaFree(M->diag); cudaFree(M->temp1); cudaFree(M->temp2); cudaFree(M->vals);
+    pool_free(M->rmL); pool_free(M->indL); pool_free(M->rmU); pool_free(M->indU);
+    pool_free(M->valL); pool_free(M->valU); pool_free(M->diag); pool_free(M->temp1); pool_free(M->temp2); pool_free(M->vals);
     delete M;
     return MPG_OK;
 }
@@ -290,7 +290,7 @@ int ilu_jacobi_create(mpg_ctx* ctx, const mpg_csr* A, const double* ilu_vals64, 
     const size_t nb = sizeof(int) * (size_t)(n + 1);
     int *nl = nullptr, *nu = nullptr;
     MPG_CUDA(ctx, pool_alloc(ctx, &nl, nb)); MPG_CUDA(ctx, pool_alloc(ctx, &nu, nb));
-    struct Tmp { int* a; int* b; ~Tmp() { cudaFree(a); cudaFree(b); } } tmp{nl, nu};
+    struct Tmp { int* a; int* b; ~Tmp() { pool_free(a); pool_free(b); } } tmp{nl, nu};
     MPG_CUDA(ctx, pool_alloc(ctx, &M->rmL, nb)); MPG_CUDA(ctx, pool_alloc(ctx, &M->rmU, nb));
     MPG_CUDA(ctx, pool_alloc(ctx, &M->vals, sizeof(T) * (size_t)std::max<int64_t>(A->nnz, 1)));
     MPG_CUDA(ctx, pool_alloc(ctx, &M->diag, sizeof(T) * (size_t)std::max(n, 1)));

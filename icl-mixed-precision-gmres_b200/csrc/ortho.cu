@@ -38,6 +38,7 @@ int dot_dev(mpg_ctx* ctx, int64_t n, const float* x, const float* y, float* out)
 int dot_dev(mpg_ctx* ctx, int64_t n, const double* x, const double* y, double* out);
 int axpy_host(mpg_ctx* ctx, int64_t n, float a, const float* x, float* y);
 int axpy_host(mpg_ctx* ctx, int64_t n, double a, const double* x, double* y);
+template <class T> int mgs_step(mpg_ctx*, int64_t, const T*, const T*, T*, const T*, T*);
 }  // namespace mpg
 
 namespace {
@@ -704,26 +705,15 @@ struct VpassCfg;
 template <> struct VpassCfg<float> { static constexpr int TR = 256; };
 template <> struct VpassCfg<double> { static constexpr int TR = 128; };
 
+template <class T>
+int cached_maps(mpg_ctx* ctx, const T* V, int64_t ldv, const T* w, int64_t n, int k1, int box_rows, const CUtensorMap** mapV, const CUtensorMap** mapW);
+
 template <class T, int TR, int MAXJ>
 int launch_vpass_inst(mpg_ctx* ctx, int64_t n, int k1, const T* V, int64_t ldv, T* w, const T* h_in, int fin, T* coef_out, T* hcol) {
-    // tensor maps are pure functions of (pointer, n, ldv, k1): keep the last few (one Arnoldi cycle re-uses one per width)
-    struct MapKey { const void* V; const void* w; int64_t n, ldv; int k1, tr, ts; };
-    struct MapSlot { MapKey key; CUtensorMap mapV, mapW; bool valid; };
-    static MapSlot cache[512];   // contexts are single-threaded by contract
-    MapSlot& slot = cache[((size_t)k1 * 2 + (sizeof(T) == 8)) & 511];
-    const MapKey key{V, w, n, ldv, k1, TR, (int)sizeof(T)};
-    int mrc = 0;
-    if (!slot.valid || memcmp(&slot.key, &key, sizeof(MapKey)) != 0) {
-        memset(&slot.key, 0, sizeof(MapKey));
-        mrc = make_maps<T>(V, ldv, w, n, k1, TR, &slot.mapV, &slot.mapW);
-        slot.key = key;
-        slot.valid = (mrc == 0);
-    }
-    const CUtensorMap& mapV = slot.mapV;
-    const CUtensorMap& mapW = slot.mapW;
-    if (mrc != 0)
-        return fail(ctx, MPG_ERR_CUDA, "vpass: cuTensorMapEncodeTiled failed, code " + std::to_string(mrc) + " (n=" + std::to_string(n) + " k1=" +
-                                           std::to_string(k1) + " ldv=" + std::to_string(ldv) + ")");
+    const CUtensorMap *pmapV, *pmapW;
+    MPG_TRY(cached_maps<T>(ctx, V, ldv, w, n, k1, TR, &pmapV, &pmapW));
+    const CUtensorMap& mapV = *pmapV;
+    const CUtensorMap& mapW = *pmapW;
     const size_t stage_bytes = (size_t)(k1 + 2) * TR * sizeof(T);
     const size_t extra = sizeof(T) * (size_t)(((k1 + 3) & ~3) + 4) + 8 * 2 * 8 + 32;
     int stages = (int)std::min<size_t>(8, (kMaxDynSmem - extra) / stage_bytes);
@@ -753,13 +743,23 @@ int launch_vpass_inst(mpg_ctx* ctx, int64_t n, int k1, const T* V, int64_t ldv, 
     return dist_finish_reduction(ctx, epi, k1, (int)sizeof(T));
 }
 
-// tensor maps are pure functions of (pointer, n, ldv, k1, box rows): keep the last few (one Arnoldi cycle re-uses one per width)
+// tensor maps are pure functions of (pointer, n, ldv, k1, box rows): keep the last few (one Arnoldi cycle re-uses one per width).
+// The cache belongs to the CONTEXT (contexts on different threads / devices never share mutable state).
+struct MapKey { const void* V; const void* w; int64_t n, ldv; int k1, tr, ts; };
+struct MapSlot { MapKey key; CUtensorMap mapV, mapW; bool valid; };
+struct MapCache { MapSlot slot[2048]; };
+void map_cache_free(void* p) { delete static_cast<MapCache*>(p); }
+
 template <class T>
 int cached_maps(mpg_ctx* ctx, const T* V, int64_t ldv, const T* w, int64_t n, int k1, int box_rows, const CUtensorMap** mapV, const CUtensorMap** mapW) {
-    struct MapKey { const void* V; const void* w; int64_t n, ldv; int k1, tr, ts; };
-    struct MapSlot { MapKey key; CUtensorMap mapV, mapW; bool valid; };
-    static MapSlot cache[1024];   // contexts are single-threaded by contract
-    MapSlot& slot = cache[(((size_t)k1 * 2 + (sizeof(T) == 8)) * 2 + (box_rows == VROW_BOX)) & 1023];
+    if (!ctx->ortho_cache) {
+        MapCache* c = new MapCache();
+        memset(c, 0, sizeof(MapCache));
+        ctx->ortho_cache = c;
+        ctx->ortho_cache_free = map_cache_free;
+    }
+    MapCache* cache = static_cast<MapCache*>(ctx->ortho_cache);
+    MapSlot& slot = cache->slot[(((size_t)k1 * 2 + (sizeof(T) == 8)) * 4 + (box_rows == VROW_BOX ? 0 : (box_rows == 256 ? 1 : 2))) & 2047];
     MapKey key;
     memset(&key, 0, sizeof(MapKey));
     key.V = V; key.w = w; key.n = n; key.ldv = ldv; key.k1 = k1; key.tr = box_rows; key.ts = (int)sizeof(T);
@@ -821,10 +821,12 @@ template <class T, int MAXK, bool HAS_H>
 int launch_vdirect_inst(mpg_ctx* ctx, int64_t n, int k1, const T* V, int64_t ldv, T* w, const T* h_in, int fin, T* coef_out, T* hcol) {
     constexpr int VEC = 16 / sizeof(T);
     auto kern = vdirect_kernel<T, MAXK, HAS_H>;
-    static int ctas_per_sm = 0;   // per instantiation; one device per process
+    static int occ[64] = {};   // per instantiation and device (an int store is atomic; two contexts computing it write the same value)
+    int ctas_per_sm = occ[ctx->device & 63];
     if (ctas_per_sm == 0) {
         MPG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, 256, 0));
         ctas_per_sm = std::max(1, std::min(ctas_per_sm, 4));
+        occ[ctx->device & 63] = ctas_per_sm;
     }
     const int64_t groups = std::max<int64_t>(1, n / VEC);
     int grid = (int)std::min<int64_t>(cdiv(groups, 256), (int64_t)ctx->num_sms * ctas_per_sm);
@@ -978,12 +980,20 @@ int add_vector(mpg_ctx* ctx, int orth, int64_t n, int64_t k, T* V, int64_t ldv, 
     T* vnext = V + (size_t)(k + 1) * ldv;
     if (orth == MPG_ORTH_MGS) {
         // Orthogonalization.hpp:98-106: k+1 x { dot -> h(j,k) on device ; w -= h(j,k) v_j }
-        for (int j = 0; j < k1; ++j) {
-            MPG_TRY(dot_dev(ctx, n, w, V + (size_t)j * ldv, hcol + j));
-            MPG_TRY(naxpy_devp(ctx, n, hcol + j, V + (size_t)j * ldv, w));
+        if (ctx->tune.mgs_fused && aligned16(V) && aligned16(w) && (ldv * sizeof(T)) % 16 == 0) {
+            // pairwise fused: the naxpy of column j and the dot of column j + 1 share one pass over w (k + 2 launches instead of
+            // 2 k + 3, 4 n s instead of 5 n s bytes per column); the last naxpy carries the norm.  Bit-identical to the loop below.
+            MPG_TRY(dot_dev(ctx, n, w, V, hcol));
+            for (int j = 0; j + 1 < k1; ++j) MPG_TRY(mgs_step<T>(ctx, n, V + (size_t)j * ldv, V + (size_t)(j + 1) * ldv, w, hcol + j, hcol + j + 1));
+            MPG_TRY(gemvn<T>(ctx, n, 1, V + (size_t)(k1 - 1) * ldv, ldv, T(-1), hcol + (k1 - 1), T(1), w, true, hcol + k1, inv, nullptr));
+        } else {
+            for (int j = 0; j < k1; ++j) {
+                MPG_TRY(dot_dev(ctx, n, w, V + (size_t)j * ldv, hcol + j));
+                MPG_TRY(naxpy_devp(ctx, n, hcol + j, V + (size_t)j * ldv, w));
+            }
+            // nrm2(w, h(k+1,k)) as a gemv-N with zero columns would be wasteful: reuse the NORM epilogue with k1 = 0
+            MPG_TRY(gemvn<T>(ctx, n, 0, V, ldv, T(0), hcol, T(1), w, true, hcol + k1, inv, nullptr));
         }
-        // nrm2(w, h(k+1,k)) as a gemv-N with zero columns would be wasteful: reuse the NORM epilogue with k1 = 0
-        MPG_TRY(gemvn<T>(ctx, n, 0, V, ldv, T(0), hcol, T(1), w, true, hcol + k1, inv, nullptr));
     } else {
         // narrow bases (k1 < fuse_min_cols) are dominated by the staged kernel's per-tile cost: the register kernels
         // (gemv-T row-block sweep + gemv-N) are faster there even though they read V four times instead of three

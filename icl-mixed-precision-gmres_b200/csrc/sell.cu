@@ -385,8 +385,8 @@ namespace mpg {
 
 void sell_plan_free(mpg_sell_plan* p) {
     if (!p) return;
-    cudaFree(p->slice_off); cudaFree(p->sinds); cudaFree(p->slice_list);
-    cudaFree(p->vstart); cudaFree(p->vlen); cudaFree(p->vout); cudaFree(p->split_rows); cudaFree(p->chunk_base); cudaFree(p->partial);
+    pool_free(p->slice_off); pool_free(p->sinds); pool_free(p->slice_list);
+    pool_free(p->vstart); pool_free(p->vlen); pool_free(p->vout); pool_free(p->split_rows); pool_free(p->chunk_base); pool_free(p->partial);
     delete p;
 }
 
@@ -399,7 +399,7 @@ static int plan_slices(mpg_ctx* ctx, const mpg_csr* A, mpg_sell_plan* p) {
     p->nslices = (int)cdiv(p->nlanes, SLICE);
     int64_t* len = nullptr;
     MPG_CUDA(ctx, pool_alloc(ctx, &len, sizeof(int64_t) * (size_t)(p->nslices + 2)));
-    cudaFree(p->slice_off);
+    pool_free(p->slice_off);
     p->slice_off = nullptr;
     MPG_CUDA(ctx, pool_alloc(ctx, &p->slice_off, sizeof(int64_t) * (size_t)(p->nslices + 1)));
     MPG_CUDA(ctx, cudaMemsetAsync(len, 0, sizeof(int64_t) * (size_t)(p->nslices + 2), ctx->stream));
@@ -411,7 +411,7 @@ static int plan_slices(mpg_ctx* ctx, const mpg_csr* A, mpg_sell_plan* p) {
     MPG_CUDA(ctx, cudaMemcpyAsync(&p->total, p->slice_off + p->nslices, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
     MPG_CUDA(ctx, cudaMemcpyAsync(&p->has_rem, rem_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     MPG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    cudaFree(len);
+    pool_free(len);
     return MPG_OK;
 }
 
@@ -420,8 +420,8 @@ static int plan_sigma(mpg_ctx* ctx, const mpg_csr* A, mpg_sell_plan* p) {
     const int n = A->nrows;
     int *nch = nullptr, *is_split = nullptr, *nch_split = nullptr, *vrow_off = nullptr, *split_off = nullptr, *chunk_off = nullptr;
     int *vstart = nullptr, *vlen = nullptr, *vout = nullptr;
-    auto drop = [&]() { cudaFree(nch); cudaFree(is_split); cudaFree(nch_split); cudaFree(vrow_off); cudaFree(split_off); cudaFree(chunk_off);
-                        cudaFree(vstart); cudaFree(vlen); cudaFree(vout); };
+    auto drop = [&]() { pool_free(nch); pool_free(is_split); pool_free(nch_split); pool_free(vrow_off); pool_free(split_off); pool_free(chunk_off);
+                        pool_free(vstart); pool_free(vlen); pool_free(vout); };
 #define MPG_CUDA_D(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { (void)cudaGetLastError(); drop(); return fail(ctx, MPG_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); } } while (0)
     const size_t nb = sizeof(int) * (size_t)(n + 1);
     MPG_CUDA_D(pool_alloc(ctx, &nch, nb)); MPG_CUDA_D(pool_alloc(ctx, &is_split, nb)); MPG_CUDA_D(pool_alloc(ctx, &nch_split, nb));
@@ -531,7 +531,7 @@ template int pack_create<double>(mpg_ctx*, const mpg_csr*, const double*, mpg_pa
 
 void pack_free(mpg_packed* P) {
     if (!P) return;
-    cudaFree(P->svals);
+    pool_free(P->svals);
     delete P;
 }
 

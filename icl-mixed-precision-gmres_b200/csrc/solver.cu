@@ -443,8 +443,11 @@ int solve_mixed(mpg_ctx* ctx, const mpg_gmres_params& p, const mpg_csr* A, const
                 mpg_ilu_jacobi* ilu, const double* b, double* x, mpg_gmres_stats* st, History& hist) {
     const int64_t n = A->nrows, m = p.restart_length;
     Workspace* ws = nullptr;
+    Trace tr(ctx);
     MPG_TRY(get_workspace(ctx, n, m, 4, p.conv == MPG_CONV_ORTHLOSS, false, &ws));
+    tr.mark("workspace");
     MPG_TRY(dist_exchange_basis(ctx, ws->V, ws->ldv, 4));
+    tr.mark("exchange_basis");
     float* w = static_cast<float*>(ws->w);
     float* h = static_cast<float*>(ws->h);
     float* s = static_cast<float*>(ws->s);
@@ -454,7 +457,9 @@ int solve_mixed(mpg_ctx* ctx, const mpg_gmres_params& p, const mpg_csr* A, const
     // fp64 operator of the outer residual on the same packed structure (one more pass over the values per solve; the CSR kernel
     // gathers x once per nonzero and runs at ~0.55 of the roofline, the packed one at ~0.9)
     const mpg_packed* packed64 = nullptr;
+    tr.mark("packed fp32 (plan + values)");
     if (ctx->tune.residual_packed && packed) MPG_TRY(get_packed<double>(ctx, ws, 1, A, vals64, &packed64));
+    tr.mark("packed fp64");
     Policy pol(p);
     MPG_TRY(size_estimate(ctx, A, pol));
     if (p.conv == MPG_CONV_ORTHLOSS) {
@@ -473,6 +478,7 @@ int solve_mixed(mpg_ctx* ctx, const mpg_gmres_params& p, const mpg_csr* A, const
     const double Minvb_norm = hs<float>(ctx, 1);
     const double A_norm = hs<float>(ctx, 2);
     st->b_norm = b_norm; st->Minvb_norm = Minvb_norm; st->A_norm = A_norm;
+    tr.mark("set-up norms");
 
     for (int64_t i = 0;; ++i) {
         // r = b - A x (fp64), w = (float) r : one fused kernel  (gmres.cpp:173-175)
@@ -506,6 +512,7 @@ int solve_mixed(mpg_ctx* ctx, const mpg_gmres_params& p, const mpg_csr* A, const
         // solution_update, gmres.cpp:276-290: y = triu(H)^-1 s ; x += (double)(V_k y)  (Orthogonalization.hpp:67-73)
         MPG_TRY(trsv<float>(ctx, 1, 0, k, h, m + 1, s));
         MPG_TRY(gemvn<float>(ctx, n, (int)k, V, ws->ldv, 1.f, s, 0.f, w, false, nullptr, nullptr, x));
+        tr.mark("cycle + update");
     }
     st->total_iters = pol.total_iters;
     st->total_restarts = pol.total_restarts;
@@ -615,8 +622,8 @@ extern "C" int mpg_gmres_solve(mpg_ctx* ctx, const mpg_gmres_params* pp, const m
     auto cleanup = [&]() {
         cudaStreamSynchronize(ctx->stream);
         mpg_ilu_jacobi_destroy(ilu);
-        cudaFree(ilu_vals);
-        cudaFree(vals32_own); cudaFree(vals_rt); cudaFree(jac32); cudaFree(jac64); cudaFree(b32); cudaFree(x32);
+        pool_free(ilu_vals);
+        pool_free(vals32_own); pool_free(vals_rt); pool_free(jac32); pool_free(jac64); pool_free(b32); pool_free(x32);
         cudaEventDestroy(e0); cudaEventDestroy(e1);
     };
 #define MPG_TRY_C(expr) do { rc = (expr); if (rc != MPG_OK) { cleanup(); return rc; } } while (0)

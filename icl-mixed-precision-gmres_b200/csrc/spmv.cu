@@ -303,9 +303,9 @@ extern "C" int mpg_csr_create(mpg_ctx* ctx, int nrows, int ncols, int64_t nnz, c
 extern "C" int mpg_csr_destroy(mpg_csr* A) {
     if (!A) return MPG_OK;
     cudaSetDevice(A->device);
-    cudaFree(A->tile_row);
-    cudaFree(A->carry);
-    cudaFree(A->tile_list);
+    mpg::pool_free(A->tile_row);
+    mpg::pool_free(A->carry);
+    mpg::pool_free(A->tile_list);
     mpg::sell_plan_free(A->sell);
     mpg::ilu_plan_free(A->ilu);
     delete A;

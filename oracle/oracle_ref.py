@@ -85,3 +85,19 @@ def load_vector(path, col=0):
     out = np.empty(n.value, np.float64)
     lib().ref_load_vector(str(path).encode(), C.c_int(col), C.byref(n), _p(out), err, 256)
     return out
+
+
+def sweep_spmv(rm, ind, val64, is_float, trials=3):
+    """seconds per call of the reference's spmv<T,MKL> (one warm pass first)"""
+    rm = np.ascontiguousarray(rm, np.int32); ind = np.ascontiguousarray(ind, np.int32); val64 = np.ascontiguousarray(val64, np.float64)
+    out = np.zeros(trials, np.float64)
+    lib().ref_sweep_spmv(C.c_int(len(rm) - 1), _p(rm), _p(ind), _p(val64), C.c_int(int(is_float)), C.c_int(trials), _p(out))
+    return out
+
+
+def sweep_add_vector(n, m, orth, is_float, ks, trials=3):
+    """seconds per call of the reference's GS<T, Kernel<T,MKL>, MKL>::add_vector at every k in ks: array (len(ks), trials)"""
+    ks = np.ascontiguousarray(ks, np.int32)
+    out = np.zeros(len(ks) * trials, np.float64)
+    lib().ref_sweep_add_vector(C.c_int64(n), C.c_int(m), C.c_int(ORTHS[orth]), C.c_int(int(is_float)), _p(ks), C.c_int(len(ks)), C.c_int(trials), _p(out))
+    return out.reshape(len(ks), trials)

@@ -8,7 +8,9 @@
 #include <chrono>
 #include <cstdint>
 #include <cstring>
+#include <cmath>
 #include <iostream>
+#include <random>
 #include <sstream>
 #include <vector>
 
@@ -198,6 +200,79 @@ int ref_load_vector(const char* path, int col, long* n, double* out, char* err, 
 }
 
 int ref_num_threads() { return MKL_Get_Max_Threads(); }
+
+// ---- per-op timings of the reference's OWN MKL backend (BASELINE.json configs[4], the kernel_perf_test sweep) ----------------
+// spmv<T,MKL> (kernels_mkl.cpp:326-352) and Orthogonalization::GS<T, Kernel<T,MKL>, MKL>::add_vector (Orthogonalization.hpp:51-60 with
+// the kernels of :76-136) - one warm pass, then `trials` timed passes (kernel_perf_test.cpp:170-179 shape), basis and vectors
+// filled from mt19937 floats as kernel_perf_test.cpp:11-39 does.
+}  // extern "C" (templates below)
+namespace {
+template <class T>
+void fill_random(T* p, size_t n, uint32_t seed) {
+    std::mt19937 engine(seed);
+    std::uniform_real_distribution<float> dist;
+    for (size_t i = 0; i < n; ++i) p[i] = dist(engine);
+}
+template <class T>
+void sweep_spmv(int n, int* rm, int* ind, double* vals64, int trials, double* seconds) {
+    const size_t nnz = rm[n];
+    using IV = Kokkos::View<int*, Kokkos::HostSpace>;
+    using DV = Kokkos::View<double*, Kokkos::HostSpace>;
+    SparseMatrix<double, MKL> A64(n, n, IV(rm, n + 1), IV(ind, nnz), DV(vals64, nnz));
+    SparseMatrix<T, MKL> A(A64);
+    Vect<T, MKL> x(n), y(n);
+    fill_random(x.data(), n, 42);
+    spmv(T(1), A, x, T(0), y);   // warm
+    for (int t = 0; t < trials; ++t) {
+        auto t0 = std::chrono::high_resolution_clock::now();
+        spmv(T(1), A, x, T(0), y);
+        seconds[t] = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count();
+    }
+}
+template <class T, template <class, class> class Kernel>
+void sweep_add_vector(size_t n, size_t m, const int* ks, int nk, int trials, double* seconds) {
+    Orthogonalization::GS<T, Kernel<T, MKL>, MKL> gs(n, m);
+    T* v = gs.v.data();
+    // an orthonormal-ish basis is not needed for timing; scale the random columns so that norms stay O(1)
+    fill_random(v, n * (m + 1), 45);
+    const T sc = T(1) / std::sqrt((T)n);
+    for (size_t i = 0; i < n * (m + 1); ++i) v[i] *= sc;
+    MultiVect<T, MKL> h(m + 1, m);
+    Vect<T, MKL> w(n), w0(n);
+    fill_random(w0.data(), n, 43);
+    for (int q = 0; q < nk; ++q) {
+        const size_t k = (size_t)ks[q];
+        copy(w0, w);
+        gs.add_vector(k, w, h);   // warm
+        for (int t = 0; t < trials; ++t) {
+            copy(w0, w);
+            auto t0 = std::chrono::high_resolution_clock::now();
+            gs.add_vector(k, w, h);
+            seconds[(size_t)q * trials + t] = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count();
+        }
+    }
+}
+template <class A, class B> using CGSR2K_sweep = Orthogonalization::CGSR_Kernel<A, B, 2>;
+}  // namespace
+extern "C" {
+
+int ref_sweep_spmv(int n, int* rm, int* ind, double* vals64, int is_float, int trials, double* seconds) {
+    if (is_float) sweep_spmv<float>(n, rm, ind, vals64, trials, seconds); else sweep_spmv<double>(n, rm, ind, vals64, trials, seconds);
+    return 0;
+}
+// orth: 0 CGS, 1 MGS, 2 CGSR<2>; ks[nk]: the values of k (basis width k + 1) to time; seconds[nk * trials]
+int ref_sweep_add_vector(int64_t n, int m, int orth, int is_float, const int* ks, int nk, int trials, double* seconds) {
+    if (is_float) {
+        if (orth == 0) sweep_add_vector<float, Orthogonalization::CGS_Kernel>(n, m, ks, nk, trials, seconds);
+        else if (orth == 1) sweep_add_vector<float, Orthogonalization::MGS_Kernel>(n, m, ks, nk, trials, seconds);
+        else sweep_add_vector<float, CGSR2K_sweep>(n, m, ks, nk, trials, seconds);
+    } else {
+        if (orth == 0) sweep_add_vector<double, Orthogonalization::CGS_Kernel>(n, m, ks, nk, trials, seconds);
+        else if (orth == 1) sweep_add_vector<double, Orthogonalization::MGS_Kernel>(n, m, ks, nk, trials, seconds);
+        else sweep_add_vector<double, CGSR2K_sweep>(n, m, ks, nk, trials, seconds);
+    }
+    return 0;
+}
 
 // same argument meaning as orc_gmres (oracle/oracle.cpp); true_x may be null (then err_norm = ||x||)
 int ref_gmres(int mode, int orth, int conv_kind, int prec, int64_t rlen, double tol, double rtol, int64_t max_restarts, int n, int* row_map, int* inds,

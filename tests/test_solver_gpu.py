@@ -235,7 +235,7 @@ def test_packed_and_csr_inner_operator_agree(ctx, g, orc, spec, mode, prec):
     assert np.linalg.norm(x1 - x0) <= 1e-6 * np.linalg.norm(x0)
 
 
-@pytest.mark.parametrize("knob", ["fuse_tail", "use_pdl"])
+@pytest.mark.parametrize("knob", ["fuse_tail", "use_pdl", "mgs_fused"])
 @pytest.mark.parametrize("spec,mode,orth", [("cd27:14", "mixed", "cgsr"), ("lap2d:40", "baseline", "mgs"), ("powerlaw:3000", "mixed", "cgs")])
 def test_launch_structure_knobs_do_not_change_bits(ctx, g, orc, knob, spec, mode, orth):
     """fusing the normalisation with the Givens update, and programmatic dependent launch, only change how the same

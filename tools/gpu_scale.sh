@@ -1,6 +1,29 @@
 #!/bin/bash
+# multi-GPU scaling point: bash tools/gpu_scale.sh N   (dist_check + cd27:256 + powerlaw:8000000 at N ranks)
 mkdir -p gpurun_out
-for n in 8 4; do
-  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2960$n bench.py --gpus $n --steps 5 --warmup 3 > gpurun_out/bench_n$n.log 2>&1
-  echo "== bench_n$n"; grep "^{" gpurun_out/bench_n$n.log | tail -n 1 | cut -c1-2200; tail -n 2 gpurun_out/bench_n$n.log | grep -v "^{" | cut -c1-300
+N=${1:-8}
+DIST_CHECK_CASES=0,3,7,10,12 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29611 tools/dist_check.py > gpurun_out/r02_dist_check_n$N.json 2> gpurun_out/r02_dist_check_n$N.err; echo "dist_check rc=$?"
+python - <<PY
+import json
+try:
+    d=json.loads([l for l in open("gpurun_out/r02_dist_check_n$N.json") if l.startswith("{")][-1])
+    print("dist_check ok", d["ok"], [(c["spec"], c["orth"], c["split"], c["ok"], c["peers"], c["n_halo"]) for c in d["cases"]])
+except Exception as e:
+    print("ERR", e)
+PY
+tail -n 6 gpurun_out/r02_dist_check_n$N.err | cut -c1-300
+for cfg in "cd27:256 rows" "powerlaw:8000000 nnz"; do
+set -- $cfg; wl=$1; part=$2
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29612 bench.py --gpus $N --steps 10 --warmup 3 --workload $wl --partition $part > gpurun_out/r02_bench_${wl/:/_}_n${N}.json 2> gpurun_out/r02_bench_${wl/:/_}_n${N}.err; echo "bench $wl rc=$?"
+python - <<PY
+import json
+try:
+    d=json.loads([l for l in open("gpurun_out/r02_bench_${wl/:/_}_n${N}.json") if l.startswith("{")][-1])
+    print(d["config"]["workload"], "n_gpus", d["n_gpus"], "it/s %.1f"%d["value"], "ms %.2f"%d["ms_per_step"], d["config"]["iters_per_solve"], "resNorm", d["config"]["resNorm"], "e2e", d["e2e"]["value"] if d["e2e"] else None)
+    print("   ", {k:(round(v["share"],3),v["frac_of_peak"],v["launches"]) for k,v in d["kernels"].items()})
+    print("   ", d["config"]["partition"])
+except Exception as e:
+    print("ERR", e)
+PY
+tail -n 3 gpurun_out/r02_bench_${wl/:/_}_n${N}.err | grep -v "OMP_NUM_THREADS\|^\*\*\*" | cut -c1-300
 done
