@@ -334,17 +334,14 @@ static int allgather_host(mpg_ctx* ctx, mpg_dist* d, const void* mine, size_t by
     return MPG_OK;
 }
 
-extern "C" int mpg_dist_setup(mpg_ctx* ctx, mpg_dist* d, int64_t n_global, const int64_t* bounds, int64_t nnz_local, int* inds, int64_t* n_halo_out) {
-    MPG_REQUIRE(ctx, d && bounds && (inds || nnz_local == 0) && n_global >= 0 && n_global < (int64_t)2147483647 && nnz_local >= 0, "dist_setup: bad argument");
-    MPG_REQUIRE(ctx, d->world <= kMaxPeers, "dist_setup: at most 8 ranks");
-    const int P = d->world, me = d->rank;
-    for (int q = 0; q < P; ++q) MPG_REQUIRE(ctx, bounds[q] <= bounds[q + 1], "dist_setup: bounds must be non-decreasing");
-    MPG_REQUIRE(ctx, bounds[0] == 0 && bounds[P] == n_global, "dist_setup: bounds must cover [0, n_global]");
-    const int64_t lo = bounds[me], hi = bounds[me + 1], n_local = hi - lo;
-    MPG_REQUIRE(ctx, n_local >= 1, "dist_setup: every rank must own at least one row (a rank without rows would never join the reductions)");
-    int *mark = nullptr, *rank = nullptr, *need_idx = nullptr;
+// device part of the set-up, no communication: halo list, column renumbering, owner offsets and the row lists to request.
+// halo_cols / need_idx are cudaMalloc'ed here (caller frees); off gets P + 1 entries.
+static int partition_slab_device(mpg_ctx* ctx, int64_t n_global, int P, const int64_t* bounds, int me, int64_t nnz_local, int* inds, int* nh_out,
+                                 int** halo_cols_out, int** need_idx_out, std::vector<long long>& off) {
+    const int64_t lo = bounds[me], hi = bounds[me + 1];
+    int *mark = nullptr, *rank = nullptr;
     long long *bounds_d = nullptr, *off_d = nullptr;
-    struct Tmp { int** a; int** b; int** c; long long** e; long long** f; ~Tmp() { cudaFree(*a); cudaFree(*b); cudaFree(*c); cudaFree(*e); cudaFree(*f); } } tmp{&mark, &rank, &need_idx, &bounds_d, &off_d};
+    struct Tmp { int** a; int** b; long long** e; long long** f; ~Tmp() { cudaFree(*a); cudaFree(*b); cudaFree(*e); cudaFree(*f); } } tmp{&mark, &rank, &bounds_d, &off_d};
     MPG_CUDA(ctx, cudaMalloc(&mark, sizeof(int) * (size_t)(n_global + 1)));
     MPG_CUDA(ctx, cudaMalloc(&rank, sizeof(int) * (size_t)(n_global + 1)));
     MPG_CUDA(ctx, cudaMalloc(&bounds_d, sizeof(long long) * (size_t)(P + 1)));
@@ -361,26 +358,64 @@ extern "C" int mpg_dist_setup(mpg_ctx* ctx, mpg_dist* d, int64_t n_global, const
     int nh = 0;
     MPG_CUDA(ctx, cudaMemcpyAsync(&nh, rank + n_global, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     MPG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    cudaFree(d->halo_cols_dev); d->halo_cols_dev = nullptr;
-    MPG_CUDA(ctx, cudaMalloc(&d->halo_cols_dev, sizeof(int) * (size_t)std::max(nh, 1)));
-    MPG_CUDA(ctx, cudaMalloc(&need_idx, sizeof(int) * (size_t)std::max(nh, 1)));
+    MPG_CUDA(ctx, cudaMalloc(halo_cols_out, sizeof(int) * (size_t)std::max(nh, 1)));
+    MPG_CUDA(ctx, cudaMalloc(need_idx_out, sizeof(int) * (size_t)std::max(nh, 1)));
     if (n_global > 0) {
-        compact_halo_kernel<<<(int)cdiv(n_global, 256), 256, 0, ctx->stream>>>(n_global, mark, rank, d->halo_cols_dev);
+        compact_halo_kernel<<<(int)cdiv(n_global, 256), 256, 0, ctx->stream>>>(n_global, mark, rank, *halo_cols_out);
         MPG_CHECK_LAUNCH(ctx);
     }
     if (nnz_local > 0) {
         renumber_kernel<<<(int)cdiv(nnz_local, 256), 256, 0, ctx->stream>>>(nnz_local, inds, (int)lo, (int)hi, rank);
         MPG_CHECK_LAUNCH(ctx);
     }
-    owner_offsets_kernel<<<1, 32, 0, ctx->stream>>>(P, bounds_d, nh, d->halo_cols_dev, off_d);
+    owner_offsets_kernel<<<1, 32, 0, ctx->stream>>>(P, bounds_d, nh, *halo_cols_out, off_d);
     MPG_CHECK_LAUNCH(ctx);
     if (nh > 0) {
-        need_idx_kernel<<<(int)cdiv(nh, 256), 256, 0, ctx->stream>>>(P, bounds_d, nh, d->halo_cols_dev, need_idx);
+        need_idx_kernel<<<(int)cdiv(nh, 256), 256, 0, ctx->stream>>>(P, bounds_d, nh, *halo_cols_out, *need_idx_out);
         MPG_CHECK_LAUNCH(ctx);
     }
-    std::vector<long long> off((size_t)P + 1);
+    off.assign((size_t)P + 1, 0);
     MPG_CUDA(ctx, cudaMemcpyAsync(off.data(), off_d, sizeof(long long) * off.size(), cudaMemcpyDeviceToHost, ctx->stream));
     MPG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *nh_out = nh;
+    return MPG_OK;
+}
+
+// The device kernels of the set-up alone (no communicator): what rank `rank` of `P` would compute for its slab.  Lets a single GPU
+// check every rank's halo list, renumbering and request lists against the oracle (tests/test_ops_gpu.py).
+extern "C" int mpg_partition_slab_dev(mpg_ctx* ctx, int64_t n_global, int P, const int64_t* bounds, int rank, int64_t nnz_local, int* inds,
+                                      int64_t* n_halo, int* halo_cols_dev, int* need_idx_dev, int64_t cap, int64_t* owner_off_host) {
+    MPG_REQUIRE(ctx, bounds && P >= 1 && rank >= 0 && rank < P && (inds || nnz_local == 0) && n_halo && n_global >= 0 && n_global < (int64_t)2147483647,
+                "partition_slab_dev: bad argument");
+    int nh = 0;
+    int *hc = nullptr, *ni = nullptr;
+    std::vector<long long> off;
+    const int rc = partition_slab_device(ctx, n_global, P, bounds, rank, nnz_local, inds, &nh, &hc, &ni, off);
+    struct Free { int* a; int* b; ~Free() { cudaFree(a); cudaFree(b); } } guard{hc, ni};
+    if (rc != MPG_OK) return rc;
+    *n_halo = nh;
+    if (nh > cap && (halo_cols_dev || need_idx_dev)) return fail(ctx, MPG_ERR_ARG, "partition_slab_dev: output capacity too small");
+    if (halo_cols_dev && nh) MPG_CUDA(ctx, cudaMemcpyAsync(halo_cols_dev, hc, sizeof(int) * (size_t)nh, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (need_idx_dev && nh) MPG_CUDA(ctx, cudaMemcpyAsync(need_idx_dev, ni, sizeof(int) * (size_t)nh, cudaMemcpyDeviceToDevice, ctx->stream));
+    MPG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (owner_off_host) for (int q = 0; q <= P; ++q) owner_off_host[q] = off[(size_t)q];
+    return MPG_OK;
+}
+
+extern "C" int mpg_dist_setup(mpg_ctx* ctx, mpg_dist* d, int64_t n_global, const int64_t* bounds, int64_t nnz_local, int* inds, int64_t* n_halo_out) {
+    MPG_REQUIRE(ctx, d && bounds && (inds || nnz_local == 0) && n_global >= 0 && n_global < (int64_t)2147483647 && nnz_local >= 0, "dist_setup: bad argument");
+    MPG_REQUIRE(ctx, d->world <= kMaxPeers, "dist_setup: at most 8 ranks");
+    const int P = d->world, me = d->rank;
+    for (int q = 0; q < P; ++q) MPG_REQUIRE(ctx, bounds[q] <= bounds[q + 1], "dist_setup: bounds must be non-decreasing");
+    MPG_REQUIRE(ctx, bounds[0] == 0 && bounds[P] == n_global, "dist_setup: bounds must cover [0, n_global]");
+    const int64_t n_local = bounds[me + 1] - bounds[me];
+    MPG_REQUIRE(ctx, n_local >= 1, "dist_setup: every rank must own at least one row (a rank without rows would never join the reductions)");
+    int nh = 0;
+    int* need_idx = nullptr;
+    std::vector<long long> off;
+    cudaFree(d->halo_cols_dev); d->halo_cols_dev = nullptr;
+    MPG_TRY(partition_slab_device(ctx, n_global, P, bounds, me, nnz_local, inds, &nh, &d->halo_cols_dev, &need_idx, off));
+    struct Free { int* a; ~Free() { cudaFree(a); } } guard{need_idx};
     // counts: need[q] = halo slots owned by q; all-gathered into cnt[r][q]
     std::vector<long long> need((size_t)P), cnt((size_t)P * P);
     for (int q = 0; q < P; ++q) need[(size_t)q] = off[(size_t)q + 1] - off[(size_t)q];

@@ -535,6 +535,9 @@ void pack_free(mpg_packed* P) {
     delete P;
 }
 
+// slices of a partitioned slab that reference halo columns (0 without a slice list)
+int pack_boundary_slices(const mpg_packed* P) { return (P && P->plan && P->plan->slice_list) ? P->plan->nslices - P->plan->n_interior : 0; }
+
 bool pack_matches(const mpg_packed* P, const mpg_csr* A, int tsize) {
     const mpg_sell_plan* cur = A->sell;
     return P && P->A == A && P->tsize == tsize && cur && cur == P->plan && cur->uid == P->plan_uid;

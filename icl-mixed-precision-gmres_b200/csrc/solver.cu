@@ -48,6 +48,7 @@ template <class T> int pack_create(mpg_ctx*, const mpg_csr*, const T*, mpg_packe
 template <class T> int pack_update(mpg_ctx*, mpg_packed*, const T*);
 void pack_free(mpg_packed*);
 bool pack_matches(const mpg_packed*, const mpg_csr*, int tsize);
+int pack_boundary_slices(const mpg_packed*);
 template <class T> int spmv_packed(mpg_ctx*, const mpg_packed*, T, const T*, T, const T*, T*, float*, const T*, int, const HaloWait* = nullptr, const T* xadd = nullptr);
 template <class T> int ilu_jacobi_apply_t(mpg_ctx*, mpg_ilu_jacobi*, T*);
 template <class T> int halo_exchange(mpg_ctx*, T*);
@@ -322,9 +323,15 @@ int run_cycle(mpg_ctx* ctx, const mpg_gmres_params& p, Policy& pol, Workspace* w
             if (pushed_col != kk) MPG_TRY(halo_push_direct<T>(ctx, vk, kk));
             HaloWait hw;
             MPG_TRY(halo_wait_args(ctx, &hw));
-            if (P) {
+            if (P && pack_boundary_slices(P) <= 16384) {
                 MPG_TRY(spmv_packed<T>(ctx, P, T(1), vk, T(0), w, w, nullptr, rowscale, SPMV_INTERIOR));
                 MPG_TRY(spmv_packed<T>(ctx, P, T(1), vk, T(0), w, w, nullptr, rowscale, SPMV_BOUNDARY, &hw));
+            } else if (P) {
+                // nearly every slice reads halo columns (all-to-all halos of power-law matrices): tens of thousands of CTAs would each
+                // spin on system-scope flags - one tiny wait kernel in front of the product is cheaper than that
+                MPG_TRY(spmv_packed<T>(ctx, P, T(1), vk, T(0), w, w, nullptr, rowscale, SPMV_INTERIOR));
+                MPG_TRY(halo_wait_only(ctx));
+                MPG_TRY(spmv_packed<T>(ctx, P, T(1), vk, T(0), w, w, nullptr, rowscale, SPMV_BOUNDARY));
             } else {
                 MPG_TRY(mult(SPMV_INTERIOR));
                 MPG_TRY(halo_wait_only(ctx));

@@ -262,6 +262,7 @@ extern "C" int mpg_csr_create(mpg_ctx* ctx, int nrows, int ncols, int64_t nnz, c
     MPG_REQUIRE(ctx, nrows >= 0 && ncols >= 0 && nnz >= 0, "csr_create: negative dims");
     MPG_REQUIRE(ctx, nnz < (int64_t)2147483647, "csr_create: nnz must fit int32 (types_cuda.hpp:66-70)");
     mpg_csr* A = new mpg_csr();
+    struct Guard { mpg_csr* a; ~Guard() { if (a) mpg_csr_destroy(a); } } guard{A};   // error paths release what was built so far
     A->nrows = nrows; A->ncols = ncols; A->nnz = nnz; A->row_map = row_map; A->inds = inds;
     A->tile_nnz = SPMV_TILE;
     A->ntiles = (int)cdiv(nnz, SPMV_TILE);
@@ -296,6 +297,7 @@ extern "C" int mpg_csr_create(mpg_ctx* ctx, int nrows, int ncols, int64_t nnz, c
         MPG_CUDA(ctx, cudaMemcpyAsync(A->tile_list, list.data(), sizeof(int) * list.size(), cudaMemcpyHostToDevice, ctx->stream));
         MPG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
+    guard.a = nullptr;
     *out = A;
     return MPG_OK;
 }

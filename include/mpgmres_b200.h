@@ -292,6 +292,12 @@ int mpg_dist_open_halo(mpg_ctx*, mpg_dist* d, const void* handles_world_x_64_hos
  * and inboxes over the communicator; equivalent to mpg_dist_set_partition + mailbox / halo hand-shakes.  Collective. */
 int mpg_dist_setup(mpg_ctx*, mpg_dist* d, int64_t n_global, const int64_t* bounds_host, int64_t nnz_local, int* inds_dev, int64_t* n_halo);
 int mpg_dist_halo_cols(mpg_ctx*, const mpg_dist* d, int64_t* halo_cols_host /* n_halo */);
+/* The device part of mpg_dist_setup alone, without a communicator: what rank `rank` of P computes for its slab - halo columns
+ * (ascending), renumbered inds (in place), per-owner offsets into the halo (P + 1) and the owner-local row index of every halo
+ * slot (the lists it would request).  halo_cols_dev / need_idx_dev: capacity `cap` ints (may be NULL to query n_halo only -
+ * inds is renumbered either way).  One GPU can so check every rank's plan against the oracle. */
+int mpg_partition_slab_dev(mpg_ctx*, int64_t n_global, int P, const int64_t* bounds_host, int rank, int64_t nnz_local, int* inds_dev,
+                           int64_t* n_halo, int* halo_cols_dev, int* need_idx_dev, int64_t cap, int64_t* owner_off_host);
 int mpg_dist_peer_info(mpg_ctx*, const mpg_dist* d, int i, int* peer_rank, int64_t* send_count, int64_t* recv_offset, int64_t* recv_count,
                        int* send_idx_host /* may be NULL */);
 int mpg_ctx_attach_dist(mpg_ctx*, mpg_dist* d); /* NULL detaches */

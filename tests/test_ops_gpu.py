@@ -487,3 +487,34 @@ def test_row_range_generators_equal_rows_of_the_global_matrix(ctx, g, orc, spec)
         np.testing.assert_array_equal(host(v), val[rm[lo]:rm[hi]])
     r, i, v = ctx.gen_slab(spec, 0, 0)
     assert host(r).tolist() == [0] and i.numel() == 0
+
+
+@pytest.mark.parametrize("spec,P,split", [("lap2d:20", 2, "rows"), ("cd27:8", 3, "rows"), ("cd27:8", 8, "rows"), ("powerlaw:3000", 4, "nnz"), ("powerlaw:3000", 8, "rows")])
+def test_native_partition_kernels_match_oracle_for_every_rank(ctx, g, orc, spec, P, split):
+    """the device kernels behind mpg_dist_setup (remote-column marking, prefix-sum ranks, halo compaction, in-place renumbering,
+    owner offsets, request lists), run for EVERY rank of a P-way partition on this one GPU: halo columns and renumbered local
+    column indices bit-exact vs the oracle's definition, request lists = halo columns relative to their owner"""
+    import ctypes as C
+    import torch
+    rm, ind, val = orc.gen(spec)
+    n = len(rm) - 1
+    b = g.dist.bounds_nnz(rm, P) if split == "nnz" else g.dist.bounds(n, P)
+    barr = (C.c_int64 * (P + 1))(*[int(v) for v in b])
+    for r in range(P):
+        lo, hi = b[r], b[r + 1]
+        rl, il, vl = ctx.gen_slab(spec, lo, hi)           # the slab generated alone, global columns
+        np.testing.assert_array_equal(host(il), ind[rm[lo]:rm[hi]])
+        cap = max(int(il.numel()), 1)
+        hc = torch.zeros(cap, dtype=torch.int32, device="cuda:0")
+        ni = torch.zeros(cap, dtype=torch.int32, device="cuda:0")
+        nh = C.c_int64()
+        off = (C.c_int64 * (P + 1))()
+        ctx._chk(ctx.L.mpg_partition_slab_dev(ctx.h, C.c_int64(n), C.c_int(P), barr, C.c_int(r), C.c_int64(il.numel()), C.c_void_p(il.data_ptr()),
+                                              C.byref(nh), C.c_void_p(hc.data_ptr()), C.c_void_p(ni.data_ptr()), C.c_int64(cap), off))
+        halo_o, li_o = orc.partition_local_range(lo, hi, rm, ind)
+        assert nh.value == len(halo_o)
+        np.testing.assert_array_equal(host(hc)[:nh.value], halo_o)
+        np.testing.assert_array_equal(host(il), li_o)
+        owner = np.searchsorted(np.array(b[1:]), halo_o, side="right")
+        np.testing.assert_array_equal(host(ni)[:nh.value], halo_o - np.array(b)[owner])
+        np.testing.assert_array_equal(np.array(list(off)), np.searchsorted(halo_o, np.array(b)))
