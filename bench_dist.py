@@ -61,9 +61,9 @@ def main(args, rank, world, local_rank):
 
     for _ in range(args.warmup):
         r = solve()
-    # per-kernel-class event timers inside the timed region only when a kernel lasts long enough not to be perturbed by the
-    # event records around it (slabs of >= 8 M rows); otherwise the breakdown comes from a second pass over the same K solves
-    prof_in_region = part.n_local >= 8_000_000
+    # per-kernel-class event timers never run inside the timed region (same rule at every N, bench.py): the breakdown comes from a
+    # second pass over the same K solves
+    prof_in_region = False
     ctx.prof_enable(prof_in_region)
     ctx.prof_reset()
     sampler = ClockSampler(local_rank) if rank == 0 else None
@@ -154,8 +154,8 @@ def main(args, rank, world, local_rank):
                            "time_to_solution_s": total_ms * 1e-3 / args.steps, "resNorm": res_norm, "errNorm": err_norm, "rel_res": res_norm / b_norm,
                            "l2": "per-rank working set >> 126 MB L2; no flush needed",
                            "kernel_timers": ("CUDA events around every launch inside the timed region" if prof_in_region else
-                                             "second pass over the same K solves after the timed region (kernels of < 100 us: event records between "
-                                             "launches would perturb the step)")},
+                                             "CUDA events around every launch in a second pass over the same K solves right after the timed region (same "
+                                             "rule at every N; the event records would perturb the timed step, kernel durations are unaffected)")},
                 "roofline": {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_GBps"], "peak": peak, "unit": "GB/s",
                              "frac": kernels[dom]["frac_of_peak"], "traffic": None, "peak_source": peak_src, "note": "rank 0, per GPU"},
                 "kernels": kernels, "cpu_baseline": None, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
