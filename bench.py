@@ -406,10 +406,16 @@ def main():
             r2 = ctx.gmres_host(h_rm, h_ind, h_val, h_b, h_x, hist_cap=1, **kw)
             it2 += r2["total_iters"]
         dt = time.perf_counter() - t0
-        h2d = h_rm.numel() * 4 + h_ind.numel() * 4 + h_val.numel() * 8 + 2 * n * 8
-        e2e = {"value": it2 / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(n * 8),
-               "ms_per_step": 1e3 * dt / args.e2e_steps, "steps": args.e2e_steps, "h2d_ms": r2["h2d_ms"], "solve_ms": r2["solve_ms"],
-               "d2h_ms": r2["d2h_ms"], "call": "mpg_gmres_solve_host (pinned host CSR + b in, x out)"}
+        h2d_inputs = h_rm.numel() * 4 + h_ind.numel() * 4 + h_val.numel() * 8 + 2 * n * 8
+        # bytes that actually crossed the link, counted by the library from the copies it issued: with host_overlap the fp32 values the
+        # host cores cast travel too (4 B per nonzero on top of the caller's inputs)
+        e2e = {"value": it2 / dt, "unit": UNIT, "h2d_bytes_per_step": int(r2["h2d_bytes"]), "d2h_bytes_per_step": int(n * 8),
+               "input_bytes_per_step": int(h2d_inputs), "ms_per_step": 1e3 * dt / args.e2e_steps, "steps": args.e2e_steps,
+               "h2d_ms_until_solve_starts": r2["h2d_ms"], "h2d_ms_until_last_byte": r2["h2d_all_ms"], "solve_ms": r2["solve_ms"], "d2h_ms": r2["d2h_ms"],
+               "host_cast_threads": int(r2["host_overlap"]),
+               "call": "mpg_gmres_solve_host (pinned host CSR + b in, x out)" + (
+                   "; overlapped: indices first while host threads cast the values to fp32, solve starts on the fp32 operator, fp64 values land during "
+                   "the first restart cycle" if r2["host_overlap"] else "; serial H2D")}
         del h_rm, h_ind, h_val, h_b
 
     # ---- CPU baseline on this box's host cores: ONE complete solve of the same workload by the reference's own CPU path, and the

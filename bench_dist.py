@@ -92,6 +92,10 @@ def main(args, rank, world, local_rank):
         torch.cuda.synchronize()
     prof = ctx.prof_get()
     ctx.prof_enable(False)
+    # per-rank view of the same timers (ms per class over the profiled pass): a rank that waits for its peers inside a fused
+    # reduction shows it as a longer kernel, the slowest rank as a shorter one
+    per_rank = [None] * world
+    dist.all_gather_object(per_rank, {k: round(v["ms"], 3) for k, v in prof.items() if v["launches"]})
 
     # post-solve fp64 residual / error over all rows
     xe = torch.cat([x, torch.zeros(part.n_halo, dtype=torch.float64, device=dev)])
@@ -158,7 +162,7 @@ def main(args, rank, world, local_rank):
                                              "rule at every N; the event records would perturb the timed step, kernel durations are unaffected)")},
                 "roofline": {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_GBps"], "peak": peak, "unit": "GB/s",
                              "frac": kernels[dom]["frac_of_peak"], "traffic": None, "peak_source": peak_src, "note": "rank 0, per GPU"},
-                "kernels": kernels, "cpu_baseline": None, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
+                "kernels": kernels, "kernels_ms_per_rank": per_rank, "cpu_baseline": None, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
         print(json.dumps(line), flush=True)
     dctx.close()
     dist.destroy_process_group()

@@ -29,7 +29,7 @@ class GmresStats(C.Structure):
                 ("outer_i", C.c_int64), ("rel_prec_res", C.c_double), ("b_norm", C.c_double),
                 ("Minvb_norm", C.c_double), ("A_norm", C.c_double), ("n_hist_inner", C.c_int64),
                 ("n_hist_outer", C.c_int64), ("solve_ms", C.c_double), ("h2d_ms", C.c_double), ("d2h_ms", C.c_double),
-                ("launches", C.c_int64)]
+                ("launches", C.c_int64), ("h2d_all_ms", C.c_double), ("h2d_bytes", C.c_int64), ("host_overlap", C.c_int64)]
 
 
 def library_path():

@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(HERE, "build")
 LIB = os.path.join(LIBDIR, "libmpgmres_b200.so")
-SOURCES = ["blas1.cu", "spmv.cu", "sell.cu", "ilu.cu", "ortho.cu", "gen.cu", "solver.cu", "dist.cu", "mmio.cu"]
+SOURCES = ["blas1.cu", "spmv.cu", "sell.cu", "ilu.cu", "ortho.cu", "gen.cu", "solver.cu", "hostpath.cu", "dist.cu", "mmio.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--use_fast_math=false",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "-ccbin", "/usr/bin/g++"]
 NVCC_FLAGS.remove("--use_fast_math=false")  # never: IEEE division / sqrt are part of the parity contract

@@ -140,6 +140,8 @@ extern "C" int mpg_ctx_destroy(mpg_ctx* ctx) {
     for (auto& r : ctx->prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto e : ctx->prof_pool) cudaEventDestroy(e);
     cudaFree(ctx->arena);
+    if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+    cudaFreeHost(ctx->stage32);
     pool_trim(ctx->device);
     cudaFree(ctx->red_raw);
     cudaFree(ctx->partials);
@@ -182,6 +184,7 @@ static int* tuning_slot(mpg_ctx* ctx, const std::string& k) {
     MPG_KNOB(gemvt_rows_per_block); MPG_KNOB(passA_rb); MPG_KNOB(cgs2_fused); MPG_KNOB(vpass_serpentine); MPG_KNOB(gemvn_ctas_per_sm);
     MPG_KNOB(red_ctas_per_sm); MPG_KNOB(residual_packed); MPG_KNOB(values_static); MPG_KNOB(spmv_sigma); MPG_KNOB(mgs_fused);
     MPG_KNOB(dist_fuse_halo); MPG_KNOB(spin_limit_ms); MPG_KNOB(lookahead); MPG_KNOB(sell_variant); MPG_KNOB(sell_block); MPG_KNOB(trace);
+    MPG_KNOB(dist_spmv_one_launch); MPG_KNOB(host_overlap); MPG_KNOB(host_threads); MPG_KNOB(host_overlap_min_nnz);
 #undef MPG_KNOB
     return nullptr;
 }
@@ -706,9 +709,9 @@ __global__ void __launch_bounds__(32) givens_step_kernel(int64_t k, T* h, int64_
     givens_step_body<T>(smem_raw, k, h, ldh, cs, sn, s, resid, resid_host);
 }
 
-// Tail of an Arnoldi step in ONE launch: V(:,k+1) = w * (1/h(k+1,k))  (Orthogonalization.hpp:58-59) in all blocks but the
-// last, the Givens update of column k (gmres.cpp:219-226) in warp 0 of the last block.  The two are independent: both
-// only consume what the orthogonalisation left behind (w, 1/h(k+1,k), h(:,k)).
+// Tail of an Arnoldi step in ONE launch: the Givens update of column k (gmres.cpp:219-226) in warp 0 of block 0, the halo push of
+// the new column (multi-GPU) in the next npush blocks, V(:,k+1) = w * (1/h(k+1,k))  (Orthogonalization.hpp:58-59) in all the
+// others.  The three are independent: they only consume what the orthogonalisation left behind (w, 1/h(k+1,k), h(:,k)).
 template <class T>
 __global__ void __launch_bounds__(256) arnoldi_tail_kernel(int64_t n, const T* __restrict__ inv_dev, const T* x, T* y, int aligned, int64_t k, T* h,
                                                             int64_t ldh, T* cs, T* sn, T* s, double* resid, double* resid_host,
@@ -716,19 +719,23 @@ __global__ void __launch_bounds__(256) arnoldi_tail_kernel(int64_t n, const T* _
     extern __shared__ unsigned char smem_raw[];
     pdl_trigger();
     pdl_wait();
-    if (blockIdx.x == gridDim.x - 1) {
+    // block 0: Givens chain; blocks 1..npush: halo push; the rest: normalisation.  The latency-bound parts (a dependent rotation chain,
+    // remote stores + a system-scope fence + the flag) come FIRST in the grid so that they run under the bandwidth-bound normalisation
+    // instead of after its last wave.
+    if (blockIdx.x == 0) {
         if (threadIdx.x < 32) givens_step_body<T>(smem_raw, k, h, ldh, cs, sn, s, resid, resid_host);
         return;
     }
-    const int new_blocks = (int)gridDim.x - 1 - npush;
-    if ((int)blockIdx.x >= new_blocks) {
+    if ((int)blockIdx.x <= npush) {
         // multi-GPU: the boundary rows of the NEW basis vector, w[idx] * (1/h), go straight into the halo tail of the neighbours'
         // copy of that column (same product as the local store below: bit-identical values on both sides)
-        halo_push_block<T>(push, (int)blockIdx.x - new_blocks, x, inv_dev);
+        halo_push_block<T>(push, (int)blockIdx.x - 1, x, inv_dev);
         return;
     }
+    const int new_blocks = (int)gridDim.x - 1 - npush;
+    const int bid = (int)blockIdx.x - 1 - npush;
     const T alpha = __ldg(inv_dev);
-    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t gtid = (int64_t)bid * blockDim.x + threadIdx.x;
     const int64_t gstride = (int64_t)new_blocks * blockDim.x;
     for (int64_t i0 = gtid * 4; i0 < n; i0 += gstride * 4) {
         const int cnt = (int)min((int64_t)4, n - i0);

@@ -4,6 +4,7 @@
 
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -19,7 +20,8 @@ namespace mpg {
 constexpr int kMaxCols = 256;          // widest basis block any fused kernel accepts (restart length + 1)
 constexpr int kMaxPartBlocks = 2048;   // upper bound on the grid of a reducing kernel
 
-enum SpmvPart { SPMV_ALL = 0, SPMV_INTERIOR = 1, SPMV_BOUNDARY = 2 };
+enum SpmvPart { SPMV_ALL = 0, SPMV_INTERIOR = 1, SPMV_BOUNDARY = 2, SPMV_ORDERED = 3 };   // ORDERED: every slice in ONE launch, interior slices first, the
+                                                                                     // CTAs of the boundary slices wait for the halo flags (packed operator)
 
 struct Tuning {
     int spmv_ctas_per_sm = 8;
@@ -38,10 +40,10 @@ struct Tuning {
     int red_ctas_per_sm = 4;
     int dist_peer_halo = 1;   // multi-GPU halo exchange by stores into the neighbours' memory (0: pack + ncclSend/ncclRecv)
     int fuse_tail = 1;        // solver: normalisation of the new basis vector and the Givens update of the column in one launch
-    int use_pdl = 1;          // programmatic dependent launch for the kernels of the Arnoldi loop: 0 off, 1 when the operand has at most
-                              // pdl_max_rows rows (measured: +11 % at 0.26 M rows, +1 % at 2.1 M, -1 % at 4.1 M, -8 % at 16.7 M), 2 always;
-                              // off while profiling
-    int pdl_max_rows = 2500000;
+    int use_pdl = 1;          // programmatic dependent launch for the kernels of the Arnoldi loop: 0 off, 1 on one GPU when the operand has at
+                              // most pdl_max_rows rows (measured: +11 % at 0.26 M rows, -3 % at 2.1 M, -1 % at 4.1 M, -8 % at 16.7 M; with a
+                              // communicator attached -6 % .. -21 % at 1-2 M rows per rank), 2 always; off while profiling
+    int pdl_max_rows = 1000000;
     int spmv_packed = 1;      // solver: run the inner SpMV on the packed (sliced-ELL) copy of the matrix when it packs well (sell.cu)
     int dist_overlap = 1;     // multi-GPU SpMV: rows without halo columns run between the halo push and the wait for the neighbours' data
     int dist_peer_reduce = 1; // multi-GPU reductions inside the kernels over peer memory (0: NCCL all-reduce + epilogue kernel)
@@ -51,11 +53,26 @@ struct Tuning {
     int spmv_sigma = 1;       // packed operator: sort rows by length inside windows (SELL-C-sigma) when the plain slices pad too much
     int mgs_fused = 1;        // MGS: pairwise fused passes (w -= h_j v_j ; h_{j+1} = v_{j+1}.w in one kernel) instead of k+1 x {dot, naxpy}
     int dist_fuse_halo = 1;   // multi-GPU: halo gather-and-push rides in the Arnoldi tail kernel, the wait in the boundary-slice SpMV
+    int dist_spmv_one_launch = 1;   // fused halo: interior and boundary slices in ONE launch (boundary CTAs last, they wait for the flags);
+                              // 0: two launches (measured on 2.1 M-row slabs: the second launch + its ramp cost ~10 us per iteration)
     int spin_limit_ms = 20000; // multi-GPU: a device-side wait on a peer gives up after this long and raises the context's error word
     int sell_variant = -1;    // packed SpMV kernel variant: bit 0 = x gathers bypass L1, bit 1 = 4 groups per step; -1 = chosen from the plan
     int sell_block = 0;       // packed SpMV threads per CTA (0 = 256)
     int trace = 0;            // 1: host wall-clock of the set-up phases of every solve on stderr (diagnostics)
     int lookahead = 0;        // residual-driven restart policies: speculative Arnoldi steps in flight (0 = auto from a bandwidth estimate)
+    int host_overlap = 1;     // mpg_gmres_solve_host, mixed precision: host threads cast the values to fp32 while the indices travel, the fp32
+                              // operator goes first and the fp64 values land during the first restart cycle (0: one serial H2D of everything)
+    int host_threads = 0;     // host_overlap: cast threads (0 = the CPUs this process may run on, at most 32)
+    int host_overlap_min_nnz = 4000000;   // below this the serial copy is a few hundred microseconds: not worth the threads
+};
+
+// mpg_gmres_solve_host with host_overlap: the fp64 value array of a mixed-precision solve is still on its way (copy stream) when the
+// solve starts.  The feeder thread records `ev` on the copy stream after the last fp64 chunk and then sets `recorded` (1, or -1 after a
+// failed copy); the solver waits for it the first time it needs the fp64 operator.
+struct DeferredV64 {
+    std::atomic<int> recorded{0};
+    cudaEvent_t ev = nullptr;
+    bool x0_zero = false;     // the caller verified x0 == 0 on the host: r0 = b - A*0 = b needs no operator at all
 };
 
 }  // namespace mpg
@@ -89,6 +106,12 @@ struct mpg_ctx {
     // grow-only device staging arena of the host-buffer entry point (no cudaMalloc/cudaFree per call)
     void* arena = nullptr;
     size_t arena_bytes = 0;
+    // host_overlap (hostpath.cu): copy stream, grow-only pinned staging for the fp32 values the host threads produce, and the
+    // hand-over of the late fp64 values to the running solve
+    cudaStream_t copy_stream = nullptr;
+    float* stage32 = nullptr;
+    size_t stage32_elems = 0;
+    mpg::DeferredV64* defer = nullptr;
 
     // multi-GPU (dist.cu): communicator + partition attached to this context, raw reduction buffer
     struct mpg_dist* dist = nullptr;
@@ -187,7 +210,10 @@ inline cudaError_t launch_pdl(mpg_ctx* ctx, int64_t rows, void (*kern)(KArgs...)
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    const bool on = ctx->tune.use_pdl == 2 || (ctx->tune.use_pdl == 1 && rows <= ctx->tune.pdl_max_rows);
+    // auto (1): single GPU and small operands only.  Measured in round 2 (profiles/r02h_*): at 2.1 M rows PDL costs 3 % on one GPU and
+    // 6 % (stencil) to 21 % (all-to-all halo) with a communicator attached - early-resident dependents sit on the SMs while the last
+    // CTA of a reducing kernel talks to the peers
+    const bool on = ctx->tune.use_pdl == 2 || (ctx->tune.use_pdl == 1 && rows <= ctx->tune.pdl_max_rows && ctx->dist == nullptr);
     cfg.numAttrs = (on && !ctx->prof_on) ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
 }
@@ -415,10 +441,13 @@ __device__ __forceinline__ void halo_push_block(const PushArgs& a, int pb, const
         else { dst[i] = v0; dst[i + stride] = v1; dst[i + 2 * stride] = v2; dst[i + 3 * stride] = v3; }
     }
     for (; i < cnt; i += stride) dst[i] = scale ? al * x[idx[i]] : x[idx[i]];
-    __threadfence_system();
+    // ONE system-scope fence per CTA, by thread 0 after the barrier (fences are cumulative: the barrier makes the other threads'
+    // remote stores happen-before it).  A fence in every warp costs an NVLink round trip each and they queue up per SM: with
+    // thousands of push CTAs (all-to-all halos) that was most of the kernel.
     __syncthreads();
     if (threadIdx.x == 0) {
-        // the last block of this neighbour publishes the exchange number (its fence + the counter chain order all stores)
+        __threadfence_system();
+        // the last block of this neighbour publishes the exchange number (the counter chain + its fence order all stores before it)
         if (atomicAdd(a.counters + q, 1u) == (unsigned)a.bpp - 1u) {
             a.counters[q] = 0u;
             __threadfence_system();
@@ -430,6 +459,7 @@ __device__ __forceinline__ void halo_push_block(const PushArgs& a, int pb, const
 // halo of an SpMV input that neighbour GPUs push into this GPU's memory (dist.cu): the flags to wait for
 struct HaloWait {
     int npeers = 0;
+    int wait_from = 0;                      // only CTAs that hold a slice position >= wait_from wait (SPMV_ORDERED: the interior slices come first)
     const unsigned long long* flag[kMaxPeers];
     unsigned long long seq = 0;
     unsigned int* err = nullptr;
@@ -485,7 +515,9 @@ __device__ __forceinline__ void finish_reduction(const Epi& e, int count, double
             volatile double* dst = e.peer.mbox[q] + ((size_t)slot * P + r) * kMboxStride + j;
             *dst = red_s[j];
         }
-        __threadfence_system();
+        // no fence in every warp here: the barrier orders the CTA's mailbox stores before the release stores below, and a release is
+        // cumulative - one system-scope fence (inside st.release.sys, warp 0 only) instead of one NVLink round trip per warp on the
+        // critical path of every reduction
         __syncthreads();
         if ((int)threadIdx.x < P) {
             unsigned long long* f = e.peer.flag[threadIdx.x] + slot * P + r;

@@ -268,7 +268,8 @@ __global__ void __launch_bounds__(256, UN == 4 ? 5 : (sizeof(T) == 8 ? 6 : 8)) s
                                                          const int* __restrict__ vout, T* __restrict__ partial, const T* xadd, const __grid_constant__ HaloWait hw) {
     pdl_trigger();
     pdl_wait();
-    if (hw.npeers > 0) halo_wait_block(hw);
+    // CTA-uniform: does this CTA hold a slice position that reads halo columns?
+    if (hw.npeers > 0 && (int)((((int64_t)blockIdx.x + 1) * blockDim.x - 1) >> 5) >= hw.wait_from) halo_wait_block(hw);
     const int ws = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
     if (ws >= nslices) return;
     const int s = slice_list ? __ldg(slice_list + ws) : ws;
@@ -554,7 +555,7 @@ int spmv_packed(mpg_ctx* ctx, const mpg_packed* P, T alpha, const T* x, T beta, 
     }
     const int s_first = part == SPMV_BOUNDARY ? p->n_interior : 0;
     const int s_count = part == SPMV_INTERIOR ? p->n_interior : p->nslices - s_first;
-    const int* list = part == SPMV_ALL ? nullptr : p->slice_list + s_first;
+    const int* list = part == SPMV_ALL ? nullptr : p->slice_list + s_first;   // ORDERED: the whole list, interior slices first
     // algorithmic bytes: the CSR figure of SURVEY.md §8d (padding and per-lane destinations the packed layout reads on top are not counted)
     const double n_ = A->nrows, s_ = sizeof(T);
     const double bytes = (double)A->nnz * (s_ + 4) + 4 * (n_ + 1) + n_ * s_ + (y_out ? n_ * s_ : 0) + (beta != T(0) ? n_ * s_ : 0) + (out32 ? 4 * n_ : 0) +
@@ -563,6 +564,7 @@ int spmv_packed(mpg_ctx* ctx, const mpg_packed* P, T alpha, const T* x, T beta, 
     HaloWait hw;
     hw.npeers = 0;
     if (hw_in) hw = *hw_in;
+    hw.wait_from = (part == SPMV_ORDERED) ? p->n_interior : 0;
     if (s_count > 0) {
         // measured (profiles/r02_tune_sell_sigma.txt): SIGMA plans (random columns) want 4 groups = 16 gathers in flight per lane, stencils 2;
         // x always through L1 - the no-allocate hint on the gathers also demotes x in L2 and doubles the DRAM traffic

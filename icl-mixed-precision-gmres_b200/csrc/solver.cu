@@ -16,6 +16,7 @@
 //   * the workspace is cached in the context (the reference allocates and zero-fills 2 bases per call,
 //     gmres.cpp:147,156 — the second one is never used).
 #include <algorithm>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -323,7 +324,10 @@ int run_cycle(mpg_ctx* ctx, const mpg_gmres_params& p, Policy& pol, Workspace* w
             if (pushed_col != kk) MPG_TRY(halo_push_direct<T>(ctx, vk, kk));
             HaloWait hw;
             MPG_TRY(halo_wait_args(ctx, &hw));
-            if (P && pack_boundary_slices(P) <= 16384) {
+            if (P && pack_boundary_slices(P) <= 16384 && ctx->tune.dist_spmv_one_launch) {
+                // ONE launch: the slices without halo columns first, the CTAs of the others (last in the grid) wait for the flags
+                MPG_TRY(spmv_packed<T>(ctx, P, T(1), vk, T(0), w, w, nullptr, rowscale, SPMV_ORDERED, &hw));
+            } else if (P && pack_boundary_slices(P) <= 16384) {
                 MPG_TRY(spmv_packed<T>(ctx, P, T(1), vk, T(0), w, w, nullptr, rowscale, SPMV_INTERIOR));
                 MPG_TRY(spmv_packed<T>(ctx, P, T(1), vk, T(0), w, w, nullptr, rowscale, SPMV_BOUNDARY, &hw));
             } else if (P) {
@@ -465,7 +469,22 @@ int solve_mixed(mpg_ctx* ctx, const mpg_gmres_params& p, const mpg_csr* A, const
     // gathers x once per nonzero and runs at ~0.55 of the roofline, the packed one at ~0.9)
     const mpg_packed* packed64 = nullptr;
     tr.mark("packed fp32 (plan + values)");
-    if (ctx->tune.residual_packed && packed) MPG_TRY(get_packed<double>(ctx, ws, 1, A, vals64, &packed64));
+    // host-buffer entry point with host_overlap: vals64 may still be in flight on the copy stream.  Nothing before the first fp64
+    // residual that needs the operator touches it; need_v64() makes the compute stream wait for the copy and packs it then.
+    DeferredV64* df = ctx->defer;
+    bool v64_ready = (df == nullptr);
+    auto need_v64 = [&]() -> int {
+        if (!v64_ready) {
+            int state;
+            while ((state = df->recorded.load(std::memory_order_acquire)) == 0) std::this_thread::yield();
+            if (state < 0) return fail(ctx, MPG_ERR_CUDA, "gmres_solve_host: the host-to-device copy of the fp64 values failed");
+            MPG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, df->ev, 0));
+            v64_ready = true;
+        }
+        if (!packed64 && ctx->tune.residual_packed && packed) MPG_TRY(get_packed<double>(ctx, ws, 1, A, vals64, &packed64));
+        return MPG_OK;
+    };
+    if (v64_ready) MPG_TRY(need_v64());
     tr.mark("packed fp64");
     Policy pol(p);
     MPG_TRY(size_estimate(ctx, A, pol));
@@ -496,8 +515,13 @@ int solve_mixed(mpg_ctx* ctx, const mpg_gmres_params& p, const mpg_csr* A, const
             MPG_TRY(halo_exchange<double>(ctx, xe));
             xin = xe;
         }
-        if (packed64) MPG_TRY(spmv_packed<double>(ctx, packed64, -1.0, xin, 1.0, b, nullptr, w, nullptr, SPMV_ALL));
-        else MPG_TRY(spmv<double>(ctx, A, vals64, -1.0, xin, 1.0, b, nullptr, w));
+        if (i == 0 && df && df->x0_zero && ws->halo == 0) {
+            MPG_TRY(cast_copy(ctx, n, b, w));   // x0 == 0 (checked on the host): r = b - A*0 = b, so w = (float) b - same bits, no operator needed yet
+        } else {
+            MPG_TRY(need_v64());
+            if (packed64) MPG_TRY(spmv_packed<double>(ctx, packed64, -1.0, xin, 1.0, b, nullptr, w, nullptr, SPMV_ALL));
+            else MPG_TRY(spmv<double>(ctx, A, vals64, -1.0, xin, 1.0, b, nullptr, w));
+        }
         MPG_TRY(nrm2_dev(ctx, n, w, ds<float>(ctx, 0)));                       // r_norm   :176
         MPG_TRY(apply_prec<float>(ctx, n, w, jac32, nullptr, false, nullptr, ilu)); // M(w)     :177
         if (jac32 || ilu) MPG_TRY(nrm2_dev(ctx, n, w, ds<float>(ctx, 1)));     // beta     :179 (same vector when M = I)
@@ -693,60 +717,3 @@ extern "C" int mpg_gmres_solve(mpg_ctx* ctx, const mpg_gmres_params* pp, const m
     return MPG_OK;
 }
 
-extern "C" int mpg_gmres_solve_host(mpg_ctx* ctx, const mpg_gmres_params* p, int nrows, int64_t nnz, const int* row_map_h, const int* inds_h,
-                                    const double* vals64_h, const double* b_h, double* x_h, mpg_gmres_stats* st, double* hist_inner,
-                                    int64_t cap_inner, double* hist_outer, int64_t cap_outer) {
-    MPG_REQUIRE(ctx, p && row_map_h && inds_h && vals64_h && b_h && x_h && st && nrows >= 0 && nnz >= 0, "gmres_solve_host: bad argument");
-    MPG_REQUIRE(ctx, ctx->dist == nullptr, "gmres_solve_host: takes a global matrix; with a communicator attached use mpg_gmres_solve on the local slab");
-    // carve the operands out of the context's grow-only arena: repeated solves pay no allocation cost
-    auto up = [](size_t v) { return (v + 255) & ~size_t(255); };
-    const size_t o_rm = 0;
-    const size_t o_in = o_rm + up(sizeof(int) * (size_t)(nrows + 1));
-    const size_t o_v64 = o_in + up(sizeof(int) * (size_t)nnz);
-    const size_t o_v32 = o_v64 + up(sizeof(double) * (size_t)nnz);
-    const size_t o_b = o_v32 + up(sizeof(float) * (size_t)nnz);
-    const size_t o_x = o_b + up(sizeof(double) * (size_t)nrows);
-    const size_t total = o_x + up(sizeof(double) * (size_t)nrows) + 256;
-    if (total > ctx->arena_bytes) {
-        MPG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        cudaFree(ctx->arena);
-        ctx->arena = nullptr; ctx->arena_bytes = 0;
-        MPG_CUDA(ctx, cudaMalloc(&ctx->arena, total));
-        ctx->arena_bytes = total;
-    }
-    char* base = static_cast<char*>(ctx->arena);
-    int* row_map = reinterpret_cast<int*>(base + o_rm);
-    int* inds = reinterpret_cast<int*>(base + o_in);
-    double* vals = reinterpret_cast<double*>(base + o_v64);
-    float* vals32 = reinterpret_cast<float*>(base + o_v32);
-    double* b = reinterpret_cast<double*>(base + o_b);
-    double* x = reinterpret_cast<double*>(base + o_x);
-    mpg_csr* A = nullptr;
-    cudaEvent_t e0, e1, e2, e3;
-    cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2); cudaEventCreate(&e3);
-    int rc = MPG_OK;
-    auto cleanup = [&]() {
-        cudaStreamSynchronize(ctx->stream);
-        if (A) mpg_csr_destroy(A);
-        cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); cudaEventDestroy(e3);
-    };
-    MPG_CUDA_C(cudaEventRecord(e0, ctx->stream));
-    MPG_CUDA_C(cudaMemcpyAsync(row_map, row_map_h, sizeof(int) * (size_t)(nrows + 1), cudaMemcpyHostToDevice, ctx->stream));
-    MPG_CUDA_C(cudaMemcpyAsync(inds, inds_h, sizeof(int) * (size_t)nnz, cudaMemcpyHostToDevice, ctx->stream));
-    MPG_CUDA_C(cudaMemcpyAsync(vals, vals64_h, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, ctx->stream));
-    MPG_CUDA_C(cudaMemcpyAsync(b, b_h, sizeof(double) * (size_t)nrows, cudaMemcpyHostToDevice, ctx->stream));
-    MPG_CUDA_C(cudaMemcpyAsync(x, x_h, sizeof(double) * (size_t)nrows, cudaMemcpyHostToDevice, ctx->stream));
-    MPG_CUDA_C(cudaEventRecord(e1, ctx->stream));
-    MPG_TRY_C(mpg_csr_create(ctx, nrows, nrows, nnz, row_map, inds, &A));
-    MPG_TRY_C(cast_copy(ctx, nnz, vals, vals32));   // SparseMatrix<float>(A), gmres_perf_test.cpp:136
-    MPG_TRY_C(mpg_gmres_solve(ctx, p, A, vals, vals32, b, x, st, hist_inner, cap_inner, hist_outer, cap_outer));
-    MPG_CUDA_C(cudaEventRecord(e2, ctx->stream));
-    MPG_CUDA_C(cudaMemcpyAsync(x_h, x, sizeof(double) * (size_t)nrows, cudaMemcpyDeviceToHost, ctx->stream));
-    MPG_CUDA_C(cudaEventRecord(e3, ctx->stream));
-    MPG_CUDA_C(cudaEventSynchronize(e3));
-    float t = 0.f;
-    cudaEventElapsedTime(&t, e0, e1); st->h2d_ms = t;
-    cudaEventElapsedTime(&t, e2, e3); st->d2h_ms = t;
-    cleanup();
-    return MPG_OK;
-}

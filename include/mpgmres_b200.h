@@ -225,8 +225,14 @@ typedef struct mpg_gmres_stats {
     double b_norm, Minvb_norm, A_norm;
     int64_t n_hist_inner, n_hist_outer;
     double solve_ms;   /* device time of the solve (CUDA events), excluding transfers */
-    double h2d_ms, d2h_ms; /* only set by the _host entry point */
+    double h2d_ms, d2h_ms; /* only set by the _host entry point; h2d_ms = until the solve could start */
     int64_t launches;  /* kernels launched by this solve */
+    /* _host entry point: time until the LAST input byte had landed (overlapped shape: inside the first restart cycle), bytes that
+     * crossed the link host->device (the overlapped shape also sends the fp32 values the host cores cast), and the number of host
+     * cast threads (0: serial shape) */
+    double h2d_all_ms;
+    int64_t h2d_bytes;
+    int64_t host_overlap;
 } mpg_gmres_stats;
 
 /* Device-resident operands.  vals32 may be NULL (cast from vals64 internally, types_cuda.hpp:82-101).
@@ -235,7 +241,10 @@ typedef struct mpg_gmres_stats {
 int mpg_gmres_solve(mpg_ctx*, const mpg_gmres_params* p, const mpg_csr* A, const double* vals64, const float* vals32,
                     const double* b, double* x, mpg_gmres_stats* stats, double* hist_inner_host, int64_t cap_inner,
                     double* hist_outer_host, int64_t cap_outer);
-/* End-to-end: HOST CSR + b in, x out (H2D, plan, solve, D2H inside).  x_host holds x0 on entry. */
+/* End-to-end: HOST CSR + b in, x out (H2D, plan, solve, D2H inside).  x_host holds x0 on entry.  Host buffers should be pinned.
+ * Mixed precision (knob host_overlap, default on): the indices go first while host threads cast the values to fp32 into a pinned
+ * staging buffer, the solve starts when the fp32 operator is complete and the fp64 values land during the first restart cycle -
+ * same bits as the serial shape (csrc/hostpath.cu). */
 int mpg_gmres_solve_host(mpg_ctx*, const mpg_gmres_params* p, int nrows, int64_t nnz, const int* row_map_host,
                          const int* inds_host, const double* vals64_host, const double* b_host, double* x_host,
                          mpg_gmres_stats* stats, double* hist_inner_host, int64_t cap_inner, double* hist_outer_host,

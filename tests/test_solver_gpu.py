@@ -138,6 +138,57 @@ def test_host_entry_point_matches_device_entry_point(ctx, g, orc):
     np.testing.assert_array_equal(r1["hist_inner"], r2["hist_inner"])
 
 
+@pytest.mark.parametrize("spec,kw", [("cd27:20", dict(rlen=30, tol=1e-9)), ("cd27:20", dict(rlen=25, tol=1e-10, prec="jacobi")),
+                                      ("powerlaw:20000", dict(rlen=30, tol=1e-8)), ("lap2d:120", dict(rlen=20, tol=1e-9, conv="relprecres", rtol=1e-2))])
+@pytest.mark.parametrize("x0", ["zero", "nonzero"])
+def test_overlapped_host_path_equals_serial_host_path(ctx, g, orc, spec, kw, x0):
+    """mpg_gmres_solve_host, overlapped shape (csrc/hostpath.cu: host threads cast the values, fp32 operator first, fp64 values land
+    during the first cycle, r0 = b when x0 == 0): same bits as the serial shape - x, histories, counts - for x0 = 0 and x0 != 0;
+    the library reports the bytes it really sent (inputs + 4 B per nonzero of host-cast fp32 values)"""
+    rm, ind, val, xt, b = problem(orc, spec)
+    n, nnz = len(b), len(ind)
+    x_init = np.zeros(n) if x0 == "zero" else 0.5 * xt
+    res = {}
+    try:
+        for shape, knobs in (("serial", dict(host_overlap=0)), ("overlap", dict(host_overlap=1, host_overlap_min_nnz=0, host_threads=3))):
+            for k_, v_ in knobs.items():
+                ctx.set_tuning(k_, v_)
+            xh = x_init.copy()
+            r = ctx.gmres_host(rm, ind, val, b, xh, mode="mixed", max_restarts=2000, **kw)
+            res[shape] = (r, xh)
+    finally:
+        ctx.set_tuning("host_overlap", 1); ctx.set_tuning("host_overlap_min_nnz", 4000000); ctx.set_tuning("host_threads", 0)
+    (r0, x_s), (r1, x_o) = res["serial"], res["overlap"]
+    assert r0["status"] == r1["status"] == 1
+    assert r0["host_overlap"] == 0 and r1["host_overlap"] >= 1
+    assert (r0["total_iters"], r0["total_restarts"]) == (r1["total_iters"], r1["total_restarts"])
+    np.testing.assert_array_equal(x_o, x_s)
+    np.testing.assert_array_equal(r1["hist_inner"], r0["hist_inner"])
+    np.testing.assert_array_equal(r1["hist_outer"], r0["hist_outer"])
+    inputs = 4 * (n + 1) + 4 * nnz + 8 * nnz + 16 * n
+    assert r0["h2d_bytes"] == inputs and r1["h2d_bytes"] == inputs + 4 * nnz
+    assert np.linalg.norm(x_o - xt) <= 1e-5 * np.linalg.norm(xt)
+
+
+def test_overlapped_host_path_many_chunks_and_uniform_modes_stay_serial(ctx, g, orc):
+    """a matrix of several 8 M-value chunks through the overlapped shape (feeder interleaving fp32 / fp64 chunks, unaligned tail chunk)
+    = the serial shape bit for bit; the uniform-precision modes never take the overlapped shape"""
+    rm, ind, val, xt, b = problem(orc, "cd27:100")      # 26.5 M nonzeros: 4 chunks
+    out = {}
+    try:
+        for shape, ov in (("serial", 0), ("overlap", 1)):
+            ctx.set_tuning("host_overlap", ov)
+            xh = np.zeros(len(b))
+            out[shape] = (ctx.gmres_host(rm, ind, val, b, xh, mode="mixed", rlen=20, tol=1e-6), xh)
+        xh = np.zeros(len(b))
+        rb = ctx.gmres_host(rm, ind, val, b, xh, mode="single", rlen=20, tol=1e-4)
+    finally:
+        ctx.set_tuning("host_overlap", 1)
+    assert out["overlap"][0]["host_overlap"] >= 1 and out["serial"][0]["host_overlap"] == 0 and rb["host_overlap"] == 0
+    np.testing.assert_array_equal(out["overlap"][1], out["serial"][1])
+    np.testing.assert_array_equal(out["overlap"][0]["hist_inner"], out["serial"][0]["hist_inner"])
+
+
 def test_kernel_variants_agree(ctx, g, orc):
     """the tuning knobs select different kernels for the same arithmetic: 3-pass fused vs 4-pass, staged vs register
     gemv-T.  Reduction grouping differs, so results agree to rounding, not bitwise."""

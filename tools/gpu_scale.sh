@@ -14,7 +14,7 @@ PY
 tail -n 6 gpurun_out/r02_dist_check_n$N.err | cut -c1-300
 for cfg in "cd27:256 rows" "powerlaw:8000000 nnz"; do
 set -- $cfg; wl=$1; part=$2
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29612 bench.py --gpus $N --steps 10 --warmup 3 --workload $wl --partition $part > gpurun_out/r02_bench_${wl/:/_}_n${N}.json 2> gpurun_out/r02_bench_${wl/:/_}_n${N}.err; echo "bench $wl rc=$?"
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29612 bench.py --gpus $N --steps 10 --warmup 3 --workload $wl --partition $part $EXTRA > gpurun_out/r02_bench_${wl/:/_}_n${N}.json 2> gpurun_out/r02_bench_${wl/:/_}_n${N}.err; echo "bench $wl rc=$?"
 python - <<PY
 import json
 try:
