@@ -12,11 +12,13 @@ namespace mpg {
 // ---- block cache on top of the stream-ordered pool (see common.cuh) --------------------------------------------------------
 namespace blockcache {
 struct CachedBlock { void* p; size_t bytes; };
+struct LiveBlock { size_t bytes; int dev; cudaStream_t stream; unsigned epoch; };
 struct BlockCache {
     std::mutex mu;
-    std::unordered_map<void*, std::pair<size_t, int>> live;      // handed out: ptr -> (bytes, device)
+    std::unordered_map<void*, LiveBlock> live;                   // handed out: ptr -> (bytes, device, stream it was allocated on, stream epoch)
     std::vector<CachedBlock> parked[64];                         // per device
     size_t parked_bytes[64] = {0};
+    unsigned epoch = 0;                                          // bumped by mpg_ctx_set_stream / mpg_ctx_use_own_stream
 };
 BlockCache& block_cache() { static BlockCache c; return c; }
 constexpr size_t kCacheMinBytes = (size_t)1 << 20;
@@ -35,35 +37,45 @@ cudaError_t pool_alloc(mpg_ctx* ctx, void** p, size_t bytes) {
             if (v[(size_t)i].bytes >= bytes && v[(size_t)i].bytes <= bytes + bytes / 4 + kCacheMinBytes && (best < 0 || v[(size_t)i].bytes < v[(size_t)best].bytes)) best = i;
         if (best >= 0) {
             *p = v[(size_t)best].p;
-            c.live[*p] = {v[(size_t)best].bytes, dev};
+            c.live[*p] = {v[(size_t)best].bytes, dev, ctx->stream, c.epoch};
             c.parked_bytes[dev] -= v[(size_t)best].bytes;
             v.erase(v.begin() + best);
             return cudaSuccess;
         }
     }
     const cudaError_t e = cudaMallocAsync(p, bytes, ctx->stream);
-    if (e == cudaSuccess && bytes >= kCacheMinBytes) {
+    if (e == cudaSuccess) {
         std::lock_guard<std::mutex> lock(c.mu);
-        c.live[*p] = {bytes, dev};
+        c.live[*p] = {bytes, dev, ctx->stream, c.epoch};
     }
     return e;
 }
+// Every library allocation is only ever touched by work on its context's stream, so "nobody is using the block any more" is a
+// synchronisation of THAT stream - not of the device: a device-wide wait would also wait for the copy stream of the overlapped host
+// path (hostpath.cu), i.e. for gigabytes still crossing PCIe, in the middle of a solve.  If the context's stream was switched since
+// the block was handed out (stream epoch), the conservative device-wide wait is kept.
 void pool_free(void* p) {
     if (!p) return;
     BlockCache& c = block_cache();
-    size_t bytes = 0;
-    int dev = 0;
+    LiveBlock b{0, 0, nullptr, 0};
+    bool same_epoch = false;
     {
         std::lock_guard<std::mutex> lock(c.mu);
         auto it = c.live.find(p);
-        if (it != c.live.end()) { bytes = it->second.first; dev = it->second.second; c.live.erase(it); }
+        if (it != c.live.end()) { b = it->second; c.live.erase(it); same_epoch = (b.epoch == c.epoch); }
     }
-    if (bytes == 0) { cudaFree(p); return; }
-    cudaDeviceSynchronize();                                     // what cudaFree guarantees: nobody is using the block any more
+    if (b.bytes == 0) { cudaFree(p); return; }                    // not ours (plain cudaMalloc)
+    if (same_epoch) cudaStreamSynchronize(b.stream); else cudaDeviceSynchronize();
+    if (b.bytes < kCacheMinBytes) { cudaFreeAsync(p, same_epoch ? b.stream : (cudaStream_t)0); return; }
     std::lock_guard<std::mutex> lock(c.mu);
-    if (c.parked_bytes[dev] + bytes > kCacheMaxParked || c.parked[dev].size() >= 256) { cudaFree(p); return; }
-    c.parked[dev].push_back({p, bytes});
-    c.parked_bytes[dev] += bytes;
+    if (c.parked_bytes[b.dev] + b.bytes > kCacheMaxParked || c.parked[b.dev].size() >= 256) { cudaFreeAsync(p, same_epoch ? b.stream : (cudaStream_t)0); return; }
+    c.parked[b.dev].push_back({p, b.bytes});
+    c.parked_bytes[b.dev] += b.bytes;
+}
+void pool_stream_changed() {
+    BlockCache& c = block_cache();
+    std::lock_guard<std::mutex> lock(c.mu);
+    ++c.epoch;
 }
 void pool_trim(int device) {
     BlockCache& c = block_cache();
@@ -156,11 +168,13 @@ extern "C" int mpg_ctx_destroy(mpg_ctx* ctx) {
 
 extern "C" int mpg_ctx_set_stream(mpg_ctx* ctx, void* s) {
     if (!ctx) return MPG_ERR_ARG;
+    if (ctx->stream != (cudaStream_t)s) mpg::pool_stream_changed();   // blocks handed out so far are freed with a device-wide wait
     ctx->stream = (cudaStream_t)s;  // NULL is a valid handle: the CUDA legacy default stream
     return MPG_OK;
 }
 extern "C" int mpg_ctx_use_own_stream(mpg_ctx* ctx) {
     if (!ctx) return MPG_ERR_ARG;
+    if (ctx->stream != ctx->own_stream) mpg::pool_stream_changed();
     ctx->stream = ctx->own_stream;
     return MPG_OK;
 }
@@ -356,7 +370,7 @@ __global__ void __launch_bounds__(RED_THREADS) mgs_step_kernel(int64_t n, const 
                                                                 const T* __restrict__ hj_dev, double* partials, unsigned int* ticket, Epi epi) {
     constexpr int VEC = 16 / sizeof(T);
     using V = typename std::conditional<sizeof(T) == 4, float4, double2>::type;
-    pdl_trigger();
+    pdl_trigger_early(n);
     pdl_wait();
     const T hj = __ldg(hj_dev);
     const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -396,6 +410,7 @@ __global__ void __launch_bounds__(RED_THREADS) mgs_step_kernel(int64_t n, const 
         for (int q = 0; q < RED_THREADS / 32; ++q) t += wsum[q];
         partials[blockIdx.x] = t;
     }
+    pdl_trigger();
     if (grid_last_block(ticket)) last_block_finish<T>(epi, partials, 1, gridDim.x, 1);
 }
 
@@ -511,7 +526,7 @@ __device__ __forceinline__ void store4(T* p, const T v[4]) {
 template <class TX, class TY, int OP>
 __global__ void __launch_bounds__(256) ew_kernel(int64_t n, TY alpha, const TY* __restrict__ alpha_dev, TY beta,
                                                   const TX* x, const TY* diag, TY* y, int aligned) {
-    pdl_trigger();
+    pdl_trigger_early(n);
     pdl_wait();
     if (alpha_dev) alpha = __ldg(alpha_dev);
     const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -717,7 +732,7 @@ __global__ void __launch_bounds__(256) arnoldi_tail_kernel(int64_t n, const T* _
                                                             int64_t ldh, T* cs, T* sn, T* s, double* resid, double* resid_host,
                                                             const __grid_constant__ PushArgs push, int npush) {
     extern __shared__ unsigned char smem_raw[];
-    pdl_trigger();
+    pdl_trigger_early(n);
     pdl_wait();
     // block 0: Givens chain; blocks 1..npush: halo push; the rest: normalisation.  The latency-bound parts (a dependent rotation chain,
     // remote stores + a system-scope fence + the flag) come FIRST in the grid so that they run under the bandwidth-bound normalisation
@@ -737,7 +752,22 @@ __global__ void __launch_bounds__(256) arnoldi_tail_kernel(int64_t n, const T* _
     const T alpha = __ldg(inv_dev);
     const int64_t gtid = (int64_t)bid * blockDim.x + threadIdx.x;
     const int64_t gstride = (int64_t)new_blocks * blockDim.x;
-    for (int64_t i0 = gtid * 4; i0 < n; i0 += gstride * 4) {
+    int64_t i0 = gtid * 4;
+    // four 16-byte loads in flight per thread (a single-wave grid, launcher below): the kernel is latency-bound at slab sizes
+    if (aligned) {
+        for (; i0 + 3 * gstride * 4 + 4 <= n; i0 += 4 * gstride * 4) {
+            T v[4][4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) load4(x + i0 + (int64_t)u * gstride * 4, v[u]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) v[u][c] = alpha * v[u][c];
+                store4(y + i0 + (int64_t)u * gstride * 4, v[u]);
+            }
+        }
+    }
+    for (; i0 < n; i0 += gstride * 4) {
         const int cnt = (int)min((int64_t)4, n - i0);
         if (aligned && cnt == 4) {
             T v[4];
@@ -831,7 +861,8 @@ int arnoldi_tail(mpg_ctx* ctx, int64_t n, const T* inv_dev, const T* w, T* vnext
     PushArgs pa;
     if (push) pa = *push;
     const int npush = pa.npeers * pa.bpp;
-    const int grid = (int)std::min<int64_t>(std::max<int64_t>(cdiv(n, 256 * 4), 1), (int64_t)ctx->num_sms * 16) + npush + 1;
+    // normalisation blocks: one wave (8 resident CTAs of 256 threads per SM), 16 elements per thread and sweep
+    const int grid = (int)std::min<int64_t>(std::max<int64_t>(cdiv(n, 256 * 16), 1), (int64_t)ctx->num_sms * 8) + npush + 1;
     const int aligned = (((uintptr_t)w | (uintptr_t)vnext) & 15) == 0;
     ProfScope prof(ctx, MPG_PROF_ELEMENTWISE, 2.0 * (double)n * sizeof(T));
     MPG_CUDA(ctx, launch_pdl(ctx, n, arnoldi_tail_kernel<T>, grid, 256, smem, n, inv_dev, w, vnext, aligned, k, h, ldh, cs, sn, s, resid, resid_host, pa, npush));

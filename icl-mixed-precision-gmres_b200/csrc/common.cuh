@@ -41,9 +41,10 @@ struct Tuning {
     int dist_peer_halo = 1;   // multi-GPU halo exchange by stores into the neighbours' memory (0: pack + ncclSend/ncclRecv)
     int fuse_tail = 1;        // solver: normalisation of the new basis vector and the Givens update of the column in one launch
     int use_pdl = 1;          // programmatic dependent launch for the kernels of the Arnoldi loop: 0 off, 1 on one GPU when the operand has at
-                              // most pdl_max_rows rows (measured: +11 % at 0.26 M rows, -3 % at 2.1 M, -1 % at 4.1 M, -8 % at 16.7 M; with a
-                              // communicator attached -6 % .. -21 % at 1-2 M rows per rank), 2 always; off while profiling
-    int pdl_max_rows = 1000000;
+                              // most pdl_max_rows rows, 2 always; off while profiling.  Measured gain (profiles/r02i_pdl_threshold.txt): lap2d 512^2
+                              // fp64 m=50 +12 %, cd27 64^3 m=100 0 %, lap2d 1024^2 m=50 +4 %, cd27 100^3 m=100 -5 %, cd27 128^3 -3 %, 16.7 M rows
+                              // -8 %; with a communicator attached -6 % .. -21 % at 1-2 M rows per rank
+    int pdl_max_rows = 600000;
     int spmv_packed = 1;      // solver: run the inner SpMV on the packed (sliced-ELL) copy of the matrix when it packs well (sell.cu)
     int dist_overlap = 1;     // multi-GPU SpMV: rows without halo columns run between the halo push and the wait for the neighbours' data
     int dist_peer_reduce = 1; // multi-GPU reductions inside the kernels over peer memory (0: NCCL all-reduce + epilogue kernel)
@@ -170,7 +171,8 @@ void ilu_plan_free(mpg_ilu_plan* p);
 // point, a new mpg_csr per call) reaches a steady state with NO driver allocation at all.  (Measured with peer access enabled on a
 // 2-GPU run: free + re-allocation of ~4 GB of plan arrays through the driver stalled 0.2-0.9 s every few solves.)
 cudaError_t pool_alloc(mpg_ctx* ctx, void** p, size_t bytes);
-void pool_free(void* p);          // synchronises the device like cudaFree; accepts null and blocks that did not come from pool_alloc
+void pool_free(void* p);          // waits for the stream the block was handed out on (see blas1.cu); accepts null and blocks that did not come from pool_alloc
+void pool_stream_changed();       // a context switched streams: blocks handed out before are freed with a device-wide wait
 void pool_trim(int device);       // releases every parked block of the device
 template <class P> inline cudaError_t pool_alloc(mpg_ctx* ctx, P** p, size_t bytes) { return pool_alloc(ctx, reinterpret_cast<void**>(p), bytes); }
 
@@ -299,6 +301,13 @@ __device__ __forceinline__ float warp_sum(float v) {
 // no-ops for kernels launched the ordinary way.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// Where a kernel lets its dependents be scheduled.  Small operands (launch-bound kernels of 5-15 us): at entry, so the whole launch
+// latency of the next kernel hides behind this one (+12 % on the 262 K-row fp64 config).  Large operands: only when the CTA has done
+// its streaming work (pdl_trigger() at that point) - dependents that become resident while this kernel still streams take shared
+// memory and registers away from it (a 200 KB V-pass CTA next to SpMV CTAs shrinks their L1) and cost 3-8 %; released late they
+// still hide their launch latency and prologue behind the last-CTA reduction and the cross-GPU combine of this kernel.
+constexpr int64_t kPdlEarlyRows = 600000;
+__device__ __forceinline__ void pdl_trigger_early(int64_t rows) { if (rows <= kPdlEarlyRows) pdl_trigger(); }
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
     unsigned long long t;

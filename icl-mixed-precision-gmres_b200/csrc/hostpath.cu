@@ -29,6 +29,7 @@ using namespace mpg;
 
 namespace mpg {
 int cast_copy(mpg_ctx*, int64_t, const double*, float*);
+int sell_plan_get(mpg_ctx*, const mpg_csr*, const mpg_sell_plan**);
 }
 
 namespace {
@@ -176,7 +177,7 @@ int solve_host_overlapped(mpg_ctx* ctx, const mpg_gmres_params* p, int nrows, in
     cudaStream_t cs = ctx->copy_stream;
     float* stage = ctx->stage32;
 
-    constexpr int64_t CH = int64_t(1) << 23;   // values per chunk: 32 MB of fp32 (0.6 ms on the wire), 64 MB of fp64
+    constexpr int64_t CH = int64_t(1) << 21;   // values per chunk: 8 MB of fp32 (0.15 ms on the wire), 16 MB of fp64
     const int64_t nch = cdiv(nnz, CH);
     std::unique_ptr<std::atomic<unsigned char>[]> done(new std::atomic<unsigned char>[(size_t)nch]);
     for (int64_t c = 0; c < nch; ++c) done[(size_t)c].store(0, std::memory_order_relaxed);
@@ -270,6 +271,10 @@ int solve_host_overlapped(mpg_ctx* ctx, const mpg_gmres_params* p, int nrows, in
     df.x0_zero = all_plus_zero(x_h, (size_t)nrows);
     MPG_CUDA_H(cudaStreamWaitEvent(ctx->stream, e_inds, 0));
     MPG_TRY_H(mpg_csr_create(ctx, nrows, nrows, nnz, o.row_map, o.inds, &A));
+    if (ctx->tune.spmv_packed) {   // the packed structure only needs the indices too: built while the fp32 values travel
+        const mpg_sell_plan* plan = nullptr;
+        MPG_TRY_H(sell_plan_get(ctx, A, &plan));
+    }
     int s32;
     while ((s32 = v32_recorded.load(std::memory_order_acquire)) == 0) std::this_thread::yield();
     if (s32 < 0) { cleanup(); return fail(ctx, MPG_ERR_CUDA, "gmres_solve_host: the host-to-device copy of the fp32 values failed"); }

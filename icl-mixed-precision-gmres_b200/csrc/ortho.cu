@@ -113,7 +113,7 @@ vpass_kernel(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ C
         return tix * TR;
     };
 
-    pdl_trigger();
+    pdl_trigger_early(n);
     pdl_wait();
     if (dbg && tid == 0) dbg[blockIdx.x * 8 + 0] = globaltimer_ns();
     if (h_in) for (int j = tid; j < k1; j += CT + 32) h_s[j] = h_in[j];
@@ -202,6 +202,7 @@ vpass_kernel(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ C
         }
         if (dbg && tid == 0) dbg[blockIdx.x * 8 + 3] = globaltimer_ns();
     }
+    pdl_trigger();   // streaming work of this CTA is done: the next kernel may be scheduled under the last-CTA reduction / cross-GPU combine
     const bool last = grid_last_block(ticket);
     if (dbg && tid == 0) dbg[blockIdx.x * 8 + 4] = globaltimer_ns();
     if (last) {
@@ -222,7 +223,7 @@ __global__ void __launch_bounds__(256) gemvn_kernel(int64_t n, int k1, const T* 
                                                      T* y, double* x64, double* partials, unsigned int* ticket, Epi epi) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     T* ax = reinterpret_cast<T*>(smem_raw);
-    pdl_trigger();
+    pdl_trigger_early(n);
     pdl_wait();
     for (int j = threadIdx.x; j < k1; j += blockDim.x) ax[j] = alpha * x[j];
     __syncthreads();
@@ -305,6 +306,7 @@ __global__ void __launch_bounds__(256) gemvn_kernel(int64_t n, int k1, const T* 
         if (XUPD) x64[i] = fma(1.0, (double)a, x64[i]);
         if (NORM) nsum += (double)(a * a);
     }
+    pdl_trigger();
     if (NORM) {
         nsum = warp_sum(nsum);
         __shared__ double wsum[8];
@@ -464,7 +466,7 @@ vrow_kernel(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CU
         return tix * TRW;
     };
 
-    pdl_trigger();
+    pdl_trigger_early(n);
     pdl_wait();
     if (tid < MAXK) h_s[tid] = (h_in && tid < k1) ? h_in[tid] : T(0);
     if (tid == 0) {
@@ -536,6 +538,7 @@ vrow_kernel(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CU
         for (int q = 0; q < NW; ++q) t += red[q][tid];
         partials[(size_t)blockIdx.x * ldp + tid] = t;
     }
+    pdl_trigger();
     if (grid_last_block(ticket)) last_block_finish<T>(epi, partials, ldp, gridDim.x, k1, reinterpret_cast<double*>(smem_raw));
 }
 
@@ -558,7 +561,7 @@ __global__ void __launch_bounds__(256) vdirect_kernel(int64_t n, int k1, const T
     __shared__ double red[8][MAXK];
     __shared__ T h_s[MAXK];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    pdl_trigger();
+    pdl_trigger_early(n);
     pdl_wait();
     if (HAS_H && tid < MAXK) h_s[tid] = (tid < k1) ? h_in[tid] : T(0);
     __syncthreads();
@@ -655,6 +658,7 @@ __global__ void __launch_bounds__(256) vdirect_kernel(int64_t n, int k1, const T
         for (int q = 0; q < 8; ++q) t += red[q][tid];
         partials[(size_t)blockIdx.x * ldp + tid] = t;
     }
+    pdl_trigger();
     if (grid_last_block(ticket)) last_block_finish<T>(epi, partials, ldp, gridDim.x, k1);
 }
 

@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(256, UN == 4 ? 5 : (sizeof(T) == 8 ? 6 : 8)) s
                                                          const T* __restrict__ svals, const T* __restrict__ x, T alpha, T beta, const T* y_in,
                                                          T* y_out, float* out32, const T* __restrict__ rowscale, const int* __restrict__ slice_list,
                                                          const int* __restrict__ vout, T* __restrict__ partial, const T* xadd, const __grid_constant__ HaloWait hw) {
-    pdl_trigger();
+    pdl_trigger_early(nlanes);
     pdl_wait();
     // CTA-uniform: does this CTA hold a slice position that reads halo columns?
     if (hw.npeers > 0 && (int)((((int64_t)blockIdx.x + 1) * blockDim.x - 1) >> 5) >= hw.wait_from) halo_wait_block(hw);
@@ -321,6 +321,7 @@ __global__ void __launch_bounds__(256, UN == 4 ? 5 : (sizeof(T) == 8 ? 6 : 8)) s
 #pragma unroll
         for (int t = 0; t < 3; ++t) if (t < nt) sum = add_rn(sum, mul_rn(vv[t], xt[t]));
     }
+    pdl_trigger();
     const int pos = s * SLICE + lane;
     if (pos >= nlanes) return;
     int r = pos;

@@ -167,13 +167,13 @@ def test_overlapped_host_path_equals_serial_host_path(ctx, g, orc, spec, kw, x0)
     np.testing.assert_array_equal(r1["hist_outer"], r0["hist_outer"])
     inputs = 4 * (n + 1) + 4 * nnz + 8 * nnz + 16 * n
     assert r0["h2d_bytes"] == inputs and r1["h2d_bytes"] == inputs + 4 * nnz
-    assert np.linalg.norm(x_o - xt) <= 1e-5 * np.linalg.norm(xt)
+    assert np.linalg.norm(x_o - xt) <= 1e-3 * np.linalg.norm(xt)
 
 
 def test_overlapped_host_path_many_chunks_and_uniform_modes_stay_serial(ctx, g, orc):
-    """a matrix of several 8 M-value chunks through the overlapped shape (feeder interleaving fp32 / fp64 chunks, unaligned tail chunk)
+    """a matrix of several 2 M-value chunks through the overlapped shape (feeder interleaving fp32 / fp64 chunks, unaligned tail chunk)
     = the serial shape bit for bit; the uniform-precision modes never take the overlapped shape"""
-    rm, ind, val, xt, b = problem(orc, "cd27:100")      # 26.5 M nonzeros: 4 chunks
+    rm, ind, val, xt, b = problem(orc, "cd27:100")      # 26.5 M nonzeros: 13 chunks
     out = {}
     try:
         for shape, ov in (("serial", 0), ("overlap", 1)):
