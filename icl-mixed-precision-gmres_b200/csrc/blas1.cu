@@ -372,7 +372,7 @@ __global__ void __launch_bounds__(RED_THREADS) mgs_step_kernel(int64_t n, const 
     using V = typename std::conditional<sizeof(T) == 4, float4, double2>::type;
     pdl_trigger_early(n);
     pdl_wait();
-    const T hj = __ldg(hj_dev);
+    const T hj = ld_fresh(hj_dev);
     const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t gstride = (int64_t)gridDim.x * blockDim.x;
     T acc[VEC];
@@ -528,7 +528,7 @@ __global__ void __launch_bounds__(256) ew_kernel(int64_t n, TY alpha, const TY* 
                                                   const TX* x, const TY* diag, TY* y, int aligned) {
     pdl_trigger_early(n);
     pdl_wait();
-    if (alpha_dev) alpha = __ldg(alpha_dev);
+    if (alpha_dev) alpha = ld_fresh(alpha_dev);
     const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t gstride = (int64_t)gridDim.x * blockDim.x;
     constexpr bool READS_X = (OP != EW_FILL);
@@ -685,8 +685,8 @@ __device__ __forceinline__ void givens_step_body(unsigned char* smem_raw, int64_
     T* sc = sh + (k + 2);                          // k
     T* ss = sc + k;                                // k
     T* hcol = h + k * ldh;
-    for (int64_t j = threadIdx.x; j < k + 2; j += 32) sh[j] = hcol[j];
-    for (int64_t j = threadIdx.x; j < k; j += 32) { sc[j] = cs[j]; ss[j] = sn[j]; }
+    for (int64_t j = threadIdx.x; j < k + 2; j += 32) sh[j] = ld_fresh(hcol + j);
+    for (int64_t j = threadIdx.x; j < k; j += 32) { sc[j] = ld_fresh(cs + j); ss[j] = ld_fresh(sn + j); }
     __syncwarp();
     if (threadIdx.x == 0) {
         T cur = sh[0];
@@ -749,7 +749,7 @@ __global__ void __launch_bounds__(256) arnoldi_tail_kernel(int64_t n, const T* _
     }
     const int new_blocks = (int)gridDim.x - 1 - npush;
     const int bid = (int)blockIdx.x - 1 - npush;
-    const T alpha = __ldg(inv_dev);
+    const T alpha = ld_fresh(inv_dev);
     const int64_t gtid = (int64_t)bid * blockDim.x + threadIdx.x;
     const int64_t gstride = (int64_t)new_blocks * blockDim.x;
     int64_t i0 = gtid * 4;
@@ -861,8 +861,9 @@ int arnoldi_tail(mpg_ctx* ctx, int64_t n, const T* inv_dev, const T* w, T* vnext
     PushArgs pa;
     if (push) pa = *push;
     const int npush = pa.npeers * pa.bpp;
-    // normalisation blocks: one wave (8 resident CTAs of 256 threads per SM), 16 elements per thread and sweep
-    const int grid = (int)std::min<int64_t>(std::max<int64_t>(cdiv(n, 256 * 16), 1), (int64_t)ctx->num_sms * 8) + npush + 1;
+    // normalisation blocks: one 16-byte group per thread for small operands (as many CTAs as there is work), at most half a wave
+    // (4 CTAs of 256 threads per SM) with up to four groups in flight per thread for large ones
+    const int grid = (int)std::min<int64_t>(std::max<int64_t>(cdiv(n, 256 * 4), 1), (int64_t)ctx->num_sms * 4) + npush + 1;
     const int aligned = (((uintptr_t)w | (uintptr_t)vnext) & 15) == 0;
     ProfScope prof(ctx, MPG_PROF_ELEMENTWISE, 2.0 * (double)n * sizeof(T));
     MPG_CUDA(ctx, launch_pdl(ctx, n, arnoldi_tail_kernel<T>, grid, 256, smem, n, inv_dev, w, vnext, aligned, k, h, ldh, cs, sn, s, resid, resid_host, pa, npush));

@@ -44,7 +44,7 @@ struct Tuning {
                               // most pdl_max_rows rows, 2 always; off while profiling.  Measured gain (profiles/r02i_pdl_threshold.txt): lap2d 512^2
                               // fp64 m=50 +12 %, cd27 64^3 m=100 0 %, lap2d 1024^2 m=50 +4 %, cd27 100^3 m=100 -5 %, cd27 128^3 -3 %, 16.7 M rows
                               // -8 %; with a communicator attached -6 % .. -21 % at 1-2 M rows per rank
-    int pdl_max_rows = 600000;
+    int pdl_max_rows = 3000000;   // with the late trigger (pdl_trigger_early): +8 % at 0.26 M rows, +4 % at 1 M, +1 % at 2.1 M, 0 at 4.2 M, -2 % at 16.7 M
     int spmv_packed = 1;      // solver: run the inner SpMV on the packed (sliced-ELL) copy of the matrix when it packs well (sell.cu)
     int dist_overlap = 1;     // multi-GPU SpMV: rows without halo columns run between the halo push and the wait for the neighbours' data
     int dist_peer_reduce = 1; // multi-GPU reductions inside the kernels over peer memory (0: NCCL all-reduce + epilogue kernel)
@@ -306,6 +306,11 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 // its streaming work (pdl_trigger() at that point) - dependents that become resident while this kernel still streams take shared
 // memory and registers away from it (a 200 KB V-pass CTA next to SpMV CTAs shrinks their L1) and cost 3-8 %; released late they
 // still hide their launch latency and prologue behind the last-CTA reduction and the cross-GPU combine of this kernel.
+// Scalars and coefficient vectors that the PREVIOUS kernel of the stream produced (h, c, 1/norm, Givens state): loaded around L1
+// (ld.global.cg).  A dependent launched programmatically shares SMs - and their L1 - with its still-running primary; a line the
+// primary's CTAs read early (h(j,k)) can hold the stale neighbour (h(j+1,k)) that the primary's last CTA writes at the end, and the
+// read-only path (ld.global.nc) is only defined for data nobody writes while the kernel runs.
+template <class T> __device__ __forceinline__ T ld_fresh(const T* p) { return __ldcg(p); }
 constexpr int64_t kPdlEarlyRows = 600000;
 __device__ __forceinline__ void pdl_trigger_early(int64_t rows) { if (rows <= kPdlEarlyRows) pdl_trigger(); }
 
@@ -440,7 +445,7 @@ __device__ __forceinline__ void halo_push_block(const PushArgs& a, int pb, const
     T* dst = static_cast<T*>(a.dst[q]);
     const int* idx = a.send_idx[q];
     const long long cnt = a.count[q];
-    const T al = scale ? __ldg(scale) : T(1);
+    const T al = scale ? ld_fresh(scale) : T(1);
     const long long stride = (long long)a.bpp * blockDim.x;
     long long i = (long long)part * blockDim.x + threadIdx.x;
     for (; i + 3 * stride < cnt; i += 4 * stride) {
@@ -565,8 +570,8 @@ __device__ __forceinline__ void last_block_finish(const Epi& e, const double* pa
         const int r = threadIdx.x / count, j = threadIdx.x - r * count;
         if (r < R) {
             double acc = 0.0;
-#pragma unroll 8
-            for (int b = r; b < nblocks; b += R) acc += __ldcg(partials + (size_t)b * ldp + j);
+#pragma unroll 16
+            for (int b = r; b < nblocks; b += R) acc += __ldcg(partials + (size_t)b * ldp + j);   // same order, 16 L2 loads in flight
             scratch[r * count + j] = acc;
         }
         __syncthreads();

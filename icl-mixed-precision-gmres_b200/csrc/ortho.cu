@@ -114,9 +114,13 @@ vpass_kernel(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ C
     };
 
     pdl_trigger_early(n);
+    if (tid == CT) {   // the descriptors are kernel parameters, not data of the previous kernel: fetch them before the dependency wait
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapV) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapW) : "memory");
+    }
     pdl_wait();
     if (dbg && tid == 0) dbg[blockIdx.x * 8 + 0] = globaltimer_ns();
-    if (h_in) for (int j = tid; j < k1; j += CT + 32) h_s[j] = h_in[j];
+    if (h_in) for (int j = tid; j < k1; j += CT + 32) h_s[j] = ld_fresh(h_in + j);
     if (tid == 0) {
         for (int s = 0; s < stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
         fence_mbar_init();
@@ -225,7 +229,7 @@ __global__ void __launch_bounds__(256) gemvn_kernel(int64_t n, int k1, const T* 
     T* ax = reinterpret_cast<T*>(smem_raw);
     pdl_trigger_early(n);
     pdl_wait();
-    for (int j = threadIdx.x; j < k1; j += blockDim.x) ax[j] = alpha * x[j];
+    for (int j = threadIdx.x; j < k1; j += blockDim.x) ax[j] = alpha * ld_fresh(x + j);
     __syncthreads();
     using V4 = typename std::conditional<sizeof(T) == 4, float4, double2>::type;
     constexpr int UN = 8;
@@ -467,8 +471,12 @@ vrow_kernel(const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CU
     };
 
     pdl_trigger_early(n);
+    if (tid == CT) {   // descriptors are kernel parameters: fetch them before the dependency wait
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapV) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapW) : "memory");
+    }
     pdl_wait();
-    if (tid < MAXK) h_s[tid] = (h_in && tid < k1) ? h_in[tid] : T(0);
+    if (tid < MAXK) h_s[tid] = (h_in && tid < k1) ? ld_fresh(h_in + tid) : T(0);
     if (tid == 0) {
         for (int s = 0; s < stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, NW); }
         fence_mbar_init();
@@ -563,7 +571,7 @@ __global__ void __launch_bounds__(256) vdirect_kernel(int64_t n, int k1, const T
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     pdl_trigger_early(n);
     pdl_wait();
-    if (HAS_H && tid < MAXK) h_s[tid] = (tid < k1) ? h_in[tid] : T(0);
+    if (HAS_H && tid < MAXK) h_s[tid] = (tid < k1) ? ld_fresh(h_in + tid) : T(0);
     __syncthreads();
 
     T acc[MAXK];
