@@ -54,6 +54,9 @@ struct Tuning {
     int spmv_sigma = 1;       // packed operator: sort rows by length inside windows (SELL-C-sigma) when the plain slices pad too much
     int mgs_fused = 1;        // MGS: pairwise fused passes (w -= h_j v_j ; h_{j+1} = v_{j+1}.w in one kernel) instead of k+1 x {dot, naxpy}
     int dist_fuse_halo = 1;   // multi-GPU: halo gather-and-push rides in the Arnoldi tail kernel, the wait in the boundary-slice SpMV
+    int dist_ll_reduce = 1;   // in-kernel all-reduce: flag-in-data mailbox words (one one-way NVLink store per value) instead of data + fence + flag
+    int dist_push_in_spmv = 1; // fused halo, stencil-like halos: the push CTAs sit at the head of the SpMV kernel that consumes the column (0: in the
+                              // Arnoldi tail that produces it)
     int dist_spmv_one_launch = 1;   // fused halo: interior and boundary slices in ONE launch (boundary CTAs last, they wait for the flags);
                               // 0: two launches (measured on 2.1 M-row slabs: the second launch + its ramp cost ~10 us per iteration)
     int spin_limit_ms = 20000; // multi-GPU: a device-side wait on a peer gives up after this long and raises the context's error word
@@ -390,6 +393,8 @@ struct PeerComm {
     unsigned long long seq = 0;
     double* mbox[kMaxPeers];
     unsigned long long* flag[kMaxPeers];
+    ulonglong2* ll[kMaxPeers];              // flag-in-data mailbox: every 8-byte word carries 32 bits of payload and the 32-bit sequence number
+    int use_ll = 0;
     unsigned int* err = nullptr;            // device error word (mpg_ctx::dev_err_d)
     unsigned long long spin_limit_ns = 0;   // 0: wait for ever
 };
@@ -521,7 +526,45 @@ __device__ __forceinline__ double reduce_partials_column(const double* partials,
 // over peer memory when a PeerComm is attached, then the epilogue.
 template <class T>
 __device__ __forceinline__ void finish_reduction(const Epi& e, int count, double* red_s) {
-    if (e.peer.world > 1) {
+    if (e.peer.world > 1 && e.peer.use_ll) {
+        // Flag-in-data exchange (the idea of NCCL's LL protocol): a double travels as two naturally aligned 8-byte words, each = 32 bits
+        // of payload + the 32-bit sequence number of this reduction.  8-byte stores are single-copy atomic, so a word whose tag matches
+        // is complete: no fence, no separate flag, no wait for NVLink write acknowledgements on the sender - the latency of a reduction
+        // is ONE one-way store instead of round trip + flag + read.  Ranks are at most one reduction apart (nobody finishes reduction s
+        // before everybody contributed to it), so kMboxSlots >= 2 slots never see a live overwrite; stale words carry older tags.
+        const int P = e.peer.world, r = e.peer.rank;
+        const int slot = (int)(e.peer.seq % kMboxSlots);
+        const unsigned long long tag = (e.peer.seq & 0xffffffffull) << 32;
+        for (int idx = threadIdx.x; idx < count * P; idx += blockDim.x) {
+            const int q = idx / count, j = idx - q * count;
+            const unsigned long long bits = (unsigned long long)__double_as_longlong(red_s[j]);
+            ulonglong2* dst = e.peer.ll[q] + ((size_t)slot * P + r) * kMboxStride + j;
+            asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(dst), "l"((bits & 0xffffffffull) | tag), "l"((bits >> 32) | tag) : "memory");
+        }
+        __syncthreads();   // red_s is overwritten below
+        for (int j = threadIdx.x; j < count; j += blockDim.x) {
+            const ulonglong2* src = e.peer.ll[r] + (size_t)slot * P * kMboxStride + j;
+            double t = 0.0;
+            for (int q = 0; q < P; ++q) {
+                unsigned long long w0, w1, t0 = 0;
+                unsigned int spins = 0;
+                for (;;) {
+                    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(src + (size_t)q * kMboxStride) : "memory");
+                    if ((w0 & 0xffffffff00000000ull) == tag && (w1 & 0xffffffff00000000ull) == tag) break;
+                    if (e.peer.spin_limit_ns && (++spins & 1023u) == 0) {
+                        unsigned long long now;
+                        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+                        if (t0 == 0) t0 = now;
+                        else if (now - t0 > e.peer.spin_limit_ns) { if (e.peer.err) atomicOr(e.peer.err, DEV_ERR_REDUCE_TIMEOUT); break; }
+                    }
+                }
+                const double c = __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
+                t = (q == 0) ? c : ((e.kind == EPI_MAX) ? fmax(t, c) : t + c);
+            }
+            red_s[j] = t;
+        }
+        __syncthreads();
+    } else if (e.peer.world > 1) {
         const int P = e.peer.world, r = e.peer.rank;
         const int slot = (int)(e.peer.seq % kMboxSlots);
         for (int idx = threadIdx.x; idx < count * P; idx += blockDim.x) {

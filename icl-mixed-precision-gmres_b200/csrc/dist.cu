@@ -121,7 +121,8 @@ struct mpg_dist {
     int64_t max_send_count = 0;            // longest send list (sizes the push grid)
     void* send_buf = nullptr;              // send_total doubles
     // peer-memory mailboxes for the in-kernel all-reduce (common.cuh PeerComm)
-    void* mbox_own = nullptr;              // [kMboxSlots][world][kMboxStride] doubles, then [kMboxSlots][world] u64 flags
+    void* mbox_own = nullptr;              // [kMboxSlots][world][kMboxStride] doubles, then [kMboxSlots][world] u64 flags, then the same shape in 16-byte
+                                           // flag-in-data words (common.cuh finish_reduction)
     void* mbox_map[kMaxPeers] = {nullptr}; // every rank's mailbox mapped into this process (own pointer for self)
     bool peer_ready = false;
     unsigned long long seq = 0;
@@ -145,7 +146,9 @@ struct mpg_dist {
     size_t inbox_data_bytes() const { return 2 * (size_t)std::max<int64_t>(n_halo, 1) * 8; }
     size_t inbox_bytes() const { return inbox_data_bytes() + sizeof(unsigned long long) * 2 * kMaxPeers; }
     size_t mbox_data_bytes() const { return sizeof(double) * (size_t)kMboxSlots * world * kMboxStride; }
-    size_t mbox_bytes() const { return mbox_data_bytes() + sizeof(unsigned long long) * (size_t)kMboxSlots * world; }
+    size_t mbox_flag_bytes() const { return sizeof(unsigned long long) * (size_t)kMboxSlots * world; }
+    size_t mbox_ll_bytes() const { return 16 * (size_t)kMboxSlots * world * kMboxStride; }   // flag-in-data words: 16 B per value
+    size_t mbox_bytes() const { return mbox_data_bytes() + mbox_flag_bytes() + mbox_ll_bytes(); }
 };
 
 extern "C" int mpg_nccl_unique_id(void* id128) {
@@ -523,7 +526,9 @@ Epi make_epi(mpg_ctx* ctx, int kind, void* p0, void* p1, double alpha, double be
         for (int q = 0; q < d->world; ++q) {
             e.peer.mbox[q] = static_cast<double*>(d->mbox_map[q]);
             e.peer.flag[q] = reinterpret_cast<unsigned long long*>(static_cast<char*>(d->mbox_map[q]) + d->mbox_data_bytes());
+            e.peer.ll[q] = reinterpret_cast<ulonglong2*>(static_cast<char*>(d->mbox_map[q]) + d->mbox_data_bytes() + d->mbox_flag_bytes());
         }
+        e.peer.use_ll = ctx->tune.dist_ll_reduce;
     } else {
         e.raw = ctx->red_raw;
     }

@@ -35,7 +35,7 @@ int cast_copy(mpg_ctx*, int64_t, const float*, float*);
 template <class T> int spmv(mpg_ctx*, const mpg_csr*, const T*, T, const T*, T, const T*, T*, float*, const T* rowscale, int part);
 template <class T> int pack_create(mpg_ctx*, const mpg_csr*, const T*, mpg_packed**);
 void pack_free(mpg_packed*);
-template <class T> int spmv_packed(mpg_ctx*, const mpg_packed*, T, const T*, T, const T*, T*, float*, const T*, int, const HaloWait*, const T* xadd);
+template <class T> int spmv_packed(mpg_ctx*, const mpg_packed*, T, const T*, T, const T*, T*, float*, const T*, int, const HaloWait*, const T* xadd, const PushArgs* push = nullptr);
 int axpy_host(mpg_ctx*, int64_t, float, const float*, float*);
 int axpy_host(mpg_ctx*, int64_t, double, const double*, double*);
 int gdmv_host(mpg_ctx*, int64_t, float, const float*, const float*, float, float*);

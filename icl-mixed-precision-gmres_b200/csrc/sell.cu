@@ -265,12 +265,19 @@ template <class T, bool HAS_REM, bool NA, int UN>
 __global__ void __launch_bounds__(256, UN == 4 ? 5 : (sizeof(T) == 8 ? 6 : 8)) spmv_sell_kernel(int nlanes, int nslices, const int64_t* __restrict__ slice_off, const int* __restrict__ sinds,
                                                          const T* __restrict__ svals, const T* __restrict__ x, T alpha, T beta, const T* y_in,
                                                          T* y_out, float* out32, const T* __restrict__ rowscale, const int* __restrict__ slice_list,
-                                                         const int* __restrict__ vout, T* __restrict__ partial, const T* xadd, const __grid_constant__ HaloWait hw) {
+                                                         const int* __restrict__ vout, T* __restrict__ partial, const T* xadd, const __grid_constant__ HaloWait hw,
+                                                         const __grid_constant__ PushArgs push, int npush) {
     pdl_trigger_early(nlanes);
     pdl_wait();
+    // multi-GPU: the first npush CTAs send this rank's boundary rows of x to the neighbours (straight into the halo tail of THEIR copy of
+    // the same basis column) while the slices without halo columns are multiplied; the CTAs of the boundary slices, last in the grid,
+    // wait for the neighbours' flags.  The NVLink round trips of the push hide under the interior product instead of sitting at the
+    // end of the Arnoldi tail kernel.
+    if ((int)blockIdx.x < npush) { halo_push_block<T>(push, (int)blockIdx.x, x, nullptr); return; }
+    const int bx = (int)blockIdx.x - npush;
     // CTA-uniform: does this CTA hold a slice position that reads halo columns?
-    if (hw.npeers > 0 && (int)((((int64_t)blockIdx.x + 1) * blockDim.x - 1) >> 5) >= hw.wait_from) halo_wait_block(hw);
-    const int ws = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (hw.npeers > 0 && (int)((((int64_t)bx + 1) * blockDim.x - 1) >> 5) >= hw.wait_from) halo_wait_block(hw);
+    const int ws = (int)(((int64_t)bx * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
     if (ws >= nslices) return;
     const int s = slice_list ? __ldg(slice_list + ws) : ws;
     const int64_t off = __ldg(slice_off + s);
@@ -547,7 +554,7 @@ bool pack_matches(const mpg_packed* P, const mpg_csr* A, int tsize) {
 
 template <class T>
 int spmv_packed(mpg_ctx* ctx, const mpg_packed* P, T alpha, const T* x, T beta, const T* y_in, T* y_out, float* out32, const T* rowscale, int part,
-                const HaloWait* hw_in, const T* xadd) {
+                const HaloWait* hw_in, const T* xadd, const PushArgs* push_in) {
     const mpg_sell_plan* p = P->plan;
     const mpg_csr* A = P->A;
     if (part != SPMV_ALL && !p->slice_list) {
@@ -571,8 +578,12 @@ int spmv_packed(mpg_ctx* ctx, const mpg_packed* P, T alpha, const T* x, T beta, 
         // x always through L1 - the no-allocate hint on the gathers also demotes x in L2 and doubles the DRAM traffic
         const int variant = ctx->tune.sell_variant >= 0 ? ctx->tune.sell_variant : (p->mode == MODE_SIGMA ? 2 : 0);
         const int block = ctx->tune.sell_block > 0 ? std::min(ctx->tune.sell_block, 256) : 128;
-        const int grid = (int)cdiv((int64_t)s_count * 32, block);
-        void (*kern)(int, int, const int64_t*, const int*, const T*, const T*, T, T, const T*, T*, float*, const T*, const int*, const int*, T*, const T*, const HaloWait);
+        PushArgs pa;
+        if (push_in) pa = *push_in;
+        const int npush = push_in ? pa.npeers * pa.bpp : 0;
+        const int grid = (int)cdiv((int64_t)s_count * 32, block) + npush;
+        void (*kern)(int, int, const int64_t*, const int*, const T*, const T*, T, T, const T*, T*, float*, const T*, const int*, const int*, T*, const T*, const HaloWait,
+                     const PushArgs, int);
         switch ((variant & 3) * 2 + (p->has_rem ? 1 : 0)) {
             case 0: kern = spmv_sell_kernel<T, false, false, 2>; break;
             case 1: kern = spmv_sell_kernel<T, true, false, 2>; break;
@@ -585,7 +596,7 @@ int spmv_packed(mpg_ctx* ctx, const mpg_packed* P, T alpha, const T* x, T beta, 
         }
         MPG_CUDA(ctx, launch_pdl(ctx, (int64_t)A->nrows, kern, grid, block, 0, p->nlanes, s_count, (const int64_t*)p->slice_off, (const int*)p->sinds,
                                  static_cast<const T*>(P->svals), x, alpha, beta, y_in, y_out, out32, rowscale, list, (const int*)p->vout,
-                                 static_cast<T*>(p->partial), xadd, hw));
+                                 static_cast<T*>(p->partial), xadd, hw, pa, npush));
         MPG_CHECK_LAUNCH(ctx);
     }
     if (p->nsplit > 0 && part != SPMV_INTERIOR) {
@@ -595,8 +606,8 @@ int spmv_packed(mpg_ctx* ctx, const mpg_packed* P, T alpha, const T* x, T beta, 
     }
     return MPG_OK;
 }
-template int spmv_packed<float>(mpg_ctx*, const mpg_packed*, float, const float*, float, const float*, float*, float*, const float*, int, const HaloWait*, const float*);
-template int spmv_packed<double>(mpg_ctx*, const mpg_packed*, double, const double*, double, const double*, double*, float*, const double*, int, const HaloWait*, const double*);
+template int spmv_packed<float>(mpg_ctx*, const mpg_packed*, float, const float*, float, const float*, float*, float*, const float*, int, const HaloWait*, const float*, const PushArgs*);
+template int spmv_packed<double>(mpg_ctx*, const mpg_packed*, double, const double*, double, const double*, double*, float*, const double*, int, const HaloWait*, const double*, const PushArgs*);
 
 int scan_i32(mpg_ctx* ctx, int64_t n, const int* in, int* out) {
     scan_kernel<int, int><<<1, 1024, 0, ctx->stream>>>(n, in, out);
@@ -618,7 +629,7 @@ int scan_i32(mpg_ctx* ctx, int64_t n, const int* in, int* out) {
     }                                                                                                                              \
     extern "C" int mpg_spmv_packed_##SFX(mpg_ctx* ctx, const mpg_packed* P, T alpha, const T* x, T beta, T* y) {                  \
         MPG_REQUIRE(ctx, P && x && y && P->tsize == (int)sizeof(T), "spmv_packed: null argument or wrong precision");             \
-        return mpg::spmv_packed<T>(ctx, P, alpha, x, beta, y, y, nullptr, nullptr, mpg::SPMV_ALL, nullptr, nullptr);              \
+        return mpg::spmv_packed<T>(ctx, P, alpha, x, beta, y, y, nullptr, nullptr, mpg::SPMV_ALL, nullptr, nullptr, nullptr);              \
     }
 MPG_DEF_PACK(f32, float)
 MPG_DEF_PACK(f64, double)

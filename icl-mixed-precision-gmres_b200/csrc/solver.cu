@@ -50,7 +50,7 @@ template <class T> int pack_update(mpg_ctx*, mpg_packed*, const T*);
 void pack_free(mpg_packed*);
 bool pack_matches(const mpg_packed*, const mpg_csr*, int tsize);
 int pack_boundary_slices(const mpg_packed*);
-template <class T> int spmv_packed(mpg_ctx*, const mpg_packed*, T, const T*, T, const T*, T*, float*, const T*, int, const HaloWait* = nullptr, const T* xadd = nullptr);
+template <class T> int spmv_packed(mpg_ctx*, const mpg_packed*, T, const T*, T, const T*, T*, float*, const T*, int, const HaloWait* = nullptr, const T* xadd = nullptr, const PushArgs* push = nullptr);
 template <class T> int ilu_jacobi_apply_t(mpg_ctx*, mpg_ilu_jacobi*, T*);
 template <class T> int halo_exchange(mpg_ctx*, T*);
 template <class T> int halo_begin(mpg_ctx*, T*);
@@ -306,6 +306,9 @@ int run_cycle(mpg_ctx* ctx, const mpg_gmres_params& p, Policy& pol, Workspace* w
     MPG_TRY(fill_host(ctx, 1, beta, s));
 
     int64_t pushed_col = -1;   // fused halo: basis column whose boundary rows are already on their way to the neighbours
+    // where the fused push rides: in the head of the SpMV kernel that consumes the column (stencil halos: its round trips hide under
+    // the interior product) or in the Arnoldi tail that produces it (all-to-all halos, where nearly every slice needs the halo at once)
+    const bool push_in_spmv = ctx->tune.dist_push_in_spmv && P && pack_boundary_slices(P) <= 16384 && ctx->tune.dist_spmv_one_launch;
     // one Arnoldi step, enqueued asynchronously
     auto enqueue_iteration = [&](int64_t kk, double* resid_host) -> int {
         // w = A v_k ; M(w)            gmres.cpp:98-102,210-215
@@ -321,12 +324,16 @@ int run_cycle(mpg_ctx* ctx, const mpg_gmres_params& p, Policy& pol, Workspace* w
         if (direct) {
             // v_k's boundary rows were pushed by the Arnoldi tail that produced v_k; the first vector of a cycle (and an unfused tail)
             // is pushed here.  No wait-and-move launch: the SpMV on the slices that read halo columns waits for the flags itself.
-            if (pushed_col != kk) MPG_TRY(halo_push_direct<T>(ctx, vk, kk));
+            const bool one_launch = P && pack_boundary_slices(P) <= 16384 && ctx->tune.dist_spmv_one_launch;
+            PushArgs spa;
+            const bool push_here = one_launch && push_in_spmv && pushed_col != kk;
+            if (push_here) MPG_TRY(halo_direct_args<T>(ctx, kk, &spa));   // the SpMV kernel itself sends v_k's boundary rows first
+            else if (pushed_col != kk) MPG_TRY(halo_push_direct<T>(ctx, vk, kk));
             HaloWait hw;
             MPG_TRY(halo_wait_args(ctx, &hw));
-            if (P && pack_boundary_slices(P) <= 16384 && ctx->tune.dist_spmv_one_launch) {
-                // ONE launch: the slices without halo columns first, the CTAs of the others (last in the grid) wait for the flags
-                MPG_TRY(spmv_packed<T>(ctx, P, T(1), vk, T(0), w, w, nullptr, rowscale, SPMV_ORDERED, &hw));
+            if (one_launch) {
+                // ONE launch: (push CTAs,) the slices without halo columns, then the CTAs of the others (last in the grid), which wait for the flags
+                MPG_TRY(spmv_packed<T>(ctx, P, T(1), vk, T(0), w, w, nullptr, rowscale, SPMV_ORDERED, &hw, nullptr, push_here ? &spa : nullptr));
             } else if (P && pack_boundary_slices(P) <= 16384) {
                 MPG_TRY(spmv_packed<T>(ctx, P, T(1), vk, T(0), w, w, nullptr, rowscale, SPMV_INTERIOR));
                 MPG_TRY(spmv_packed<T>(ctx, P, T(1), vk, T(0), w, w, nullptr, rowscale, SPMV_BOUNDARY, &hw));
@@ -357,9 +364,10 @@ int run_cycle(mpg_ctx* ctx, const mpg_gmres_params& p, Policy& pol, Workspace* w
             // orthogonalise, then ONE launch for V(:,k+1) = w / h(k+1,k) and the rotations (independent of each other)
             MPG_TRY(add_vector<T>(ctx, p.orth, n, kk, V, ldv, w, h + (size_t)kk * ldh, scratch, true));
             PushArgs pa;
-            if (direct) { MPG_TRY(halo_direct_args<T>(ctx, kk + 1, &pa)); pushed_col = kk + 1; }
+            const bool tail_push = direct && !push_in_spmv;
+            if (tail_push) { MPG_TRY(halo_direct_args<T>(ctx, kk + 1, &pa)); pushed_col = kk + 1; }
             return arnoldi_tail<T>(ctx, n, scratch + (kk + 1), w, V + (size_t)(kk + 1) * ldv, kk, h, ldh, cs, sn, s, ws->hist + kk, resid_host,
-                                   direct ? &pa : nullptr);
+                                   tail_push ? &pa : nullptr);
         }
         MPG_TRY(add_vector<T>(ctx, p.orth, n, kk, V, ldv, w, h + (size_t)kk * ldh, scratch, false));
         // rot / rotg / rot             gmres.cpp:106-110,219-222 ; |s(k+1)| stays on the device

@@ -83,9 +83,9 @@ for spec, rlen, orth, peer, split in CASES:
     r21 = ctx.gmres(Al, part.vals, bl, xl1, **kw)
     ctx.set_tuning("dist_fuse_halo", 1)
     overlap_ok = overlap_ok and bool(torch.equal(xl, xl1)) and np.array_equal(r2["hist_inner"], r21["hist_inner"])
-    # fused halo with the interior and boundary slices in two launches instead of one, and with the programmatic-dependent-launch
-    # attribute on every launch (late trigger): same bits
-    for knob, val, back in (("dist_spmv_one_launch", 0, 1), ("use_pdl", 2, 1)):
+    # fused halo with the interior and boundary slices in two launches instead of one, with the push in the Arnoldi tail instead of the
+    # head of the SpMV kernel, with the fence + flag all-reduce protocol instead of flag-in-data words, and with the programmatic-dependent-launch attribute on every launch (late trigger): same bits
+    for knob, val, back in (("dist_spmv_one_launch", 0, 1), ("dist_push_in_spmv", 0, 1), ("dist_ll_reduce", 0, 1), ("use_pdl", 2, 1)):
         ctx.set_tuning(knob, val)
         xl2 = torch.zeros(part.n_local, dtype=torch.float64, device=dev)
         r22 = ctx.gmres(Al, part.vals, bl, xl2, **kw)
