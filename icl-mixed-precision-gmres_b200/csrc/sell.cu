@@ -471,7 +471,7 @@ int sell_plan_get(mpg_ctx* ctx, const mpg_csr* A, const mpg_sell_plan** out) {
     if (Am->sell_tried) { *out = Am->sell; return MPG_OK; }
     Am->sell_tried = 1;
     if (A->nrows == 0 || A->nnz == 0) return MPG_OK;
-    static unsigned long long next_uid = 0;
+    static std::atomic<unsigned long long> next_uid{0};   // plans are created from any thread, any context
     mpg_sell_plan* p = new mpg_sell_plan();
     struct Guard { mpg_sell_plan* p; ~Guard() { if (p) sell_plan_free(p); } } guard{p};   // error paths release what was built so far
     p->uid = ++next_uid;
