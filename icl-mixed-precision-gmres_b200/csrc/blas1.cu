@@ -196,7 +196,7 @@ static int* tuning_slot(mpg_ctx* ctx, const std::string& k) {
     MPG_KNOB(use_pdl); MPG_KNOB(pdl_max_rows); MPG_KNOB(fuse_tail); MPG_KNOB(vpass_stages); MPG_KNOB(fuse_min_cols);
     MPG_KNOB(vdirect_max_cols_a); MPG_KNOB(vdirect_max_cols_b); MPG_KNOB(vrow_max_cols); MPG_KNOB(vrow_max_cols_a); MPG_KNOB(gemvt_rb);
     MPG_KNOB(gemvt_rows_per_block); MPG_KNOB(passA_rb); MPG_KNOB(cgs2_fused); MPG_KNOB(vpass_serpentine); MPG_KNOB(gemvn_ctas_per_sm);
-    MPG_KNOB(red_ctas_per_sm); MPG_KNOB(residual_packed); MPG_KNOB(values_static); MPG_KNOB(spmv_sigma); MPG_KNOB(mgs_fused);
+    MPG_KNOB(red_ctas_per_sm); MPG_KNOB(residual_packed); MPG_KNOB(values_static); MPG_KNOB(spmv_sigma); MPG_KNOB(sell_lpt); MPG_KNOB(mgs_fused);
     MPG_KNOB(dist_fuse_halo); MPG_KNOB(spin_limit_ms); MPG_KNOB(lookahead); MPG_KNOB(sell_variant); MPG_KNOB(sell_block); MPG_KNOB(trace);
     MPG_KNOB(dist_spmv_one_launch); MPG_KNOB(dist_push_in_spmv); MPG_KNOB(dist_ll_reduce); MPG_KNOB(host_overlap); MPG_KNOB(host_threads); MPG_KNOB(host_overlap_min_nnz);
 #undef MPG_KNOB

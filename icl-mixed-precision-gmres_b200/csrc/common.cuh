@@ -51,6 +51,8 @@ struct Tuning {
     int residual_packed = 1;  // solver: fp64 outer residual r = b - A x on a packed fp64 copy of the matrix (0: CSR kernel on the caller's arrays)
     int values_static = 0;    // solver: 1 = the caller promises not to change matrix VALUES between solves on the same mpg_csr / value pointers,
                               // so the packed copies are built once (the reference builds SparseMatrix<float>(A) once, outside its solve timer)
+    int sell_lpt = 1;         // SELL-C-sigma plans, launch order of the slices (read when the plan is built): 0 window order, 1 slices that would miss
+                              // their start deadline in window order move to the front, 2 all slices longest first (sell.cu sell_plan_get)
     int spmv_sigma = 1;       // packed operator: sort rows by length inside windows (SELL-C-sigma) when the plain slices pad too much
     int mgs_fused = 1;        // MGS: pairwise fused passes (w -= h_j v_j ; h_{j+1} = v_{j+1}.w in one kernel) instead of k+1 x {dot, naxpy}
     int dist_fuse_halo = 1;   // multi-GPU: halo gather-and-push rides in the Arnoldi tail kernel, the wait in the boundary-slice SpMV

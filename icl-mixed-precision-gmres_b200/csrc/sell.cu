@@ -366,8 +366,9 @@ struct mpg_sell_plan {
     int64_t total = 0;             // padded element count
     int64_t* slice_off = nullptr;  // [nslices + 1]
     int* sinds = nullptr;          // [total]
-    int* slice_list = nullptr;     // partitioned matrices: slices without halo columns first
+    int* slice_list = nullptr;     // partitioned matrices: slices without halo columns first (SIGMA: longest first inside each part)
     int n_interior = 0;
+    int* order = nullptr;          // SIGMA: all slices, longest first (launch order of an undivided product); PLAIN: null = natural order
     int has_rem = 0;               // some slice length is not a multiple of G
     // SIGMA
     int* vstart = nullptr;         // [nlanes] sorted order
@@ -394,7 +395,7 @@ namespace mpg {
 
 void sell_plan_free(mpg_sell_plan* p) {
     if (!p) return;
-    pool_free(p->slice_off); pool_free(p->sinds); pool_free(p->slice_list);
+    pool_free(p->slice_off); pool_free(p->sinds); pool_free(p->slice_list); pool_free(p->order);
     pool_free(p->vstart); pool_free(p->vlen); pool_free(p->vout); pool_free(p->split_rows); pool_free(p->chunk_base); pool_free(p->partial);
     delete p;
 }
@@ -490,6 +491,52 @@ int sell_plan_get(mpg_ctx* ctx, const mpg_csr* A, const mpg_sell_plan** out) {
     const int wgrid = (int)cdiv((int64_t)p->nslices * 32, 256);
     sell_fill_inds_kernel<<<wgrid, 256, 0, ctx->stream>>>(lane_src(A, p), p->nslices, A->nrows, A->inds, p->slice_off, p->sinds, p->slice_list);
     MPG_CHECK_LAUNCH(ctx);
+    // SIGMA plans choose the LAUNCH ORDER of their slices.  Slice lengths range from 1 to CHUNK positions and a warp walks its slice alone:
+    // under load one step of 16 gathers per lane takes ~10 us (the kernel is L1TEX / L2-sector bound, profiles/r02p_ncu_spmv_powerlaw.md),
+    // so a CHUNK-long slice lives for 16 such steps whatever the size of the matrix.  In window order the long slices of the last windows
+    // start when the grid is nearly drained and the product ends on a tail of a few lonely warps (sm__warps_active 52 % of a theoretical
+    // 62 %); on the slab of an 8-GPU run that tail is as long as the whole product.  With M resident warps and W slice-positions of work
+    // a slice of length L occupies its warp for a fraction L M / W of the kernel, so it has to START before 1 - L M / W of the grid has
+    // been handed out.  sell_lpt = 1 (default): slices whose place in window order misses that deadline (with a 1.5x margin) move to the
+    // front, longest first; everything else keeps window order - that keeps long (streaming) and short (latency-bound) slices mixed, which
+    // a full sort does not (measured: longest-first over ALL slices gains 3 % in fp32 and LOSES 6 % in fp64 on 8 M rows).  2: full sort.
+    // 0: window order.  Results do not depend on the order (every lane owns its row or piece).
+    const int lpt = p->mode == MODE_SIGMA ? ctx->tune.sell_lpt : 0;
+    std::vector<int64_t> off_h;
+    if (lpt) {
+        off_h.resize((size_t)p->nslices + 1);
+        MPG_CUDA(ctx, cudaMemcpyAsync(off_h.data(), p->slice_off, sizeof(int64_t) * off_h.size(), cudaMemcpyDeviceToHost, ctx->stream));
+        MPG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    const auto len_of = [&](int sl) { return (int)((off_h[(size_t)sl + 1] - off_h[(size_t)sl]) / SLICE); };
+    // stable counting sort of a list of slices by length, descending
+    const auto by_length = [&](int* first, int* last) {
+        if (last - first < 2) return;
+        int maxl = 0;
+        for (int* q = first; q < last; ++q) maxl = std::max(maxl, len_of(*q));
+        std::vector<int> start((size_t)maxl + 2, 0), tmp(first, last);
+        for (int sl : tmp) ++start[(size_t)(maxl - len_of(sl)) + 1];
+        for (size_t b = 1; b < start.size(); ++b) start[b] += start[b - 1];
+        for (int sl : tmp) first[start[(size_t)(maxl - len_of(sl))]++] = sl;
+    };
+    const auto longest_first = [&](int* first, int* last) {
+        const int64_t cnt = last - first;
+        if (!lpt || cnt < 2) return;
+        if (lpt >= 2) { by_length(first, last); return; }
+        double work = 0.0;
+        for (int* q = first; q < last; ++q) work += len_of(*q);
+        if (work <= 0.0) return;
+        const double warps = 40.0 * ctx->num_sms;   // resident warps of the UN = 4 kernel (launch bounds: 1280 threads per SM)
+        std::vector<int> urgent, rest;
+        for (int64_t i = 0; i < cnt; ++i) {
+            const int sl = first[i];
+            const double deadline = 1.0 - 1.5 * len_of(sl) * warps / work;
+            ((double)i / (double)cnt > deadline ? urgent : rest).push_back(sl);
+        }
+        by_length(urgent.data(), urgent.data() + urgent.size());
+        std::copy(urgent.begin(), urgent.end(), first);
+        std::copy(rest.begin(), rest.end(), first + urgent.size());
+    };
     if (slab) {
         // local slab of a partitioned matrix: order the slices [no halo column | some halo column]
         std::vector<int> flag((size_t)p->nslices), list((size_t)p->nslices);
@@ -499,7 +546,17 @@ int sell_plan_get(mpg_ctx* ctx, const mpg_csr* A, const mpg_sell_plan** out) {
         for (int s = 0; s < p->nslices; ++s) if (!flag[(size_t)s]) list[(size_t)ni++] = s;
         p->n_interior = ni;
         for (int s = 0; s < p->nslices; ++s) if (flag[(size_t)s]) list[(size_t)ni++] = s;
+        longest_first(list.data(), list.data() + p->n_interior);
+        longest_first(list.data() + p->n_interior, list.data() + p->nslices);
         MPG_CUDA(ctx, cudaMemcpyAsync(p->slice_list, list.data(), sizeof(int) * list.size(), cudaMemcpyHostToDevice, ctx->stream));
+        MPG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    if (lpt) {
+        std::vector<int> all((size_t)p->nslices);
+        for (int s = 0; s < p->nslices; ++s) all[(size_t)s] = s;
+        longest_first(all.data(), all.data() + p->nslices);
+        MPG_CUDA(ctx, pool_alloc(ctx, &p->order, sizeof(int) * all.size()));
+        MPG_CUDA(ctx, cudaMemcpyAsync(p->order, all.data(), sizeof(int) * all.size(), cudaMemcpyHostToDevice, ctx->stream));
         MPG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
     guard.p = nullptr;
@@ -563,7 +620,7 @@ int spmv_packed(mpg_ctx* ctx, const mpg_packed* P, T alpha, const T* x, T beta, 
     }
     const int s_first = part == SPMV_BOUNDARY ? p->n_interior : 0;
     const int s_count = part == SPMV_INTERIOR ? p->n_interior : p->nslices - s_first;
-    const int* list = part == SPMV_ALL ? nullptr : p->slice_list + s_first;   // ORDERED: the whole list, interior slices first
+    const int* list = part == SPMV_ALL ? p->order : p->slice_list + s_first;   // ORDERED: the whole list, interior slices first; ALL: longest first (SIGMA) or natural order
     // algorithmic bytes: the CSR figure of SURVEY.md §8d (padding and per-lane destinations the packed layout reads on top are not counted)
     const double n_ = A->nrows, s_ = sizeof(T);
     const double bytes = (double)A->nnz * (s_ + 4) + 4 * (n_ + 1) + n_ * s_ + (y_out ? n_ * s_ : 0) + (beta != T(0) ? n_ * s_ : 0) + (out32 ? 4 * n_ : 0) +

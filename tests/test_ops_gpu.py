@@ -472,6 +472,39 @@ def test_spmv_packed_sigma(ctx, g, orc, spec, dt):
     lens = np.diff(rm)
     assert (lens <= 256).sum() > 0.9 * n and (lens > 256).sum() > 0   # the case really has both kinds of rows
 
+
+@pytest.mark.parametrize("spec", ["powerlaw:5000", "powerlaw:300000"])
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_spmv_packed_sigma_launch_order_does_not_change_a_bit(ctx, g, orc, spec, dt):
+    """SIGMA plans launch their slices longest first (knob sell_lpt, read when the plan is built): a scheduling decision only -
+    y, the residual epilogue and the packed arrays are bit-identical to the window-order plan"""
+    import torch
+    rm, ind, val = orc.gen(spec)
+    n = len(rm) - 1
+    r = _rng(n + 5)
+    x, y, v = r.standard_normal(n).astype(dt), r.standard_normal(n).astype(dt), val.astype(dt)
+    vd, xd = dev(v), dev(x)
+    outs = []
+    for lpt in (1, 0):
+        ctx.set_tuning("sell_lpt", lpt)
+        try:
+            A = g.CSR(ctx, dev(rm), dev(ind))
+            P = g.Packed(ctx, A, vd)
+            assert P and P.rows()[0] == 1
+            y0 = dev(np.full(n, np.nan, dt)); ctx.spmv_packed(P, 1.0, xd, 0.0, y0)
+            y1 = dev(y); ctx.spmv_packed(P, -0.5, xd, 2.0, y1)
+            outs.append((y0, y1, P.arrays()[1], P.arrays()[2]))
+        finally:
+            ctx.set_tuning("sell_lpt", 1)
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    np.testing.assert_array_equal(outs[0][2], outs[1][2])
+    np.testing.assert_array_equal(outs[0][3], outs[1][3])
+    yo = orc.spmv(rm, ind, v, 1.0, x, 0.0, np.zeros(n, dt))
+    import scipy.sparse as sp
+    absrow = abs(sp.csr_matrix((val, ind, rm), shape=(n, n))) @ np.abs(x.astype(np.float64))
+    assert np.all(np.abs(host(outs[0][0]) - yo) <= 2 * summation_bound(absrow, int(np.diff(rm).max()), dt))
+
+
 @pytest.mark.parametrize("spec", ["lap2d:1", "lap2d:23", "cd27:1", "cd27:9", "powerlaw:5000", "powerlaw:5000:11:2:8"])
 def test_row_range_generators_equal_rows_of_the_global_matrix(ctx, g, orc, spec):
     """mpg_gen_slab_*: rows [lo, hi) generated alone == the same rows cut out of the oracle's global matrix, bit for bit (global
