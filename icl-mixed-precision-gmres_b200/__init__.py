@@ -6,9 +6,10 @@ a ctypes binding that passes torch CUDA tensor pointers through the C ABI.  Ther
 importing works anywhere, but every compute call needs the CUDA library and a CUDA device.
 """
 from .binding import (Context, CSR, Packed, IluJacobi, GmresParams, GmresStats, MODES, ORTHS, CONVS, PRECS, load_library, library_path,
-                      exported_symbols, header_symbols, MpgError, read_matrix_market, read_matrix_market_vector)
+                      exported_symbols, header_symbols, MpgError, read_matrix_market, read_matrix_market_vector,
+                      read_matrix_market_slab)
 
 from . import dist  # noqa: E402,F401  (multi-GPU plumbing: partition builder + DistContext)
 
 __all__ = ["dist", "Context", "CSR", "Packed", "IluJacobi", "GmresParams", "GmresStats", "MODES", "ORTHS", "CONVS", "PRECS", "load_library",
-           "library_path", "exported_symbols", "header_symbols", "MpgError", "read_matrix_market", "read_matrix_market_vector"]
+           "library_path", "exported_symbols", "header_symbols", "MpgError", "read_matrix_market", "read_matrix_market_vector", "read_matrix_market_slab"]

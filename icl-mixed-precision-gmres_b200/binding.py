@@ -98,6 +98,34 @@ def read_matrix_market(path):
     return rm, ind, val
 
 
+def read_matrix_market_slab(path, lo, hi, want_global_rowmap=False):
+    """rows [lo, hi) of the canonical CSR of a MatrixMarket file (mpg_mm_read_slab_host: streamed, only the slab is ever held) ->
+    (n, nnz_global, row_map_local int32[hi-lo+1], inds int32 (GLOBAL columns), vals float64[, row_map_global int32[n+1]]).
+    hi < 0: to the last row.  Equal to rows [lo, hi) of read_matrix_market bit for bit."""
+    import numpy as np
+    L = load_library()
+    n, m, nnzg, nnzl = C.c_int(), C.c_int(), C.c_int64(), C.c_int64()
+    prm, pin, pv, pg = C.POINTER(C.c_int)(), C.POINTER(C.c_int)(), C.POINTER(C.c_double)(), C.POINTER(C.c_int)()
+    err = C.create_string_buffer(256)
+    rc = L.mpg_mm_read_slab_host(str(path).encode(), C.c_int64(lo), C.c_int64(hi), C.byref(n), C.byref(m), C.byref(nnzg), C.byref(nnzl), C.byref(prm),
+                                 C.byref(pin), C.byref(pv), C.byref(pg) if want_global_rowmap else None, err, 256)
+    if rc != 0:
+        raise MpgError(err.value.decode() or f"mpg_mm_read_slab_host failed ({rc})")
+    try:
+        hi_eff = m.value if hi < 0 else hi
+        rm = np.ctypeslib.as_array(prm, shape=(hi_eff - lo + 1,)).copy()
+        ind = np.ctypeslib.as_array(pin, shape=(max(nnzl.value, 1),))[:nnzl.value].copy()
+        val = np.ctypeslib.as_array(pv, shape=(max(nnzl.value, 1),))[:nnzl.value].copy()
+        out = (m.value, nnzg.value, rm, ind, val)
+        if want_global_rowmap:
+            out = out + (np.ctypeslib.as_array(pg, shape=(m.value + 1,)).copy(),)
+    finally:
+        L.mpg_host_free(prm); L.mpg_host_free(pin); L.mpg_host_free(pv)
+        if want_global_rowmap:
+            L.mpg_host_free(pg)
+    return out
+
+
 def read_matrix_market_vector(path, col=0):
     """column `col` of a MatrixMarket array / coordinate file as a float64 numpy array (mpg_mm_read_vector_host = the reference's
     LoadVector, LoadMatrix.hpp:156-233).  Raises MpgError with the reference's exception text."""

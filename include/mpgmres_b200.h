@@ -322,6 +322,13 @@ int mpg_mm_read_host(const char* path, int* nrows, int* ncols, int64_t* nnz, int
 /* LoadVector<S>(file, col), LoadMatrix.hpp:156-233 (--bpath, gmres_perf_test.cpp:417-421): column `col` of an array or
  * coordinate MatrixMarket file as n doubles (malloc'ed, release with mpg_host_free) */
 int mpg_mm_read_vector_host(const char* path, int col, int64_t* n, double** vals_host, char* errbuf, int errlen);
+/* Partition-aware ingest: rows [lo, hi) of the canonical CSR of a MatrixMarket file, read WITHOUT ever holding the other
+ * rows - what one rank of a multi-GPU run ingests (hi < 0: to the last row).  The file is streamed in blocks; memory = O(entries of the
+ * slab).  Local row map (row_map_local[0] = 0), GLOBAL column indices (mpg_dist_setup renumbers them), nnz of the slab and of the whole
+ * matrix.  row_map_global_host may be NULL; otherwise it receives the global row map (n + 1 ints, for mpg_partition_bounds_nnz; lo = hi = 0
+ * reads nothing else).  Equal to rows [lo, hi) of mpg_mm_read_host bit for bit; same error texts. */
+int mpg_mm_read_slab_host(const char* path, int64_t lo, int64_t hi, int* nrows, int* ncols, int64_t* nnz_global, int64_t* nnz_local,
+                          int** row_map_local_host, int** inds_host, double** vals_host, int** row_map_global_host, char* errbuf, int errlen);
 void mpg_host_free(void* p);
 
 /* ---- 1-D row partition (new functionality, host-side, bit-exact vs the oracle) ------------- */

@@ -95,3 +95,93 @@ def test_live_reference_vector_loader_agrees(g):
         name, col = key.split(":")
         path = os.path.join(HERE, "golden", "mmvec", name)
         np.testing.assert_array_equal(g.read_matrix_market_vector(path, int(col)), oracle_ref.load_vector(path, int(col)))
+
+
+def _slabs(n):
+    cuts = sorted({0, n, n // 3, (2 * n) // 3, min(1, n), max(n - 1, 0), n // 2})
+    return list(zip(cuts[:-1], cuts[1:])) + [(0, 0), (n, n), (0, n), (0, -1)]
+
+
+@pytest.mark.parametrize("name", sorted(EXP))
+def test_slab_loader_equals_rows_of_the_full_read(g, name):
+    """mpg_mm_read_slab_host (partition-aware ingest): rows [lo, hi) read alone == the same rows of the canonical CSR
+    the reference's LoadMatrix builds (explicit zero diagonals, mirrored symmetric entries, unmerged duplicates in stable order), bit
+    for bit; the global row map it can return == the full one; the slabs of a partition tile the matrix"""
+    path = os.path.join(HERE, "golden", "mm", name)
+    e = EXP[name]
+    rm, ind = np.array(e["row_map"], np.int32), np.array(e["inds"], np.int32)
+    val = np.array([float.fromhex(v) for v in e["vals"]])
+    n = len(rm) - 1
+    for lo, hi in _slabs(n):
+        n_, nnzg, rl, il, vl, rg = g.read_matrix_market_slab(path, lo, hi, want_global_rowmap=True)
+        h = n if hi < 0 else hi
+        assert n_ == n and nnzg == len(ind)
+        np.testing.assert_array_equal(rg, rm)
+        np.testing.assert_array_equal(rl, rm[lo:h + 1] - rm[lo])
+        np.testing.assert_array_equal(il, ind[rm[lo]:rm[h]])
+        np.testing.assert_array_equal(vl, val[rm[lo]:rm[h]])
+    # without the global row map
+    n_, nnzg, rl, il, vl = g.read_matrix_market_slab(path, 1 if n > 1 else 0, n)
+    np.testing.assert_array_equal(il, ind[rm[1 if n > 1 else 0]:])
+
+
+def test_slab_loader_streams_in_blocks_and_feeds_the_partition(g, orc, tmp_path):
+    """a file larger than one 16 MiB block of the streaming tokenizer (tokens must never be torn at a block boundary), entries shuffled,
+    mixed white space: 4 ranks read their nnz-balanced slabs alone; together they are the full canonical CSR, and the split points
+    computed from the global row map the slab reader returns are the oracle's"""
+    rm, ind, val = orc.gen("cd27:40")      # 64 000 rows, 1.6 M nonzeros -> ~ 40 MB of text
+    n = len(rm) - 1
+    rows = np.repeat(np.arange(n), np.diff(rm))
+    perm = np.random.default_rng(5).permutation(len(ind))
+    p = tmp_path / "big.mtx"
+    with open(p, "w") as f:
+        f.write("%%MatrixMarket matrix coordinate real general\n% a comment line\n%another\n")
+        f.write(f"{n} {n} {len(ind)}\n")
+        seps = ["\n", " \n", "\t\n", "\n\n"]
+        chunks = []
+        for k, e in enumerate(perm):
+            chunks.append(f"{rows[e] + 1}  {ind[e] + 1}\t{val[e]:.17g}{'' if k % 9 else '   '}{seps[k % 4]}")
+        f.write("".join(chunks))
+    assert os.path.getsize(p) > (1 << 24) + (1 << 20)
+    full = g.read_matrix_market(p)
+    np.testing.assert_array_equal(full[0], rm); np.testing.assert_array_equal(full[1], ind); np.testing.assert_array_equal(full[2], val)
+    _, nnzg, _, _, _, rg = g.read_matrix_market_slab(p, 0, 0, want_global_rowmap=True)
+    np.testing.assert_array_equal(rg, rm)
+    assert nnzg == len(ind)
+    P = 4
+    bnd = g.dist.bounds_nnz(rg, P)
+    np.testing.assert_array_equal(bnd, orc.partition_bounds_nnz(rm, P))
+    got_ind, got_val, got_rm = [], [], [0]
+    for r in range(P):
+        _, _, rl, il, vl = g.read_matrix_market_slab(p, int(bnd[r]), int(bnd[r + 1]))
+        got_ind.append(il); got_val.append(vl); got_rm.extend((rl[1:] + got_rm[-1]).tolist())
+    np.testing.assert_array_equal(np.concatenate(got_ind), ind)
+    np.testing.assert_array_equal(np.concatenate(got_val), val)
+    np.testing.assert_array_equal(np.array(got_rm, np.int32), rm)
+
+
+@pytest.mark.parametrize("content,msg", [
+    ("%%MatrixMarket matrix array real general\n2 2\n1\n2\n3\n4\n", "Unsupported matrix type"),
+    ("%MatrixMarket matrix coordinate real general\n1 1 1\n1 1 1\n", "Banner is missing"),
+    ("%%MatrixMarket matrix coordinate real general\n", "Malformed matrix size information"),
+    ("%%MatrixMarket matrix coordinate real general\n% only comments\n", "Malformed matrix size information"),
+    ("%%MatrixMarket matrix coordinate real general\n2 2 3\n1 1 1\n2 2 1\n", "premature end of entries"),
+    ("%%MatrixMarket matrix coordinate real general\n2 2 2\n1 1 1\n2 x 1\n", "premature end of entries"),
+    ("%%MatrixMarket matrix coordinate real general\n2 2 1\n3 1 1\n", "entry index out of range"),
+    ("%%MatrixMarket matrix coordinate real general", "Missing values in banner"),
+])
+def test_slab_loader_errors_like_the_full_reader(g, tmp_path, content, msg):
+    p = tmp_path / "bad.mtx"
+    p.write_text(content)
+    with pytest.raises(g.MpgError, match=msg):
+        g.read_matrix_market_slab(p, 0, -1)
+    with pytest.raises(g.MpgError, match=msg):     # the one-block reader says the same
+        g.read_matrix_market(p)
+    with pytest.raises(g.MpgError, match="Could not access file"):
+        g.read_matrix_market_slab(tmp_path / "missing.mtx", 0, -1)
+    ok = tmp_path / "ok.mtx"
+    ok.write_text("%%MatrixMarket matrix coordinate real general\n2 2 1\n1 2 3.5\n")
+    with pytest.raises(g.MpgError, match="row range outside the matrix"):
+        g.read_matrix_market_slab(ok, 1, 3)
+    n, nnzg, rl, il, vl = g.read_matrix_market_slab(ok, 0, -1)
+    assert (n, nnzg, rl.tolist(), il.tolist(), vl.tolist()) == (2, 3, [0, 2, 3], [0, 1, 1], [0.0, 3.5, 0.0])
