@@ -185,3 +185,75 @@ def test_slab_loader_errors_like_the_full_reader(g, tmp_path, content, msg):
         g.read_matrix_market_slab(ok, 1, 3)
     n, nnzg, rl, il, vl = g.read_matrix_market_slab(ok, 0, -1)
     assert (n, nnzg, rl.tolist(), il.tolist(), vl.tolist()) == (2, 3, [0, 2, 3], [0, 1, 1], [0.0, 3.5, 0.0])
+
+
+def _canonical_csr(n, entries, symmetric):
+    """LoadMatrix.hpp:62-145 in a few lines: a diagonal slot first in every row (file diagonal overwrites it, last one wins), entries in
+    file order with the mirrored ones interleaved as read, stable sort by column"""
+    rows = [[(r, 0.0)] for r in range(n)]
+    for i, j, v in entries:
+        if i == j:
+            rows[i][0] = (i, v)
+            continue
+        rows[i].append((j, v))
+        if symmetric:
+            rows[j].append((i, v))
+    rm, ind, val = [0], [], []
+    for r in rows:
+        r = sorted(r, key=lambda t: t[0])     # Python's sort is stable
+        ind += [c for c, _ in r]; val += [v for _, v in r]; rm.append(len(ind))
+    return np.array(rm, np.int32), np.array(ind, np.int32), np.array(val, np.float64)
+
+
+@pytest.mark.parametrize("threads,block", [(1, 1 << 26), (3, 257), (7, 1000), (16, 64)])
+@pytest.mark.parametrize("symmetric", [False, True])
+def test_parallel_parser_equals_the_sequential_definition(g, tmp_path, monkeypatch, threads, block, symmetric):
+    """the loaders convert the entry stream with several host threads over byte ranges and (slab reader) over blocks of the file: whatever
+    the number of threads and the block size, tokens torn by range / block boundaries, entries spread over several lines, duplicates,
+    repeated diagonals and trailing text after the last entry give the canonical CSR of the sequential definition"""
+    rng = np.random.default_rng(100 * threads + symmetric)
+    n, nz = 37, 400
+    ent = []
+    for _ in range(nz):
+        i, j = int(rng.integers(n)), int(rng.integers(n))
+        if symmetric and j > i:
+            i, j = j, i
+        ent.append((i, j, float(np.float32(rng.standard_normal()))))
+    seps = [" ", "\t", "  ", "\n", " \n ", "\r\n"]
+    text = f"%%MatrixMarket matrix coordinate real {'symmetric' if symmetric else 'general'}\n%c\n{n} {n} {nz}\n"
+    for k, (i, j, v) in enumerate(ent):
+        text += f"{i + 1}{seps[k % 6]}{j + 1}{seps[(k + 1) % 6]}{v!r}{seps[(k + 3) % 6] if k % 5 else chr(10)}"
+    text += "\nthis is not an entry 1 2 3\n"      # ignored: the reader stops after nz entries (LoadMatrix.hpp:68)
+    p = tmp_path / "m.mtx"
+    p.write_text(text)
+    monkeypatch.setenv("MPG_LOADER_THREADS", str(threads))
+    monkeypatch.setenv("MPG_LOADER_BLOCK", str(block))
+    rm, ind, val = _canonical_csr(n, ent, symmetric)
+    a = g.read_matrix_market(p)
+    np.testing.assert_array_equal(a[0], rm); np.testing.assert_array_equal(a[1], ind); np.testing.assert_array_equal(a[2], val)
+    for lo, hi in [(0, n), (5, 21), (36, 37), (0, 0)]:
+        _, nnzg, rl, il, vl, rg = g.read_matrix_market_slab(p, lo, hi, want_global_rowmap=True)
+        assert nnzg == len(ind)
+        np.testing.assert_array_equal(rg, rm)
+        np.testing.assert_array_equal(rl, rm[lo:hi + 1] - rm[lo])
+        np.testing.assert_array_equal(il, ind[rm[lo]:rm[hi]]); np.testing.assert_array_equal(vl, val[rm[lo]:rm[hi]])
+
+
+@pytest.mark.parametrize("threads,block", [(1, 1 << 26), (4, 64)])
+@pytest.mark.parametrize("body,msg", [
+    ("1 1 1\n9 1 1\n1 1 x\n1 1 1\n", "entry index out of range"),          # the range error is in an earlier entry than the bad token
+    ("1 1 1\n1 1 x\n9 1 1\n1 1 1\n", "premature end of entries"),          # the bad token comes first
+    ("1 1 1\n9 1 x\n1 1 1\n1 1 1\n", "premature end of entries"),          # same entry: the three fields are read before the indices are checked
+    ("1 1 1\n1 0 1\n1 1 1\n1 1 1\n", "entry index out of range"),
+    ("1 1 1\n1 1 1\n1 1 1\n1 1\n", "premature end of entries"),            # the file ends inside the last entry
+    ("1 1 1\n1 1.5 1\n1 1 1\n1 1 1\n", "premature end of entries"),        # an index that is not an integer
+])
+def test_parallel_parser_reports_the_first_error_in_file_order(g, tmp_path, monkeypatch, threads, block, body, msg):
+    p = tmp_path / "bad.mtx"
+    p.write_text("%%MatrixMarket matrix coordinate real general\n2 2 4\n" + body)
+    monkeypatch.setenv("MPG_LOADER_THREADS", str(threads))
+    monkeypatch.setenv("MPG_LOADER_BLOCK", str(block))
+    with pytest.raises(g.MpgError, match=msg):
+        g.read_matrix_market(p)
+    with pytest.raises(g.MpgError, match=msg):
+        g.read_matrix_market_slab(p, 0, -1)
