@@ -209,7 +209,7 @@ enum { MPG_PREC_IDENTITY = 0, MPG_PREC_JACOBI = 1, MPG_PREC_ILU_JACOBI = 2 };   
 
 typedef struct mpg_gmres_params {
     int32_t mode, orth, conv, prec;
-    int64_t restart_length; /* --rlen  */
+    int64_t restart_length; /* --rlen; 1 .. 255 (the fused passes keep one accumulator set per basis column: wider bases are rejected with MPG_ERR_ARG; the reference has no limit) */
     double tol;             /* --tol   */
     double restart_tol;     /* --rtol  */
     int64_t max_restarts;   /* --max-restarts */
